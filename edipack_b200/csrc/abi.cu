@@ -1,0 +1,557 @@
+// extern "C" entry points declared in include/edgpu.h.
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "edgpu_internal.cuh"
+
+namespace edgpu {
+
+Engine g;
+int g_status = 0;
+int64_t g_launches = 0;
+static char g_errbuf[1024] = "";
+
+int set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_errbuf, sizeof(g_errbuf), fmt, ap);
+  va_end(ap);
+  g_status = 1;
+  return 1;
+}
+void clear_error() {
+  g_errbuf[0] = 0;
+  g_status = 0;
+}
+
+int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, double threshold,
+                        double *alanc, double *blanc, int *nused);
+int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
+                   uint64_t seed, double *egs, double *d_vect, int *niter);
+
+// A state kept on the device (ED_EIGENSPACE state_list entry)
+struct StoredState {
+  int Ns = 0, nup = 0, ndw = 0;
+  int64_t dimu = 0, dimd = 0, ldu = 0, qdw = 0, d0 = 0;
+  double *vec = nullptr;
+};
+static std::map<int, StoredState> g_states;
+static double *g_current = nullptr;   // last ground-state vector (device, padded layout)
+static int64_t g_current_len = 0;
+static double *g_seed = nullptr;      // device-resident GF seed for the open sector
+static int64_t g_seed_len = 0;
+
+static int ensure_buf(double **p, int64_t *len, int64_t need) {
+  if (*p && *len >= need) return 0;
+  cudaFree(*p);
+  *p = nullptr;
+  EDGPU_CUDA(cudaMalloc(p, sizeof(double) * need));
+  *len = need;
+  return 0;
+}
+
+// reference chunk layout (contiguous columns of DimUp) <-> padded device layout
+static int upload(Engine &E, double *d_dst, const double *h_src) {
+  Sector &S = E.sec;
+  EDGPU_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(double) * S.padded_len(), E.stream));
+  EDGPU_CUDA(cudaMemcpy2DAsync(d_dst, sizeof(double) * S.up.ld, h_src, sizeof(double) * S.up.dim,
+                               sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyHostToDevice,
+                               E.stream));
+  return 0;
+}
+static int download(Engine &E, double *h_dst, const double *d_src) {
+  Sector &S = E.sec;
+  EDGPU_CUDA(cudaMemcpy2DAsync(h_dst, sizeof(double) * S.up.dim, d_src, sizeof(double) * S.up.ld,
+                               sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyDeviceToHost,
+                               E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// apply_op_C / apply_op_CDG (ED_SECTOR.f90:465-531, 654-720), gather form on the target
+// sector:  OV(j) = sgn * V(i)  with  |j> = op |i>.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_apply_op(const double *__restrict__ vsrc, int64_t lds, double *__restrict__ out, int64_t ldo,
+           int64_t nrow, int64_t ncol, const int32_t *__restrict__ map_t, int op, int bit, int spin,
+           int lo_bits, const int32_t *__restrict__ ja, const int32_t *__restrict__ jb) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (i >= nrow) return;
+  const int64_t t = (spin == 0) ? i : c;  // index of the operated species in the target sector
+  const uint32_t m = (uint32_t)map_t[t];
+  const bool occ = (m >> bit) & 1u;
+  double val = 0.0;
+  if ((op < 0 && !occ) || (op > 0 && occ)) {
+    const uint32_t ms = m ^ (1u << bit);  // source state of that species
+    const double sgn = (__popc(ms & ((1u << bit) - 1u)) & 1) ? -1.0 : 1.0;
+    const int64_t r = ja[ms >> lo_bits] + jb[ms & ((1u << lo_bits) - 1u)];
+    const int64_t si = (spin == 0) ? r : i, sc = (spin == 0) ? c : r;
+    val = sgn * vsrc[sc * lds + si];
+  }
+  out[c * ldo + i] = val;
+}
+
+// dens / docc partial sums (ED_OBSERVABLES_NORMAL.f90:150-215): out[a] += v^2 (nu+nd),
+// out[Norb+a] += v^2 nu nd
+__global__ void __launch_bounds__(256)
+k_observables(const double *__restrict__ v, int64_t ld, int64_t nrow, int64_t ncol,
+              int64_t col_offset, const uint8_t *__restrict__ impu,
+              const uint8_t *__restrict__ impd, int Norb, double *__restrict__ out) {
+  double acc[2 * EDGPU_MAXORB];
+#pragma unroll
+  for (int k = 0; k < 2 * EDGPU_MAXORB; k++) acc[k] = 0.0;
+  for (int64_t c = blockIdx.y; c < ncol; c += gridDim.y) {
+    const int md = impd[c + col_offset];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrow;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const double x = v[c * ld + i];
+      const double w = x * x;
+      const int mu = impu[i];
+#pragma unroll
+      for (int a = 0; a < EDGPU_MAXORB; a++) {
+        if (a < Norb) {
+          const int nu = (mu >> a) & 1, nd = (md >> a) & 1;
+          acc[a] += w * (nu + nd);
+          acc[EDGPU_MAXORB + a] += w * (nu * nd);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2 * EDGPU_MAXORB; k++) {
+    double x = acc[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(out + k, x);
+  }
+}
+
+__constant__ int32_t c_binom2[33][33];
+__global__ void k_map_lite(int32_t *__restrict__ map, int64_t dim, int Ns, int nel) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= dim) return;
+  int64_t rem = r;
+  int k = nel;
+  uint32_t m = 0;
+  for (int pos = Ns - 1; pos >= 0 && k > 0; --pos) {
+    int64_t cc = c_binom2[pos][k];
+    if (rem >= cc) {
+      m |= (1u << pos);
+      rem -= cc;
+      --k;
+    }
+  }
+  map[r] = (int32_t)m;
+}
+__global__ void k_lin_ja2(const int32_t *__restrict__ map, int64_t dim, int lo_bits,
+                          int32_t *__restrict__ ja) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= dim) return;
+  uint32_t hi = (uint32_t)map[r] >> lo_bits;
+  if (r == 0 || ((uint32_t)map[r - 1] >> lo_bits) != hi) ja[hi] = (int32_t)r;
+}
+__global__ void k_lin_jb2(const int32_t *__restrict__ map, int64_t dim, int lo_bits,
+                          const int32_t *__restrict__ ja, int32_t *__restrict__ jb) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= dim) return;
+  uint32_t m = (uint32_t)map[r];
+  jb[m & ((1u << lo_bits) - 1u)] = (int32_t)(r - ja[m >> lo_bits]);
+}
+
+}  // namespace edgpu
+
+using namespace edgpu;
+
+extern "C" {
+
+int edgpu_init(int device) {
+  clear_error();
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_error("no CUDA device available (%s); this engine has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return set_error("device %d out of range (%d devices)", device, ndev);
+  EDGPU_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  EDGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_error("device %d is sm_%d%d; this library is built for sm_100a only", device,
+                     prop.major, prop.minor);
+  if (g.inited && g.device == device) return 0;
+  if (g.inited) edgpu_finalize();
+  g.device = device;
+  g.sm_count = prop.multiProcessorCount;
+  g.smem_optin = prop.sharedMemPerBlockOptin;
+  EDGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (auto &ev : g.ev) EDGPU_CUDA(cudaEventCreate(&ev));
+  g.part_cap = (int64_t)g.sm_count * 8;
+  EDGPU_CUDA(cudaMalloc(&g.d_part, sizeof(double) * g.part_cap));
+  EDGPU_CUDA(cudaMalloc(&g.d_scal, sizeof(double) * 64));
+  EDGPU_CUDA(cudaMallocHost(&g.h_scal, sizeof(double) * 64));
+  g.rank = 0;
+  g.nranks = 1;
+  g.inited = true;
+  return 0;
+}
+
+int edgpu_finalize(void) {
+  if (!g.inited) return 0;
+  sector_close(g);
+  for (auto &kv : g_states) cudaFree(kv.second.vec);
+  g_states.clear();
+  cudaFree(g_current);
+  g_current = nullptr;
+  g_current_len = 0;
+  cudaFree(g_seed);
+  g_seed = nullptr;
+  g_seed_len = 0;
+  comm_finalize(g);
+  cudaFree(g.d_part);
+  cudaFree(g.d_scal);
+  cudaFreeHost(g.h_scal);
+  for (auto &ev : g.ev) cudaEventDestroy(ev);
+  for (auto &ev : g.prof_ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(g.stream);
+  g = Engine();
+  return 0;
+}
+
+int edgpu_comm_unique_id(void *uid) {
+  clear_error();
+  return comm_unique_id(uid);
+}
+int edgpu_comm_init(int rank, int nranks, const void *uid) {
+  clear_error();
+  return comm_init(g, rank, nranks, uid);
+}
+int edgpu_comm_rank(void) { return g.rank; }
+int edgpu_comm_size(void) { return g.nranks; }
+
+int edgpu_sector_open_normal(const edgpu_normal_params *p, int nup, int ndw) {
+  clear_error();
+  if (!p) return set_error("null params");
+  return sector_open(g, p, nup, ndw);
+}
+int edgpu_sector_close(void) {
+  clear_error();
+  return sector_close(g);
+}
+int64_t edgpu_sector_vecdim(void) { return g.sec.open ? g.sec.up.dim * g.sec.qdw : 0; }
+int64_t edgpu_sector_dim(void) { return g.sec.open ? g.sec.up.dim * g.sec.dw.dim : 0; }
+int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_start) {
+  if (!g.sec.open) return set_error("no sector open");
+  if (DimUp) *DimUp = g.sec.up.dim;
+  if (DimDw) *DimDw = g.sec.dw.dim;
+  if (qdw) *qdw = g.sec.qdw;
+  if (dw_start) *dw_start = g.sec.d0;
+  return 0;
+}
+
+int edgpu_sector_get_map(int spin, int32_t *map) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  SpinSpace &S = spin == 0 ? g.sec.up : g.sec.dw;
+  EDGPU_CUDA(cudaMemcpy(map, S.map, sizeof(int32_t) * S.dim, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int64_t edgpu_sector_hop_count(int spin) {
+  clear_error();
+  if (!g.sec.open) {
+    set_error("no sector open");
+    return -1;
+  }
+  SpinSpace &S = spin == 0 ? g.sec.up : g.sec.dw;
+  std::vector<uint32_t> ell((size_t)std::max(S.W, 1) * S.ld);
+  if (cudaMemcpy(ell.data(), S.ell, sizeof(uint32_t) * ell.size(), cudaMemcpyDeviceToHost) !=
+      cudaSuccess) {
+    set_error("hop table download failed");
+    return -1;
+  }
+  int64_t n = 0;
+  for (int e = 0; e < S.W; e++)
+    for (int64_t r = 0; r < S.dim; r++)
+      if (((ell[(size_t)e * S.ld + r] >> HOP_AMP_SHIFT) & HOP_AMP_MASK) != (uint32_t)S.nterms) n++;
+  return n;
+}
+
+int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *value) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  SpinSpace &S = spin == 0 ? g.sec.up : g.sec.dw;
+  std::vector<uint32_t> ell((size_t)std::max(S.W, 1) * S.ld);
+  EDGPU_CUDA(cudaMemcpy(ell.data(), S.ell, sizeof(uint32_t) * ell.size(), cudaMemcpyDeviceToHost));
+  std::vector<double> amp(S.nterms + 1);
+  EDGPU_CUDA(cudaMemcpy(amp.data(), S.amp, sizeof(double) * amp.size(), cudaMemcpyDeviceToHost));
+  int64_t n = 0;
+  for (int64_t r = 0; r < S.dim; r++) {
+    rowptr[r] = n;
+    for (int e = 0; e < S.W; e++) {
+      uint32_t ent = ell[(size_t)e * S.ld + r];
+      uint32_t id = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
+      if (id == (uint32_t)S.nterms) continue;
+      target[n] = (int32_t)(ent & HOP_TGT_MASK) + 1;
+      value[n] = (ent & HOP_SIGN) ? -amp[id] : amp[id];
+      n++;
+    }
+  }
+  rowptr[S.dim] = n;
+  return 0;
+}
+
+int64_t edgpu_vec_padded_len(void) { return g.sec.open ? g.sec.padded_len() : 0; }
+int edgpu_vec_upload(double *d_dst, const double *h_src) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  EDGPU_TRY(upload(g, d_dst, h_src));
+  EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+int edgpu_vec_download(double *h_dst, const double *d_src) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  return download(g, h_dst, d_src);
+}
+
+int edgpu_hxv_dev(const double *d_v, double *d_Hv) {
+  clear_error();
+  return hxv_device(g, d_v, d_Hv, false, true);
+}
+
+static double *g_hx_in = nullptr, *g_hx_out = nullptr;
+static int64_t g_hx_in_len = 0, g_hx_out_len = 0;
+
+void edgpu_hxv_d(const int32_t *Nloc, const double *v, double *Hv) {
+  clear_error();
+  if (!g.sec.open) {
+    set_error("edgpu_hxv_d: no sector open (spHtimesV_p used outside build/delete_Hv_sector)");
+    return;
+  }
+  // "if(Nloc/=getdim(isector))stop" (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:52)
+  if ((int64_t)*Nloc != edgpu_sector_vecdim()) {
+    set_error("edgpu_hxv_d: Nloc=%d /= vecDim=%lld", (int)*Nloc, (long long)edgpu_sector_vecdim());
+    return;
+  }
+  const int64_t n = g.sec.padded_len();
+  if (ensure_buf(&g_hx_in, &g_hx_in_len, n) || ensure_buf(&g_hx_out, &g_hx_out_len, n)) return;
+  if (upload(g, g_hx_in, v)) return;
+  if (hxv_device(g, g_hx_in, g_hx_out, false, false)) return;
+  download(g, Hv, g_hx_out);
+}
+
+int edgpu_status(void) { return g_status; }
+const char *edgpu_last_error(void) { return g_errbuf; }
+
+int64_t edgpu_launch_count(int reset) {
+  int64_t n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+int edgpu_last_hxv_stage_ms(float *out4) {
+  for (int i = 0; i < 4; i++) out4[i] = g.stage_ms[i];
+  return 0;
+}
+
+void *edgpu_stream(void) { return (void *)g.stream; }
+
+int edgpu_profile_begin(int max_steps) {
+  clear_error();
+  if (!g.inited) return set_error("edgpu_init was not called");
+  if (max_steps < 1) max_steps = 1;
+  while ((int)g.prof_ev.size() < 4 * max_steps) {
+    cudaEvent_t e;
+    EDGPU_CUDA(cudaEventCreate(&e));
+    g.prof_ev.push_back(e);
+  }
+  g.prof_cap = max_steps;
+  g.prof_n = 0;
+  g.prof_on = true;
+  return 0;
+}
+
+int edgpu_profile_end(float *ms3, int *nsteps) {
+  clear_error();
+  g.prof_on = false;
+  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  *nsteps = g.prof_n;
+  if (g.prof_n == 0) return 0;
+  EDGPU_CUDA(cudaEventSynchronize(g.prof_ev[(size_t)4 * (g.prof_n - 1) + 3]));
+  for (int i = 0; i < g.prof_n; i++)
+    for (int k = 0; k < 3; k++) {
+      float ms = 0.f;
+      EDGPU_CUDA(cudaEventElapsedTime(&ms, g.prof_ev[(size_t)4 * i + k], g.prof_ev[(size_t)4 * i + k + 1]));
+      ms3[k] += ms;
+    }
+  return 0;
+}
+
+int edgpu_set_kernel_variant(int variant) {
+  g.variant_request = variant;
+  if (g.sec.open) g.sec.variant = variant;
+  return 0;
+}
+
+int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, uint64_t seed,
+                     double *egs, double *vec_host, int *niter) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  const int64_t n = g.sec.padded_len();
+  EDGPU_TRY(ensure_buf(&g_current, &g_current_len, n));
+  double *d_start = nullptr;
+  if (use_start) {
+    if (!vec_host) return set_error("use_start set but vec_host is NULL");
+    EDGPU_CUDA(cudaMalloc(&d_start, sizeof(double) * n));
+    int rc = upload(g, d_start, vec_host);
+    if (rc) {
+      cudaFree(d_start);
+      return rc;
+    }
+  }
+  int rc = lanczos_gs_dev(g, nitermax, threshold, ncheck, d_start, seed, egs, g_current, niter);
+  cudaFree(d_start);
+  if (rc) return rc;
+  if (vec_host) EDGPU_TRY(download(g, vec_host, g_current));
+  return 0;
+}
+
+int edgpu_lanczos_tridiag(const double *seed_host, int nlanc, double threshold, double *alanc,
+                          double *blanc, int *nused, double *norm2) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  const int64_t n = g.sec.padded_len();
+  if (seed_host) {
+    EDGPU_TRY(ensure_buf(&g_seed, &g_seed_len, n));
+    EDGPU_TRY(upload(g, g_seed, seed_host));
+  } else if (!g_seed || g_seed_len < n) {
+    return set_error("no device-resident seed: call edgpu_apply_op first or pass seed_host");
+  }
+  // norm2 = <vvinit|vvinit>; vvinit /= sqrt(norm2) (ED_HAMILTONIAN_NORMAL.f90:344-347)
+  double n2 = 0.0;
+  EDGPU_TRY(vec_dot(g, g_seed, g_seed, &n2));
+  if (norm2) *norm2 = n2;
+  for (int i = 0; i < nlanc; i++) alanc[i] = blanc[i] = 0.0;
+  *nused = 0;
+  if (n2 == 0.0) return 0;  // "if(norm2/=0d0)" (:355)
+  const int64_t dim_global = g.sec.up.dim * g.sec.dw.dim;
+  if (nlanc > dim_global) nlanc = (int)dim_global;
+  double *work = nullptr;
+  EDGPU_CUDA(cudaMalloc(&work, sizeof(double) * n));
+  int rc = lanczos_tridiag_dev(g, g_seed, work, nlanc, threshold, alanc, blanc, nused);
+  cudaFree(work);
+  return rc;
+}
+
+int edgpu_state_store(int slot) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  if (!g_current) return set_error("no current state (run edgpu_lanczos_gs first)");
+  edgpu_state_free(slot);
+  StoredState st;
+  Sector &S = g.sec;
+  st.Ns = S.Ns;
+  st.nup = S.up.nel;
+  st.ndw = S.dw.nel;
+  st.dimu = S.up.dim;
+  st.dimd = S.dw.dim;
+  st.ldu = S.up.ld;
+  st.qdw = S.qdw;
+  st.d0 = S.d0;
+  const int64_t n = S.padded_len();
+  EDGPU_CUDA(cudaMalloc(&st.vec, sizeof(double) * n));
+  EDGPU_CUDA(cudaMemcpyAsync(st.vec, g_current, sizeof(double) * n, cudaMemcpyDeviceToDevice, g.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+  g_states[slot] = st;
+  return 0;
+}
+
+int edgpu_state_free(int slot) {
+  auto it = g_states.find(slot);
+  if (it != g_states.end()) {
+    cudaFree(it->second.vec);
+    g_states.erase(it);
+  }
+  return 0;
+}
+
+int edgpu_apply_op(int slot, int op, int iorb, int spin) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  auto it = g_states.find(slot);
+  if (it == g_states.end()) return set_error("state slot %d is empty", slot);
+  StoredState &st = it->second;
+  Sector &S = g.sec;
+  if (op != 1 && op != -1) return set_error("op must be +1 (CDG) or -1 (C)");
+  if (spin != 0 && spin != 1) return set_error("spin must be 0 or 1");
+  if (iorb < 0 || iorb >= S.Norb) return set_error("iorb out of range");
+  const int tnup = st.nup + (spin == 0 ? op : 0), tndw = st.ndw + (spin == 1 ? op : 0);
+  if (S.Ns != st.Ns || S.up.nel != tnup || S.dw.nel != tndw)
+    return set_error("open sector (%d,%d) is not the target sector (%d,%d) of the operator",
+                     S.up.nel, S.dw.nel, tnup, tndw);
+  if (g.nranks > 1 && spin == 1)
+    return set_error("apply_op on the dw species with nranks>1 is not implemented yet");
+  // ranking tables of the SOURCE species
+  const int nel_src = spin == 0 ? st.nup : st.ndw;
+  const int64_t dim_src = spin == 0 ? st.dimu : st.dimd;
+  const int lo_bits = S.Ns / 2, hi_bits = S.Ns - lo_bits;
+  int32_t *map = nullptr, *ja = nullptr, *jb = nullptr;
+  int32_t hb[33][33];
+  for (int n = 0; n < 33; n++)
+    for (int k = 0; k < 33; k++) hb[n][k] = (int32_t)std::min<int64_t>(host_binomial(n, k), INT32_MAX);
+  EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_binom2, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, g.stream));
+  EDGPU_CUDA(cudaMalloc(&map, sizeof(int32_t) * dim_src));
+  EDGPU_CUDA(cudaMalloc(&ja, sizeof(int32_t) * ((size_t)1 << hi_bits)));
+  EDGPU_CUDA(cudaMalloc(&jb, sizeof(int32_t) * ((size_t)1 << lo_bits)));
+  EDGPU_CUDA(cudaMemsetAsync(ja, 0, sizeof(int32_t) * ((size_t)1 << hi_bits), g.stream));
+  EDGPU_CUDA(cudaMemsetAsync(jb, 0, sizeof(int32_t) * ((size_t)1 << lo_bits), g.stream));
+  const unsigned gb = (unsigned)((dim_src + 255) / 256);
+  k_map_lite<<<gb, 256, 0, g.stream>>>(map, dim_src, S.Ns, nel_src);
+  k_lin_ja2<<<gb, 256, 0, g.stream>>>(map, dim_src, lo_bits, ja);
+  k_lin_jb2<<<gb, 256, 0, g.stream>>>(map, dim_src, lo_bits, ja, jb);
+  g_launches += 3;
+  const int64_t n = S.padded_len();
+  EDGPU_TRY(ensure_buf(&g_seed, &g_seed_len, n));
+  EDGPU_CUDA(cudaMemsetAsync(g_seed, 0, sizeof(double) * n, g.stream));
+  dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
+  k_apply_op<<<grid, 128, 0, g.stream>>>(st.vec, st.ldu, g_seed, S.up.ld, S.up.dim, S.qdw,
+                                         spin == 0 ? S.up.map : S.dw.map + S.d0, op, iorb, spin,
+                                         lo_bits, ja, jb);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+  cudaFree(map);
+  cudaFree(ja);
+  cudaFree(jb);
+  return 0;
+}
+
+int edgpu_state_observables(int slot, double *dens, double *docc) {
+  clear_error();
+  auto it = g_states.find(slot);
+  if (it == g_states.end()) return set_error("state slot %d is empty", slot);
+  StoredState &st = it->second;
+  Sector &S = g.sec;
+  if (!S.open || S.up.nel != st.nup || S.dw.nel != st.ndw || S.Ns != st.Ns)
+    return set_error("the state's own sector must be open for observables");
+  double *d_out = g.d_scal + 8;
+  EDGPU_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * EDGPU_MAXORB, g.stream));
+  dim3 grid((unsigned)std::min<int64_t>((S.up.dim + 255) / 256, 64),
+            (unsigned)std::min<int64_t>(S.qdw, 1024));
+  k_observables<<<grid, 256, 0, g.stream>>>(st.vec, st.ldu, S.up.dim, S.qdw, S.d0, S.up.imp,
+                                            S.dw.imp, S.Norb, d_out);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_TRY(comm_allreduce_sum(g, d_out, 2 * EDGPU_MAXORB));
+  EDGPU_CUDA(cudaMemcpyAsync(g.h_scal + 8, d_out, sizeof(double) * 2 * EDGPU_MAXORB,
+                             cudaMemcpyDeviceToHost, g.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+  for (int a = 0; a < S.Norb; a++) {
+    dens[a] = g.h_scal[8 + a];
+    docc[a] = g.h_scal[8 + EDGPU_MAXORB + a];
+  }
+  return 0;
+}
+
+}  // extern "C"

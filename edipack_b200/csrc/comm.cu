@@ -1,0 +1,220 @@
+// Rank plumbing for the dw-split layout: NCCL (loaded at run time) + the distributed
+// matrix transpose that replaces vector_transpose_MPI
+// (ED_HAMILTONIAN_NORMAL_COMMON.f90:66-178).
+//
+// The reference issues one MPI_Alltoallv per local column plus one MPI_Alltoall of counts
+// per column (:115-162).  Here each rank packs ONE transposed tile per peer with a
+// shared-memory tile-transpose kernel, exchanges all tiles in a single
+// ncclGroupStart/End of ncclSend/ncclRecv over NVLink, and unpacks (or accumulates) with a
+// strided copy kernel; the rank's own tile never leaves the device.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "edgpu_internal.cuh"
+
+namespace edgpu {
+
+// ---- minimal NCCL surface, resolved with dlopen so that the library has no link-time
+// ---- dependency (torch ships its own libnccl.so.2; the system one is used otherwise)
+typedef struct {
+  char internal[128];
+} nccl_uid_t;
+typedef void *nccl_comm_t;
+enum { NCCL_SUM = 0, NCCL_FLOAT64 = 8 };
+static struct {
+  void *h = nullptr;
+  int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+  int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+} N;
+
+static int nccl_load() {
+  if (N.h) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    N.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (N.h) break;
+  }
+  if (!N.h) return set_error("cannot load libnccl.so.2: %s", dlerror());
+#define EDGPU_SYM(field, name)                                            \
+  *(void **)(&N.field) = dlsym(N.h, name);                                \
+  if (!N.field) return set_error("NCCL symbol %s not found", name);
+  EDGPU_SYM(GetUniqueId, "ncclGetUniqueId");
+  EDGPU_SYM(CommInitRank, "ncclCommInitRank");
+  EDGPU_SYM(CommDestroy, "ncclCommDestroy");
+  EDGPU_SYM(Send, "ncclSend");
+  EDGPU_SYM(Recv, "ncclRecv");
+  EDGPU_SYM(GroupStart, "ncclGroupStart");
+  EDGPU_SYM(GroupEnd, "ncclGroupEnd");
+  EDGPU_SYM(AllReduce, "ncclAllReduce");
+  EDGPU_SYM(AllGather, "ncclAllGather");
+  EDGPU_SYM(GetErrorString, "ncclGetErrorString");
+#undef EDGPU_SYM
+  return 0;
+}
+
+#define EDGPU_NCCL(call)                                                                   \
+  do {                                                                                     \
+    int _r = (call);                                                                       \
+    if (_r != 0) return set_error("%s failed: %s", #call, N.GetErrorString(_r));           \
+  } while (0)
+
+int comm_unique_id(void *uid) {
+  EDGPU_TRY(nccl_load());
+  static_assert(sizeof(nccl_uid_t) == EDGPU_UID_BYTES, "uid size");
+  nccl_uid_t id;
+  EDGPU_NCCL(N.GetUniqueId(&id));
+  memcpy(uid, &id, sizeof(id));
+  return 0;
+}
+
+int comm_init(Engine &E, int rank, int nranks, const void *uid) {
+  if (!E.inited) return set_error("edgpu_init was not called");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return set_error("bad rank %d / %d", rank, nranks);
+  if (E.sec.open) return set_error("close the sector before (re)initialising the communicator");
+  comm_finalize(E);
+  E.rank = rank;
+  E.nranks = nranks;
+  if (nranks == 1) return 0;
+  EDGPU_TRY(nccl_load());
+  nccl_uid_t id;
+  memcpy(&id, uid, sizeof(id));
+  nccl_comm_t c = nullptr;
+  EDGPU_NCCL(N.CommInitRank(&c, nranks, id, rank));
+  E.nccl = c;
+  return 0;
+}
+
+int comm_finalize(Engine &E) {
+  if (E.nccl) {
+    N.CommDestroy((nccl_comm_t)E.nccl);
+    E.nccl = nullptr;
+  }
+  E.rank = 0;
+  E.nranks = 1;
+  return 0;
+}
+
+int comm_allreduce_sum(Engine &E, double *d_buf, int n) {
+  if (E.nranks == 1) return 0;
+  EDGPU_NCCL(N.AllReduce(d_buf, d_buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)E.nccl,
+                         E.stream));
+  return 0;
+}
+
+// out[(i - i0) * ldo + j] = in[j * ldi + i]   for i in [i0, i0+ni), j in [0, nj)
+// (tile transpose of a ni x nj block through shared memory; in has i fast, out has j fast)
+template <bool ACCUM>
+__global__ void __launch_bounds__(256)
+k_transpose_tile(const double *__restrict__ in, int64_t ldi, double *__restrict__ out,
+                 int64_t ldo, int64_t i0, int64_t ni, int64_t nj) {
+  __shared__ double t[32][33];
+  const int64_t ib = (int64_t)blockIdx.x * 32, jb = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    int64_t i = ib + tx, j = jb + ty + k;
+    if (i < ni && j < nj) t[ty + k][tx] = in[j * ldi + i0 + i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    int64_t j = jb + tx, i = ib + ty + k;
+    if (i < ni && j < nj) {
+      double *o = out + i * ldo + j;
+      *o = ACCUM ? (*o + t[tx][ty + k]) : t[tx][ty + k];
+    }
+  }
+}
+
+// out[i * ldo + j] (+)= in[i * nj + j] : unpack a received (already transposed) tile
+template <bool ACCUM>
+__global__ void __launch_bounds__(256)
+k_unpack(const double *__restrict__ in, double *__restrict__ out, int64_t ldo, int64_t ni,
+         int64_t nj) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j < nj && i < ni) {
+    double *o = out + i * ldo + j;
+    *o = ACCUM ? (*o + in[i * nj + j]) : in[i * nj + j];
+  }
+}
+
+// B(j_global, i_loc) = A_global(i0_me + i_loc, j): A is this rank's [nrow x qcol] column
+// block (lda), B its [ncol x qrow] block of the transposed matrix (ldb).
+// vector_transpose_MPI(nrow,qcol,a,ncol,qrow,b), ..._COMMON.f90:66.
+int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int64_t qcol,
+                   double *d_b, int64_t ncol, int64_t ldb, int64_t qrow, bool accumulate) {
+  const int P = E.nranks, me = E.rank;
+  Sector &S = E.sec;
+  cudaStream_t st = E.stream;
+  int64_t c0_me, qc_me, r0_me, qr_me;
+  block_split(ncol, P, me, &qc_me, &c0_me);
+  block_split(nrow, P, me, &qr_me, &r0_me);
+  if (qc_me != qcol || qr_me != qrow) return set_error("comm_transpose: split mismatch");
+  const size_t need = (size_t)nrow * qcol > (size_t)ncol * qrow ? (size_t)nrow * qcol
+                                                                 : (size_t)ncol * qrow;
+  if (P > 1 && !S.sendbuf) {
+    // both directions of one H x v use the same element count
+    EDGPU_CUDA(cudaMalloc(&S.sendbuf, sizeof(double) * need));
+    EDGPU_CUDA(cudaMalloc(&S.recvbuf, sizeof(double) * need));
+  }
+  // pack: for peer p the tile rows [r0_p, r0_p+qr_p) x my columns, stored [i_loc][jc]
+  std::vector<int64_t> soff(P + 1, 0), roff(P + 1, 0);
+  for (int p = 0; p < P; p++) {
+    int64_t qr, r0, qc, c0;
+    block_split(nrow, P, p, &qr, &r0);
+    block_split(ncol, P, p, &qc, &c0);
+    soff[p + 1] = soff[p] + (p == me ? 0 : qr * qcol);
+    roff[p + 1] = roff[p] + (p == me ? 0 : qrow * qc);
+  }
+  for (int p = 0; p < P; p++) {
+    int64_t qr, r0;
+    block_split(nrow, P, p, &qr, &r0);
+    dim3 grid((unsigned)((qr + 31) / 32), (unsigned)((qcol + 31) / 32));
+    if (p == me) {
+      // own tile: straight into B at column offset c0_me
+      if (accumulate)
+        k_transpose_tile<true><<<grid, 256, 0, st>>>(d_a, lda, d_b + c0_me, ldb, r0, qr, qcol);
+      else
+        k_transpose_tile<false><<<grid, 256, 0, st>>>(d_a, lda, d_b + c0_me, ldb, r0, qr, qcol);
+    } else {
+      k_transpose_tile<false><<<grid, 256, 0, st>>>(d_a, lda, S.sendbuf + soff[p], qcol, r0, qr,
+                                                    qcol);
+    }
+    EDGPU_COUNT_LAUNCH();
+  }
+  EDGPU_CUDA(cudaGetLastError());
+  if (P == 1) return 0;
+  EDGPU_NCCL(N.GroupStart());
+  for (int p = 0; p < P; p++) {
+    if (p == me) continue;
+    size_t ns = (size_t)(soff[p + 1] - soff[p]), nr = (size_t)(roff[p + 1] - roff[p]);
+    EDGPU_NCCL(N.Send(S.sendbuf + soff[p], ns, NCCL_FLOAT64, p, (nccl_comm_t)E.nccl, st));
+    EDGPU_NCCL(N.Recv(S.recvbuf + roff[p], nr, NCCL_FLOAT64, p, (nccl_comm_t)E.nccl, st));
+  }
+  EDGPU_NCCL(N.GroupEnd());
+  for (int p = 0; p < P; p++) {
+    if (p == me) continue;
+    int64_t qc, c0;
+    block_split(ncol, P, p, &qc, &c0);
+    dim3 grid((unsigned)((qc + 255) / 256), (unsigned)qrow);
+    if (accumulate)
+      k_unpack<true><<<grid, 256, 0, st>>>(S.recvbuf + roff[p], d_b + c0, ldb, qrow, qc);
+    else
+      k_unpack<false><<<grid, 256, 0, st>>>(S.recvbuf + roff[p], d_b + c0, ldb, qrow, qc);
+    EDGPU_COUNT_LAUNCH();
+  }
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace edgpu

@@ -1,0 +1,164 @@
+// Internal declarations of the edgpu engine (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/edgpu.h"
+
+namespace edgpu {
+
+// ---------------------------------------------------------------------------------------
+// error latch (the reference aborts with `stop "msg"`; the ABI returns codes instead)
+// ---------------------------------------------------------------------------------------
+int set_error(const char *fmt, ...);
+void clear_error();
+extern int g_status;
+
+#define EDGPU_CUDA(call)                                                                  \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return ::edgpu::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),   \
+                                __FILE__, __LINE__);                                      \
+  } while (0)
+
+#define EDGPU_TRY(call)        \
+  do {                         \
+    int _rc = (call);          \
+    if (_rc != 0) return _rc;  \
+  } while (0)
+
+extern int64_t g_launches;  // kernels launched by this library (bench "gpu_launches")
+#define EDGPU_COUNT_LAUNCH() (++::edgpu::g_launches)
+
+// ---------------------------------------------------------------------------------------
+// hop-table entry packing: [19:0] target row, [30:20] amplitude id, [31] sign
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t HOP_TGT_MASK = 0xFFFFFu;
+constexpr int HOP_AMP_SHIFT = 20;
+constexpr uint32_t HOP_AMP_MASK = 0x7FFu;
+constexpr uint32_t HOP_SIGN = 0x80000000u;
+constexpr int HOP_MAX_TERMS = 2046;
+
+struct Term {  // one directed one-body term  h * c^+_alpha c_beta  (bit positions, 0-based)
+  int32_t alpha, beta;
+  double h;
+};
+
+// Lin two-table ranking: rank(m) = ja[m >> lo_bits] + jb[m & lo_mask]
+struct LinTable {
+  int lo_bits = 0;
+  int32_t *ja = nullptr;  // [2^(Ns-lo_bits)]
+  int32_t *jb = nullptr;  // [2^lo_bits]
+};
+
+// One spin species of the open sector
+struct SpinSpace {
+  int nel = 0;
+  int64_t dim = 0;         // DimUp or DimDw
+  int64_t ld = 0;          // dim padded to a multiple of 16 (128 B)
+  int32_t *map = nullptr;  // [dim] sector index -> Fock integer (ascending)
+  LinTable lin;
+  double *eps = nullptr;   // [ld] single-spin diagonal energy
+  uint8_t *imp = nullptr;  // [ld] impurity occupation bits (map & (2^Norb-1))
+  // hop table, ELL, column-major: ell[e*ld + row]
+  int W = 0;
+  int nterms = 0;
+  uint32_t *ell = nullptr;
+  double *amp = nullptr;   // [nterms+1], amp[nterms] = 0 (padding slot)
+  std::vector<Term> terms; // host copy
+};
+
+struct Sector {
+  bool open = false;
+  edgpu_normal_params prm;
+  int Ns = 0, Norb = 0;
+  SpinSpace up, dw;
+  // dw split of ED_HAMILTONIAN_NORMAL.f90:128-142
+  int64_t qdw = 0, d0 = 0;  // local dw columns [d0, d0+qdw)
+  int64_t qup = 0, u0 = 0;  // local up rows of the transposed layout
+  double *xud = nullptr;    // [2^Norb (dw imp)][2^Norb (up imp)] cross interaction + constants
+  bool nonlocal = false;
+  double *jx = nullptr, *jp = nullptr;  // [Norb*Norb] device copies
+  // dw-range segmentation for the tiled dw kernel (single GPU)
+  std::vector<int64_t> seg_start;  // host, nseg+1
+  int64_t *d_seg_start = nullptr;
+  int nseg = 0;
+  int64_t max_seg = 0;
+  int dw_rows = 8;  // R
+  // up-range tiling
+  int64_t up_tile = 0;  // rows per tile
+  int up_cols = 1;      // columns per CTA
+  int variant = 0;
+  // scratch for the distributed transposes
+  double *vt = nullptr, *hvt = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
+  int64_t padded_len() const { return up.ld * qdw; }
+  int64_t padded_len_t() const { return dw.ld * qup; }
+};
+
+struct Engine {
+  bool inited = false;
+  int device = -1;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  // communicator
+  int rank = 0, nranks = 1;
+  void *nccl = nullptr;  // ncclComm_t
+  // scalar scratch
+  double *d_scal = nullptr;   // device scalars (dots etc.)
+  double *h_scal = nullptr;   // pinned host mirror
+  double *d_part = nullptr;   // block partials
+  int64_t part_cap = 0;
+  Sector sec;
+  int variant_request = 0;
+  float stage_ms[4] = {0, 0, 0, 0};
+  // profiling ring (edgpu_profile_begin/end): 4 events per recorded H x v
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_cap = 0, prof_n = 0;
+  bool prof_on = false;
+};
+
+extern Engine g;
+
+// sector.cu
+int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw);
+int sector_close(Engine &E);
+int64_t host_binomial(int n, int k);
+void block_split(int64_t n, int P, int r, int64_t *q, int64_t *start);
+
+// hxv.cu
+int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed);
+
+// comm.cu
+int comm_unique_id(void *uid);
+int comm_init(Engine &E, int rank, int nranks, const void *uid);
+int comm_allreduce_sum(Engine &E, double *d_buf, int n);
+int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int64_t qcol,
+                   double *d_b, int64_t ncol, int64_t ldb, int64_t qrow, bool accumulate);
+int comm_finalize(Engine &E);
+
+// vecops.cu
+int vec_fill_random(Engine &E, double *d_v, uint64_t seed);
+int vec_zero(Engine &E, double *d_v, int64_t n);
+int vec_dot(Engine &E, const double *a, const double *b, double *h_out);  // all-reduced
+int vec_scale(Engine &E, double *a, double s);
+// (a,b) <- (b/beta, -beta*a)
+int vec_swap_scale(Engine &E, double *a, double *b, double beta);
+// w += t ; alpha = <v,w>
+int vec_add_dot(Engine &E, double *w, const double *t, const double *v, double *h_alpha);
+// w -= alpha v ; beta2 = <w,w>
+int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2);
+int vec_axpy(Engine &E, double *y, const double *x, double a);
+
+// lanczos.cu
+int tridiag_eig(int n, const double *diag, const double *sub, double *evals, double *evecs,
+                bool want_vecs);
+
+}  // namespace edgpu

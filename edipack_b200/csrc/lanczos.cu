@@ -1,0 +1,205 @@
+// Device-resident Lanczos drivers: replacements for SciFortran SF_SP_LINALG
+// sp_lanc_eigh / sp_lanc_tridiag as called from ED_DIAG_NORMAL.f90:206-213 and
+// ED_HAMILTONIAN_NORMAL.f90:360-365.  SciFortran is not part of the reference tree
+// (unpinned external dependency); the recurrence below is its published three-term form:
+//
+//   iter==1 : vin /= |vin|                       else : (vin,vout) <- (vout/beta, -beta*vin)
+//   vout += H vin ; alfa = <vin,vout> ; vout -= alfa*vin ; beta = |vout|
+//
+// All Lanczos vectors stay in HBM; per iteration the host only sees alfa and beta.
+#include <algorithm>
+#include <cmath>
+
+#include "edgpu_internal.cuh"
+
+namespace edgpu {
+
+// Symmetric tridiagonal eigen-solver (implicit QL with Wilkinson shifts), the role of
+// SciFortran's tql2 / LAPACK dstev used at ED_GF_NORMAL.f90:416.
+// diag[n], sub[n-1] (sub[i] couples i,i+1).  evals ascending.  evecs: column-major n x n
+// (evecs[j*n+i] = component i of eigenvector j) when want_vecs, else only the FIRST ROW
+// Z(1,j) is returned in evecs[0..n-1].
+int tridiag_eig(int n, const double *diag, const double *sub, double *evals, double *evecs,
+                bool want_vecs) {
+  if (n <= 0) return 0;
+  std::vector<double> d(diag, diag + n), e(n, 0.0);
+  for (int i = 0; i + 1 < n; i++) e[i] = sub[i];
+  const int zr = want_vecs ? n : 1;  // rows of Z that are tracked
+  std::vector<double> z((size_t)zr * n, 0.0);  // z[r*n + j] : row r, eigenvector j
+  for (int r = 0; r < zr; r++) z[(size_t)r * n + r] = 1.0;
+  for (int l = 0; l < n; l++) {
+    int iter = 0, m;
+    do {
+      for (m = l; m < n - 1; m++) {
+        double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+        if (std::fabs(e[m]) <= 2.3e-16 * dd) break;
+      }
+      if (m != l) {
+        if (iter++ == 200) return set_error("tridiag_eig: no convergence");
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = std::hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = m - 1; i >= l; i--) {
+          double f = s * e[i], b = c * e[i];
+          e[i + 1] = (r = std::hypot(f, g));
+          if (r == 0.0) {
+            d[i + 1] -= p;
+            e[m] = 0.0;
+            break;
+          }
+          s = f / r;
+          c = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * b;
+          d[i + 1] = g + (p = s * r);
+          g = c * r - b;
+          for (int k = 0; k < zr; k++) {
+            double *zk = &z[(size_t)k * n];
+            f = zk[i + 1];
+            zk[i + 1] = s * zk[i] + c * f;
+            zk[i] = c * zk[i] - s * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p;
+        e[l] = g;
+        e[m] = 0.0;
+      }
+    } while (m != l);
+  }
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; i++) idx[i] = i;
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return d[a] < d[b]; });
+  for (int j = 0; j < n; j++) {
+    evals[j] = d[idx[j]];
+    if (evecs) {
+      if (want_vecs)
+        for (int i = 0; i < n; i++) evecs[(size_t)j * n + i] = z[(size_t)i * n + idx[j]];
+      else
+        evecs[j] = z[idx[j]];
+    }
+  }
+  return 0;
+}
+
+struct LanczosVecs {
+  double *vin = nullptr, *vout = nullptr;
+};
+
+// One step of the recurrence on device vectors; returns alfa, beta on the host.
+static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, double *beta) {
+  if (iter == 1) {
+    double n2;
+    EDGPU_TRY(vec_dot(E, L.vin, L.vin, &n2));
+    if (n2 == 0.0) return set_error("lanczos_iteration: norm = 0");
+    EDGPU_TRY(vec_scale(E, L.vin, 1.0 / std::sqrt(n2)));
+    EDGPU_TRY(vec_zero(E, L.vout, E.sec.padded_len()));
+  } else {
+    EDGPU_TRY(vec_swap_scale(E, L.vin, L.vout, *beta));
+  }
+  EDGPU_TRY(hxv_device(E, L.vin, L.vout, /*accum=*/true, /*timed=*/false));
+  EDGPU_TRY(vec_dot(E, L.vin, L.vout, alfa));
+  double b2;
+  EDGPU_TRY(vec_axpy_norm(E, L.vout, L.vin, *alfa, &b2));
+  *beta = std::sqrt(b2);
+  return 0;
+}
+
+// sp_lanc_tridiag: alanc(iter)=alfa, blanc(iter+1)=beta, early exit when |beta|<threshold.
+// d_seed is consumed (used as vin).  d_work is a second vector of the same padded length.
+int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, double threshold,
+                        double *alanc, double *blanc, int *nused) {
+  LanczosVecs L{d_seed, d_work};
+  for (int i = 0; i < nlanc; i++) alanc[i] = blanc[i] = 0.0;
+  double alfa = 0.0, beta = 0.0;
+  *nused = 0;
+  for (int it = 1; it <= nlanc; it++) {
+    EDGPU_TRY(lanczos_step(E, it, L, &alfa, &beta));
+    alanc[it - 1] = alfa;
+    *nused = it;
+    if (std::fabs(beta) < threshold) break;
+    if (it < nlanc) blanc[it] = beta;
+  }
+  return 0;
+}
+
+// sp_lanc_eigh: pass 1 builds T until the lowest Ritz value is stationary (checked every
+// iteration once nlanc >= ncheck) or beta -> 0 or nitermax; pass 2 replays the recurrence
+// from the same start vector accumulating vect += Z(iter,1) * v_iter; vect normalised.
+// d_start: start vector (kept intact, copied) or nullptr for the seeded random start.
+// d_vect: output (padded length).  Scratch: two more vectors allocated here.
+int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
+                   uint64_t seed, double *egs, double *d_vect, int *niter) {
+  Sector &S = E.sec;
+  const int64_t n = S.padded_len();
+  const int64_t dim_global = S.up.dim * S.dw.dim;
+  if (nitermax > dim_global) nitermax = (int)dim_global;
+  if (nitermax < 1) nitermax = 1;
+  if (ncheck < 1) ncheck = 1;
+  double *vin = nullptr, *vout = nullptr;
+  EDGPU_CUDA(cudaMalloc(&vin, sizeof(double) * n));
+  EDGPU_CUDA(cudaMalloc(&vout, sizeof(double) * n));
+  auto cleanup = [&]() {
+    cudaFree(vin);
+    cudaFree(vout);
+  };
+  auto init_start = [&]() -> int {
+    if (d_start) {
+      EDGPU_CUDA(cudaMemcpyAsync(vin, d_start, sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream));
+    } else {
+      EDGPU_TRY(vec_fill_random(E, vin, seed));
+    }
+    return 0;
+  };
+  int rc = init_start();
+  if (rc) { cleanup(); return rc; }
+  std::vector<double> a, b(1, 0.0), ev, esave;
+  LanczosVecs L{vin, vout};
+  double alfa = 0.0, beta = 0.0;
+  int nlanc = 0;
+  for (int it = 1; it <= nitermax; it++) {
+    rc = lanczos_step(E, it, L, &alfa, &beta);
+    if (rc) { cleanup(); return rc; }
+    a.push_back(alfa);
+    nlanc = it;
+    if (std::fabs(beta) < threshold && it > 1) break;
+    b.push_back(beta);
+    if (nlanc >= ncheck) {
+      ev.resize(nlanc);
+      rc = tridiag_eig(nlanc, a.data(), b.data() + 1, ev.data(), nullptr, false);
+      if (rc) { cleanup(); return rc; }
+      esave.push_back(ev[0]);
+      if (esave.size() >= 2 &&
+          std::fabs(esave[esave.size() - 1] - esave[esave.size() - 2]) <= threshold)
+        break;
+    }
+  }
+  ev.resize(nlanc);
+  std::vector<double> Z((size_t)nlanc * nlanc);
+  rc = tridiag_eig(nlanc, a.data(), b.data() + 1, ev.data(), Z.data(), true);
+  if (rc) { cleanup(); return rc; }
+  *egs = ev[0];
+  *niter = nlanc;
+  // pass 2
+  rc = init_start();
+  if (rc) { cleanup(); return rc; }
+  vec_zero(E, d_vect, n);
+  L = LanczosVecs{vin, vout};
+  beta = 0.0;
+  for (int it = 1; it <= nlanc; it++) {
+    rc = lanczos_step(E, it, L, &alfa, &beta);
+    if (rc) { cleanup(); return rc; }
+    rc = vec_axpy(E, d_vect, L.vin, Z[it - 1]);  // Z(iter,1): component iter of eigenvector 1
+    if (rc) { cleanup(); return rc; }
+  }
+  double n2;
+  rc = vec_dot(E, d_vect, d_vect, &n2);
+  if (!rc) rc = vec_scale(E, d_vect, 1.0 / std::sqrt(n2));
+  cudaStreamSynchronize(E.stream);
+  cleanup();
+  return rc;
+}
+
+}  // namespace edgpu

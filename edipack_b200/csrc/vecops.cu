@@ -1,0 +1,194 @@
+// Vector kernels of the device-resident Lanczos recurrence (what SciFortran's
+// lanczos_iteration does with Fortran array syntax + MPI_Allreduce): every kernel streams
+// its operands once with 16-byte accesses and reduces through warp shuffles -> per-block
+// partials -> one fixed-order final block (deterministic), then NCCL all-reduce of the scalar.
+#include "edgpu_internal.cuh"
+
+namespace edgpu {
+
+constexpr int VT = 256;
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+__device__ __forceinline__ void block_partial(double x, double *__restrict__ part) {
+  __shared__ double sh[VT / 32];
+  x = warp_sum(x);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double y = threadIdx.x < VT / 32 ? sh[threadIdx.x] : 0.0;
+    y = warp_sum(y);
+    if (threadIdx.x == 0) part[blockIdx.x] = y;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_final_sum(const double *__restrict__ part, int n,
+                                                    double *__restrict__ out) {
+  __shared__ double sh[32];
+  double x = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) x += part[i];
+  x = warp_sum(x);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double y = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    y = warp_sum(y);
+    if (threadIdx.x == 0) *out = y;
+  }
+}
+
+// n2 = number of double2 elements (vectors are padded to multiples of 16 doubles)
+__global__ void __launch_bounds__(VT) k_dot(const double2 *__restrict__ a,
+                                            const double2 *__restrict__ b, int64_t n2,
+                                            double *__restrict__ part) {
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
+    double2 x = a[i], y = b[i];
+    s += x.x * y.x + x.y * y.y;
+  }
+  block_partial(s, part);
+}
+
+__global__ void __launch_bounds__(VT) k_scale(double2 *__restrict__ a, int64_t n2, double s) {
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
+    double2 x = a[i];
+    x.x *= s;
+    x.y *= s;
+    a[i] = x;
+  }
+}
+
+// (a,b) <- (b/beta, -beta*a)
+__global__ void __launch_bounds__(VT) k_swap_scale(double2 *__restrict__ a, double2 *__restrict__ b,
+                                                   int64_t n2, double inv_beta, double mbeta) {
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
+    double2 x = a[i], y = b[i];
+    a[i] = make_double2(y.x * inv_beta, y.y * inv_beta);
+    b[i] = make_double2(mbeta * x.x, mbeta * x.y);
+  }
+}
+
+// w -= alpha*v ; partial of <w,w>
+__global__ void __launch_bounds__(VT) k_axpy_norm(double2 *__restrict__ w,
+                                                  const double2 *__restrict__ v, int64_t n2,
+                                                  double alpha, double *__restrict__ part) {
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
+    double2 x = w[i], y = v[i];
+    x.x -= alpha * y.x;
+    x.y -= alpha * y.y;
+    w[i] = x;
+    s += x.x * x.x + x.y * x.y;
+  }
+  block_partial(s, part);
+}
+
+__global__ void __launch_bounds__(VT) k_axpy(double2 *__restrict__ y, const double2 *__restrict__ x,
+                                             int64_t n2, double a) {
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
+    double2 p = y[i], q = x[i];
+    p.x += a * q.x;
+    p.y += a * q.y;
+    y[i] = p;
+  }
+}
+
+// splitmix64 -> uniform(0,1), indexed by the GLOBAL state index so that the start vector
+// does not depend on the number of ranks (the test-side checker regenerates it).
+__global__ void __launch_bounds__(VT) k_random(double *__restrict__ v, int64_t nrow, int64_t ld,
+                                               int64_t ncol, int64_t col_offset, uint64_t seed) {
+  const int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (i >= ld) return;
+  double x = 0.0;
+  if (i < nrow) {
+    uint64_t z = ((uint64_t)(i + (c + col_offset) * nrow) + seed) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    x = ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  v[c * ld + i] = x;
+}
+
+static int grid_for(Engine &E, int64_t n2) {
+  int64_t want = (n2 + VT - 1) / VT;
+  int64_t cap = (int64_t)E.sm_count * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+static int finish_scalar(Engine &E, int nblocks, double *h_out) {
+  k_final_sum<<<1, 1024, 0, E.stream>>>(E.d_part, nblocks, E.d_scal);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_TRY(comm_allreduce_sum(E, E.d_scal, 1));
+  EDGPU_CUDA(cudaMemcpyAsync(E.h_scal, E.d_scal, sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  *h_out = E.h_scal[0];
+  return 0;
+}
+
+int vec_zero(Engine &E, double *d_v, int64_t n) {
+  EDGPU_CUDA(cudaMemsetAsync(d_v, 0, sizeof(double) * n, E.stream));
+  return 0;
+}
+
+int vec_fill_random(Engine &E, double *d_v, uint64_t seed) {
+  Sector &S = E.sec;
+  dim3 grid((unsigned)((S.up.ld + VT - 1) / VT), (unsigned)S.qdw);
+  k_random<<<grid, VT, 0, E.stream>>>(d_v, S.up.dim, S.up.ld, S.qdw, S.d0, seed);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vec_dot(Engine &E, const double *a, const double *b, double *h_out) {
+  const int64_t n2 = E.sec.padded_len() / 2;
+  int gb = grid_for(E, n2);
+  k_dot<<<gb, VT, 0, E.stream>>>((const double2 *)a, (const double2 *)b, n2, E.d_part);
+  EDGPU_COUNT_LAUNCH();
+  return finish_scalar(E, gb, h_out);
+}
+
+int vec_scale(Engine &E, double *a, double s) {
+  const int64_t n2 = E.sec.padded_len() / 2;
+  k_scale<<<grid_for(E, n2), VT, 0, E.stream>>>((double2 *)a, n2, s);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vec_swap_scale(Engine &E, double *a, double *b, double beta) {
+  const int64_t n2 = E.sec.padded_len() / 2;
+  k_swap_scale<<<grid_for(E, n2), VT, 0, E.stream>>>((double2 *)a, (double2 *)b, n2, 1.0 / beta,
+                                                     -beta);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2) {
+  const int64_t n2 = E.sec.padded_len() / 2;
+  int gb = grid_for(E, n2);
+  k_axpy_norm<<<gb, VT, 0, E.stream>>>((double2 *)w, (const double2 *)v, n2, alpha, E.d_part);
+  EDGPU_COUNT_LAUNCH();
+  return finish_scalar(E, gb, h_beta2);
+}
+
+int vec_axpy(Engine &E, double *y, const double *x, double a) {
+  const int64_t n2 = E.sec.padded_len() / 2;
+  k_axpy<<<grid_for(E, n2), VT, 0, E.stream>>>((double2 *)y, (const double2 *)x, n2, a);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vec_add_dot(Engine &E, double *w, const double *t, const double *v, double *h_alpha) {
+  EDGPU_TRY(vec_axpy(E, w, t, 1.0));
+  return vec_dot(E, v, w, h_alpha);
+}
+
+}  // namespace edgpu

@@ -1,0 +1,399 @@
+"""Host-side mirror of the reference's interface for the NORMAL-mode hot path, on top of the
+C ABI (``include/edgpu.h``).  Names and argument meaning follow the reference so that the
+parity tests read like the reference's own call sequence:
+
+=============================  ==========================================================
+reference                      here
+=============================  ==========================================================
+ed_init_solver / set_umatrix   :class:`EDModel` (plain numbers -> ``edgpu_normal_params``)
+build_Hv_sector_normal         :func:`build_Hv_sector_normal`   ED_HAMILTONIAN_NORMAL.f90:31
+delete_Hv_sector_normal        :func:`delete_Hv_sector_normal`  :212
+vecDim_Hv_sector_normal        :func:`vecDim_Hv_sector_normal`  :286
+spHtimesV_p(Nloc,v,Hv)         :func:`spHtimesV_p`              ED_VARS_GLOBAL.f90:111-120,196
+sp_lanc_eigh                   :func:`sp_lanc_eigh`             call site ED_DIAG_NORMAL.f90:206
+sp_lanc_tridiag                :func:`sp_lanc_tridiag`          ED_HAMILTONIAN_NORMAL.f90:360
+tridiag_Hv_sector_normal       :func:`tridiag_Hv_sector_normal` :321
+ed_diag_d                      :func:`ed_diag_d`                ED_DIAG_NORMAL.f90:76
+lanc_build_gf_normal_diag      :func:`lanc_build_gf_normal_diag` ED_GF_NORMAL.f90:131
+observables_normal             :func:`observables_normal`       ED_OBSERVABLES_NORMAL.f90:78
+=============================  ==========================================================
+
+Everything heavy runs in hand-written CUDA behind the ABI; this module only sequences calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from ._abi import EdgpuError, MAXBATH, MAXORB, NormalParams, check, ptr
+
+BATH_CODES = {"normal": 0, "hybrid": 1, "replica": 2, "general": 3}
+
+
+def binomial(n: int, k: int) -> int:
+    return math.comb(n, k) if 0 <= k <= n else 0
+
+
+@dataclass
+class EDModel:
+    """What ``ed_read_input`` + ``ed_init_solver`` + ``ed_set_Hloc`` + ``set_umatrix`` leave in
+    the reference's module globals for the NORMAL-mode H x v (SURVEY 8b "Semantics")."""
+
+    Norb: int = 1
+    Nbath: int = 1
+    Nspin: int = 1
+    bath_type: str = "normal"
+    Uloc: tuple = (2.0,)
+    Ust: float = 0.0
+    Jh: float = 0.0
+    Jx: float = 0.0
+    Jp: float = 0.0
+    xmu: float = 0.0
+    hfmode: bool = True
+    beta: float = 1000.0
+    ed_hw_bath: float = 2.0
+    hloc: np.ndarray | None = None     # [2, Norb, Norb]   impHloc(s,s,a,b)
+    bath_e: np.ndarray | None = None   # [2, Nfoo, Nbath]  dmft_bath%e
+    bath_v: np.ndarray | None = None   # [2, Norb, Nbath]  dmft_bath%v
+    spin_field_z: tuple = ()
+    exc_field: tuple = (0.0, 0.0, 0.0, 0.0)
+    hbath: np.ndarray | None = None    # replica/general Hbath_tmp [2, Norb, Norb, Nbath]
+    lanc_niter: int = 512              # LANC_NITER      (ED_INPUT_VARS.f90:723-732)
+    lanc_ngfiter: int = 200            # LANC_NGFITER
+    lanc_tolerance: float = 1e-12      # LANC_TOLERANCE (reference default 1e-18)
+    lanc_dim_threshold: int = 1024     # LANC_DIM_THRESHOLD
+    gs_threshold: float = 1e-9         # GS_THRESHOLD
+    _params: NormalParams | None = field(default=None, repr=False)
+
+    @property
+    def Ns(self) -> int:  # ED_SETUP.f90:118-126
+        return self.Nbath + self.Norb if self.bath_type == "hybrid" else (self.Nbath + 1) * self.Norb
+
+    @property
+    def Nfoo(self) -> int:
+        return 1 if self.bath_type == "hybrid" else self.Norb
+
+    def getBathStride(self, a: int, k: int) -> int:
+        """ED_SETUP.f90:605-622 (a, k 0-based; returns the 1-based site)."""
+        if self.bath_type == "normal":
+            return self.Norb + a * self.Nbath + k + 1
+        if self.bath_type == "hybrid":
+            return self.Norb + k + 1
+        return (a + 1) + (k + 1) * self.Norb
+
+    def init_dmft_bath(self):
+        """Default bath of ``init_dmft_bath`` (ED_BATH_DMFT.f90:211-244), normal/hybrid."""
+        Nb, hw = self.Nbath, self.ed_hw_bath
+        e = np.zeros(Nb)
+        e[0], e[-1] = -hw, hw
+        Nh = Nb // 2
+        if Nb % 2 == 0 and Nb >= 4:
+            de = hw / max(Nh - 1, 1)
+            e[Nh - 1], e[Nh] = -0.1, 0.1
+            for i in range(2, Nh):
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        elif Nb % 2 != 0 and Nb >= 3:
+            de = hw / Nh
+            e[Nh] = 0.0
+            for i in range(2, Nh + 1):
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        self.bath_e = np.broadcast_to(e, (2, self.Nfoo, Nb)).copy()
+        self.bath_v = np.full((2, self.Norb, Nb), max(0.1, 1.0 / math.sqrt(Nb)))
+        self._params = None
+        return self
+
+    def params(self) -> NormalParams:
+        if self._params is not None:
+            return self._params
+        if self.bath_e is None:
+            self.init_dmft_bath()
+        No, Nb = self.Norb, self.Nbath
+        if No > MAXORB or Nb > MAXBATH or self.Ns > 31:
+            raise EdgpuError("model too large for edgpu_normal_params")
+        p = NormalParams()
+        p.Ns, p.Norb, p.Nbath = self.Ns, No, Nb
+        p.bath_type = BATH_CODES[self.bath_type]
+        p.hfmode, p.Nfoo, p.xmu = int(self.hfmode), self.Nfoo, self.xmu
+        eloc = np.zeros((2, MAXORB, MAXORB))
+        if self.hloc is not None:
+            eloc[:, :No, :No] = self.hloc
+        p.eloc[:] = eloc.ravel().tolist()
+        sf = np.zeros(MAXORB)
+        sf[: len(self.spin_field_z)] = self.spin_field_z
+        p.spin_field_z[:] = sf.tolist()
+        p.exc_field[:] = list(self.exc_field)
+        # ED_USE_KANAMORI=T branch of set_umatrix (ED_PARSE_UMATRIX.f90:136-143)
+        U = np.zeros(MAXORB)
+        U[:No] = np.asarray(self.Uloc, float)[:No]
+        p.Uloc[:] = U.tolist()
+        off = np.zeros((MAXORB, MAXORB))
+        off[:No, :No] = 1.0 - np.eye(No)
+        for name, val in (("Ust", self.Ust), ("Jh", self.Jh), ("Jx", self.Jx), ("Jp", self.Jp)):
+            getattr(p, name)[:] = (val * off).ravel().tolist()
+        dh = np.zeros((2, MAXORB, MAXBATH))
+        dh[:, :No, :Nb] = self.bath_v
+        bd = np.zeros((2, MAXORB, MAXBATH))
+        bd[:, : self.Nfoo, :Nb] = self.bath_e
+        hb = np.zeros((2, MAXORB, MAXORB, MAXBATH))
+        if self.hbath is not None:
+            hb[:, :No, :No, :Nb] = self.hbath
+            for s in range(2):
+                for a in range(No):
+                    bd[s, a, :Nb] = self.hbath[s, a, a, :]
+        p.diag_hybr[:] = dh.ravel().tolist()
+        p.bath_diag[:] = bd.ravel().tolist()
+        p.hbath[:] = hb.ravel().tolist()
+        st = np.zeros((MAXORB, MAXBATH), np.int32)
+        for a in range(No):
+            for k in range(Nb):
+                st[a, k] = self.getBathStride(a, k)
+        p.stride[:] = st.ravel().tolist()
+        self._params = p
+        return p
+
+
+# ------------------------------------------------------------------------------------------
+# engine / communicator
+# ------------------------------------------------------------------------------------------
+def ed_init(device: int = 0):
+    check(_abi.load().edgpu_init(device))
+
+
+def ed_finalize():
+    check(_abi.load().edgpu_finalize())
+
+
+def ed_set_comm(rank: int, nranks: int, uid: bytes | None):
+    """ed_set_MpiComm (ED_VARS_GLOBAL.f90:341): uid from :func:`comm_unique_id` on rank 0."""
+    buf = C.create_string_buffer(uid, _abi.UID_BYTES) if uid is not None else None
+    check(_abi.load().edgpu_comm_init(rank, nranks, buf))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(_abi.UID_BYTES)
+    check(_abi.load().edgpu_comm_unique_id(buf))
+    return buf.raw
+
+
+# ------------------------------------------------------------------------------------------
+# sector + H x v
+# ------------------------------------------------------------------------------------------
+def build_Hv_sector_normal(model: EDModel, nup: int, ndw: int):
+    check(_abi.load().edgpu_sector_open_normal(C.byref(model.params()), nup, ndw))
+
+
+def delete_Hv_sector_normal():
+    check(_abi.load().edgpu_sector_close())
+
+
+def vecDim_Hv_sector_normal() -> int:
+    return int(_abi.load().edgpu_sector_vecdim())
+
+
+def sector_dims():
+    L = _abi.load()
+    a, b, c, d = (C.c_int64() for _ in range(4))
+    check(L.edgpu_sector_dims(C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+    return a.value, b.value, c.value, d.value
+
+
+def sector_map(spin: int) -> np.ndarray:
+    DimUp, DimDw, _, _ = sector_dims()
+    m = np.empty(DimUp if spin == 0 else DimDw, np.int32)
+    check(_abi.load().edgpu_sector_get_map(spin, ptr(m)))
+    return m
+
+
+def sector_hops(spin: int):
+    """Hop table as CSR (rowptr, 1-based targets, signed values), one row per source state."""
+    L = _abi.load()
+    DimUp, DimDw, _, _ = sector_dims()
+    dim = DimUp if spin == 0 else DimDw
+    n = int(L.edgpu_sector_hop_count(spin))
+    if n < 0:
+        check(1)
+    rp = np.zeros(dim + 1, np.int64)
+    tg = np.zeros(max(n, 1), np.int32)
+    va = np.zeros(max(n, 1), np.float64)
+    check(L.edgpu_sector_get_hops(spin, ptr(rp), ptr(tg), ptr(va)))
+    return rp, tg[:n], va[:n]
+
+
+def spHtimesV_p(v: np.ndarray) -> np.ndarray:
+    """``call spHtimesV_p(Nloc,v,Hv)`` with host arrays (the drop-in procedure pointer)."""
+    L = _abi.load()
+    v = np.ascontiguousarray(v, np.float64)
+    hv = np.empty_like(v)
+    n = C.c_int32(v.size)
+    L.edgpu_hxv_d(C.byref(n), ptr(v), ptr(hv))
+    check(L.edgpu_status())
+    return hv
+
+
+def set_kernel_variant(variant: int):
+    check(_abi.load().edgpu_set_kernel_variant(variant))
+
+
+# ------------------------------------------------------------------------------------------
+# Lanczos drivers
+# ------------------------------------------------------------------------------------------
+def sp_lanc_eigh(nitermax: int, threshold: float = 1e-12, ncheck: int = 10, vect=None,
+                 seed: int = 4321, want_vector: bool = True):
+    """sp_lanc_eigh(MatVec, egs, vect, Nitermax, threshold=): returns (egs, vect, niter)."""
+    L = _abi.load()
+    n = vecDim_Hv_sector_normal()
+    use_start = vect is not None
+    buf = None
+    if use_start:
+        buf = np.ascontiguousarray(vect, np.float64).copy()
+    elif want_vector:
+        buf = np.zeros(n)
+    egs, nit = C.c_double(), C.c_int()
+    check(L.edgpu_lanczos_gs(nitermax, threshold, ncheck, int(use_start), seed, C.byref(egs),
+                             ptr(buf) if buf is not None else None, C.byref(nit)))
+    return egs.value, buf, nit.value
+
+
+def sp_lanc_tridiag(vin, nlanc: int, threshold: float = 1e-12):
+    """sp_lanc_tridiag(MatVec, vin, alanc, blanc); vin=None uses the device-resident seed
+    left by :func:`apply_op`.  Returns (alanc, blanc, nused, norm2)."""
+    L = _abi.load()
+    a, b = np.zeros(nlanc), np.zeros(nlanc)
+    nused, n2 = C.c_int(), C.c_double()
+    seed = None if vin is None else np.ascontiguousarray(vin, np.float64)
+    check(L.edgpu_lanczos_tridiag(ptr(seed) if seed is not None else None, nlanc, threshold,
+                                  ptr(a), ptr(b), C.byref(nused), C.byref(n2)))
+    return a, b, nused.value, n2.value
+
+
+def tridiag_Hv_sector_normal(model: EDModel, nup: int, ndw: int, vvinit, nlanc=None):
+    """ED_HAMILTONIAN_NORMAL.f90:321-369: norm2, normalise, build sector, tridiagonalise, delete."""
+    build_Hv_sector_normal(model, nup, ndw)
+    try:
+        DimUp, DimDw, _, _ = sector_dims()
+        nl = min(DimUp * DimDw, model.lanc_ngfiter) if nlanc is None else nlanc
+        a, b, nused, n2 = sp_lanc_tridiag(vvinit, nl)
+    finally:
+        delete_Hv_sector_normal()
+    return a, b, nused, n2
+
+
+def state_store(slot: int):
+    check(_abi.load().edgpu_state_store(slot))
+
+
+def state_free(slot: int):
+    check(_abi.load().edgpu_state_free(slot))
+
+
+def apply_op(slot: int, op: int, iorb: int, spin: int):
+    """apply_op_CDG (op=+1) / apply_op_C (op=-1) on stored state -> device-resident seed."""
+    check(_abi.load().edgpu_apply_op(slot, op, iorb, spin))
+
+
+def state_observables(slot: int, Norb: int):
+    dens, docc = np.zeros(Norb), np.zeros(Norb)
+    check(_abi.load().edgpu_state_observables(slot, ptr(dens), ptr(docc)))
+    return dens, docc
+
+
+# ------------------------------------------------------------------------------------------
+# solver-level sequencing (T = 0)
+# ------------------------------------------------------------------------------------------
+@dataclass
+class EState:
+    e: float
+    nup: int
+    ndw: int
+    slot: int
+
+
+def ed_diag_d(model: EDModel, sectors=None):
+    """Sector loop of ``ed_diag_d`` (ED_DIAG_NORMAL.f90:76-296) with LANC_METHOD=lanczos for
+    every sector: plain Lanczos ground state per sector on the device, T=0 state list with the
+    gs_threshold rule (:262-278).  Ground-state vectors stay in HBM (state slots)."""
+    Ns = model.Ns
+    if sectors is None:
+        sectors = [(nu, nd) for nu in range(Ns + 1) for nd in range(Ns + 1)]
+    states: list[EState] = []
+    oldzero = 1000.0
+    next_slot = 0
+    for nup, ndw in sectors:
+        dim = binomial(Ns, nup) * binomial(Ns, ndw)
+        build_Hv_sector_normal(model, nup, ndw)
+        try:
+            e0, _, _ = sp_lanc_eigh(min(dim, model.lanc_niter), model.lanc_tolerance,
+                                    want_vector=False)
+            if e0 < oldzero - 10.0 * model.gs_threshold:
+                oldzero = e0
+                for s in states:
+                    state_free(s.slot)
+                states = []
+                keep = True
+            elif abs(e0 - oldzero) <= model.gs_threshold:
+                oldzero = min(oldzero, e0)
+                keep = True
+            else:
+                keep = False
+            if keep:
+                state_store(next_slot)
+                states.append(EState(e0, nup, ndw, next_slot))
+                next_slot += 1
+        finally:
+            delete_Hv_sector_normal()
+    return states
+
+
+def observables_normal(model: EDModel, states):
+    """dens/docc of ED_OBSERVABLES_NORMAL.f90:150-215 at T=0."""
+    dens, docc = np.zeros(model.Norb), np.zeros(model.Norb)
+    for st in states:
+        build_Hv_sector_normal(model, st.nup, st.ndw)
+        try:
+            d, o = state_observables(st.slot, model.Norb)
+        finally:
+            delete_Hv_sector_normal()
+        dens += d / len(states)
+        docc += o / len(states)
+    return dens, docc
+
+
+def tridiag_eigh(a, b_sub):
+    """eigh(diag,subdiag,Ev=Z) of ED_GF_NORMAL.f90:416 (host, tiny)."""
+    n = len(a)
+    T = np.diag(np.asarray(a, float))
+    for i in range(n - 1):
+        T[i, i + 1] = T[i + 1, i] = b_sub[i]
+    return np.linalg.eigh(T)
+
+
+def lanc_build_gf_normal_diag(model: EDModel, states, iorb: int, ispin: int = 0):
+    """ED_GF_NORMAL.f90:131-177 + add_to_lanczos_gf_normal :363-427: list of (weight, pole).
+    Seeds c^+|gs>, c|gs> are built on the device from the resident ground states."""
+    out = []
+    zeta = len(states)
+    Ns = model.Ns
+    for st in states:
+        for op, isign in ((+1, 1), (-1, -1)):
+            jn = (st.nup + (op if ispin == 0 else 0), st.ndw + (op if ispin == 1 else 0))
+            if min(jn) < 0 or max(jn) > Ns:
+                continue
+            build_Hv_sector_normal(model, jn[0], jn[1])
+            try:
+                apply_op(st.slot, op, iorb, ispin)
+                dim = binomial(Ns, jn[0]) * binomial(Ns, jn[1])
+                a, b, nused, norm2 = sp_lanc_tridiag(None, min(dim, model.lanc_ngfiter))
+            finally:
+                delete_Hv_sector_normal()
+            if norm2 == 0.0 or nused == 0:
+                continue
+            ev, Z = tridiag_eigh(a[:nused], b[1:nused])
+            for j in range(nused):
+                out.append((norm2 / zeta * Z[0, j] ** 2, isign * (ev[j] - st.e)))
+    return out

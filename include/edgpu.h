@@ -1,0 +1,169 @@
+/*
+ * edgpu.h -- C ABI of the B200-native Lanczos H x v engine for EDIpack (NORMAL mode).
+ *
+ * This is the drop-in boundary: plain C symbols, plain pointers and sizes, no torch / C++
+ * types.  Each entry point names the reference interface it replaces (paths relative to the
+ * EDIpack source tree, v6.1.0).  The Fortran side binds them with `bind(C)` interfaces, see
+ * INTEGRATION.md.  All functions returning int return 0 on success and a non-zero code on
+ * failure; edgpu_last_error() gives the message (the reference `stop`s with a message, e.g.
+ * ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:49,52 -- the Fortran shim turns non-zero into `stop`).
+ *
+ * State model = the reference's: module-global, one sector "open" at a time
+ * (build_Hv_sector_normal ... delete_Hv_sector_normal), not re-entrant, one engine per
+ * process (= one MPI rank = one GPU).
+ *
+ * There is NO CPU fallback: every call fails with an error if no sm_100 device is usable.
+ */
+#ifndef EDGPU_H
+#define EDGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDGPU_MAXORB 5
+#define EDGPU_MAXBATH 32
+#define EDGPU_UID_BYTES 128
+
+/* bath_type (ED_INPUT_VARS.f90:598) */
+enum { EDGPU_BATH_NORMAL = 0, EDGPU_BATH_HYBRID = 1, EDGPU_BATH_REPLICA = 2, EDGPU_BATH_GENERAL = 3 };
+
+/*
+ * Everything directMatVec_normal_main reads from module globals
+ * (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:23-130, ED_VARS_GLOBAL.f90), as one POD.
+ * Spin slot s: 0 = up, 1 = dw; with Nspin=1 the caller stores the same numbers in both
+ * (that is what the reference's index `Nspin` does, direct/HxV_dw.f90:14).
+ * Orbital / bath indices are 0-based here (1-based in the reference).
+ */
+typedef struct edgpu_normal_params {
+  int32_t Ns;        /* levels per spin, ED_SETUP.f90:118-126 */
+  int32_t Norb;
+  int32_t Nbath;
+  int32_t bath_type; /* EDGPU_BATH_* */
+  int32_t hfmode;    /* direct/HxV_local.f90:58 */
+  int32_t Nfoo;      /* size(bath_diag,2): Norb, or 1 for hybrid */
+  int32_t pad0, pad1;
+  double xmu;
+  double eloc[2][EDGPU_MAXORB][EDGPU_MAXORB]; /* impHloc(s,s,a,b)+mfHloc(s,s,a,b) */
+  double spin_field_z[EDGPU_MAXORB];          /* spin_field(a,3) */
+  double exc_field[4];
+  double Uloc[EDGPU_MAXORB];                  /* Uloc_internal */
+  double Ust[EDGPU_MAXORB][EDGPU_MAXORB];     /* Ust_internal  */
+  double Jh[EDGPU_MAXORB][EDGPU_MAXORB];      /* Jh_internal   */
+  double Jx[EDGPU_MAXORB][EDGPU_MAXORB];      /* Jx_internal   */
+  double Jp[EDGPU_MAXORB][EDGPU_MAXORB];      /* Jp_internal   */
+  double diag_hybr[2][EDGPU_MAXORB][EDGPU_MAXBATH];             /* diag_hybr(s,a,k) */
+  double bath_diag[2][EDGPU_MAXORB][EDGPU_MAXBATH];             /* bath_diag(s,a|1,k) */
+  double hbath[2][EDGPU_MAXORB][EDGPU_MAXORB][EDGPU_MAXBATH];   /* hbath_tmp(s,s,a,b,k) */
+  int32_t stride[EDGPU_MAXORB][EDGPU_MAXBATH];                  /* getBathStride(a,k), 1-based */
+} edgpu_normal_params;
+
+/* ---------------- engine / communicator ---------------- */
+
+/* Selects the CUDA device and creates the engine's stream.  Replaces nothing in the
+ * reference (it has no device); called once from ed_init_solver (ED_MAIN.f90:90). */
+int edgpu_init(int device);
+int edgpu_finalize(void); /* ed_finalize_solver, ED_MAIN.f90:224 */
+
+/* Replaces ed_set_MpiComm (ED_VARS_GLOBAL.f90:341-357): rank/size of the dw-split.
+ * uid is an NCCL unique id (EDGPU_UID_BYTES) created on rank 0 by edgpu_comm_unique_id and
+ * broadcast by the caller (MPI_Bcast in the Fortran host, torch.distributed in bench.py). */
+int edgpu_comm_unique_id(void *uid);
+int edgpu_comm_init(int rank, int nranks, const void *uid);
+int edgpu_comm_rank(void);
+int edgpu_comm_size(void);
+
+/* ---------------- sector: build_Hv_sector_normal / delete_Hv_sector_normal ------------ */
+
+/* build_Hv_sector_normal(isector) (ED_HAMILTONIAN_NORMAL.f90:31-204): builds the
+ * DEVICE-RESIDENT sector maps (build_sector, ED_SECTOR.f90:165-242), the dw split
+ * (:128-142), the per-spin hop tables and diagonal tables, and selects the H x v kernels.
+ * The sector is addressed by (nup,ndw) = get_Nup/get_Ndw(isector). */
+int edgpu_sector_open_normal(const edgpu_normal_params *p, int nup, int ndw);
+int edgpu_sector_close(void);           /* delete_Hv_sector_normal, :212-279 */
+int64_t edgpu_sector_vecdim(void);      /* vecDim_Hv_sector_normal, :286-313 (local chunk) */
+int64_t edgpu_sector_dim(void);         /* getDim(isector) */
+int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_start);
+
+/* Parity hooks: download the device-resident structures for bit-exact comparison with the
+ * oracle (sector maps ED_SECTOR.f90:217-242; hop tables = spH0ups(1)/spH0dws(1) content
+ * of stored/H_up.f90, H_dw.f90, one row per source state, targets 1-based). */
+int edgpu_sector_get_map(int spin, int32_t *map);
+int64_t edgpu_sector_hop_count(int spin);                      /* total entries */
+int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *value);
+
+/* ---------------- H x v ---------------- */
+
+/* Signature-compatible with the abstract interface dd_sparse_HxV(Nloc,v,Hv)
+ * (ED_VARS_GLOBAL.f90:111-120) so that `spHtimesV_p => edgpu_hxv_d` works: HOST arrays of
+ * the local chunk length, Hv fully overwritten, v untouched.  Errors are latched and
+ * reported by edgpu_last_error()/edgpu_status(). */
+void edgpu_hxv_d(const int32_t *Nloc, const double *v, double *Hv);
+int edgpu_status(void);
+
+/* Device-resident variant on the engine's internal (padded) layout; d_v/d_Hv are device
+ * pointers obtained from edgpu_vec_* below. */
+int edgpu_hxv_dev(const double *d_v, double *d_Hv);
+
+/* Internal layout helpers: vectors live on the device as qdw columns of length DimUp with a
+ * padded leading dimension.  upload/download convert from/to the reference's contiguous
+ * chunk layout i = iup + (idw-1)*DimUp (ED_SECTOR.f90:1681). */
+int64_t edgpu_vec_padded_len(void);
+int edgpu_vec_upload(double *d_dst, const double *h_src);
+int edgpu_vec_download(double *h_dst, const double *d_src);
+
+/* ---------------- Lanczos drivers (SciFortran SF_SP_LINALG replacements) -------------- */
+
+/* sp_lanc_eigh([MpiComm,]MatVec,egs,vect,Nitermax,threshold=) as called at
+ * ED_DIAG_NORMAL.f90:206-213: two-pass plain Lanczos ground state with all vectors in HBM.
+ * vec_host: in  -- start vector (local chunk) if use_start != 0, else a seeded random start;
+ *           out -- normalised ground-state chunk (may be NULL: the vector then only stays
+ *                  resident on the device as the "current state", see edgpu_state_*). */
+int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, uint64_t seed,
+                     double *egs, double *vec_host, int *niter);
+
+/* sp_lanc_tridiag([MpiComm,]MatVec,vin,alanc,blanc) as called from
+ * tridiag_Hv_sector_normal (ED_HAMILTONIAN_NORMAL.f90:321-369).  seed_host = local chunk of
+ * the (un-normalised) start vector, or NULL to use the device-resident seed produced by
+ * edgpu_apply_op.  Outputs: alanc[nlanc], blanc[nlanc] (blanc[0] unused like blanc(1)),
+ * *nused iterations actually done (early exit when beta < threshold), *norm2 = <seed|seed>. */
+int edgpu_lanczos_tridiag(const double *seed_host, int nlanc, double threshold, double *alanc,
+                          double *blanc, int *nused, double *norm2);
+
+/* ---------------- state hand-off (ED_EIGENSPACE es_add_state / es_return_dvec) --------- */
+
+/* Keeps the last edgpu_lanczos_gs eigenvector on the device as state `slot` together with
+ * its sector, so that Green's-function seeds never visit the host. */
+int edgpu_state_store(int slot);
+int edgpu_state_free(int slot);
+/* apply_op_C (op=-1) / apply_op_CDG (op=+1) of ED_SECTOR.f90:465 / :654 on the stored state:
+ * builds c_{iorb,spin}|state> (iorb 0-based, spin 0 up / 1 dw) directly in the layout of the
+ * CURRENTLY OPEN sector, which must be the target sector getCsector/getCDGsector. */
+int edgpu_apply_op(int slot, int op, int iorb, int spin);
+/* dens(a), docc(a) of ED_OBSERVABLES_NORMAL.f90:150-215 for the stored state (weight 1). */
+int edgpu_state_observables(int slot, double *dens, double *docc);
+
+/* ---------------- diagnostics ---------------- */
+const char *edgpu_last_error(void);
+/* number of kernels launched by this library since the last reset (bench "gpu_launches") */
+int64_t edgpu_launch_count(int reset);
+/* elapsed device time (ms) of the H x v kernels of the last edgpu_hxv_* call, per stage:
+ * out[0]=up+diag kernel, out[1]=dw kernel, out[2]=non-local kernel, out[3]=transposes */
+int edgpu_last_hxv_stage_ms(float *out4);
+/* select kernel variant: 0 = auto, 1 = generic gather kernels, 2 = shared-memory tiled */
+int edgpu_set_kernel_variant(int variant);
+/* the cudaStream_t every kernel of this library is launched on (so that callers can put their
+ * own CUDA events on it) */
+void *edgpu_stream(void);
+/* Per-stage device timing over a run of edgpu_hxv_dev calls without host synchronisation:
+ * begin arms a ring of CUDA events for up to max_steps calls; end synchronises and returns the
+ * SUMS (ms) over the recorded calls: ms[0]=up+diag, ms[1]=dw (incl. transposes when nranks>1),
+ * ms[2]=non-local, and the number of calls recorded. */
+int edgpu_profile_begin(int max_steps);
+int edgpu_profile_end(float *ms3, int *nsteps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,581 @@
+"""CPU oracle for the EDIpack NORMAL-mode Lanczos H x v hot path.
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this module, and
+only as the checker / the timed CPU baseline -- never from the product package.
+
+The heavy loops live in ``ed_oracle.c`` (C restatement of the reference's Fortran include
+fragments, each function citing reference file:line); this module adds the host-side
+contracts needed to reproduce the reference's golden ``*.check`` files end to end:
+
+* default bath / interaction set-up  (ED_BATH_DMFT.f90:211-244, ED_PARSE_UMATRIX.f90:88-165)
+* sector bookkeeping                 (ED_SECTOR.f90:1559-1718, ED_SETUP.f90:525-665)
+* plain Lanczos drivers              (SciFortran SF_SP_LINALG sp_lanc_eigh / sp_lanc_tridiag
+                                      -- NOT in the reference tree, unpinned dependency;
+                                      restated from their published algorithm, parity with
+                                      the reference pinned only through end-to-end goldens)
+* solver / GF / observables contracts (ED_DIAG_NORMAL.f90:76-296, ED_GF_NORMAL.f90:131-177,
+                                      363-427, 568-605, 698-739, ED_OBSERVABLES_NORMAL.f90:150-215)
+
+All paths relative to /root/reference/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAXORB, MAXBATH = 5, 32
+BATH_CODES = {"normal": 0, "hybrid": 1, "replica": 2, "general": 3}
+
+
+class OraParams(C.Structure):
+    """Mirror of ``ora_params`` in ed_oracle.h (same field order and sizes)."""
+
+    _fields_ = [
+        ("Ns", C.c_int32), ("Norb", C.c_int32), ("Nbath", C.c_int32), ("bath_type", C.c_int32),
+        ("hfmode", C.c_int32), ("Nfoo", C.c_int32), ("pad0", C.c_int32), ("pad1", C.c_int32),
+        ("xmu", C.c_double),
+        ("eloc", C.c_double * (2 * MAXORB * MAXORB)),
+        ("spin_field_z", C.c_double * MAXORB),
+        ("exc_field", C.c_double * 4),
+        ("Uloc", C.c_double * MAXORB),
+        ("Ust", C.c_double * (MAXORB * MAXORB)),
+        ("Jh", C.c_double * (MAXORB * MAXORB)),
+        ("Jx", C.c_double * (MAXORB * MAXORB)),
+        ("Jp", C.c_double * (MAXORB * MAXORB)),
+        ("diag_hybr", C.c_double * (2 * MAXORB * MAXBATH)),
+        ("bath_diag", C.c_double * (2 * MAXORB * MAXBATH)),
+        ("hbath", C.c_double * (2 * MAXORB * MAXORB * MAXBATH)),
+        ("stride", C.c_int32 * (MAXORB * MAXBATH)),
+    ]
+
+
+def build_library(force: bool = False) -> str:
+    """Compile ed_oracle.c -> libed_oracle.so (gcc, reference release flags)."""
+    so = os.path.join(_HERE, "libed_oracle.so")
+    src = os.path.join(_HERE, "ed_oracle.c")
+    hdr = os.path.join(_HERE, "ed_oracle.h")
+    stale = (not os.path.exists(so)) or any(
+        os.path.getmtime(f) > os.path.getmtime(so) for f in (src, hdr))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libed_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build_library())
+        L = _lib
+        dp = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+        ip32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        ip64 = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        PP = C.POINTER(OraParams)
+        L.ora_build_map.restype = C.c_int64
+        L.ora_build_map.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.ora_binary_search.restype = C.c_int64
+        L.ora_binary_search.argtypes = [ip32, C.c_int64, C.c_int32]
+        L.ora_binomial.restype = C.c_int64
+        L.ora_binomial.argtypes = [C.c_int, C.c_int]
+        L.ora_c.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L.ora_cdg.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L.ora_direct_hxv.argtypes = [PP, C.c_int, C.c_int, dp, dp]
+        L.ora_direct_hxv_mpi.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]
+        L.ora_direct_hxv_mpi_sample.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp,
+                                                dp, C.POINTER(C.c_double)]
+        L.ora_stored_hxv.argtypes = [PP, C.c_int, C.c_int, dp, dp]
+        L.ora_stored_hxv_mpi.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp,
+                                         C.POINTER(C.c_double)]
+        L.ora_build_hop_csr.restype = C.c_int64
+        L.ora_build_hop_csr.argtypes = [PP, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ora_build_diag.argtypes = [PP, C.c_int, C.c_int, dp]
+        L.ora_build_nonlocal_csr.restype = C.c_int64
+        L.ora_build_nonlocal_csr.argtypes = [PP, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ora_apply_op.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]
+    return _lib
+
+
+# --------------------------------------------------------------------------------------
+# model description (what ed_read_input + ed_init_solver + ed_set_Hloc + set_umatrix leave
+# in the reference's module globals)
+# --------------------------------------------------------------------------------------
+@dataclass
+class Model:
+    Norb: int = 1
+    Nbath: int = 1
+    Nspin: int = 1
+    bath_type: str = "normal"
+    Uloc: tuple = (2.0,)
+    Ust: float = 0.0
+    Jh: float = 0.0
+    Jx: float = 0.0
+    Jp: float = 0.0
+    xmu: float = 0.0
+    hfmode: bool = True
+    beta: float = 1000.0
+    ed_hw_bath: float = 2.0
+    hloc: np.ndarray | None = None      # [2(spin), Norb, Norb] real, impHloc(s,s,a,b)
+    bath_e: np.ndarray | None = None    # [2, Nfoo, Nbath]
+    bath_v: np.ndarray | None = None    # [2, Norb, Nbath]
+    spin_field_z: tuple = ()
+    exc_field: tuple = (0.0, 0.0, 0.0, 0.0)
+    hbath: np.ndarray | None = None     # replica/general [2, Norb, Norb, Nbath]
+    lanc_ngfiter: int = 200
+    lanc_niter: int = 512
+    lanc_tolerance: float = 1e-18
+    lanc_dim_threshold: int = 1024
+    gs_threshold: float = 1e-9
+    _params: OraParams | None = field(default=None, repr=False)
+
+    @property
+    def Ns(self) -> int:
+        # ED_SETUP.f90:118-126
+        if self.bath_type == "hybrid":
+            return self.Nbath + self.Norb
+        return (self.Nbath + 1) * self.Norb
+
+    @property
+    def Nfoo(self) -> int:
+        return 1 if self.bath_type == "hybrid" else self.Norb
+
+    def bath_stride(self, a: int, k: int) -> int:
+        """getBathStride(a+1,k+1) (1-based site), ED_SETUP.f90:605-622; a,k 0-based."""
+        if self.bath_type == "normal":
+            return self.Norb + a * self.Nbath + (k + 1)
+        if self.bath_type == "hybrid":
+            return self.Norb + (k + 1)
+        return (a + 1) + (k + 1) * self.Norb
+
+    def default_bath(self):
+        """init_dmft_bath for normal/hybrid baths, ED_BATH_DMFT.f90:211-244."""
+        Nb, hw = self.Nbath, self.ed_hw_bath
+        e = np.zeros(Nb)
+        e[0] = -hw
+        e[Nb - 1] = hw
+        Nh = Nb // 2
+        if Nb % 2 == 0 and Nb >= 4:
+            de = hw / max(Nh - 1, 1)
+            e[Nh - 1] = -0.1
+            e[Nh] = 0.1
+            for i in range(2, Nh):  # i=2..Nh-1 (1-based)
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        elif Nb % 2 != 0 and Nb >= 3:
+            de = hw / Nh
+            e[Nh] = 0.0
+            for i in range(2, Nh + 1):
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        self.bath_e = np.broadcast_to(e, (2, self.Nfoo, Nb)).copy()
+        v = max(0.1, 1.0 / math.sqrt(Nb))
+        self.bath_v = np.full((2, self.Norb, Nb), v)
+        self._params = None
+        return self
+
+    def params(self) -> OraParams:
+        if self._params is not None:
+            return self._params
+        p = OraParams()
+        No, Nb = self.Norb, self.Nbath
+        assert No <= MAXORB and Nb <= MAXBATH and self.Ns <= 31
+        p.Ns, p.Norb, p.Nbath = self.Ns, No, Nb
+        p.bath_type = BATH_CODES[self.bath_type]
+        p.hfmode = int(self.hfmode)
+        p.Nfoo = self.Nfoo
+        p.xmu = self.xmu
+        if self.bath_e is None:
+            self.default_bath()
+        hloc = np.zeros((2, No, No)) if self.hloc is None else np.asarray(self.hloc, float)
+        eloc = np.zeros((2, MAXORB, MAXORB))
+        eloc[:, :No, :No] = hloc
+        p.eloc[:] = eloc.ravel().tolist()
+        sf = np.zeros(MAXORB)
+        sf[: len(self.spin_field_z)] = self.spin_field_z
+        p.spin_field_z[:] = sf.tolist()
+        p.exc_field[:] = list(self.exc_field)
+        # set_umatrix with ED_USE_KANAMORI=T (ED_PARSE_UMATRIX.f90:136-143)
+        U = np.zeros(MAXORB)
+        U[:No] = np.asarray(self.Uloc, float)[:No]
+        p.Uloc[:] = U.tolist()
+        off = np.zeros((MAXORB, MAXORB))
+        off[:No, :No] = 1.0 - np.eye(No)
+        p.Ust[:] = (self.Ust * off).ravel().tolist()
+        p.Jh[:] = (self.Jh * off).ravel().tolist()
+        p.Jx[:] = (self.Jx * off).ravel().tolist()
+        p.Jp[:] = (self.Jp * off).ravel().tolist()
+        dh = np.zeros((2, MAXORB, MAXBATH))
+        dh[:, :No, :Nb] = self.bath_v
+        bd = np.zeros((2, MAXORB, MAXBATH))
+        bd[:, : self.Nfoo, :Nb] = self.bath_e
+        p.diag_hybr[:] = dh.ravel().tolist()
+        p.bath_diag[:] = bd.ravel().tolist()
+        hb = np.zeros((2, MAXORB, MAXORB, MAXBATH))
+        if self.hbath is not None:
+            hb[:, :No, :No, :Nb] = self.hbath
+            # replica/general: bath_diag = diagonal of Hbath_tmp (DIRECT_HxV.f90:71-92)
+            for s in range(2):
+                for a in range(No):
+                    bd[s, a, :Nb] = self.hbath[s, a, a, :]
+            p.bath_diag[:] = bd.ravel().tolist()
+        p.hbath[:] = hb.ravel().tolist()
+        st = np.zeros((MAXORB, MAXBATH), np.int32)
+        for a in range(No):
+            for k in range(Nb):
+                st[a, k] = self.bath_stride(a, k)
+        p.stride[:] = st.ravel().tolist()
+        self._params = p
+        return p
+
+
+# --------------------------------------------------------------------------------------
+# sector bookkeeping
+# --------------------------------------------------------------------------------------
+def binomial(n: int, k: int) -> int:
+    return int(lib().ora_binomial(n, k))
+
+
+def sector_index(Ns: int, nup: int, ndw: int) -> int:
+    """get_Sector_normal (ED_SECTOR.f90:1559-1570), QN=[nup,ndw], 1-based."""
+    return 1 + nup * (Ns + 1) + ndw
+
+
+def sector_qn(Ns: int, isector: int):
+    """get_Nup / get_Ndw (ED_SECTOR.f90:1618-1640)."""
+    c = isector - 1
+    ndw = c % (Ns + 1)
+    nup = c // (Ns + 1)
+    return nup, ndw
+
+
+def build_map(Ns: int, nel: int) -> np.ndarray:
+    dim = binomial(Ns, nel)
+    m = np.empty(dim, np.int32)
+    got = lib().ora_build_map(Ns, nel, m.ctypes.data)
+    assert got == dim
+    return m
+
+
+def sector_dims(Ns, nup, ndw):
+    return binomial(Ns, nup), binomial(Ns, ndw)
+
+
+def direct_hxv(model: Model, nup, ndw, v):
+    v = np.ascontiguousarray(v, np.float64)
+    hv = np.empty_like(v)
+    rc = lib().ora_direct_hxv(C.byref(model.params()), nup, ndw, v, hv)
+    assert rc == 0
+    return hv
+
+
+def direct_hxv_mpi(model: Model, nup, ndw, v, P, nthreads=1):
+    v = np.ascontiguousarray(v, np.float64)
+    hv = np.empty_like(v)
+    rc = lib().ora_direct_hxv_mpi(C.byref(model.params()), nup, ndw, P, nthreads, v, hv)
+    assert rc == 0
+    return hv
+
+
+def direct_hxv_mpi_sample(model: Model, nup, ndw, v, P, nrun, nthreads):
+    """Timing sample: run ranks [0,nrun) of P emulated ranks; returns seconds (product only)."""
+    v = np.ascontiguousarray(v, np.float64)
+    hv = np.empty_like(v)
+    sec = C.c_double(0.0)
+    rc = lib().ora_direct_hxv_mpi_sample(C.byref(model.params()), nup, ndw, P, nrun, nthreads, v,
+                                         hv, C.byref(sec))
+    assert rc == 0
+    return sec.value
+
+
+def stored_hxv(model: Model, nup, ndw, v):
+    v = np.ascontiguousarray(v, np.float64)
+    hv = np.empty_like(v)
+    rc = lib().ora_stored_hxv(C.byref(model.params()), nup, ndw, v, hv)
+    assert rc == 0
+    return hv
+
+
+def stored_hxv_mpi(model: Model, nup, ndw, v, P, nthreads=1, ncalls=1):
+    v = np.ascontiguousarray(v, np.float64)
+    hv = np.empty_like(v)
+    sec = C.c_double(0.0)
+    rc = lib().ora_stored_hxv_mpi(C.byref(model.params()), nup, ndw, P, nthreads, ncalls, v, hv,
+                                  C.byref(sec))
+    assert rc == 0
+    return hv, sec.value
+
+
+def hop_csr(model: Model, spin: int, nel: int):
+    """spH0ups(1)/spH0dws(1) as CSR in the reference's insertion order; cols 1-based."""
+    p = C.byref(model.params())
+    dim = binomial(model.Ns, nel)
+    nnz = lib().ora_build_hop_csr(p, spin, nel, None, None, None)
+    rp = np.zeros(dim + 1, np.int64)
+    cols = np.zeros(max(nnz, 1), np.int32)
+    vals = np.zeros(max(nnz, 1), np.float64)
+    lib().ora_build_hop_csr(p, spin, nel, rp.ctypes.data, cols.ctypes.data, vals.ctypes.data)
+    return rp, cols[:nnz], vals[:nnz]
+
+
+def diag_vector(model: Model, nup, ndw):
+    DimUp, DimDw = sector_dims(model.Ns, nup, ndw)
+    d = np.empty(DimUp * DimDw)
+    lib().ora_build_diag(C.byref(model.params()), nup, ndw, d)
+    return d
+
+
+def nonlocal_csr(model: Model, nup, ndw):
+    p = C.byref(model.params())
+    DimUp, DimDw = sector_dims(model.Ns, nup, ndw)
+    nnz = lib().ora_build_nonlocal_csr(p, nup, ndw, None, None, None)
+    rp = np.zeros(DimUp * DimDw + 1, np.int64)
+    cols = np.zeros(max(nnz, 1), np.int64)
+    vals = np.zeros(max(nnz, 1), np.float64)
+    lib().ora_build_nonlocal_csr(p, nup, ndw, rp.ctypes.data, cols.ctypes.data, vals.ctypes.data)
+    return rp, cols[:nnz], vals[:nnz]
+
+
+def dense_H(model: Model, nup, ndw) -> np.ndarray:
+    """Hmat = Hd + Hnd + Hdw (x) 1 + 1 (x) Hup (STORED_HxV.f90:199-262)."""
+    DimUp, DimDw = sector_dims(model.Ns, nup, ndw)
+    H = np.diag(diag_vector(model, nup, ndw))
+    rp, cols, vals = nonlocal_csr(model, nup, ndw)
+    for i in range(DimUp * DimDw):
+        for k in range(rp[i], rp[i + 1]):
+            H[i, cols[k] - 1] += vals[k]
+
+    def small(spin, nel, dim):
+        rp, cols, vals = hop_csr(model, spin, nel)
+        M = np.zeros((dim, dim))
+        for i in range(dim):
+            for k in range(rp[i], rp[i + 1]):
+                M[i, cols[k] - 1] += vals[k]
+        return M
+
+    Hup = small(0, nup, DimUp)
+    Hdw = small(1, ndw, DimDw)
+    H += np.kron(Hdw, np.eye(DimUp)) + np.kron(np.eye(DimDw), Hup)
+    return H
+
+
+def apply_op(model: Model, op: int, iorb: int, spin: int, nup, ndw, v):
+    """apply_op_C (op=-1) / apply_op_CDG (op=+1); returns (vector, (nup',ndw'))."""
+    Ns = model.Ns
+    jn = (nup + (op if spin == 0 else 0), ndw + (op if spin == 1 else 0))
+    if min(jn) < 0 or max(jn) > Ns:
+        return None, None
+    ov = np.zeros(binomial(Ns, jn[0]) * binomial(Ns, jn[1]))
+    rc = lib().ora_apply_op(Ns, op, iorb, spin, nup, ndw, np.ascontiguousarray(v, np.float64), ov)
+    assert rc == 0
+    return ov, jn
+
+
+# --------------------------------------------------------------------------------------
+# Lanczos drivers (SciFortran SF_SP_LINALG semantics).  "hxv" is any callable
+# v -> H v, i.e. the role of the spHtimesV_p procedure pointer.
+# --------------------------------------------------------------------------------------
+def start_vector(n: int, seed: int = 4321) -> np.ndarray:
+    """Deterministic pseudo-random start vector shared by the oracle and the product
+    (splitmix64 -> uniform(0,1)); the reference uses the compiler's random_number."""
+    idx = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (idx + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def lanczos_iteration(hxv, it, vin, vout, beta):
+    """One step of the three-term recurrence in the sp_lanc_* drivers:
+    iter==1: vin/=|vin|; else (vin,vout) <- (vout/beta, -beta*vin);
+    vout += H vin; alfa = <vin,vout>; vout -= alfa*vin; beta = |vout|."""
+    if it == 1:
+        nrm = math.sqrt(float(vin @ vin))
+        vin = vin / nrm
+        vout = np.zeros_like(vin)
+    else:
+        vin, vout = vout / beta, -beta * vin
+    vout = vout + hxv(vin)
+    alfa = float(vin @ vout)
+    vout = vout - alfa * vin
+    beta = math.sqrt(float(vout @ vout))
+    return vin, vout, alfa, beta
+
+
+def lanc_tridiag(hxv, vin, nlanc, threshold=1e-12):
+    """sp_lanc_tridiag(MatVec, vin, alanc(N), blanc(N)): alanc(iter)=alfa, blanc(iter+1)=beta,
+    early exit when |beta| < threshold (call site ED_HAMILTONIAN_NORMAL.f90:360-365)."""
+    a = np.zeros(nlanc)
+    b = np.zeros(nlanc)
+    vin = np.array(vin, np.float64)
+    vout = np.zeros_like(vin)
+    beta = 0.0
+    nused = 0
+    for it in range(1, nlanc + 1):
+        vin, vout, alfa, beta = lanczos_iteration(hxv, it, vin, vout, beta)
+        a[it - 1] = alfa
+        nused = it
+        if abs(beta) < threshold:
+            break
+        if it < nlanc:
+            b[it] = beta
+    return a, b, nused
+
+
+def tridiag_eigh(a, b_sub):
+    from scipy.linalg import eigh_tridiagonal
+
+    if len(a) == 1:
+        return np.array(a, float), np.ones((1, 1))
+    return eigh_tridiagonal(np.asarray(a), np.asarray(b_sub))
+
+
+def lanc_eigh(hxv, n, nitermax, threshold=1e-12, ncheck=10, v0=None, seed=4321):
+    """sp_lanc_eigh(MatVec, egs, vect, Nitermax, threshold): two-pass plain Lanczos GS
+    (call site ED_DIAG_NORMAL.f90:206-213).  Pass 1 builds T, diagonalising it each step and
+    stopping when the lowest Ritz value moved less than threshold over one check window or
+    beta -> 0; pass 2 replays the recurrence accumulating vect += Z(iter,1) v_iter."""
+    v0 = start_vector(n, seed) if v0 is None else np.array(v0, np.float64)
+    v0 = v0 / math.sqrt(float(v0 @ v0))
+    a, b = [], [0.0]
+    vin, vout, beta = v0.copy(), np.zeros(n), 0.0
+    esave = []
+    nlanc = 0
+    for it in range(1, min(nitermax, n) + 1):
+        vin, vout, alfa, beta = lanczos_iteration(hxv, it, vin, vout, beta)
+        if abs(beta) < threshold and it > 1:
+            a.append(alfa)
+            nlanc = it
+            break
+        a.append(alfa)
+        b.append(beta)
+        nlanc = it
+        ev, _ = tridiag_eigh(a, b[1:nlanc])
+        if nlanc >= ncheck:
+            esave.append(ev[0])
+            if len(esave) >= 2 and abs(esave[-1] - esave[-2]) <= threshold:
+                break
+    ev, Z = tridiag_eigh(a[:nlanc], b[1:nlanc])
+    egs = float(ev[0])
+    vect = np.zeros(n)
+    vin, vout, beta = v0.copy(), np.zeros(n), 0.0
+    for it in range(1, nlanc + 1):
+        vin, vout, _, beta = lanczos_iteration(hxv, it, vin, vout, beta)
+        vect += Z[it - 1, 0] * vin
+    vect /= math.sqrt(float(vect @ vect))
+    return egs, vect, nlanc
+
+
+# --------------------------------------------------------------------------------------
+# ed_solve contract for NORMAL mode at T=0 (enough to reproduce the golden files)
+# --------------------------------------------------------------------------------------
+@dataclass
+class GState:
+    e: float
+    nup: int
+    ndw: int
+    vec: np.ndarray
+
+
+def diagonalize(model: Model, use_lanczos_above: int | None = None, hxv_kind="stored"):
+    """ed_diag_d (ED_DIAG_NORMAL.f90:76-296) without ed_twin: scan all (nup,ndw) sectors,
+    dense LAPACK when dim <= lanc_dim_threshold else plain Lanczos; T=0 state list with the
+    gs_threshold degeneracy rule (:262-278)."""
+    Ns = model.Ns
+    thr = model.lanc_dim_threshold if use_lanczos_above is None else use_lanczos_above
+    states: list[GState] = []
+    oldzero = 1000.0
+    fn = stored_hxv if hxv_kind == "stored" else direct_hxv
+    for isector in range(1, (Ns + 1) ** 2 + 1):
+        nup, ndw = sector_qn(Ns, isector)
+        DimUp, DimDw = sector_dims(Ns, nup, ndw)
+        dim = DimUp * DimDw
+        if dim <= thr:
+            ev, evec = np.linalg.eigh(dense_H(model, nup, ndw))
+            e0, v0 = float(ev[0]), evec[:, 0].copy()
+        else:
+            e0, v0, _ = lanc_eigh(lambda x: fn(model, nup, ndw, x), dim,
+                                  min(dim, model.lanc_niter), threshold=1e-12)
+        if e0 < oldzero - 10.0 * model.gs_threshold:
+            oldzero = e0
+            states = [GState(e0, nup, ndw, v0)]
+        elif abs(e0 - oldzero) <= model.gs_threshold:
+            oldzero = min(oldzero, e0)
+            states.append(GState(e0, nup, ndw, v0))
+    return states
+
+
+def observables(model: Model, states):
+    """dens / docc of ED_OBSERVABLES_NORMAL.f90:150-215 at T=0 (peso = 1/zeta)."""
+    Ns, No = model.Ns, model.Norb
+    dens = np.zeros(No)
+    docc = np.zeros(No)
+    zeta = len(states)
+    for st in states:
+        mu, md = build_map(Ns, st.nup), build_map(Ns, st.ndw)
+        w = (st.vec ** 2).reshape(len(md), len(mu)) / zeta  # [idw, iup]
+        for a in range(No):
+            nu = ((mu >> a) & 1).astype(float)[None, :]
+            nd = ((md >> a) & 1).astype(float)[:, None]
+            dens[a] += float((w * (nu + nd)).sum())
+            docc[a] += float((w * (nu * nd)).sum())
+    return dens, docc
+
+
+def gf_poles_weights(model: Model, states, iorb: int, spin: int = 0, hxv_kind="direct"):
+    """lanc_build_gf_normal_diag + add_to_lanczos_gf_normal (ED_GF_NORMAL.f90:131-177,
+    363-427): list of (weight, pole)."""
+    fn = stored_hxv if hxv_kind == "stored" else direct_hxv
+    zeta = len(states)
+    out = []
+    for st in states:
+        for op, isign in ((+1, 1), (-1, -1)):
+            seed, jn = apply_op(model, op, iorb, spin, st.nup, st.ndw, st.vec)
+            if seed is None:
+                continue
+            norm2 = float(seed @ seed)
+            if norm2 == 0.0:
+                continue
+            seed = seed / math.sqrt(norm2)
+            nlanc = min(len(seed), model.lanc_ngfiter)
+            a, b, nused = lanc_tridiag(lambda x: fn(model, jn[0], jn[1], x), seed, nlanc)
+            ev, Z = tridiag_eigh(a[:nused], b[1:nused])
+            for j in range(nused):
+                out.append((norm2 / zeta * Z[0, j] ** 2, isign * (ev[j] - st.e)))
+    return out
+
+
+def gf_eval(pw, z):
+    g = np.zeros_like(z, dtype=complex)
+    for w, p in pw:
+        g += w / (z - p)
+    return g
+
+
+def sigma_matsubara(model: Model, pw, iorb: int, spin: int, Lmats: int):
+    """Sigma = G0^-1 - G^-1 for the normal bath (ED_GF_NORMAL.f90:698-739,
+    invg0_normal.f90:22-28, delta_normal.f90:33-42)."""
+    wm = math.pi / model.beta * (2 * np.arange(1, Lmats + 1) - 1)
+    z = 1j * wm
+    e = model.bath_e[spin, iorb if model.bath_type == "normal" else 0]
+    v = model.bath_v[spin, iorb]
+    delta = (v[None, :] ** 2 / (z[:, None] - e[None, :])).sum(axis=1)
+    hl = 0.0 if model.hloc is None else model.hloc[spin, iorb, iorb]
+    invg0 = z + model.xmu - hl - delta
+    return wm, invg0 - 1.0 / gf_eval(pw, z)
+
+
+def momenta(wm, F, nmom=4):
+    """compute_momentum of test/src/COMMON.f90:178-192."""
+    den = np.abs(F).sum()
+    return np.array([(np.abs(F) * wm ** n).sum() / den for n in range(1, nmom + 1)])

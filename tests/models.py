@@ -1,0 +1,80 @@
+"""Model definitions shared by the oracle-side and product-side tests: the same plain numbers
+are fed to edipack_oracle.Model and to edipack_b200.EDModel."""
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def golden(name):
+    with open(os.path.join(HERE, "golden", name + ".json")) as f:
+        return json.load(f)
+
+
+def _f(s):
+    return float(s.replace("d", "e").replace("D", "e"))
+
+
+def normal_normal_kwargs():
+    """test/src/NORMAL_NORMAL: inputED.in + Hloc = Delta*sigma_z(orbital)
+    (ed_normal_normal.f90:60-66), default bath from init_dmft_bath."""
+    g = golden("normal_normal")["inputs"]
+    norb = int(g["NORB"])
+    delta = _f(g["DELTA"])
+    hloc = np.zeros((2, norb, norb))
+    for s in range(2):
+        hloc[s] = np.diag([delta, -delta])
+    return dict(Norb=norb, Nbath=int(g["NBATH"]), Nspin=int(g["NSPIN"]), bath_type=g["BATH_TYPE"],
+                Uloc=tuple(_f(x) for x in g["ULOC"].split(",")), Ust=_f(g["UST"]), Jh=_f(g["JH"]),
+                Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
+                beta=_f(g["BETA"]), ed_hw_bath=_f(g["ED_HW_BATH"]), hloc=hloc)
+
+
+def star_kwargs(nbath, U=2.0):
+    """Synthetic single-band Anderson impurity of SURVEY 8d (cfg1/2/4 family): Norb=1, normal
+    bath from init_dmft_bath, hfmode, xmu=0, Hloc=0."""
+    return dict(Norb=1, Nbath=nbath, Uloc=(U,), hfmode=True, xmu=0.0)
+
+
+def two_orb_kwargs(nbath, with_nd=True):
+    """cfg3 family: Norb=2, normal bath, U=U'=2, Jh=Jx=Jp=0.125, Hloc=0.5 sigma_z."""
+    hloc = np.zeros((2, 2, 2))
+    for s in range(2):
+        hloc[s] = np.diag([0.5, -0.5])
+    j = 0.125
+    return dict(Norb=2, Nbath=nbath, Uloc=(2.0, 2.0), Ust=2.0, Jh=j, Jx=j if with_nd else 0.0,
+                Jp=j if with_nd else 0.0, hfmode=True, hloc=hloc)
+
+
+def messy_kwargs(bath_type="normal"):
+    """Everything switched on with irrational-ish numbers: spin-dependent bath, spin field,
+    inter-orbital Hloc, xmu != 0, no hfmode -- exercises every term of HxV_local/up/dw."""
+    rng = np.random.default_rng(7)
+    norb, nbath = 2, 2
+    hloc = np.zeros((2, norb, norb))
+    for s in range(2):
+        a = rng.standard_normal((norb, norb))
+        hloc[s] = 0.3 * (a + a.T)
+    nfoo = 1 if bath_type == "hybrid" else norb
+    kw = dict(Norb=norb, Nbath=nbath, Nspin=2, bath_type=bath_type, Uloc=(1.7, 2.3), Ust=1.1,
+              Jh=0.21, Jx=0.13, Jp=0.17, xmu=0.37, hfmode=False, hloc=hloc,
+              bath_e=rng.standard_normal((2, nfoo, nbath)),
+              bath_v=0.5 + rng.random((2, norb, nbath)), spin_field_z=(0.11, -0.07))
+    return kw
+
+
+def replica_kwargs():
+    rng = np.random.default_rng(11)
+    norb, nbath = 2, 2
+    hb = np.zeros((2, norb, norb, nbath))
+    for k in range(nbath):
+        a = rng.standard_normal((norb, norb))
+        a = 0.4 * (a + a.T)
+        hb[0, :, :, k] = a
+        hb[1, :, :, k] = a
+    kw = two_orb_kwargs(nbath)
+    kw.update(bath_type="replica", hbath=hb, bath_e=np.zeros((2, norb, nbath)),
+              bath_v=np.full((2, norb, nbath), 0.6))
+    return kw

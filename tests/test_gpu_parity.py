@@ -1,0 +1,264 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star):
+  sector maps / fermionic signs / hop tables : bit-exact
+  H x v                                      : 1e-12 relative
+  ground-state energies                      : 1e-10 absolute
+  Green's functions / observables            : 1e-8
+"""
+import numpy as np
+import pytest
+
+from models import (golden, messy_kwargs, normal_normal_kwargs, replica_kwargs, star_kwargs,
+                    two_orb_kwargs)
+
+pytestmark = pytest.mark.gpu
+
+MODELS = {
+    "normal_normal": normal_normal_kwargs,
+    "star5": lambda: star_kwargs(5),
+    "star7": lambda: star_kwargs(7),
+    "two_orb": lambda: two_orb_kwargs(2),
+    "two_orb_nb3": lambda: two_orb_kwargs(3),
+    "messy": messy_kwargs,
+    "messy_hybrid": lambda: messy_kwargs("hybrid"),
+    "replica": replica_kwargs,
+}
+
+
+def sectors_for(ns):
+    h = ns // 2
+    return [(h, h), (h + 1, h - 1), (h - 1, h), (1, ns - 1), (0, 2), (ns, 0), (0, 0), (ns, ns)]
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("ns,nel", [(6, 3), (8, 4), (8, 0), (8, 8), (12, 5), (16, 8), (17, 3)])
+def test_sector_maps_bit_exact(engine, oracle, ns, nel):
+    E = engine
+    nb = ns - 1
+    m = E.EDModel(**star_kwargs(nb))
+    E.build_Hv_sector_normal(m, nel, max(0, min(ns, ns - nel)))
+    try:
+        got = E.sector_map(0)
+        got_dw = E.sector_map(1)
+    finally:
+        E.delete_Hv_sector_normal()
+    assert np.array_equal(got, oracle.build_map(ns, nel))
+    assert np.array_equal(got_dw, oracle.build_map(ns, max(0, min(ns, ns - nel))))
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_hop_tables_bit_exact(engine, oracle, name):
+    """Device hop tables (targets, fermionic signs, amplitudes) == the oracle's
+    c/cdg/binary_search products, as exact (i,j,value) sets per spin."""
+    E = engine
+    kw = MODELS[name]()
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    ns = m.Ns
+    for nup, ndw in sectors_for(ns)[:5]:
+        E.build_Hv_sector_normal(m, nup, ndw)
+        try:
+            for spin, nel in ((0, nup), (1, ndw)):
+                rp, tg, va = E.sector_hops(spin)
+                got = {}
+                for j in range(len(rp) - 1):
+                    for k in range(rp[j], rp[j + 1]):
+                        key = (int(tg[k]), j + 1)
+                        got[key] = got.get(key, 0.0) + va[k]
+                orp, oc, ov = oracle.hop_csr(mo, spin, nel)
+                exp = {}
+                for i in range(len(orp) - 1):
+                    for k in range(orp[i], orp[i + 1]):
+                        exp[(i + 1, int(oc[k]))] = ov[k]
+                # exc_field == 0 in these models -> at most one term per (i,j): bit-exact
+                assert got == exp
+        finally:
+            E.delete_Hv_sector_normal()
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("name", list(MODELS))
+def test_hxv_matches_oracle(engine, oracle, name, variant):
+    E = engine
+    kw = MODELS[name]()
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    ns = m.Ns
+    rng = np.random.default_rng(123)
+    E.set_kernel_variant(variant)
+    try:
+        for nup, ndw in sectors_for(ns):
+            du, dd = oracle.sector_dims(ns, nup, ndw)
+            v = rng.standard_normal(du * dd)
+            ref = oracle.direct_hxv(mo, nup, ndw, v)
+            E.build_Hv_sector_normal(m, nup, ndw)
+            try:
+                assert E.vecDim_Hv_sector_normal() == du * dd
+                hv = E.spHtimesV_p(v)
+            finally:
+                E.delete_Hv_sector_normal()
+            assert rel_err(hv, ref) < 1e-12, (name, nup, ndw)
+    finally:
+        E.set_kernel_variant(0)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_hxv_ns12_and_14(engine, oracle, variant):
+    """Sizes where the tiled kernels use several segments / columns per CTA."""
+    E = engine
+    rng = np.random.default_rng(5)
+    E.set_kernel_variant(variant)
+    try:
+        for kw, sec in ((star_kwargs(11), (6, 6)), (star_kwargs(11), (5, 7)),
+                        (two_orb_kwargs(5), (6, 6)), (star_kwargs(13), (7, 7))):
+            m, mo = E.EDModel(**kw), oracle.Model(**kw)
+            du, dd = oracle.sector_dims(m.Ns, *sec)
+            v = rng.standard_normal(du * dd)
+            ref = oracle.stored_hxv_mpi(mo, sec[0], sec[1], v, 8, 8)[0]
+            E.build_Hv_sector_normal(m, *sec)
+            try:
+                hv = E.spHtimesV_p(v)
+            finally:
+                E.delete_Hv_sector_normal()
+            assert rel_err(hv, ref) < 1e-12
+    finally:
+        E.set_kernel_variant(0)
+
+
+def test_hxv_error_behaviour(engine):
+    """spHtimesV_p outside build/delete and with a wrong Nloc fails loudly
+    (reference: stop, ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:49,52)."""
+    E = engine
+    with pytest.raises(E.EdgpuError, match="no sector open"):
+        E.spHtimesV_p(np.zeros(10))
+    m = E.EDModel(**star_kwargs(3))
+    E.build_Hv_sector_normal(m, 2, 2)
+    try:
+        with pytest.raises(E.EdgpuError, match="Nloc"):
+            E.spHtimesV_p(np.zeros(7))
+    finally:
+        E.delete_Hv_sector_normal()
+    with pytest.raises(E.EdgpuError):
+        E.build_Hv_sector_normal(m, 9, 0)
+
+
+def test_hxv_linearity_and_symmetry_large(engine):
+    """Size-independent properties at a size the oracle does not reach in seconds
+    (Ns=14 half filling, 11.8M states): linearity and <x|Hy> = <Hx|y>."""
+    E = engine
+    m = E.EDModel(**star_kwargs(13))
+    rng = np.random.default_rng(1)
+    E.build_Hv_sector_normal(m, 7, 7)
+    try:
+        n = E.vecDim_Hv_sector_normal()
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        hx, hy = E.spHtimesV_p(x), E.spHtimesV_p(y)
+        hxy = E.spHtimesV_p(2.0 * x - 3.0 * y)
+        assert rel_err(hxy, 2.0 * hx - 3.0 * hy) < 1e-12
+        assert abs(x @ hy - hx @ y) < 1e-9 * abs(x @ hy)
+    finally:
+        E.delete_Hv_sector_normal()
+
+
+@pytest.mark.parametrize("name,sec", [("normal_normal", (3, 3)), ("star7", (4, 4)),
+                                      ("messy", (3, 2)), ("two_orb_nb3", (4, 4))])
+def test_lanczos_tridiag_alpha_beta(engine, oracle, name, sec):
+    """alanc/blanc of sp_lanc_tridiag: device recurrence vs the oracle's on the same seed."""
+    E = engine
+    kw = MODELS[name]()
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    du, dd = oracle.sector_dims(m.Ns, *sec)
+    n = du * dd
+    seed = oracle.start_vector(n, 99) - 0.5
+    nl = min(n, 40)
+    a0, b0, nu0 = oracle.lanc_tridiag(lambda x: oracle.direct_hxv(mo, sec[0], sec[1], x),
+                                      seed / np.linalg.norm(seed), nl)
+    a1, b1, nu1, n2 = E.tridiag_Hv_sector_normal(m, sec[0], sec[1], seed, nl)
+    assert nu0 == nu1
+    assert abs(n2 - seed @ seed) < 1e-12 * (seed @ seed)
+    # early Lanczos coefficients agree to rounding; later ones drift with loss of orthogonality
+    k = min(nu0, 12)
+    assert np.abs(a1[:k] - a0[:k]).max() < 1e-9
+    assert np.abs(b1[:k] - b0[:k]).max() < 1e-9
+
+
+@pytest.mark.parametrize("name,sec", [("normal_normal", (3, 3)), ("star7", (4, 4)),
+                                      ("two_orb_nb3", (4, 4)), ("messy", (3, 3))])
+def test_lanczos_ground_state(engine, oracle, name, sec):
+    """sp_lanc_eigh on the device vs dense LAPACK of the oracle's H: energy 1e-10, vector
+    residual small, returned vector normalised."""
+    E = engine
+    kw = MODELS[name]()
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    H = oracle.dense_H(mo, *sec)
+    ev = np.linalg.eigvalsh(H)
+    E.build_Hv_sector_normal(m, *sec)
+    try:
+        e, v, nit = E.sp_lanc_eigh(min(H.shape[0], 300), 1e-14)
+    finally:
+        E.delete_Hv_sector_normal()
+    assert abs(e - ev[0]) < 1e-10
+    assert abs(np.linalg.norm(v) - 1.0) < 1e-12
+    assert np.abs(H @ v - e * v).max() < 1e-6
+
+
+def test_golden_normal_normal_end_to_end(engine, oracle):
+    """The reference's own fixture through the GPU path: sector scan with device Lanczos,
+    device-resident ground state, device seeds c/c^+, device tridiagonalisation ->
+    evals / dens / docc (1e-9) and Sigma(iw) moments (1e-8), test/src/NORMAL_NORMAL/*.check."""
+    E = engine
+    g = golden("normal_normal")
+    kw = normal_normal_kwargs()
+    m = E.EDModel(**kw)
+    mo = oracle.Model(**kw)
+    states = E.ed_diag_d(m)
+    assert len(states) == 1 and (states[0].nup, states[0].ndw) == (3, 3)
+    assert abs(states[0].e - g["evals"][0]) < 1e-9
+    dens, docc = E.observables_normal(m, states)
+    assert np.abs(dens - np.array(g["dens"])).max() < 1e-8
+    assert np.abs(docc - np.array(g["docc"])).max() < 1e-8
+    lmats = int(g["inputs"]["LMATS"])
+    gold = np.array(g["Sigma_momenta"]).reshape(m.Norb, 4)
+    for iorb in range(m.Norb):
+        pw = E.lanc_build_gf_normal_diag(m, states, iorb, 0)
+        wm, sig = oracle.sigma_matsubara(mo, pw, iorb, 0, lmats)
+        assert np.abs(oracle.momenta(wm, sig) / gold[iorb] - 1.0).max() < 1e-8
+    for s in states:
+        E.state_free(s.slot)
+
+
+def test_apply_op_matches_oracle(engine, oracle):
+    E = engine
+    kw = normal_normal_kwargs()
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    nup, ndw = 3, 2
+    du, dd = oracle.sector_dims(m.Ns, nup, ndw)
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal(du * dd)
+    v /= np.linalg.norm(v)
+    E.build_Hv_sector_normal(m, nup, ndw)
+    try:
+        # make v the "current state": one Lanczos step from v converges nowhere, so instead
+        # run the GS driver with v as start and a single iteration: vect == v
+        e, vec, nit = E.sp_lanc_eigh(1, 1e-14, vect=v)
+        assert np.abs(vec - v).max() < 1e-14
+        E.state_store(7)
+    finally:
+        E.delete_Hv_sector_normal()
+    for spin in (0, 1):
+        for iorb in range(m.Norb):
+            for op in (+1, -1):
+                ref, jn = oracle.apply_op(mo, op, iorb, spin, nup, ndw, v)
+                E.build_Hv_sector_normal(m, jn[0], jn[1])
+                try:
+                    E.apply_op(7, op, iorb, spin)
+                    # read the seed back through a 1-step tridiag: norm2 and alpha_1
+                    a, b, nused, n2 = E.sp_lanc_tridiag(None, 1)
+                finally:
+                    E.delete_Hv_sector_normal()
+                assert abs(n2 - ref @ ref) < 1e-13
+                if n2 > 0:
+                    hv = oracle.direct_hxv(mo, jn[0], jn[1], ref)
+                    assert abs(a[0] - (ref @ hv) / n2) < 1e-11
+    E.state_free(7)
