@@ -185,6 +185,7 @@ int edgpu_init(int device) {
   g.device = device;
   g.sm_count = prop.multiProcessorCount;
   g.smem_optin = prop.sharedMemPerBlockOptin;
+  g.smem_per_sm = prop.sharedMemPerMultiprocessor;
   EDGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto &ev : g.ev) EDGPU_CUDA(cudaEventCreate(&ev));
   g.part_cap = (int64_t)g.sm_count * 8;
@@ -258,6 +259,16 @@ int edgpu_sector_get_map(int spin, int32_t *map) {
   return 0;
 }
 
+// hop table of one species as (row-major) lists: entry s of row r lives in group s/4
+static int download_hops(SpinSpace &S, std::vector<uint32_t> &ell, std::vector<double> &amp) {
+  const int G = std::max(S.Wl4 + S.Wf4, 1);
+  ell.resize((size_t)4 * G * S.ld);
+  amp.resize((size_t)2 * S.nterms + 2);
+  EDGPU_CUDA(cudaMemcpy(ell.data(), S.ell4, sizeof(uint32_t) * ell.size(), cudaMemcpyDeviceToHost));
+  EDGPU_CUDA(cudaMemcpy(amp.data(), S.amp2, sizeof(double) * amp.size(), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int64_t edgpu_sector_hop_count(int spin) {
   clear_error();
   if (!g.sec.open) {
@@ -265,16 +276,15 @@ int64_t edgpu_sector_hop_count(int spin) {
     return -1;
   }
   SpinSpace &S = spin == 0 ? g.sec.up : g.sec.dw;
-  std::vector<uint32_t> ell((size_t)std::max(S.W, 1) * S.ld);
-  if (cudaMemcpy(ell.data(), S.ell, sizeof(uint32_t) * ell.size(), cudaMemcpyDeviceToHost) !=
-      cudaSuccess) {
-    set_error("hop table download failed");
-    return -1;
-  }
+  std::vector<uint32_t> ell;
+  std::vector<double> amp;
+  if (download_hops(S, ell, amp)) return -1;
+  const int G = S.Wl4 + S.Wf4;
   int64_t n = 0;
-  for (int e = 0; e < S.W; e++)
+  for (int gi = 0; gi < G; gi++)
     for (int64_t r = 0; r < S.dim; r++)
-      if (((ell[(size_t)e * S.ld + r] >> HOP_AMP_SHIFT) & HOP_AMP_MASK) != (uint32_t)S.nterms) n++;
+      for (int k = 0; k < 4; k++)
+        if ((ell[((size_t)gi * S.ld + r) * 4 + k] >> HOP_AMP_SHIFT) != (uint32_t)(2 * S.nterms)) n++;
   return n;
 }
 
@@ -282,21 +292,22 @@ int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *va
   clear_error();
   if (!g.sec.open) return set_error("no sector open");
   SpinSpace &S = spin == 0 ? g.sec.up : g.sec.dw;
-  std::vector<uint32_t> ell((size_t)std::max(S.W, 1) * S.ld);
-  EDGPU_CUDA(cudaMemcpy(ell.data(), S.ell, sizeof(uint32_t) * ell.size(), cudaMemcpyDeviceToHost));
-  std::vector<double> amp(S.nterms + 1);
-  EDGPU_CUDA(cudaMemcpy(amp.data(), S.amp, sizeof(double) * amp.size(), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> ell;
+  std::vector<double> amp;
+  EDGPU_TRY(download_hops(S, ell, amp));
+  const int G = S.Wl4 + S.Wf4;
   int64_t n = 0;
   for (int64_t r = 0; r < S.dim; r++) {
     rowptr[r] = n;
-    for (int e = 0; e < S.W; e++) {
-      uint32_t ent = ell[(size_t)e * S.ld + r];
-      uint32_t id = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
-      if (id == (uint32_t)S.nterms) continue;
-      target[n] = (int32_t)(ent & HOP_TGT_MASK) + 1;
-      value[n] = (ent & HOP_SIGN) ? -amp[id] : amp[id];
-      n++;
-    }
+    for (int gi = 0; gi < G; gi++)
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ell[((size_t)gi * S.ld + r) * 4 + k];
+        const uint32_t id = ent >> HOP_AMP_SHIFT;
+        if (id == (uint32_t)(2 * S.nterms)) continue;
+        target[n] = (int32_t)(ent & HOP_TGT_MASK) + 1;
+        value[n] = amp[id];
+        n++;
+      }
   }
   rowptr[S.dim] = n;
   return 0;

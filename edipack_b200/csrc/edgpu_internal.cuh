@@ -37,12 +37,11 @@ extern int64_t g_launches;  // kernels launched by this library (bench "gpu_laun
 #define EDGPU_COUNT_LAUNCH() (++::edgpu::g_launches)
 
 // ---------------------------------------------------------------------------------------
-// hop-table entry packing: [19:0] target row, [30:20] amplitude id, [31] sign
+// hop-table entry packing: [19:0] target row, [31:20] signed amplitude index
+// (2*term + sign; amp2[2t] = +h_t, amp2[2t+1] = -h_t, amp2[2*nterms] = 0 for padding)
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t HOP_TGT_MASK = 0xFFFFFu;
 constexpr int HOP_AMP_SHIFT = 20;
-constexpr uint32_t HOP_AMP_MASK = 0x7FFu;
-constexpr uint32_t HOP_SIGN = 0x80000000u;
 constexpr int HOP_MAX_TERMS = 2046;
 
 struct Term {  // one directed one-body term  h * c^+_alpha c_beta  (bit positions, 0-based)
@@ -57,6 +56,8 @@ struct LinTable {
   int32_t *jb = nullptr;  // [2^lo_bits]
 };
 
+enum SpinRole { ROLE_FAST = 0, ROLE_SLOW = 1 };
+
 // One spin species of the open sector
 struct SpinSpace {
   int nel = 0;
@@ -66,11 +67,20 @@ struct SpinSpace {
   LinTable lin;
   double *eps = nullptr;   // [ld] single-spin diagonal energy
   uint8_t *imp = nullptr;  // [ld] impurity occupation bits (map & (2^Norb-1))
-  // hop table, ELL, column-major: ell[e*ld + row]
-  int W = 0;
+  // Ranges: states sharing their top `tbits` bits are contiguous in the sorted map.  A hop is
+  // "local" when it stays inside its range (served from shared memory by the tiled kernels)
+  // and "far" when it moves an electron into / out of the top bits.
+  int tbits = 0;
+  int nranges = 1;
+  int64_t max_range = 0;
+  std::vector<int64_t> range_start;  // host, nranges+1
+  int64_t *d_range_start = nullptr;
+  // hop table, ELL in groups of 4 entries: ell4[g*ld + row] (uint4), groups [0,Wl4) local,
+  // [Wl4, Wl4+Wf4) far; unused slots point at the row itself with the zero amplitude.
+  int Wl = 0, Wf = 0, Wl4 = 0, Wf4 = 0;
   int nterms = 0;
-  uint32_t *ell = nullptr;
-  double *amp = nullptr;   // [nterms+1], amp[nterms] = 0 (padding slot)
+  uint4 *ell4 = nullptr;
+  double *amp2 = nullptr;  // [2*nterms+2]
   std::vector<Term> terms; // host copy
 };
 
@@ -85,15 +95,6 @@ struct Sector {
   double *xud = nullptr;    // [2^Norb (dw imp)][2^Norb (up imp)] cross interaction + constants
   bool nonlocal = false;
   double *jx = nullptr, *jp = nullptr;  // [Norb*Norb] device copies
-  // dw-range segmentation for the tiled dw kernel (single GPU)
-  std::vector<int64_t> seg_start;  // host, nseg+1
-  int64_t *d_seg_start = nullptr;
-  int nseg = 0;
-  int64_t max_seg = 0;
-  int dw_rows = 8;  // R
-  // up-range tiling
-  int64_t up_tile = 0;  // rows per tile
-  int up_cols = 1;      // columns per CTA
   int variant = 0;
   // scratch for the distributed transposes
   double *vt = nullptr, *hvt = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
@@ -106,6 +107,7 @@ struct Engine {
   int device = -1;
   int sm_count = 148;
   size_t smem_optin = 0;
+  size_t smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   // communicator

@@ -2,57 +2,64 @@
 // on the vector viewed as a [DimUp (fast), qdw] matrix with padded leading dimension.
 //
 // Reference loops being replaced (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:23-130, 236-375):
-//   direct/HxV_local.f90      -> diagonal, fused into the "up" kernel
-//   direct/HxV_up.f90         -> k_up_*   : sparse Hup applied along the fast index
-//   direct/HxV_dw.f90         -> k_dw_*   : sparse Hdw applied along the slow index
+//   direct/HxV_local.f90      -> diagonal, fused into the "fast" kernel
+//   direct/HxV_up.f90         -> k_fast    : sparse Hup applied along the fast index
+//   direct/HxV_dw.f90         -> k_slow    : sparse Hdw applied along the slow index
 //   direct/HxV_non_local.f90  -> k_nonlocal
 // The reference recomputes every matrix element (bdecomp, c/cdg sign loops, recursive
 // binary_search) for every state on every call; here the two small operators are ELL hop
-// tables built once per sector (sector.cu) and the kernels are pure streaming + gathers.
+// tables built once per sector (sector.cu) and the kernels are streaming passes whose gathers
+// are served from shared memory.
 //
-// Kernel variants
-//   generic : thread per state, gathers through L1/L2 (any size; also the fallback for
-//             ranges that do not fit shared memory)
-//   tiled   : a CTA stages a window of v in shared memory with TMA bulk copies
-//             (cp.async.bulk + mbarrier) and serves all in-window hops from it; hops that
-//             leave the window fall back to global loads.
+// Two-pass structure (DESIGN.md "Why two passes"): a tile that is closed under the up hops is a
+// set of full columns, a tile closed under the dw hops is a set of full rows; no 227 KB tile is
+// closed under both, so
+//   pass A  k_slow : CTA = 8 rows x one dw range  (all dw hops of the range from shared memory)
+//   pass B  k_fast : CTA = one up range x 2 columns (diagonal + all up hops from shared memory)
+// A "range" is a maximal run of sector states sharing their top `tbits` bits (contiguous in
+// the ascending map); hops that leave the range ("far", they move an electron into / out of
+// the top bits) are read from global memory (L2: the sibling ranges of the same rows / columns
+// are scheduled next to each other).
 #include "edgpu_internal.cuh"
 
 namespace edgpu {
 
-__device__ __forceinline__ double signed_amp(const double *__restrict__ amp, uint32_t ent) {
-  double a = amp[(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
-  return __hiloint2double(__double2hiint(a) ^ (int)(ent & HOP_SIGN), __double2loint(a));
-}
-
 struct SpinView {
   int64_t dim, ld;
-  int W;
+  int Wl4, Wf4;  // local / far groups of 4 entries
   int nterms;
-  const uint32_t *ell;
-  const double *amp;
+  const uint4 *ell4;
+  const double *amp2;
   const double *eps;
   const uint8_t *imp;
+  const int64_t *range_start;
+  int nranges;
 };
 
 static SpinView view_of(const SpinSpace &S) {
   SpinView v;
   v.dim = S.dim;
   v.ld = S.ld;
-  v.W = S.W;
+  v.Wl4 = S.Wl4;
+  v.Wf4 = S.Wf4;
   v.nterms = S.nterms;
-  v.ell = S.ell;
-  v.amp = S.amp;
+  v.ell4 = S.ell4;
+  v.amp2 = S.amp2;
   v.eps = S.eps;
   v.imp = S.imp;
+  v.range_start = S.d_range_start;
+  v.nranges = S.nranges;
   return v;
 }
 
+__device__ __forceinline__ uint32_t ent_of(const uint4 &q, int k) {
+  return k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w));
+}
+
 // ---------------------------------------------------------------------------------------
-// generic kernels
+// generic kernel: thread per state, gathers through L1/L2 (any size; parity cross-check of
+// the tiled kernels = "variant 1")
 // ---------------------------------------------------------------------------------------
-// Hv[:,c] = diag * v[:,c] + Hfast v[:,c]  (+ optional Hslow contribution when all slow
-// columns are local).  grid = (ceil(rows/128), ncols)
 template <bool WITH_DIAG, bool WITH_SLOW>
 __global__ void __launch_bounds__(128)
 k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, int64_t ldv,
@@ -68,197 +75,208 @@ k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, i
     double d = F.eps[i] + S.eps[cg] + xud[(int)S.imp[cg] * nimp + (int)F.imp[i]];
     acc += d * vc[i];
   }
-  for (int e = 0; e < F.W; e++) {
-    uint32_t ent = F.ell[(int64_t)e * F.ld + i];
-    acc += signed_amp(F.amp, ent) * vc[ent & HOP_TGT_MASK];
+  for (int g = 0; g < F.Wl4 + F.Wf4; g++) {
+    const uint4 q = F.ell4[(int64_t)g * F.ld + i];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t ent = ent_of(q, k);
+      acc += F.amp2[ent >> HOP_AMP_SHIFT] * vc[ent & HOP_TGT_MASK];
+    }
   }
   if (WITH_SLOW) {
-    for (int e = 0; e < S.W; e++) {
-      uint32_t ent = S.ell[(int64_t)e * S.ld + cg];
-      acc += signed_amp(S.amp, ent) * v[(int64_t)(ent & HOP_TGT_MASK) * ldv + i];
+    for (int g = 0; g < S.Wl4 + S.Wf4; g++) {
+      const uint4 q = S.ell4[(int64_t)g * S.ld + cg];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ent_of(q, k);
+        acc += S.amp2[ent >> HOP_AMP_SHIFT] * v[(int64_t)(ent & HOP_TGT_MASK) * ldv + i];
+      }
     }
   }
   hv[c * ldv + i] = acc;
 }
 
 // ---------------------------------------------------------------------------------------
-// mbarrier / TMA bulk-copy helpers (sm_90+; SASS: UBLKCP / SYNCS)
+// pass B, "fast index" kernel.  CTA = rows [r0, r1) of one range x 2 columns, staged in shared
+// memory interleaved as tile[row][2] so that one 16-byte shared load serves both columns.
+// grid = (nranges, ceil(ncol / 2)); range index fastest so that the ranges of one column pair
+// run next to each other and the far gathers hit L2.
+// shared layout: tile[trows][2] | xc[2][nimp] | amp[2*nterms+2]
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
-                                             uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
+constexpr int FAST_THREADS = 512;
 
-// ---------------------------------------------------------------------------------------
-// tiled "fast index" kernel: CTA = C columns x rows [r0, r0+tl) staged in shared memory.
-// shared layout: [C][tile] doubles | amp[nterms+1] | mbarrier
-// ---------------------------------------------------------------------------------------
-constexpr int UP_THREADS = 512;
-constexpr uint32_t BULK_CHUNK = 32768;  // bytes per bulk copy
-
-template <int C, bool WITH_DIAG, bool ACCUM>
-__global__ void __launch_bounds__(UP_THREADS, 2)
-k_fast_tiled(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, int64_t ldv,
-             int64_t ncol, int64_t col_offset, int64_t tile, SpinView F, SpinView S,
-             const double *__restrict__ xud, int nimp) {
+template <int WL4, bool WITH_DIAG, bool ACCUM>
+__global__ void __launch_bounds__(FAST_THREADS, 2)
+k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
+       int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *tl = reinterpret_cast<double *>(smem_raw);
-  double *amp_s = tl + (size_t)C * tile;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(amp_s + ((F.nterms + 1 + 1) & ~1));
-
-  const int64_t r0 = (int64_t)blockIdx.x * tile;
-  const int64_t rows = min(tile, F.ld - r0);  // padded rows are zero and 16-aligned
-  const int64_t c0 = (int64_t)blockIdx.y * C;
   const int tid = threadIdx.x;
+  const int r0 = (int)F.range_start[blockIdx.x], r1 = (int)F.range_start[blockIdx.x + 1];
+  const int tr0 = r0 & ~15;
+  const int tr1 = (r1 + 15) & ~15;  // <= F.ld
+  const int trows = tr1 - tr0;
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw);
+  double *xc = reinterpret_cast<double *>(tile + trows);
+  double *amp_s = xc + 2 * nimp;
 
-  if (tid == 0) mbar_init(bar, 1);
-  for (int t = tid; t <= F.nterms; t += UP_THREADS) amp_s[t] = F.amp[t];
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t total = 0;
-#pragma unroll
-    for (int c = 0; c < C; c++)
-      if (c0 + c < ncol) total += (uint32_t)(rows * 8);
-    mbar_expect_tx(bar, total);
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-      if (c0 + c >= ncol) continue;
-      const char *src = reinterpret_cast<const char *>(v + (c0 + c) * ldv + r0);
-      char *dst = reinterpret_cast<char *>(tl + (size_t)c * tile);
-      uint32_t left = (uint32_t)(rows * 8);
-      while (left) {
-        uint32_t n = left < BULK_CHUNK ? left : BULK_CHUNK;
-        tma_bulk_g2s(dst, src, n, bar);
-        dst += n;
-        src += n;
-        left -= n;
-      }
+  const int64_t c0 = (int64_t)blockIdx.y * 2;
+  const bool has2 = (c0 + 1 < ncol);
+  const double *v0 = v + c0 * ldv;
+  const double *v1 = v + (has2 ? c0 + 1 : c0) * ldv;
+
+  // stage: two rows of both columns per step, 16-byte global loads, 16-byte shared stores
+  for (int p = tid; p < trows / 2; p += FAST_THREADS) {
+    const double2 a = *reinterpret_cast<const double2 *>(v0 + tr0 + 2 * p);
+    const double2 b = *reinterpret_cast<const double2 *>(v1 + tr0 + 2 * p);
+    tile[2 * p] = make_double2(a.x, b.x);
+    tile[2 * p + 1] = make_double2(a.y, b.y);
+  }
+  for (int t = tid; t < 2 * F.nterms + 2; t += FAST_THREADS) amp_s[t] = F.amp2[t];
+  if (WITH_DIAG) {
+    // xc[cc][m] = eps_S(c) + X[imp_S(c)][m]
+    for (int t = tid; t < 2 * nimp; t += FAST_THREADS) {
+      const int cc = t / nimp, m = t - cc * nimp;
+      const int64_t cg = (cc == 0 || has2 ? c0 + cc : c0) + col_offset;
+      xc[t] = S.eps[cg] + xud[(int)S.imp[cg] * nimp + m];
     }
   }
-  mbar_wait(bar, 0);
+  __syncthreads();
 
-  double xrow_d[C];  // slow-index diagonal part per column
-  const double *xrow[C];
+  const uint32_t PAD = 2u * (uint32_t)F.nterms;
+  double *h0 = hv + c0 * ldv;
+  double *h1 = hv + (c0 + 1) * ldv;
+  // the last range also owns the pad rows [dim, ld): their entries are all padding -> zeros
+  const int rend = (blockIdx.x + 1 == gridDim.x) ? (int)F.ld : r1;
+  for (int i = r0 + tid; i < rend; i += FAST_THREADS) {
+    uint4 q[WL4 > 0 ? WL4 : 1];
 #pragma unroll
-  for (int c = 0; c < C; c++) {
-    int64_t cg = min(c0 + c, ncol - 1) + col_offset;
-    xrow_d[c] = WITH_DIAG ? S.eps[cg] : 0.0;
-    xrow[c] = WITH_DIAG ? xud + (int)S.imp[cg] * nimp : xud;
-  }
-
-  for (int64_t il = tid; il < rows; il += UP_THREADS) {
-    const int64_t i = r0 + il;
-    if (i >= nrow) break;
-    double acc[C];
+    for (int g = 0; g < WL4; g++) q[g] = F.ell4[(int64_t)g * F.ld + i];
+    double2 acc = make_double2(0.0, 0.0);
     if (WITH_DIAG) {
       const double eu = F.eps[i];
-      const int iu = (int)F.imp[i];
-#pragma unroll
-      for (int c = 0; c < C; c++) acc[c] = (eu + xrow_d[c] + xrow[c][iu]) * tl[(size_t)c * tile + il];
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; c++) acc[c] = 0.0;
+      const int m = (int)F.imp[i];
+      const double2 own = tile[i - tr0];
+      acc.x = (eu + xc[m]) * own.x;
+      acc.y = (eu + xc[nimp + m]) * own.y;
     }
-    for (int e = 0; e < F.W; e++) {
-      const uint32_t ent = F.ell[(int64_t)e * F.ld + i];
-      const double a = signed_amp(amp_s, ent);
-      const int64_t t = (int64_t)(ent & HOP_TGT_MASK) - r0;
-      if ((uint64_t)t < (uint64_t)rows) {
-#pragma unroll
-        for (int c = 0; c < C; c++) acc[c] += a * tl[(size_t)c * tile + t];
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; c++)
-          if (c0 + c < ncol) acc[c] += a * v[(c0 + c) * ldv + r0 + t];
-      }
+    if (ACCUM) {
+      acc.x += h0[i];
+      if (has2) acc.y += h1[i];
     }
 #pragma unroll
-    for (int c = 0; c < C; c++)
-      if (c0 + c < ncol) {
-        double *o = hv + (c0 + c) * ldv + i;
-        *o = ACCUM ? (*o + acc[c]) : acc[c];
+    for (int g = 0; g < WL4; g++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ent_of(q[g], k);
+        const double a = amp_s[ent >> HOP_AMP_SHIFT];
+        const double2 x = tile[(int)(ent & HOP_TGT_MASK) - tr0];
+        acc.x += a * x.x;
+        acc.y += a * x.y;
       }
+    }
+    if (WL4 == 0) {  // dynamic width
+      for (int g = 0; g < F.Wl4; g++) {
+        const uint4 qq = F.ell4[(int64_t)g * F.ld + i];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t ent = ent_of(qq, k);
+          const double a = amp_s[ent >> HOP_AMP_SHIFT];
+          const double2 x = tile[(int)(ent & HOP_TGT_MASK) - tr0];
+          acc.x += a * x.x;
+          acc.y += a * x.y;
+        }
+      }
+    }
+    for (int g = 0; g < F.Wf4; g++) {
+      const uint4 qq = F.ell4[(int64_t)(F.Wl4 + g) * F.ld + i];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ent_of(qq, k);
+        const uint32_t idx = ent >> HOP_AMP_SHIFT;
+        if (idx != PAD) {
+          const double a = amp_s[idx];
+          const uint32_t t = ent & HOP_TGT_MASK;
+          acc.x += a * v0[t];
+          acc.y += a * v1[t];
+        }
+      }
+    }
+    h0[i] = acc.x;
+    if (has2) h1[i] = acc.y;
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// tiled "slow index" kernel (single rank): CTA = R consecutive fast rows x the slow range
-// [s0, s1) of one segment (states sharing their top bits), staged as tile[j][R].
-//   hv[r, s0+j] += sum_e amp * v[r, tgt_e]     in-range targets from shared memory
+// pass A, "slow index" kernel.  CTA = 8 consecutive fast rows x the slow range [s0, s1),
+// staged as tile[j][8] with cp.async (LDGSTS) 16-byte copies.  A thread owns two rows of one
+// column; the hop entries of a column are shared by its 4 threads.
+//   hv[r, s0+j] (+)= sum_e amp_e * v[r, tgt_e]
+// grid = (nranges, ceil(nrow / 8)), range index fastest (far gathers hit L2).
 // ---------------------------------------------------------------------------------------
-constexpr int DW_THREADS = 512;
+constexpr int SLOW_THREADS = 512;
+constexpr int SLOW_R = 8;
 
-template <int R>
-__global__ void __launch_bounds__(DW_THREADS, 2)
-k_slow_tiled(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, int64_t ldv,
-             const int64_t *__restrict__ seg_start, SpinView S) {
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool ACCUM>
+__global__ void __launch_bounds__(SLOW_THREADS, 2)
+k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinView S) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *tl = reinterpret_cast<double *>(smem_raw);
-  const int seg = blockIdx.y;
-  const int64_t s0 = seg_start[seg], s1 = seg_start[seg + 1];
-  const int64_t len = s1 - s0;
-  double *amp_s = tl + (size_t)len * R;
-  const int64_t r0 = (int64_t)blockIdx.x * R;
+  double *tile = reinterpret_cast<double *>(smem_raw);
   const int tid = threadIdx.x;
-  for (int t = tid; t <= S.nterms; t += DW_THREADS) amp_s[t] = S.amp[t];
-  // stage: each R-row piece (R*8 bytes, contiguous) with 16-byte loads
-  constexpr int V2 = R / 2;  // double2 per piece
-  for (int64_t q = tid; q < len * V2; q += DW_THREADS) {
-    const int64_t j = q / V2;
-    const int h = (int)(q % V2);
-    const double2 x = *reinterpret_cast<const double2 *>(v + (s0 + j) * ldv + r0 + 2 * h);
-    *reinterpret_cast<double2 *>(tl + j * R + 2 * h) = x;
+  const int s0 = (int)S.range_start[blockIdx.x], s1 = (int)S.range_start[blockIdx.x + 1];
+  const int len = s1 - s0;
+  double *amp_s = tile + (size_t)len * SLOW_R;
+  const int64_t i0 = (int64_t)blockIdx.y * SLOW_R;
+
+  for (int q = tid; q < len * 4; q += SLOW_THREADS) {
+    const int j = q >> 2, part = q & 3;
+    cp_async16(tile + j * SLOW_R + part * 2, v + (int64_t)(s0 + j) * ldv + i0 + part * 2);
   }
+  for (int t = tid; t < 2 * S.nterms + 2; t += SLOW_THREADS) amp_s[t] = S.amp2[t];
+  cp_async_wait_all();
   __syncthreads();
-  for (int64_t q = tid; q < len * R; q += DW_THREADS) {
-    const int64_t j = q / R;
-    const int r = (int)(q % R);
-    if (r0 + r >= nrow) continue;
-    const int64_t cg = s0 + j;
-    double acc = 0.0;
-    for (int e = 0; e < S.W; e++) {
-      const uint32_t ent = S.ell[(int64_t)e * S.ld + cg];
-      const double a = signed_amp(amp_s, ent);
-      const int64_t t = (int64_t)(ent & HOP_TGT_MASK);
-      const int64_t tloc = t - s0;
-      double x;
-      if ((uint64_t)tloc < (uint64_t)len)
-        x = tl[tloc * R + r];
-      else
-        x = v[t * ldv + r0 + r];
-      acc += a * x;
+
+  const uint32_t PAD = 2u * (uint32_t)S.nterms;
+  const int rp2 = (tid & 3) * 2;  // first of the thread's two rows
+  for (int j = tid >> 2; j < len; j += SLOW_THREADS / 4) {
+    const int c = s0 + j;
+    double *o = hv + (int64_t)c * ldv + i0 + rp2;
+    double2 acc = ACCUM ? *reinterpret_cast<const double2 *>(o) : make_double2(0.0, 0.0);
+    for (int g = 0; g < S.Wl4; g++) {
+      const uint4 qq = S.ell4[(int64_t)g * S.ld + c];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ent_of(qq, k);
+        const double a = amp_s[ent >> HOP_AMP_SHIFT];
+        const double2 x =
+            *reinterpret_cast<const double2 *>(tile + ((int)(ent & HOP_TGT_MASK) - s0) * SLOW_R + rp2);
+        acc.x += a * x.x;
+        acc.y += a * x.y;
+      }
     }
-    hv[cg * ldv + r0 + r] += acc;
+    for (int g = 0; g < S.Wf4; g++) {
+      const uint4 qq = S.ell4[(int64_t)(S.Wl4 + g) * S.ld + c];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ent_of(qq, k);
+        const uint32_t idx = ent >> HOP_AMP_SHIFT;
+        if (idx != PAD) {
+          const double a = amp_s[idx];
+          const double2 x = *reinterpret_cast<const double2 *>(
+              v + (int64_t)(ent & HOP_TGT_MASK) * ldv + i0 + rp2);
+          acc.x += a * x.x;
+          acc.y += a * x.y;
+        }
+      }
+    }
+    *reinterpret_cast<double2 *>(o) = acc;
   }
 }
 
@@ -318,16 +336,22 @@ k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nr
 // ---------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------
-template <int C, bool WITH_DIAG, bool ACCUM>
-static int launch_fast_tiled(Engine &E, const double *v, double *hv, int64_t nrow, int64_t ldv,
-                             int64_t ncol, int64_t col_offset, int64_t tile, const SpinView &F,
-                             const SpinView &S, const double *xud, int nimp) {
-  size_t smem = sizeof(double) * ((size_t)C * tile + ((F.nterms + 2) & ~1)) + 16;
-  auto kern = k_fast_tiled<C, WITH_DIAG, ACCUM>;
+size_t fast_smem_bytes(int64_t max_range, int nterms, int nimp) {
+  return sizeof(double) * (2 * (size_t)(max_range + 32) + 2 * (size_t)nimp + 2 * (size_t)nterms + 2);
+}
+size_t slow_smem_bytes(int64_t max_range, int nterms) {
+  return sizeof(double) * ((size_t)max_range * SLOW_R + 2 * (size_t)nterms + 2);
+}
+
+template <int WL4, bool WITH_DIAG, bool ACCUM>
+static int launch_fast(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
+                       int64_t col_offset, const SpinView &F, const SpinView &S, int64_t max_range,
+                       const double *xud, int nimp) {
+  const size_t smem = fast_smem_bytes(max_range, F.nterms, nimp);
+  auto kern = k_fast<WL4, WITH_DIAG, ACCUM>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((F.ld + tile - 1) / tile), (unsigned)((ncol + C - 1) / C));
-  kern<<<grid, UP_THREADS, smem, E.stream>>>(v, hv, nrow, ldv, ncol, col_offset, tile, F, S, xud,
-                                             nimp);
+  dim3 grid((unsigned)F.nranges, (unsigned)((ncol + 1) / 2));
+  kern<<<grid, FAST_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
@@ -335,8 +359,8 @@ static int launch_fast_tiled(Engine &E, const double *v, double *hv, int64_t nro
 
 // Applies (diag +) the fast-index operator F to an [F.ld x ncol] block.
 static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const double *v, double *hv,
-                      int64_t ncol, int64_t col_offset, int64_t tile, int cols,
-                      const SpinView &F, const SpinView &S, const double *xud, int nimp) {
+                      int64_t ncol, int64_t col_offset, const SpinSpace &Fs, const SpinView &F,
+                      const SpinView &S, const double *xud, int nimp) {
   if (ncol <= 0) return 0;
   if (!tiled) {
     dim3 grid((unsigned)((F.dim + 127) / 128), (unsigned)ncol);
@@ -350,18 +374,35 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
     EDGPU_CUDA(cudaGetLastError());
     return 0;
   }
-#define EDGPU_FAST2(CC, DD, AA) \
-  launch_fast_tiled<CC, DD, AA>(E, v, hv, F.dim, F.ld, ncol, col_offset, tile, F, S, xud, nimp)
-#define EDGPU_FAST(CC)                                                      \
-  (with_diag ? (accum ? EDGPU_FAST2(CC, true, true) : EDGPU_FAST2(CC, true, false)) \
-             : (accum ? EDGPU_FAST2(CC, false, true) : EDGPU_FAST2(CC, false, false)))
-  switch (cols) {
-    case 4: return EDGPU_FAST(4);
+#define EDGPU_FAST2(WW, DD, AA) \
+  launch_fast<WW, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_range, xud, nimp)
+#define EDGPU_FAST(WW)                                                              \
+  (with_diag ? (accum ? EDGPU_FAST2(WW, true, true) : EDGPU_FAST2(WW, true, false)) \
+             : (accum ? EDGPU_FAST2(WW, false, true) : EDGPU_FAST2(WW, false, false)))
+  switch (F.Wl4) {
+    case 1: return EDGPU_FAST(1);
     case 2: return EDGPU_FAST(2);
-    default: return EDGPU_FAST(1);
+    case 3: return EDGPU_FAST(3);
+    default: return EDGPU_FAST(0);
   }
 #undef EDGPU_FAST2
 #undef EDGPU_FAST
+}
+
+static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const SpinSpace &Ss,
+                      const SpinView &Fv, const SpinView &S) {
+  const size_t smem = slow_smem_bytes(Ss.max_range, S.nterms);
+  dim3 grid((unsigned)S.nranges, (unsigned)((Fv.ld + SLOW_R - 1) / SLOW_R));
+  if (accum) {
+    EDGPU_CUDA(cudaFuncSetAttribute(k_slow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_slow<true><<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S);
+  } else {
+    EDGPU_CUDA(cudaFuncSetAttribute(k_slow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_slow<false><<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S);
+  }
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed) {
@@ -396,19 +437,12 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
       EDGPU_MARK(1);
       EDGPU_MARK(2);
     } else {
-      EDGPU_TRY(apply_fast(E, true, true, accum, d_v, d_hv, S.qdw, 0, S.up_tile, S.up_cols, U, D, S.xud,
-                           nimp));
+      // pass A (dw hops) writes / accumulates first, pass B (diag + up hops) adds on top
+      const bool have_slow = (D.Wl4 + D.Wf4) > 0;
+      if (have_slow) EDGPU_TRY(apply_slow(E, accum, d_v, d_hv, S.dw, U, D));
       EDGPU_MARK(1);
-      if (D.W > 0) {
-        constexpr int R = 8;
-        size_t smem = sizeof(double) * ((size_t)S.max_seg * R + ((D.nterms + 2) & ~1));
-        EDGPU_CUDA(cudaFuncSetAttribute(k_slow_tiled<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-        dim3 grid((unsigned)((U.dim + R - 1) / R), (unsigned)S.nseg);
-        k_slow_tiled<R><<<grid, DW_THREADS, smem, st>>>(d_v, d_hv, U.dim, U.ld, S.d_seg_start, D);
-        EDGPU_COUNT_LAUNCH();
-        EDGPU_CUDA(cudaGetLastError());
-      }
+      EDGPU_TRY(apply_fast(E, true, true, accum || have_slow, d_v, d_hv, S.qdw, 0, S.up, U, D, S.xud,
+                           nimp));
       EDGPU_MARK(2);
     }
     if (S.nonlocal) {
@@ -427,8 +461,7 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
     //   vt  = transpose(v)                            NCCL all-to-all of tiles
     //   Hvt = Hdw vt                                  dw is now the fast index
     //   Hv += transpose(Hvt)
-    EDGPU_TRY(apply_fast(E, tiled, true, accum, d_v, d_hv, S.qdw, S.d0, S.up_tile, S.up_cols, U, D, S.xud,
-                         nimp));
+    EDGPU_TRY(apply_fast(E, tiled, true, accum, d_v, d_hv, S.qdw, S.d0, S.up, U, D, S.xud, nimp));
     EDGPU_MARK(1);
     const size_t nt = (size_t)S.padded_len_t();
     if (!S.vt) {
@@ -438,21 +471,7 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
       EDGPU_CUDA(cudaMemsetAsync(S.hvt, 0, sizeof(double) * nt, st));
     }
     EDGPU_TRY(comm_transpose(E, d_v, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false));
-    {
-      // tiling plan for the transposed block (fast index = dw)
-      const size_t budget = std::min<size_t>(E.smem_optin, 227 * 1024) / 2 - 2048;
-      size_t amp_bytes = sizeof(double) * (D.nterms + 2);
-      size_t avail = budget - amp_bytes;
-      int64_t tile = D.ld;
-      int cols = 1;
-      if ((size_t)tile * 8 <= avail) {
-        while (cols < 4 && (size_t)tile * 8 * (cols * 2) <= avail && cols * 2 <= S.qup) cols *= 2;
-      } else {
-        int64_t parts = ((size_t)tile * 8 + avail - 1) / avail;
-        tile = ((D.ld + parts - 1) / parts + 15) / 16 * 16;
-      }
-      EDGPU_TRY(apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, tile, cols, D, U, S.xud, nimp));
-    }
+    EDGPU_TRY(apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp));
     EDGPU_MARK(2);
     EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, d_hv, U.dim, U.ld, S.qdw, true));
     if (S.nonlocal) return set_error("non-local (Jx/Jp) terms with nranks>1 are not implemented yet");

@@ -99,34 +99,39 @@ __device__ __forceinline__ int lin_rank(uint32_t m, int lo_bits, const int32_t *
 __device__ __forceinline__ uint32_t hop_sign(uint32_t m, int alpha, int beta) {
   int lo = min(alpha, beta), hi = max(alpha, beta);
   uint32_t between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
-  return (__popc(m & between) & 1) ? HOP_SIGN : 0u;
+  return (uint32_t)(__popc(m & between) & 1);
 }
 
+// per-row counts of local / far allowed terms; far = the term touches a bit >= far_bit
 __global__ void k_hop_count(const int32_t *__restrict__ map, int64_t dim,
-                            const Term *__restrict__ terms, int nterms, int *__restrict__ wmax,
-                            int32_t *__restrict__ counts) {
+                            const Term *__restrict__ terms, int nterms, int far_bit,
+                            int *__restrict__ wmax) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= dim) return;
   uint32_t m = (uint32_t)map[r];
-  int n = 0;
+  int nl = 0, nf = 0;
   for (int t = 0; t < nterms; t++) {
     int a = terms[t].alpha, b = terms[t].beta;
-    if (((m >> b) & 1u) && !((m >> a) & 1u)) n++;
+    if (((m >> b) & 1u) && !((m >> a) & 1u)) {
+      if (a >= far_bit || b >= far_bit) nf++; else nl++;
+    }
   }
-  counts[r] = n;
-  atomicMax(wmax, n);
+  atomicMax(wmax, nl);
+  atomicMax(wmax + 1, nf);
 }
 
-// Row r (source state j of direct/HxV_up.f90): entry e holds the target row i of the e-th
-// allowed term in the reference's term order and the signed amplitude id, so that
-//   Hv(j) += amp * sign * v(i)          (gather form of HxV_up.f90:23-27)
+// Row r (source state j of direct/HxV_up.f90): each entry holds the target row i of an
+// allowed term (in the reference's term order within its section) and the signed amplitude
+// index, so that   Hv(j) += amp2[idx] * v(i)     (gather form of HxV_up.f90:23-27)
 __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t ld,
-                           const Term *__restrict__ terms, int nterms, int W, int lo_bits,
-                           const int32_t *__restrict__ ja, const int32_t *__restrict__ jb,
-                           uint32_t *__restrict__ ell) {
+                           const Term *__restrict__ terms, int nterms, int far_bit, int Wl4,
+                           int Wf4, int lo_bits, const int32_t *__restrict__ ja,
+                           const int32_t *__restrict__ jb, uint32_t *__restrict__ ell) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= ld) return;
-  int e = 0;
+  // slot s of this row lives at ell[((s/4)*ld + r)*4 + s%4]
+  auto put = [&](int s, uint32_t val) { ell[((int64_t)(s >> 2) * ld + r) * 4 + (s & 3)] = val; };
+  int el = 0, ef = 4 * Wl4;
   if (r < dim) {
     uint32_t m = (uint32_t)map[r];
     for (int t = 0; t < nterms; t++) {
@@ -134,13 +139,15 @@ __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t
       if (((m >> b) & 1u) && !((m >> a) & 1u)) {
         uint32_t m2 = (m & ~(1u << b)) | (1u << a);
         uint32_t tgt = (uint32_t)lin_rank(m2, lo_bits, ja, jb);
-        ell[(int64_t)e * ld + r] = tgt | ((uint32_t)t << HOP_AMP_SHIFT) | hop_sign(m, a, b);
-        e++;
+        uint32_t val = tgt | ((uint32_t)(2 * t + hop_sign(m, a, b)) << HOP_AMP_SHIFT);
+        if (a >= far_bit || b >= far_bit) put(ef++, val); else put(el++, val);
       }
     }
   }
-  uint32_t self = (uint32_t)(r < dim ? r : 0);
-  for (; e < W; e++) ell[(int64_t)e * ld + r] = self | ((uint32_t)nterms << HOP_AMP_SHIFT);
+  // padding slots gather the row itself (always inside the row's own tile) with amplitude 0
+  const uint32_t pad = (uint32_t)r | ((uint32_t)(2 * nterms) << HOP_AMP_SHIFT);
+  for (; el < 4 * Wl4; el++) put(el, pad);
+  for (; ef < 4 * (Wl4 + Wf4); ef++) put(ef, pad);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -207,13 +214,16 @@ static int free_spin(SpinSpace &S) {
   cudaFree(S.lin.jb);
   cudaFree(S.eps);
   cudaFree(S.imp);
-  cudaFree(S.ell);
-  cudaFree(S.amp);
+  cudaFree(S.ell4);
+  cudaFree(S.amp2);
+  cudaFree(S.d_range_start);
   S = SpinSpace();
   return 0;
 }
 
-static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, SpinSpace &S) {
+// cap = largest range (in states of this species) the tiled kernel of this role can stage
+static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, SpinSpace &S,
+                      int64_t cap) {
   const int Ns = p.Ns;
   cudaStream_t st = E.stream;
   S.nel = nel;
@@ -246,39 +256,71 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   EDGPU_CUDA(cudaMemsetAsync(S.imp, 0, S.ld, st));
   k_eps<<<gb, T, 0, st>>>(S.map, S.dim, Ns, c, S.eps, S.imp);
   EDGPU_COUNT_LAUNCH();
+  // ranges: smallest number of fixed top bits such that every range fits `cap`
+  {
+    int t = 0;
+    auto max_range = [&](int tt) {
+      int64_t mx = 0;
+      for (int j = 0; j <= tt; j++) mx = std::max(mx, host_binomial(Ns - tt, nel - j));
+      return mx;
+    };
+    while (t < Ns && max_range(t) > cap) t++;
+    S.tbits = t;
+    S.range_start.clear();
+    int64_t pos = 0;
+    S.max_range = 0;
+    for (uint32_t h = 0; h < (1u << t); h++) {
+      int64_t cnt = host_binomial(Ns - t, nel - __builtin_popcount(h));
+      if (cnt <= 0) continue;
+      S.range_start.push_back(pos);
+      pos += cnt;
+      S.max_range = std::max(S.max_range, cnt);
+    }
+    S.range_start.push_back(pos);
+    S.nranges = (int)S.range_start.size() - 1;
+    if (pos != S.dim) return set_error("internal: range partition mismatch");
+    EDGPU_CUDA(cudaMalloc(&S.d_range_start, sizeof(int64_t) * S.range_start.size()));
+    EDGPU_CUDA(cudaMemcpyAsync(S.d_range_start, S.range_start.data(),
+                               sizeof(int64_t) * S.range_start.size(), cudaMemcpyHostToDevice, st));
+  }
   // hop table
   build_terms(p, s, S.terms);
   S.nterms = (int)S.terms.size();
   if (S.nterms > HOP_MAX_TERMS) return set_error("too many one-body terms (%d)", S.nterms);
+  const int far_bit = Ns - S.tbits;
   Term *d_terms = nullptr;
   int *d_w = nullptr;
-  int32_t *d_counts = nullptr;
   EDGPU_CUDA(cudaMalloc(&d_terms, sizeof(Term) * (S.nterms + 1)));
-  EDGPU_CUDA(cudaMalloc(&d_w, sizeof(int)));
-  EDGPU_CUDA(cudaMalloc(&d_counts, sizeof(int32_t) * S.ld));
+  EDGPU_CUDA(cudaMalloc(&d_w, 2 * sizeof(int)));
   if (S.nterms)
     EDGPU_CUDA(cudaMemcpyAsync(d_terms, S.terms.data(), sizeof(Term) * S.nterms,
                                cudaMemcpyHostToDevice, st));
-  EDGPU_CUDA(cudaMemsetAsync(d_w, 0, sizeof(int), st));
-  k_hop_count<<<gb, T, 0, st>>>(S.map, S.dim, d_terms, S.nterms, d_w, d_counts);
+  EDGPU_CUDA(cudaMemsetAsync(d_w, 0, 2 * sizeof(int), st));
+  k_hop_count<<<gb, T, 0, st>>>(S.map, S.dim, d_terms, S.nterms, far_bit, d_w);
   EDGPU_COUNT_LAUNCH();
-  int W = 0;
-  EDGPU_CUDA(cudaMemcpyAsync(&W, d_w, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int W[2] = {0, 0};
+  EDGPU_CUDA(cudaMemcpyAsync(W, d_w, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   EDGPU_CUDA(cudaStreamSynchronize(st));
-  S.W = W;
-  EDGPU_CUDA(cudaMalloc(&S.ell, sizeof(uint32_t) * (size_t)std::max(W, 1) * S.ld));
-  k_hop_fill<<<gl, T, 0, st>>>(S.map, S.dim, S.ld, d_terms, S.nterms, W, S.lin.lo_bits, S.lin.ja,
-                               S.lin.jb, S.ell);
+  S.Wl = W[0];
+  S.Wf = W[1];
+  S.Wl4 = (W[0] + 3) / 4;
+  S.Wf4 = (W[1] + 3) / 4;
+  const int G = std::max(S.Wl4 + S.Wf4, 1);
+  EDGPU_CUDA(cudaMalloc(&S.ell4, sizeof(uint4) * (size_t)G * S.ld));
+  k_hop_fill<<<gl, T, 0, st>>>(S.map, S.dim, S.ld, d_terms, S.nterms, far_bit, S.Wl4, S.Wf4,
+                               S.lin.lo_bits, S.lin.ja, S.lin.jb, (uint32_t *)S.ell4);
   EDGPU_COUNT_LAUNCH();
-  std::vector<double> amp(S.nterms + 1, 0.0);
-  for (int t = 0; t < S.nterms; t++) amp[t] = S.terms[t].h;
-  EDGPU_CUDA(cudaMalloc(&S.amp, sizeof(double) * (S.nterms + 1)));
-  EDGPU_CUDA(cudaMemcpyAsync(S.amp, amp.data(), sizeof(double) * (S.nterms + 1),
+  std::vector<double> amp(2 * S.nterms + 2, 0.0);
+  for (int t = 0; t < S.nterms; t++) {
+    amp[2 * t] = S.terms[t].h;
+    amp[2 * t + 1] = -S.terms[t].h;
+  }
+  EDGPU_CUDA(cudaMalloc(&S.amp2, sizeof(double) * amp.size()));
+  EDGPU_CUDA(cudaMemcpyAsync(S.amp2, amp.data(), sizeof(double) * amp.size(),
                              cudaMemcpyHostToDevice, st));
   EDGPU_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_terms);
   cudaFree(d_w);
-  cudaFree(d_counts);
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
@@ -292,15 +334,12 @@ int sector_close(Engine &E) {
   cudaFree(S.xud);
   cudaFree(S.jx);
   cudaFree(S.jp);
-  cudaFree(S.d_seg_start);
   cudaFree(S.vt);
   cudaFree(S.hvt);
   cudaFree(S.sendbuf);
   cudaFree(S.recvbuf);
   S.xud = S.jx = S.jp = nullptr;
-  S.d_seg_start = nullptr;
   S.vt = S.hvt = S.sendbuf = S.recvbuf = nullptr;
-  S.seg_start.clear();
   S.open = false;
   return 0;
 }
@@ -324,8 +363,23 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
       hb[n][k] = (int32_t)std::min<int64_t>(b, INT32_MAX);
     }
   EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_binom, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, E.stream));
-  EDGPU_TRY(build_spin(E, *p, 0, nup, S.up));
-  EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw));
+  // shared-memory capacities of the tiled kernels at 2 CTAs per SM (hxv.cu):
+  //   fast role: tile[range + 32][2] doubles ; slow role: tile[range][8] doubles ; + tables
+  {
+    std::vector<Term> tu, td;
+    build_terms(*p, 0, tu);
+    build_terms(*p, 1, td);
+    const size_t per_cta = (E.smem_per_sm - 2 * 1024) / 2;
+    const int nimp_ = 1 << p->Norb;
+    auto cap_of = [&](size_t nterms, size_t bytes_per_state, int64_t slack) {
+      const size_t tables = 8 * (2 * nterms + 2 + 2 * (size_t)nimp_) + 64;
+      const size_t avail = per_cta > tables ? per_cta - tables : 0;
+      return std::max<int64_t>((int64_t)(avail / bytes_per_state) - slack, 1);
+    };
+    EDGPU_TRY(build_spin(E, *p, 0, nup, S.up, cap_of(tu.size(), 16, 32)));
+    EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw,
+                         E.nranks == 1 ? cap_of(td.size(), 64, 0) : cap_of(td.size(), 16, 32)));
+  }
   // dw split (ED_HAMILTONIAN_NORMAL.f90:128-142).  The reference shrinks the communicator
   // when DimDw < MpiSize (:98-126); here every rank must own at least one column and one row.
   if (E.nranks > 1 && (S.dw.dim < E.nranks || S.up.dim < E.nranks))
@@ -375,54 +429,6 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
   }
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
 
-  // ---- tiling plan for the shared-memory kernels --------------------------------------
-  // up kernel: a CTA owns `up_cols` columns x a contiguous row range of `up_tile` rows.
-  const size_t budget = std::min<size_t>(E.smem_optin, 227 * 1024) / 2 - 2048;  // 2 CTAs / SM
-  {
-    int64_t rows = S.up.ld;
-    int cols = 1;
-    size_t amp_bytes = sizeof(double) * (S.up.nterms + 1);
-    size_t avail = budget > amp_bytes ? budget - amp_bytes : 0;
-    if ((size_t)rows * 8 <= avail) {
-      while (cols < 4 && (size_t)rows * 8 * (cols * 2) <= avail && cols * 2 <= S.qdw) cols *= 2;
-    } else {
-      int64_t parts = ((size_t)rows * 8 + avail - 1) / avail;
-      rows = ((S.up.ld + parts - 1) / parts + 15) / 16 * 16;
-    }
-    S.up_tile = rows;
-    S.up_cols = cols;
-  }
-  // dw kernel (single rank only): R rows x a contiguous dw range that shares the top-t bits
-  {
-    S.dw_rows = 8;
-    size_t amp_bytes = sizeof(double) * (S.dw.nterms + 1);
-    size_t avail = budget > amp_bytes ? budget - amp_bytes : 0;
-    int64_t cap = (int64_t)(avail / (8 * S.dw_rows));
-    int t = 0;
-    const int Ns = S.Ns;
-    auto max_seg = [&](int tt) {
-      int64_t mx = 0;
-      for (int j = 0; j <= tt; j++) mx = std::max(mx, host_binomial(Ns - tt, ndw - j));
-      return mx;
-    };
-    while (t < Ns && max_seg(t) > cap) t++;
-    S.seg_start.clear();
-    int64_t pos = 0;
-    S.max_seg = 0;
-    for (uint32_t h = 0; h < (1u << t); h++) {
-      int64_t cnt = host_binomial(Ns - t, ndw - __builtin_popcount(h));
-      if (cnt <= 0) continue;
-      S.seg_start.push_back(pos);
-      pos += cnt;
-      S.max_seg = std::max(S.max_seg, cnt);
-    }
-    S.seg_start.push_back(pos);
-    S.nseg = (int)S.seg_start.size() - 1;
-    if (pos != S.dw.dim) return set_error("internal: dw segmentation mismatch");
-    EDGPU_CUDA(cudaMalloc(&S.d_seg_start, sizeof(int64_t) * S.seg_start.size()));
-    EDGPU_CUDA(cudaMemcpy(S.d_seg_start, S.seg_start.data(), sizeof(int64_t) * S.seg_start.size(),
-                          cudaMemcpyHostToDevice));
-  }
   S.variant = E.variant_request;
   S.open = true;
   return 0;

@@ -211,6 +211,7 @@ def test_golden_normal_normal_end_to_end(engine, oracle):
     g = golden("normal_normal")
     kw = normal_normal_kwargs()
     m = E.EDModel(**kw)
+    m.lanc_tolerance = 1e-18  # the reference's LANC_TOLERANCE default (ED_INPUT_VARS.f90:726)
     mo = oracle.Model(**kw)
     states = E.ed_diag_d(m)
     assert len(states) == 1 and (states[0].nup, states[0].ndw) == (3, 3)
