@@ -51,20 +51,70 @@ static int ensure_buf(double **p, int64_t *len, int64_t need) {
   return 0;
 }
 
-// reference chunk layout (contiguous columns of DimUp) <-> padded device layout
+// reference chunk layout (contiguous columns of DimUp, ascending Fock order of both species,
+// i = iup + (idw-1)*DimUp, ED_SECTOR.f90:1681) <-> padded device layout in the internal
+// enumeration order (SiteOrder): a plain strided copy when both orders are the reference's,
+// else through a device staging buffer and a permutation kernel.
+__global__ void __launch_bounds__(256)
+k_permute_in(double *__restrict__ dst, int64_t ld, const double *__restrict__ src, int64_t nrow,
+             int64_t col_offset, const int32_t *__restrict__ refup,
+             const int32_t *__restrict__ refdw) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (i >= ld) return;
+  double x = 0.0;
+  if (i < nrow) x = src[((int64_t)refdw[c + col_offset] - col_offset) * nrow + refup[i]];
+  dst[c * ld + i] = x;
+}
+__global__ void __launch_bounds__(256)
+k_permute_out(double *__restrict__ dst, const double *__restrict__ src, int64_t ld, int64_t nrow,
+              int64_t col_offset, const int32_t *__restrict__ refup,
+              const int32_t *__restrict__ refdw) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (i >= nrow) return;
+  dst[((int64_t)refdw[c + col_offset] - col_offset) * nrow + refup[i]] = src[c * ld + i];
+}
+
+static double *g_stage = nullptr;
+static int64_t g_stage_len = 0;
+
 static int upload(Engine &E, double *d_dst, const double *h_src) {
   Sector &S = E.sec;
-  EDGPU_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(double) * S.padded_len(), E.stream));
-  EDGPU_CUDA(cudaMemcpy2DAsync(d_dst, sizeof(double) * S.up.ld, h_src, sizeof(double) * S.up.dim,
-                               sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyHostToDevice,
-                               E.stream));
+  if (S.up.ord.identity && S.dw.ord.identity) {
+    EDGPU_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(double) * S.padded_len(), E.stream));
+    EDGPU_CUDA(cudaMemcpy2DAsync(d_dst, sizeof(double) * S.up.ld, h_src, sizeof(double) * S.up.dim,
+                                 sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyHostToDevice,
+                                 E.stream));
+    return 0;
+  }
+  const int64_t n = S.up.dim * S.qdw;
+  EDGPU_TRY(ensure_buf(&g_stage, &g_stage_len, n));
+  EDGPU_CUDA(cudaMemcpyAsync(g_stage, h_src, sizeof(double) * n, cudaMemcpyHostToDevice, E.stream));
+  dim3 grid((unsigned)((S.up.ld + 255) / 256), (unsigned)S.qdw);
+  k_permute_in<<<grid, 256, 0, E.stream>>>(d_dst, S.up.ld, g_stage, S.up.dim, S.d0, S.up.refidx,
+                                           S.dw.refidx);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
 static int download(Engine &E, double *h_dst, const double *d_src) {
   Sector &S = E.sec;
-  EDGPU_CUDA(cudaMemcpy2DAsync(h_dst, sizeof(double) * S.up.dim, d_src, sizeof(double) * S.up.ld,
-                               sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyDeviceToHost,
-                               E.stream));
+  if (S.up.ord.identity && S.dw.ord.identity) {
+    EDGPU_CUDA(cudaMemcpy2DAsync(h_dst, sizeof(double) * S.up.dim, d_src, sizeof(double) * S.up.ld,
+                                 sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyDeviceToHost,
+                                 E.stream));
+    EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+    return 0;
+  }
+  const int64_t n = S.up.dim * S.qdw;
+  EDGPU_TRY(ensure_buf(&g_stage, &g_stage_len, n));
+  dim3 grid((unsigned)((S.up.dim + 255) / 256), (unsigned)S.qdw);
+  k_permute_out<<<grid, 256, 0, E.stream>>>(g_stage, d_src, S.up.ld, S.up.dim, S.d0, S.up.refidx,
+                                            S.dw.refidx);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  EDGPU_CUDA(cudaMemcpyAsync(h_dst, g_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, E.stream));
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
   return 0;
 }
@@ -76,7 +126,7 @@ static int download(Engine &E, double *h_dst, const double *d_src) {
 __global__ void __launch_bounds__(128)
 k_apply_op(const double *__restrict__ vsrc, int64_t lds, double *__restrict__ out, int64_t ldo,
            int64_t nrow, int64_t ncol, const int32_t *__restrict__ map_t, int op, int bit, int spin,
-           int lo_bits, const int32_t *__restrict__ ja, const int32_t *__restrict__ jb) {
+           RankView Rsrc) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t c = blockIdx.y;
   if (i >= nrow) return;
@@ -87,7 +137,7 @@ k_apply_op(const double *__restrict__ vsrc, int64_t lds, double *__restrict__ ou
   if ((op < 0 && !occ) || (op > 0 && occ)) {
     const uint32_t ms = m ^ (1u << bit);  // source state of that species
     const double sgn = (__popc(ms & ((1u << bit) - 1u)) & 1) ? -1.0 : 1.0;
-    const int64_t r = ja[ms >> lo_bits] + jb[ms & ((1u << lo_bits) - 1u)];
+    const int64_t r = rank_of(ms, Rsrc);
     const int64_t si = (spin == 0) ? r : i, sc = (spin == 0) ? c : r;
     val = sgn * vsrc[sc * lds + si];
   }
@@ -126,38 +176,6 @@ k_observables(const double *__restrict__ v, int64_t ld, int64_t nrow, int64_t nc
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(out + k, x);
   }
-}
-
-__constant__ int32_t c_binom2[33][33];
-__global__ void k_map_lite(int32_t *__restrict__ map, int64_t dim, int Ns, int nel) {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= dim) return;
-  int64_t rem = r;
-  int k = nel;
-  uint32_t m = 0;
-  for (int pos = Ns - 1; pos >= 0 && k > 0; --pos) {
-    int64_t cc = c_binom2[pos][k];
-    if (rem >= cc) {
-      m |= (1u << pos);
-      rem -= cc;
-      --k;
-    }
-  }
-  map[r] = (int32_t)m;
-}
-__global__ void k_lin_ja2(const int32_t *__restrict__ map, int64_t dim, int lo_bits,
-                          int32_t *__restrict__ ja) {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= dim) return;
-  uint32_t hi = (uint32_t)map[r] >> lo_bits;
-  if (r == 0 || ((uint32_t)map[r - 1] >> lo_bits) != hi) ja[hi] = (int32_t)r;
-}
-__global__ void k_lin_jb2(const int32_t *__restrict__ map, int64_t dim, int lo_bits,
-                          const int32_t *__restrict__ ja, int32_t *__restrict__ jb) {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= dim) return;
-  uint32_t m = (uint32_t)map[r];
-  jb[m & ((1u << lo_bits) - 1u)] = (int32_t)(r - ja[m >> lo_bits]);
 }
 
 }  // namespace edgpu
@@ -209,6 +227,9 @@ int edgpu_finalize(void) {
   cudaFree(g_seed);
   g_seed = nullptr;
   g_seed_len = 0;
+  cudaFree(g_stage);
+  g_stage = nullptr;
+  g_stage_len = 0;
   comm_finalize(g);
   cudaFree(g.d_part);
   cudaFree(g.d_scal);
@@ -255,7 +276,11 @@ int edgpu_sector_get_map(int spin, int32_t *map) {
   clear_error();
   if (!g.sec.open) return set_error("no sector open");
   SpinSpace &S = spin == 0 ? g.sec.up : g.sec.dw;
-  EDGPU_CUDA(cudaMemcpy(map, S.map, sizeof(int32_t) * S.dim, cudaMemcpyDeviceToHost));
+  // the device map is in the internal enumeration order; report the reference's ascending one
+  std::vector<int32_t> m((size_t)S.dim), ref((size_t)S.dim);
+  EDGPU_CUDA(cudaMemcpy(m.data(), S.map, sizeof(int32_t) * S.dim, cudaMemcpyDeviceToHost));
+  EDGPU_CUDA(cudaMemcpy(ref.data(), S.refidx, sizeof(int32_t) * S.dim, cudaMemcpyDeviceToHost));
+  for (int64_t r = 0; r < S.dim; r++) map[ref[(size_t)r]] = m[(size_t)r];
   return 0;
 }
 
@@ -284,7 +309,7 @@ int64_t edgpu_sector_hop_count(int spin) {
   for (int gi = 0; gi < G; gi++)
     for (int64_t r = 0; r < S.dim; r++)
       for (int k = 0; k < 4; k++)
-        if ((ell[((size_t)gi * S.ld + r) * 4 + k] >> HOP_AMP_SHIFT) != (uint32_t)(2 * S.nterms)) n++;
+        if (((ell[((size_t)gi * S.ld + r) * 4 + k] >> HOP_AMP_SHIFT) & HOP_AMP_MASK) != (uint32_t)(2 * S.nterms)) n++;
   return n;
 }
 
@@ -295,16 +320,20 @@ int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *va
   std::vector<uint32_t> ell;
   std::vector<double> amp;
   EDGPU_TRY(download_hops(S, ell, amp));
+  std::vector<int32_t> ref((size_t)S.dim), inv((size_t)S.dim);
+  EDGPU_CUDA(cudaMemcpy(ref.data(), S.refidx, sizeof(int32_t) * S.dim, cudaMemcpyDeviceToHost));
+  for (int64_t r = 0; r < S.dim; r++) inv[(size_t)ref[(size_t)r]] = (int32_t)r;
   const int G = S.Wl4 + S.Wf4;
   int64_t n = 0;
-  for (int64_t r = 0; r < S.dim; r++) {
-    rowptr[r] = n;
+  for (int64_t rr = 0; rr < S.dim; rr++) {  // rows in the reference's order
+    const int64_t r = inv[(size_t)rr];
+    rowptr[rr] = n;
     for (int gi = 0; gi < G; gi++)
       for (int k = 0; k < 4; k++) {
         const uint32_t ent = ell[((size_t)gi * S.ld + r) * 4 + k];
-        const uint32_t id = ent >> HOP_AMP_SHIFT;
+        const uint32_t id = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
         if (id == (uint32_t)(2 * S.nterms)) continue;
-        target[n] = (int32_t)(ent & HOP_TGT_MASK) + 1;
+        target[n] = ref[(size_t)(ent & HOP_TGT_MASK)] + 1;
         value[n] = amp[id];
         n++;
       }
@@ -504,38 +533,25 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
                      S.up.nel, S.dw.nel, tnup, tndw);
   if (g.nranks > 1 && spin == 1)
     return set_error("apply_op on the dw species with nranks>1 is not implemented yet");
-  // ranking tables of the SOURCE species
+  // enumeration order + ranking tables of the operated species in the SOURCE sector
   const int nel_src = spin == 0 ? st.nup : st.ndw;
-  const int64_t dim_src = spin == 0 ? st.dimu : st.dimd;
-  const int lo_bits = S.Ns / 2, hi_bits = S.Ns - lo_bits;
-  int32_t *map = nullptr, *ja = nullptr, *jb = nullptr;
-  int32_t hb[33][33];
-  for (int n = 0; n < 33; n++)
-    for (int k = 0; k < 33; k++) hb[n][k] = (int32_t)std::min<int64_t>(host_binomial(n, k), INT32_MAX);
-  EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_binom2, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, g.stream));
-  EDGPU_CUDA(cudaMalloc(&map, sizeof(int32_t) * dim_src));
-  EDGPU_CUDA(cudaMalloc(&ja, sizeof(int32_t) * ((size_t)1 << hi_bits)));
-  EDGPU_CUDA(cudaMalloc(&jb, sizeof(int32_t) * ((size_t)1 << lo_bits)));
-  EDGPU_CUDA(cudaMemsetAsync(ja, 0, sizeof(int32_t) * ((size_t)1 << hi_bits), g.stream));
-  EDGPU_CUDA(cudaMemsetAsync(jb, 0, sizeof(int32_t) * ((size_t)1 << lo_bits), g.stream));
-  const unsigned gb = (unsigned)((dim_src + 255) / 256);
-  k_map_lite<<<gb, 256, 0, g.stream>>>(map, dim_src, S.Ns, nel_src);
-  k_lin_ja2<<<gb, 256, 0, g.stream>>>(map, dim_src, lo_bits, ja);
-  k_lin_jb2<<<gb, 256, 0, g.stream>>>(map, dim_src, lo_bits, ja, jb);
-  g_launches += 3;
+  int32_t *map = nullptr;
+  LinTable lin;
+  SiteOrder ord;
+  EDGPU_TRY(species_ranking(g, S.prm, spin, nel_src, &map, &lin, &ord));
   const int64_t n = S.padded_len();
   EDGPU_TRY(ensure_buf(&g_seed, &g_seed_len, n));
   EDGPU_CUDA(cudaMemsetAsync(g_seed, 0, sizeof(double) * n, g.stream));
   dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
   k_apply_op<<<grid, 128, 0, g.stream>>>(st.vec, st.ldu, g_seed, S.up.ld, S.up.dim, S.qdw,
                                          spin == 0 ? S.up.map : S.dw.map + S.d0, op, iorb, spin,
-                                         lo_bits, ja, jb);
+                                         rank_view(lin, ord));
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   EDGPU_CUDA(cudaStreamSynchronize(g.stream));
   cudaFree(map);
-  cudaFree(ja);
-  cudaFree(jb);
+  cudaFree(lin.ja);
+  cudaFree(lin.jb);
   return 0;
 }
 

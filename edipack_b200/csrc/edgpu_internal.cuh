@@ -37,46 +37,89 @@ extern int64_t g_launches;  // kernels launched by this library (bench "gpu_laun
 #define EDGPU_COUNT_LAUNCH() (++::edgpu::g_launches)
 
 // ---------------------------------------------------------------------------------------
-// hop-table entry packing: [19:0] target row, [31:20] signed amplitude index
-// (2*term + sign; amp2[2t] = +h_t, amp2[2t+1] = -h_t, amp2[2*nterms] = 0 for padding)
+// hop-table entry packing: [19:0] target row, [30:20] signed amplitude index
+// (2*term + sign; amp2[2t] = +h_t, amp2[2t+1] = -h_t, amp2[2*nterms] = 0 for padding),
+// [31] "far" flag (slow-role tables only: the target lies outside the row's range)
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t HOP_TGT_MASK = 0xFFFFFu;
 constexpr int HOP_AMP_SHIFT = 20;
-constexpr int HOP_MAX_TERMS = 2046;
+constexpr uint32_t HOP_AMP_MASK = 0x7FFu;
+constexpr uint32_t HOP_FAR = 0x80000000u;
+constexpr int HOP_MAX_TERMS = 1022;
 
 struct Term {  // one directed one-body term  h * c^+_alpha c_beta  (bit positions, 0-based)
   int32_t alpha, beta;
   double h;
 };
 
-// Lin two-table ranking: rank(m) = ja[m >> lo_bits] + jb[m & lo_mask]
+// Internal enumeration order of one species: the sector states are listed in ascending order
+// of the bit-PERMUTED Fock integer (site `site[p]` sits at permuted position p, p = Ns-1 most
+// significant), not of the Fock integer itself.  The permutation puts a few bath sites on top
+// (range bits), then the impurity sites, then the other bath sites: consecutive states then
+// share their hop structure ("runs"), so that the gathers of a warp hit consecutive rows.
+// The reference's ascending order (ED_SECTOR.f90:217-242) is restored at the host boundary
+// through refidx[] (internal index -> reference index).
+struct SiteOrder {
+  uint8_t pos[32];   // original bit b -> permuted position
+  uint8_t site[32];  // permuted position p -> original bit
+  int32_t Ns;
+  int32_t identity;
+};
+
+// Lin two-table ranking on the permuted integer mp: rank = ja[mp >> lo_bits] + jb[mp & lo_mask]
 struct LinTable {
   int lo_bits = 0;
   int32_t *ja = nullptr;  // [2^(Ns-lo_bits)]
   int32_t *jb = nullptr;  // [2^lo_bits]
 };
 
+// device view of the ranking function of a species: ORIGINAL Fock integer -> internal index
+struct RankView {
+  int lo_bits;
+  const int32_t *ja, *jb;
+  SiteOrder ord;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t permute_bits(uint32_t m, const SiteOrder &o) {
+  if (o.identity) return m;
+  uint32_t r = 0;
+  for (int b = 0; b < o.Ns; b++) r |= ((m >> b) & 1u) << o.pos[b];
+  return r;
+}
+__device__ __forceinline__ int rank_of(uint32_t m, const RankView &R) {
+  const uint32_t mp = permute_bits(m, R.ord);
+  return R.ja[mp >> R.lo_bits] + R.jb[mp & ((1u << R.lo_bits) - 1u)];
+}
+#endif
+
 enum SpinRole { ROLE_FAST = 0, ROLE_SLOW = 1 };
+constexpr int SLOW_ROWS = 16;  // fast-index rows per CTA of the slow-index kernel (128 B segments)
 
 // One spin species of the open sector
 struct SpinSpace {
   int nel = 0;
   int64_t dim = 0;         // DimUp or DimDw
   int64_t ld = 0;          // dim padded to a multiple of 16 (128 B)
-  int32_t *map = nullptr;  // [dim] sector index -> Fock integer (ascending)
+  SiteOrder ord;
+  int32_t *map = nullptr;     // [ld] internal index -> Fock integer (original bit order)
+  int32_t *refidx = nullptr;  // [ld] internal index -> reference (ascending Fock) index
   LinTable lin;
   double *eps = nullptr;   // [ld] single-spin diagonal energy
   uint8_t *imp = nullptr;  // [ld] impurity occupation bits (map & (2^Norb-1))
-  // Ranges: states sharing their top `tbits` bits are contiguous in the sorted map.  A hop is
-  // "local" when it stays inside its range (served from shared memory by the tiled kernels)
-  // and "far" when it moves an electron into / out of the top bits.
-  int tbits = 0;
+  // Ranges: contiguous runs of states sharing a prefix of top bits, each small enough for the
+  // shared-memory tile of the species' role.  A hop is "local" when it stays inside its range
+  // and "far" when it moves an electron into / out of the range's prefix bits.
+  int role = ROLE_FAST;
   int nranges = 1;
   int64_t max_range = 0;
   std::vector<int64_t> range_start;  // host, nranges+1
+  std::vector<int> range_tbits;      // host, prefix length of each range
   int64_t *d_range_start = nullptr;
-  // hop table, ELL in groups of 4 entries: ell4[g*ld + row] (uint4), groups [0,Wl4) local,
-  // [Wl4, Wl4+Wf4) far; unused slots point at the row itself with the zero amplitude.
+  // hop table, ELL in groups of 4 entries: ell4[g*ld + row] (uint4).
+  //   fast role: groups [0,Wl4) local, [Wl4, Wl4+Wf4) far; unused slots = padding entries
+  //   slow role: one list of Wl4 groups (Wf4 = 0), local entries first, far entries flagged
+  // padding entries point at the row itself with the zero amplitude.
   int Wl = 0, Wf = 0, Wl4 = 0, Wf4 = 0;
   int nterms = 0;
   uint4 *ell4 = nullptr;
@@ -131,6 +174,11 @@ extern Engine g;
 
 // sector.cu
 int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw);
+// enumeration order + ranking tables of a species with `nel` electrons of the model `p`, exactly
+// as sector_open builds them (apply_op needs those of the SOURCE sector's species)
+int species_ranking(Engine &E, const edgpu_normal_params &p, int s, int nel, int32_t **map,
+                    LinTable *lin, SiteOrder *ord);
+RankView rank_view(const LinTable &lin, const SiteOrder &ord);
 int sector_close(Engine &E);
 int64_t host_binomial(int n, int k);
 void block_split(int64_t n, int P, int r, int64_t *q, int64_t *start);

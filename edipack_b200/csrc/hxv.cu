@@ -14,7 +14,7 @@
 // Two-pass structure (DESIGN.md "Why two passes"): a tile that is closed under the up hops is a
 // set of full columns, a tile closed under the dw hops is a set of full rows; no 227 KB tile is
 // closed under both, so
-//   pass A  k_slow : CTA = 8 rows x one dw range  (all dw hops of the range from shared memory)
+//   pass A  k_slow : CTA = 16 rows x one dw range  (all dw hops of the range from shared memory)
 //   pass B  k_fast : CTA = one up range x 2 columns (diagonal + all up hops from shared memory)
 // A "range" is a maximal run of sector states sharing their top `tbits` bits (contiguous in
 // the ascending map); hops that leave the range ("far", they move an electron into / out of
@@ -27,6 +27,7 @@ namespace edgpu {
 struct SpinView {
   int64_t dim, ld;
   int Wl4, Wf4;  // local / far groups of 4 entries
+  int Wf;        // largest number of far entries of a row
   int nterms;
   const uint4 *ell4;
   const double *amp2;
@@ -42,6 +43,7 @@ static SpinView view_of(const SpinSpace &S) {
   v.ld = S.ld;
   v.Wl4 = S.Wl4;
   v.Wf4 = S.Wf4;
+  v.Wf = S.Wf;
   v.nterms = S.nterms;
   v.ell4 = S.ell4;
   v.amp2 = S.amp2;
@@ -50,6 +52,25 @@ static SpinView view_of(const SpinSpace &S) {
   v.range_start = S.d_range_start;
   v.nranges = S.nranges;
   return v;
+}
+
+// explicit shared-window loads (32-bit addresses: no generic->shared conversion per access)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ double2 lds128(uint32_t a) {
+  double2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ double lds64(uint32_t a) {
+  double r;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+  return r;
+}
+// byte offset of amp2[idx] from the packed entry
+__device__ __forceinline__ uint32_t amp_off(uint32_t ent) {
+  return (ent >> (HOP_AMP_SHIFT - 3)) & (HOP_AMP_MASK << 3);
 }
 
 __device__ __forceinline__ uint32_t ent_of(const uint4 &q, int k) {
@@ -80,7 +101,7 @@ k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, i
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const uint32_t ent = ent_of(q, k);
-      acc += F.amp2[ent >> HOP_AMP_SHIFT] * vc[ent & HOP_TGT_MASK];
+      acc += F.amp2[(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK] * vc[ent & HOP_TGT_MASK];
     }
   }
   if (WITH_SLOW) {
@@ -89,7 +110,7 @@ k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, i
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const uint32_t ent = ent_of(q, k);
-        acc += S.amp2[ent >> HOP_AMP_SHIFT] * v[(int64_t)(ent & HOP_TGT_MASK) * ldv + i];
+        acc += S.amp2[(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK] * v[(int64_t)(ent & HOP_TGT_MASK) * ldv + i];
       }
     }
   }
@@ -124,13 +145,11 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
   const double *v0 = v + c0 * ldv;
   const double *v1 = v + (has2 ? c0 + 1 : c0) * ldv;
 
-  // stage: two rows of both columns per step, 16-byte global loads, 16-byte shared stores
-  for (int p = tid; p < trows / 2; p += FAST_THREADS) {
-    const double2 a = *reinterpret_cast<const double2 *>(v0 + tr0 + 2 * p);
-    const double2 b = *reinterpret_cast<const double2 *>(v1 + tr0 + 2 * p);
-    tile[2 * p] = make_double2(a.x, b.x);
-    tile[2 * p + 1] = make_double2(a.y, b.y);
-  }
+  // stage: one row of both columns per thread: coalesced 8-byte global loads, contiguous
+  // (conflict-free) 16-byte shared stores
+#pragma unroll 4
+  for (int p = tid; p < trows; p += FAST_THREADS)
+    tile[p] = make_double2(v0[tr0 + p], v1[tr0 + p]);
   for (int t = tid; t < 2 * F.nterms + 2; t += FAST_THREADS) amp_s[t] = F.amp2[t];
   if (WITH_DIAG) {
     // xc[cc][m] = eps_S(c) + X[imp_S(c)][m]
@@ -145,6 +164,9 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
   const uint32_t PAD = 2u * (uint32_t)F.nterms;
   double *h0 = hv + c0 * ldv;
   double *h1 = hv + (c0 + 1) * ldv;
+  const uint32_t tile_sa = smem_u32(tile) - (uint32_t)tr0 * 16u;  // + row * 16
+  const uint32_t amp_sa = smem_u32(amp_s);
+  const uint32_t xc_sa = smem_u32(xc);
   // the last range also owns the pad rows [dim, ld): their entries are all padding -> zeros
   const int rend = (blockIdx.x + 1 == gridDim.x) ? (int)F.ld : r1;
   for (int i = r0 + tid; i < rend; i += FAST_THREADS) {
@@ -154,10 +176,10 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
     double2 acc = make_double2(0.0, 0.0);
     if (WITH_DIAG) {
       const double eu = F.eps[i];
-      const int m = (int)F.imp[i];
-      const double2 own = tile[i - tr0];
-      acc.x = (eu + xc[m]) * own.x;
-      acc.y = (eu + xc[nimp + m]) * own.y;
+      const uint32_t m = (uint32_t)F.imp[i];
+      const double2 own = lds128(tile_sa + (uint32_t)i * 16u);
+      acc.x = (eu + lds64(xc_sa + m * 8u)) * own.x;
+      acc.y = (eu + lds64(xc_sa + ((uint32_t)nimp + m) * 8u)) * own.y;
     }
     if (ACCUM) {
       acc.x += h0[i];
@@ -168,8 +190,8 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const uint32_t ent = ent_of(q[g], k);
-        const double a = amp_s[ent >> HOP_AMP_SHIFT];
-        const double2 x = tile[(int)(ent & HOP_TGT_MASK) - tr0];
+        const double a = lds64(amp_sa + amp_off(ent));
+        const double2 x = lds128(tile_sa + (ent & HOP_TGT_MASK) * 16u);
         acc.x += a * x.x;
         acc.y += a * x.y;
       }
@@ -180,8 +202,8 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const uint32_t ent = ent_of(qq, k);
-          const double a = amp_s[ent >> HOP_AMP_SHIFT];
-          const double2 x = tile[(int)(ent & HOP_TGT_MASK) - tr0];
+          const double a = lds64(amp_sa + amp_off(ent));
+          const double2 x = lds128(tile_sa + (ent & HOP_TGT_MASK) * 16u);
           acc.x += a * x.x;
           acc.y += a * x.y;
         }
@@ -191,10 +213,11 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
       const uint4 qq = F.ell4[(int64_t)(F.Wl4 + g) * F.ld + i];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
+        if (4 * g + k >= F.Wf) break;  // uniform: slots beyond the widest far row
         const uint32_t ent = ent_of(qq, k);
-        const uint32_t idx = ent >> HOP_AMP_SHIFT;
+        const uint32_t idx = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
         if (idx != PAD) {
-          const double a = amp_s[idx];
+          const double a = lds64(amp_sa + idx * 8u);
           const uint32_t t = ent & HOP_TGT_MASK;
           acc.x += a * v0[t];
           acc.y += a * v1[t];
@@ -207,14 +230,16 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
 }
 
 // ---------------------------------------------------------------------------------------
-// pass A, "slow index" kernel.  CTA = 8 consecutive fast rows x the slow range [s0, s1),
-// staged as tile[j][8] with cp.async (LDGSTS) 16-byte copies.  A thread owns two rows of one
-// column; the hop entries of a column are shared by its 4 threads.
+// pass A, "slow index" kernel.  CTA = SLOW_ROWS (16) consecutive fast rows x the slow range
+// [s0, s1), staged as tile[j][16] with cp.async (LDGSTS) 16-byte copies.  A thread owns two rows
+// of one column; the 8 threads of a column read one contiguous 128-byte segment per hop
+// (= one conflict-free shared-memory wavefront) and share the column's hop entries.
 //   hv[r, s0+j] (+)= sum_e amp_e * v[r, tgt_e]
-// grid = (nranges, ceil(nrow / 8)), range index fastest (far gathers hit L2).
+// Entries: one list per column, local targets first, far ones flagged (read from global / L2).
+// grid = (nranges, ceil(nrow / 16)), range index fastest (far gathers hit L2).
 // ---------------------------------------------------------------------------------------
 constexpr int SLOW_THREADS = 512;
-constexpr int SLOW_R = 8;
+constexpr int SLOW_R = SLOW_ROWS;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -224,7 +249,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-template <bool ACCUM>
+// W4 = entry groups per column (0 = dynamic, slow generic loop), NF = number of leading slots
+// that may hold far entries (the table is sorted far-first, sector.cu): their loads are issued
+// first and consumed last, so that the L2 latency of the far gathers hides behind the local
+// hops.  Entries of the next column are prefetched into registers.
+template <int W4, int NF, bool ACCUM>
 __global__ void __launch_bounds__(SLOW_THREADS, 2)
 k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinView S) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -234,47 +263,102 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
   const int len = s1 - s0;
   double *amp_s = tile + (size_t)len * SLOW_R;
   const int64_t i0 = (int64_t)blockIdx.y * SLOW_R;
+  constexpr int PARTS = SLOW_R / 2;              // 16-byte pieces (= threads) per column
+  constexpr int CSTEP = SLOW_THREADS / PARTS;    // columns per sweep of the CTA
+  const int rp2 = (tid % PARTS) * 2;             // first of the thread's two rows
+  const int jl = tid / PARTS;
+  const uint32_t ld32 = (uint32_t)ldv;
 
-  for (int q = tid; q < len * 4; q += SLOW_THREADS) {
-    const int j = q >> 2, part = q & 3;
-    cp_async16(tile + j * SLOW_R + part * 2, v + (int64_t)(s0 + j) * ldv + i0 + part * 2);
+  {
+    const double *src = v + (int64_t)(s0 + jl) * ldv + i0 + rp2;
+    double *dst = tile + jl * SLOW_R + rp2;
+    for (int j = jl; j < len; j += CSTEP) {
+      cp_async16(dst, src);
+      src += (int64_t)CSTEP * ldv;
+      dst += CSTEP * SLOW_R;
+    }
   }
   for (int t = tid; t < 2 * S.nterms + 2; t += SLOW_THREADS) amp_s[t] = S.amp2[t];
   cp_async_wait_all();
   __syncthreads();
 
-  const uint32_t PAD = 2u * (uint32_t)S.nterms;
-  const int rp2 = (tid & 3) * 2;  // first of the thread's two rows
-  for (int j = tid >> 2; j < len; j += SLOW_THREADS / 4) {
-    const int c = s0 + j;
-    double *o = hv + (int64_t)c * ldv + i0 + rp2;
-    double2 acc = ACCUM ? *reinterpret_cast<const double2 *>(o) : make_double2(0.0, 0.0);
-    for (int g = 0; g < S.Wl4; g++) {
-      const uint4 qq = S.ell4[(int64_t)g * S.ld + c];
+  const double *vrow = v + i0 + rp2;  // + t * ldv : far target column
+  // + t * 128 : local target column (wraps mod 2^32 before the add, exact after it)
+  const uint32_t trow_sa = smem_u32(tile) + (uint32_t)rp2 * 8u - (uint32_t)s0 * (SLOW_R * 8u);
+  const uint32_t amp_sa = smem_u32(amp_s);
+  const uint4 *ell = S.ell4 + s0;
+  constexpr int NG = W4 > 0 ? W4 : 1;
+  uint4 nq[NG];
+  double2 nh = make_double2(0.0, 0.0);  // Hv of the next column (accumulate mode), prefetched
+  if (jl < len) {
+    if (W4 > 0) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t ent = ent_of(qq, k);
-        const double a = amp_s[ent >> HOP_AMP_SHIFT];
-        const double2 x =
-            *reinterpret_cast<const double2 *>(tile + ((int)(ent & HOP_TGT_MASK) - s0) * SLOW_R + rp2);
+      for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * S.ld + jl];
+    }
+    if (ACCUM) nh = *reinterpret_cast<const double2 *>(hv + (int64_t)(s0 + jl) * ldv + i0 + rp2);
+  }
+  for (int j = jl; j < len; j += CSTEP) {
+    double *o = hv + (int64_t)(s0 + j) * ldv + i0 + rp2;
+    double2 acc = make_double2(0.0, 0.0);
+    const double2 hcur = nh;
+    if (ACCUM && j + CSTEP < len)
+      nh = *reinterpret_cast<const double2 *>(o + (int64_t)CSTEP * ldv);
+    if (W4 > 0) {
+      uint4 q[NG];
+#pragma unroll
+      for (int g = 0; g < W4; g++) q[g] = nq[g];
+      if (j + CSTEP < len) {
+#pragma unroll
+        for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * S.ld + j + CSTEP];
+      }
+      // leading NF slots: far or local, loads first
+      double2 xf[NF > 0 ? NF : 1];
+#pragma unroll
+      for (int e = 0; e < NF; e++) {
+        const uint32_t ent = ent_of(q[e >> 2], e & 3);
+        const uint32_t t = ent & HOP_TGT_MASK;
+        if (ent & HOP_FAR)
+          xf[e] = *reinterpret_cast<const double2 *>(vrow + (size_t)(t * ld32));
+        else
+          xf[e] = lds128(trow_sa + t * (SLOW_R * 8u));
+      }
+#pragma unroll
+      for (int e = NF; e < 4 * W4; e++) {
+        const uint32_t ent = ent_of(q[e >> 2], e & 3);
+        const double a = lds64(amp_sa + amp_off(ent));
+        const double2 x = lds128(trow_sa + (ent & HOP_TGT_MASK) * (SLOW_R * 8u));
         acc.x += a * x.x;
         acc.y += a * x.y;
       }
-    }
-    for (int g = 0; g < S.Wf4; g++) {
-      const uint4 qq = S.ell4[(int64_t)(S.Wl4 + g) * S.ld + c];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t ent = ent_of(qq, k);
-        const uint32_t idx = ent >> HOP_AMP_SHIFT;
-        if (idx != PAD) {
-          const double a = amp_s[idx];
-          const double2 x = *reinterpret_cast<const double2 *>(
-              v + (int64_t)(ent & HOP_TGT_MASK) * ldv + i0 + rp2);
+      for (int e = 0; e < NF; e++) {
+        const uint32_t ent = ent_of(q[e >> 2], e & 3);
+        const double a = lds64(amp_sa + amp_off(ent));
+        acc.x += a * xf[e].x;
+        acc.y += a * xf[e].y;
+      }
+    } else {
+      const int c = s0 + j;
+      for (int g = 0; g < S.Wl4; g++) {
+        const uint4 qq = S.ell4[(int64_t)g * S.ld + c];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t ent = ent_of(qq, k);
+          const double a = amp_s[(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
+          const uint32_t t = ent & HOP_TGT_MASK;
+          double2 x;
+          if (ent & HOP_FAR)
+            x = *reinterpret_cast<const double2 *>(vrow + (size_t)t * ldv);
+          else
+            x = lds128(trow_sa + t * (SLOW_R * 8u));
           acc.x += a * x.x;
           acc.y += a * x.y;
         }
       }
+    }
+    if (ACCUM) {
+      acc.x += hcur.x;
+      acc.y += hcur.y;
     }
     *reinterpret_cast<double2 *>(o) = acc;
   }
@@ -287,13 +371,6 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
 // All four operators act on impurity bits, so signs depend on impurity bits only.
 // vfull is the full (all-gathered) vector with leading dimension ldv.
 // ---------------------------------------------------------------------------------------
-struct LinView {
-  int lo_bits;
-  const int32_t *ja, *jb;
-};
-__device__ __forceinline__ int lin_rank_v(uint32_t m, LinView L) {
-  return L.ja[m >> L.lo_bits] + L.jb[m & ((1u << L.lo_bits) - 1u)];
-}
 __device__ __forceinline__ double pair_sign(uint32_t m, int a, int b) {
   int lo = min(a, b), hi = max(a, b);
   uint32_t between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
@@ -303,7 +380,7 @@ __device__ __forceinline__ double pair_sign(uint32_t m, int a, int b) {
 __global__ void __launch_bounds__(128)
 k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nrow, int64_t ldv,
            int64_t ncol, int64_t col_offset, const int32_t *__restrict__ mapu,
-           const int32_t *__restrict__ mapd, LinView Lu, LinView Ld, int Norb,
+           const int32_t *__restrict__ mapd, RankView Lu, RankView Ld, int Norb,
            const double *__restrict__ jx, const double *__restrict__ jp) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t c = blockIdx.y;
@@ -319,14 +396,14 @@ k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nr
         // dw: c(iorb), cdg(jorb) ; up: c(jorb), cdg(iorb)
         const uint32_t md2 = (md & ~bi) | bj, mu2 = (mu & ~bj) | bi;
         const double sg = pair_sign(md, io, jo) * pair_sign(mu, io, jo);
-        const int64_t iu = lin_rank_v(mu2, Lu), id = lin_rank_v(md2, Ld);
+        const int64_t iu = rank_of(mu2, Lu), id = rank_of(md2, Ld);
         acc += x * sg * vfull[id * ldv + iu];
       }
       const double y = jp[io * Norb + jo];
       if (y != 0.0 && (mu & bj) && (md & bj) && !(md & bi) && !(mu & bi)) {
         const uint32_t md2 = (md & ~bj) | bi, mu2 = (mu & ~bj) | bi;
         const double sg = pair_sign(md, io, jo) * pair_sign(mu, io, jo);
-        const int64_t iu = lin_rank_v(mu2, Lu), id = lin_rank_v(md2, Ld);
+        const int64_t iu = rank_of(mu2, Lu), id = rank_of(md2, Ld);
         acc += y * sg * vfull[id * ldv + iu];
       }
     }
@@ -389,20 +466,47 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
 #undef EDGPU_FAST
 }
 
-static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const SpinSpace &Ss,
-                      const SpinView &Fv, const SpinView &S) {
+template <int W4, int NF, bool ACCUM>
+static int launch_slow(Engine &E, const double *v, double *hv, const SpinSpace &Ss,
+                       const SpinView &Fv, const SpinView &S) {
   const size_t smem = slow_smem_bytes(Ss.max_range, S.nterms);
   dim3 grid((unsigned)S.nranges, (unsigned)((Fv.ld + SLOW_R - 1) / SLOW_R));
-  if (accum) {
-    EDGPU_CUDA(cudaFuncSetAttribute(k_slow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_slow<true><<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S);
-  } else {
-    EDGPU_CUDA(cudaFuncSetAttribute(k_slow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_slow<false><<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S);
-  }
+  auto kern = k_slow<W4, NF, ACCUM>;
+  EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
+}
+
+static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const SpinSpace &Ss,
+                      const SpinView &Fv, const SpinView &S) {
+  // the element offset t * ld of a far gather is formed in 32 bits
+  const bool small = (uint64_t)Ss.dim * (uint64_t)Fv.ld < (1ull << 32);
+  const int W4 = Ss.Wl4, NF = Ss.Wf;  // Wf = largest number of far entries of a column
+#define EDGPU_SLOW(WW, FF) \
+  (accum ? launch_slow<WW, FF, true>(E, v, hv, Ss, Fv, S) : launch_slow<WW, FF, false>(E, v, hv, Ss, Fv, S))
+  if (small && W4 >= 1 && W4 <= 3 && NF <= 4 && NF <= 4 * W4) {
+    switch (W4 * 8 + NF) {
+      case 8 + 0: return EDGPU_SLOW(1, 0);
+      case 8 + 1: return EDGPU_SLOW(1, 1);
+      case 8 + 2: return EDGPU_SLOW(1, 2);
+      case 8 + 3: return EDGPU_SLOW(1, 3);
+      case 8 + 4: return EDGPU_SLOW(1, 4);
+      case 16 + 0: return EDGPU_SLOW(2, 0);
+      case 16 + 1: return EDGPU_SLOW(2, 1);
+      case 16 + 2: return EDGPU_SLOW(2, 2);
+      case 16 + 3: return EDGPU_SLOW(2, 3);
+      case 16 + 4: return EDGPU_SLOW(2, 4);
+      case 24 + 0: return EDGPU_SLOW(3, 0);
+      case 24 + 1: return EDGPU_SLOW(3, 1);
+      case 24 + 2: return EDGPU_SLOW(3, 2);
+      case 24 + 3: return EDGPU_SLOW(3, 3);
+      case 24 + 4: return EDGPU_SLOW(3, 4);
+    }
+  }
+  return EDGPU_SLOW(0, 0);
+#undef EDGPU_SLOW
 }
 
 int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed) {
@@ -437,18 +541,16 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
       EDGPU_MARK(1);
       EDGPU_MARK(2);
     } else {
-      // pass A (dw hops) writes / accumulates first, pass B (diag + up hops) adds on top
-      const bool have_slow = (D.Wl4 + D.Wf4) > 0;
-      if (have_slow) EDGPU_TRY(apply_slow(E, accum, d_v, d_hv, S.dw, U, D));
+      // pass B (diag + up hops) writes / accumulates first: it is the pass that saturates the
+      // shared-memory pipe, so the read-modify-write of Hv is left to pass A (dw hops)
+      EDGPU_TRY(apply_fast(E, true, true, accum, d_v, d_hv, S.qdw, 0, S.up, U, D, S.xud, nimp));
       EDGPU_MARK(1);
-      EDGPU_TRY(apply_fast(E, true, true, accum || have_slow, d_v, d_hv, S.qdw, 0, S.up, U, D, S.xud,
-                           nimp));
+      if ((D.Wl4 + D.Wf4) > 0) EDGPU_TRY(apply_slow(E, true, d_v, d_hv, S.dw, U, D));
       EDGPU_MARK(2);
     }
     if (S.nonlocal) {
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      LinView Lu{S.up.lin.lo_bits, S.up.lin.ja, S.up.lin.jb};
-      LinView Ld{S.dw.lin.lo_bits, S.dw.lin.ja, S.dw.lin.jb};
+      const RankView Lu = rank_view(S.up.lin, S.up.ord), Ld = rank_view(S.dw.lin, S.dw.ord);
       k_nonlocal<<<grid, 128, 0, st>>>(d_v, d_hv, U.dim, U.ld, S.qdw, 0, S.up.map, S.dw.map, Lu, Ld,
                                        S.Norb, S.jx, S.jp);
       EDGPU_COUNT_LAUNCH();

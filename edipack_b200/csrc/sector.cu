@@ -32,37 +32,54 @@ void block_split(int64_t n, int P, int r, int64_t *q, int64_t *start) {
 
 __constant__ int32_t c_binom[33][33];
 
-// r-th (0-based) Ns-bit pattern with nel bits set in ascending integer order
-// = combinadic unranking; identical to the reference's popcount scan order.
-__global__ void k_build_map(int32_t *__restrict__ map, int64_t dim, int Ns, int nel) {
+// r-th (0-based) Ns-bit pattern with nel bits set in ascending order of the PERMUTED integer
+// (combinadic unranking), mapped back to the original bit order.  With the identity order this
+// is the reference's popcount scan order (ED_SECTOR.f90:217-242).
+__global__ void k_build_map(int32_t *__restrict__ map, int32_t *__restrict__ mapp, int64_t dim,
+                            int Ns, int nel, SiteOrder ord) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= dim) return;
   int64_t rem = r;
   int k = nel;
-  uint32_t m = 0;
+  uint32_t mp = 0, m = 0;
   for (int pos = Ns - 1; pos >= 0 && k > 0; --pos) {
     int64_t c = c_binom[pos][k];
     if (rem >= c) {
-      m |= (1u << pos);
+      mp |= (1u << pos);
+      m |= (1u << ord.site[pos]);
       rem -= c;
       --k;
     }
   }
   map[r] = (int32_t)m;
+  mapp[r] = (int32_t)mp;
 }
 
-__global__ void k_lin_ja(const int32_t *__restrict__ map, int64_t dim, int lo_bits,
+// reference index of internal state r = combinadic rank of its Fock integer
+__global__ void k_ref_rank(const int32_t *__restrict__ map, int64_t dim, int Ns,
+                           int32_t *__restrict__ refidx) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= dim) return;
+  const uint32_t m = (uint32_t)map[r];
+  int j = 0;
+  int64_t rk = 0;
+  for (int b = 0; b < Ns; b++)
+    if ((m >> b) & 1u) rk += c_binom[b][++j];
+  refidx[r] = (int32_t)rk;
+}
+
+__global__ void k_lin_ja(const int32_t *__restrict__ mapp, int64_t dim, int lo_bits,
                          int32_t *__restrict__ ja) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= dim) return;
-  uint32_t hi = (uint32_t)map[r] >> lo_bits;
-  if (r == 0 || ((uint32_t)map[r - 1] >> lo_bits) != hi) ja[hi] = (int32_t)r;
+  uint32_t hi = (uint32_t)mapp[r] >> lo_bits;
+  if (r == 0 || ((uint32_t)mapp[r - 1] >> lo_bits) != hi) ja[hi] = (int32_t)r;
 }
-__global__ void k_lin_jb(const int32_t *__restrict__ map, int64_t dim, int lo_bits,
+__global__ void k_lin_jb(const int32_t *__restrict__ mapp, int64_t dim, int lo_bits,
                          const int32_t *__restrict__ ja, int32_t *__restrict__ jb) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= dim) return;
-  uint32_t m = (uint32_t)map[r];
+  uint32_t m = (uint32_t)mapp[r];
   uint32_t hi = m >> lo_bits, lo = m & ((1u << lo_bits) - 1u);
   jb[lo] = (int32_t)(r - ja[hi]);  // same value from every writer
 }
@@ -88,11 +105,6 @@ __global__ void k_eps(const int32_t *__restrict__ map, int64_t dim, int Ns, EpsC
   imp[r] = (uint8_t)(m & ((1u << c.Norb) - 1u));
 }
 
-__device__ __forceinline__ int lin_rank(uint32_t m, int lo_bits, const int32_t *ja,
-                                        const int32_t *jb) {
-  return ja[m >> lo_bits] + jb[m & ((1u << lo_bits) - 1u)];
-}
-
 // Fermionic sign of c^+_alpha c_beta on m (beta occupied, alpha empty): parity of the
 // occupied sites strictly between the two positions = sg1*sg2 of c(), cdg()
 // (ED_AUX_FUNX.f90:353-357, 379-383).
@@ -102,52 +114,78 @@ __device__ __forceinline__ uint32_t hop_sign(uint32_t m, int alpha, int beta) {
   return (uint32_t)(__popc(m & between) & 1);
 }
 
-// per-row counts of local / far allowed terms; far = the term touches a bit >= far_bit
+// per-row counts of local / far allowed terms; far = the term touches a bit >= far_bit[r]
 __global__ void k_hop_count(const int32_t *__restrict__ map, int64_t dim,
-                            const Term *__restrict__ terms, int nterms, int far_bit,
+                            const Term *__restrict__ terms, int nterms,
+                            const uint8_t *__restrict__ far_bit, SiteOrder ord,
                             int *__restrict__ wmax) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= dim) return;
   uint32_t m = (uint32_t)map[r];
+  const int fb = far_bit[r];
   int nl = 0, nf = 0;
   for (int t = 0; t < nterms; t++) {
     int a = terms[t].alpha, b = terms[t].beta;
     if (((m >> b) & 1u) && !((m >> a) & 1u)) {
-      if (a >= far_bit || b >= far_bit) nf++; else nl++;
+      if (ord.pos[a] >= fb || ord.pos[b] >= fb) nf++; else nl++;
     }
   }
   atomicMax(wmax, nl);
   atomicMax(wmax + 1, nf);
+  atomicMax(wmax + 2, nl + nf);
 }
 
 // Row r (source state j of direct/HxV_up.f90): each entry holds the target row i of an
 // allowed term (in the reference's term order within its section) and the signed amplitude
-// index, so that   Hv(j) += amp2[idx] * v(i)     (gather form of HxV_up.f90:23-27)
+// index, so that   Hv(j) += amp2[idx] * v(i)     (gather form of HxV_up.f90:23-27).
+// merged == 0 (fast role): local entries in slots [0, 4*Wl4), far entries in [4*Wl4, ...)
+// merged == 1 (slow role): one list, far entries (flagged HOP_FAR) first, then the local ones
 __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t ld,
-                           const Term *__restrict__ terms, int nterms, int far_bit, int Wl4,
-                           int Wf4, int lo_bits, const int32_t *__restrict__ ja,
-                           const int32_t *__restrict__ jb, uint32_t *__restrict__ ell) {
+                           const Term *__restrict__ terms, int nterms,
+                           const uint8_t *__restrict__ far_bit, int merged, int Wl4, int Wf4,
+                           RankView R, uint32_t *__restrict__ ell) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= ld) return;
   // slot s of this row lives at ell[((s/4)*ld + r)*4 + s%4]
   auto put = [&](int s, uint32_t val) { ell[((int64_t)(s >> 2) * ld + r) * 4 + (s & 3)] = val; };
-  int el = 0, ef = 4 * Wl4;
+  const int nslots = 4 * (Wl4 + Wf4);
+  int el = 0, ef = merged ? 0 : 4 * Wl4;
   if (r < dim) {
     uint32_t m = (uint32_t)map[r];
-    for (int t = 0; t < nterms; t++) {
-      int a = terms[t].alpha, b = terms[t].beta;
-      if (((m >> b) & 1u) && !((m >> a) & 1u)) {
-        uint32_t m2 = (m & ~(1u << b)) | (1u << a);
-        uint32_t tgt = (uint32_t)lin_rank(m2, lo_bits, ja, jb);
-        uint32_t val = tgt | ((uint32_t)(2 * t + hop_sign(m, a, b)) << HOP_AMP_SHIFT);
-        if (a >= far_bit || b >= far_bit) put(ef++, val); else put(el++, val);
+    const int fb = far_bit[r];
+    if (merged) {  // first pass: far entries, second pass: local entries behind them
+      for (int pass = 0; pass < 2; pass++)
+        for (int t = 0; t < nterms; t++) {
+          int a = terms[t].alpha, b = terms[t].beta;
+          if (((m >> b) & 1u) && !((m >> a) & 1u)) {
+            const bool far = (R.ord.pos[a] >= fb || R.ord.pos[b] >= fb);
+            if ((int)far == pass) continue;
+            uint32_t m2 = (m & ~(1u << b)) | (1u << a);
+            uint32_t tgt = (uint32_t)rank_of(m2, R);
+            put(el++, tgt | ((uint32_t)(2 * t + hop_sign(m, a, b)) << HOP_AMP_SHIFT) |
+                          (far ? HOP_FAR : 0u));
+          }
+        }
+    } else {
+      for (int t = 0; t < nterms; t++) {
+        int a = terms[t].alpha, b = terms[t].beta;
+        if (((m >> b) & 1u) && !((m >> a) & 1u)) {
+          uint32_t m2 = (m & ~(1u << b)) | (1u << a);
+          uint32_t tgt = (uint32_t)rank_of(m2, R);
+          uint32_t val = tgt | ((uint32_t)(2 * t + hop_sign(m, a, b)) << HOP_AMP_SHIFT);
+          if (R.ord.pos[a] >= fb || R.ord.pos[b] >= fb) put(ef++, val); else put(el++, val);
+        }
       }
     }
   }
   // padding slots gather the row itself (always inside the row's own tile) with amplitude 0
   const uint32_t pad = (uint32_t)r | ((uint32_t)(2 * nterms) << HOP_AMP_SHIFT);
-  for (; el < 4 * Wl4; el++) put(el, pad);
-  for (; ef < 4 * (Wl4 + Wf4); ef++) put(ef, pad);
+  if (merged) {
+    for (; el < nslots; el++) put(el, pad);
+  } else {
+    for (; el < 4 * Wl4; el++) put(el, pad);
+    for (; ef < nslots; ef++) put(ef, pad);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -210,6 +248,7 @@ static void build_eps_coef(const edgpu_normal_params &p, int s, EpsCoef &c) {
 
 static int free_spin(SpinSpace &S) {
   cudaFree(S.map);
+  cudaFree(S.refidx);
   cudaFree(S.lin.ja);
   cudaFree(S.lin.jb);
   cudaFree(S.eps);
@@ -221,31 +260,179 @@ static int free_spin(SpinSpace &S) {
   return 0;
 }
 
-// cap = largest range (in states of this species) the tiled kernel of this role can stage
-static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, SpinSpace &S,
-                      int64_t cap) {
+// Recursive range construction: the states whose top `t` bits equal a prefix with `p` set
+// bits are contiguous in the ascending map (C(Ns-t, nel-p) of them); a prefix whose block
+// exceeds `cap` is split on the next bit (0-child first = ascending order).
+static void split_ranges(int Ns, int nel, int t, int p, int64_t cap, int64_t &pos,
+                         std::vector<int64_t> &start, std::vector<int> &tbits) {
+  const int64_t cnt = host_binomial(Ns - t, nel - p);
+  if (cnt <= 0) return;
+  if (cnt <= cap || t == Ns) {
+    start.push_back(pos);
+    tbits.push_back(t);
+    pos += cnt;
+    return;
+  }
+  split_ranges(Ns, nel, t + 1, p, cap, pos, start, tbits);
+  split_ranges(Ns, nel, t + 1, p + 1, cap, pos, start, tbits);
+}
+
+// Site order of a species (see SiteOrder): MSB -> LSB = the last T bath sites (range bits),
+// the impurity sites, the remaining bath sites; identity when asked (the species whose index is
+// split over ranks keeps the reference order so that the rank-local chunk is the reference's).
+static SiteOrder make_site_order(int Ns, int Norb, int T, bool identity) {
+  SiteOrder o;
+  memset(&o, 0, sizeof(o));
+  o.Ns = Ns;
+  o.identity = identity ? 1 : 0;
+  std::vector<int> msb;  // sites from most to least significant
+  if (identity) {
+    for (int b = Ns - 1; b >= 0; b--) msb.push_back(b);
+  } else {
+    const int nb = Ns - Norb;
+    const int top = std::min(T, nb);
+    for (int k = 0; k < top; k++) msb.push_back(Ns - 1 - k);
+    for (int a = Norb - 1; a >= 0; a--) msb.push_back(a);
+    for (int b = Ns - 1 - top; b >= Norb; b--) msb.push_back(b);
+  }
+  for (int k = 0; k < Ns; k++) {
+    const int p = Ns - 1 - k;
+    o.site[p] = (uint8_t)msb[k];
+    o.pos[msb[k]] = (uint8_t)p;
+  }
+  bool id = true;
+  for (int b = 0; b < Ns; b++) id = id && (o.pos[b] == b);
+  o.identity = id ? 1 : 0;
+  return o;
+}
+
+RankView rank_view(const LinTable &lin, const SiteOrder &ord) {
+  RankView R;
+  R.lo_bits = lin.lo_bits;
+  R.ja = lin.ja;
+  R.jb = lin.jb;
+  R.ord = ord;
+  return R;
+}
+
+static int upload_binom(Engine &E) {
+  int32_t hb[33][33];
+  for (int n = 0; n < 33; n++)
+    for (int k = 0; k < 33; k++) {
+      int64_t b = host_binomial(n, k);
+      hb[n][k] = (int32_t)std::min<int64_t>(b, INT32_MAX);
+    }
+  EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_binom, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, E.stream));
+  return 0;
+}
+
+// role and tile capacity (in states) of species s in the current communicator
+static void species_role(Engine &E, const edgpu_normal_params &p, int s, int *role, int64_t *cap,
+                         bool *identity) {
+  std::vector<Term> terms;
+  build_terms(p, s, terms);
+  const size_t per_cta = (E.smem_per_sm - 2 * 1024) / 2;
+  const size_t tables = 8 * (2 * terms.size() + 2 + 2 * ((size_t)1 << p.Norb)) + 64;
+  const size_t avail = per_cta > tables ? per_cta - tables : 0;
+  // shared-memory tiles at 2 CTAs per SM (hxv.cu): fast role tile[range + 32][2] doubles,
+  // slow role tile[range][SLOW_ROWS] doubles
+  if (s == 1 && E.nranks == 1) {
+    *role = ROLE_SLOW;
+    *cap = std::max<int64_t>((int64_t)(avail / (8 * SLOW_ROWS)), 1);
+  } else {
+    *role = ROLE_FAST;
+    *cap = std::max<int64_t>((int64_t)(avail / 16) - 32, 1);
+  }
+  *identity = (s == 1 && E.nranks > 1);
+}
+
+// map (original Fock integers in internal order) + ranking tables of one species
+static int build_ranking(Engine &E, int Ns, int nel, const SiteOrder &ord, int64_t dim, int64_t ld,
+                         int32_t **map, LinTable *lin) {
+  cudaStream_t st = E.stream;
+  const int T = 256;
+  const unsigned gb = (unsigned)((dim + T - 1) / T);
+  int32_t *mapp = nullptr;
+  EDGPU_CUDA(cudaMalloc(map, sizeof(int32_t) * ld));
+  EDGPU_CUDA(cudaMalloc(&mapp, sizeof(int32_t) * ld));
+  EDGPU_CUDA(cudaMemsetAsync(*map, 0, sizeof(int32_t) * ld, st));
+  k_build_map<<<gb, T, 0, st>>>(*map, mapp, dim, Ns, nel, ord);
+  EDGPU_COUNT_LAUNCH();
+  lin->lo_bits = Ns / 2;
+  const int hi_bits = Ns - lin->lo_bits;
+  EDGPU_CUDA(cudaMalloc(&lin->ja, sizeof(int32_t) * ((size_t)1 << hi_bits)));
+  EDGPU_CUDA(cudaMalloc(&lin->jb, sizeof(int32_t) * ((size_t)1 << lin->lo_bits)));
+  EDGPU_CUDA(cudaMemsetAsync(lin->ja, 0, sizeof(int32_t) * ((size_t)1 << hi_bits), st));
+  EDGPU_CUDA(cudaMemsetAsync(lin->jb, 0, sizeof(int32_t) * ((size_t)1 << lin->lo_bits), st));
+  k_lin_ja<<<gb, T, 0, st>>>(mapp, dim, lin->lo_bits, lin->ja);
+  EDGPU_COUNT_LAUNCH();
+  k_lin_jb<<<gb, T, 0, st>>>(mapp, dim, lin->lo_bits, lin->ja, lin->jb);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(mapp);
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int species_ranking(Engine &E, const edgpu_normal_params &p, int s, int nel, int32_t **map,
+                    LinTable *lin, SiteOrder *ord) {
+  int role;
+  int64_t cap;
+  bool identity;
+  species_role(E, p, s, &role, &cap, &identity);
+  std::vector<int64_t> start;
+  std::vector<int> tbits;
+  int64_t pos = 0;
+  split_ranges(p.Ns, nel, 0, 0, cap, pos, start, tbits);
+  int T = 0;
+  for (int t : tbits) T = std::max(T, t);
+  *ord = make_site_order(p.Ns, p.Norb, T, identity);
+  EDGPU_TRY(upload_binom(E));
+  const int64_t dim = host_binomial(p.Ns, nel);
+  return build_ranking(E, p.Ns, nel, *ord, dim, (dim + 15) / 16 * 16, map, lin);
+}
+
+static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, SpinSpace &S) {
   const int Ns = p.Ns;
   cudaStream_t st = E.stream;
+  int role;
+  int64_t cap;
+  bool identity;
+  species_role(E, p, s, &role, &cap, &identity);
   S.nel = nel;
+  S.role = role;
   S.dim = host_binomial(Ns, nel);
   S.ld = (S.dim + 15) / 16 * 16;
   if (S.dim > (int64_t)HOP_TGT_MASK) return set_error("sector species dimension %lld too large", (long long)S.dim);
   const int T = 256;
   const unsigned gb = (unsigned)((S.dim + T - 1) / T), gl = (unsigned)((S.ld + T - 1) / T);
-  EDGPU_CUDA(cudaMalloc(&S.map, sizeof(int32_t) * S.ld));
-  EDGPU_CUDA(cudaMemsetAsync(S.map, 0, sizeof(int32_t) * S.ld, st));
-  k_build_map<<<gb, T, 0, st>>>(S.map, S.dim, Ns, nel);
-  EDGPU_COUNT_LAUNCH();
-  // ranking tables
-  S.lin.lo_bits = Ns / 2;
-  const int hi_bits = Ns - S.lin.lo_bits;
-  EDGPU_CUDA(cudaMalloc(&S.lin.ja, sizeof(int32_t) * ((size_t)1 << hi_bits)));
-  EDGPU_CUDA(cudaMalloc(&S.lin.jb, sizeof(int32_t) * ((size_t)1 << S.lin.lo_bits)));
-  EDGPU_CUDA(cudaMemsetAsync(S.lin.ja, 0, sizeof(int32_t) * ((size_t)1 << hi_bits), st));
-  EDGPU_CUDA(cudaMemsetAsync(S.lin.jb, 0, sizeof(int32_t) * ((size_t)1 << S.lin.lo_bits), st));
-  k_lin_ja<<<gb, T, 0, st>>>(S.map, S.dim, S.lin.lo_bits, S.lin.ja);
-  EDGPU_COUNT_LAUNCH();
-  k_lin_jb<<<gb, T, 0, st>>>(S.map, S.dim, S.lin.lo_bits, S.lin.ja, S.lin.jb);
+  // ranges (they depend on (Ns, nel, cap) only) -> number of range bits -> site order
+  std::vector<uint8_t> far_bit((size_t)S.ld, (uint8_t)Ns);
+  {
+    S.range_start.clear();
+    S.range_tbits.clear();
+    int64_t pos = 0;
+    split_ranges(Ns, nel, 0, 0, cap, pos, S.range_start, S.range_tbits);
+    S.range_start.push_back(pos);
+    S.nranges = (int)S.range_start.size() - 1;
+    if (pos != S.dim) return set_error("internal: range partition mismatch");
+    S.max_range = 0;
+    int Tmax = 0;
+    for (int k = 0; k < S.nranges; k++) {
+      S.max_range = std::max(S.max_range, S.range_start[k + 1] - S.range_start[k]);
+      Tmax = std::max(Tmax, S.range_tbits[k]);
+      for (int64_t r = S.range_start[k]; r < S.range_start[k + 1]; r++)
+        far_bit[(size_t)r] = (uint8_t)(Ns - S.range_tbits[k]);
+    }
+    S.ord = make_site_order(Ns, p.Norb, Tmax, identity);
+    EDGPU_CUDA(cudaMalloc(&S.d_range_start, sizeof(int64_t) * S.range_start.size()));
+    EDGPU_CUDA(cudaMemcpyAsync(S.d_range_start, S.range_start.data(),
+                               sizeof(int64_t) * S.range_start.size(), cudaMemcpyHostToDevice, st));
+  }
+  EDGPU_TRY(build_ranking(E, Ns, nel, S.ord, S.dim, S.ld, &S.map, &S.lin));
+  EDGPU_CUDA(cudaMalloc(&S.refidx, sizeof(int32_t) * S.ld));
+  EDGPU_CUDA(cudaMemsetAsync(S.refidx, 0, sizeof(int32_t) * S.ld, st));
+  k_ref_rank<<<gb, T, 0, st>>>(S.map, S.dim, Ns, S.refidx);
   EDGPU_COUNT_LAUNCH();
   // diagonal single-spin energies
   EpsCoef c;
@@ -256,59 +443,40 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   EDGPU_CUDA(cudaMemsetAsync(S.imp, 0, S.ld, st));
   k_eps<<<gb, T, 0, st>>>(S.map, S.dim, Ns, c, S.eps, S.imp);
   EDGPU_COUNT_LAUNCH();
-  // ranges: smallest number of fixed top bits such that every range fits `cap`
-  {
-    int t = 0;
-    auto max_range = [&](int tt) {
-      int64_t mx = 0;
-      for (int j = 0; j <= tt; j++) mx = std::max(mx, host_binomial(Ns - tt, nel - j));
-      return mx;
-    };
-    while (t < Ns && max_range(t) > cap) t++;
-    S.tbits = t;
-    S.range_start.clear();
-    int64_t pos = 0;
-    S.max_range = 0;
-    for (uint32_t h = 0; h < (1u << t); h++) {
-      int64_t cnt = host_binomial(Ns - t, nel - __builtin_popcount(h));
-      if (cnt <= 0) continue;
-      S.range_start.push_back(pos);
-      pos += cnt;
-      S.max_range = std::max(S.max_range, cnt);
-    }
-    S.range_start.push_back(pos);
-    S.nranges = (int)S.range_start.size() - 1;
-    if (pos != S.dim) return set_error("internal: range partition mismatch");
-    EDGPU_CUDA(cudaMalloc(&S.d_range_start, sizeof(int64_t) * S.range_start.size()));
-    EDGPU_CUDA(cudaMemcpyAsync(S.d_range_start, S.range_start.data(),
-                               sizeof(int64_t) * S.range_start.size(), cudaMemcpyHostToDevice, st));
-  }
   // hop table
   build_terms(p, s, S.terms);
   S.nterms = (int)S.terms.size();
   if (S.nterms > HOP_MAX_TERMS) return set_error("too many one-body terms (%d)", S.nterms);
-  const int far_bit = Ns - S.tbits;
   Term *d_terms = nullptr;
   int *d_w = nullptr;
+  uint8_t *d_far = nullptr;
   EDGPU_CUDA(cudaMalloc(&d_terms, sizeof(Term) * (S.nterms + 1)));
-  EDGPU_CUDA(cudaMalloc(&d_w, 2 * sizeof(int)));
+  EDGPU_CUDA(cudaMalloc(&d_w, 3 * sizeof(int)));
+  EDGPU_CUDA(cudaMalloc(&d_far, (size_t)S.ld));
   if (S.nterms)
     EDGPU_CUDA(cudaMemcpyAsync(d_terms, S.terms.data(), sizeof(Term) * S.nterms,
                                cudaMemcpyHostToDevice, st));
-  EDGPU_CUDA(cudaMemsetAsync(d_w, 0, 2 * sizeof(int), st));
-  k_hop_count<<<gb, T, 0, st>>>(S.map, S.dim, d_terms, S.nterms, far_bit, d_w);
+  EDGPU_CUDA(cudaMemcpyAsync(d_far, far_bit.data(), (size_t)S.ld, cudaMemcpyHostToDevice, st));
+  EDGPU_CUDA(cudaMemsetAsync(d_w, 0, 3 * sizeof(int), st));
+  k_hop_count<<<gb, T, 0, st>>>(S.map, S.dim, d_terms, S.nterms, d_far, S.ord, d_w);
   EDGPU_COUNT_LAUNCH();
-  int W[2] = {0, 0};
-  EDGPU_CUDA(cudaMemcpyAsync(W, d_w, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  int W[3] = {0, 0, 0};
+  EDGPU_CUDA(cudaMemcpyAsync(W, d_w, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   EDGPU_CUDA(cudaStreamSynchronize(st));
-  S.Wl = W[0];
-  S.Wf = W[1];
-  S.Wl4 = (W[0] + 3) / 4;
-  S.Wf4 = (W[1] + 3) / 4;
+  const int merged = (role == ROLE_SLOW);
+  if (merged) {
+    S.Wl = W[2];
+    S.Wf = W[1];  // largest number of far entries of a row (they lead the list)
+  } else {
+    S.Wl = W[0];
+    S.Wf = W[1];
+  }
+  S.Wl4 = (S.Wl + 3) / 4;
+  S.Wf4 = merged ? 0 : (S.Wf + 3) / 4;
   const int G = std::max(S.Wl4 + S.Wf4, 1);
   EDGPU_CUDA(cudaMalloc(&S.ell4, sizeof(uint4) * (size_t)G * S.ld));
-  k_hop_fill<<<gl, T, 0, st>>>(S.map, S.dim, S.ld, d_terms, S.nterms, far_bit, S.Wl4, S.Wf4,
-                               S.lin.lo_bits, S.lin.ja, S.lin.jb, (uint32_t *)S.ell4);
+  k_hop_fill<<<gl, T, 0, st>>>(S.map, S.dim, S.ld, d_terms, S.nterms, d_far, merged, S.Wl4, S.Wf4,
+                               rank_view(S.lin, S.ord), (uint32_t *)S.ell4);
   EDGPU_COUNT_LAUNCH();
   std::vector<double> amp(2 * S.nterms + 2, 0.0);
   for (int t = 0; t < S.nterms; t++) {
@@ -321,6 +489,7 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   EDGPU_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_terms);
   cudaFree(d_w);
+  cudaFree(d_far);
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
@@ -356,30 +525,9 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
   S.prm = *p;
   S.Ns = p->Ns;
   S.Norb = p->Norb;
-  int32_t hb[33][33];
-  for (int n = 0; n < 33; n++)
-    for (int k = 0; k < 33; k++) {
-      int64_t b = host_binomial(n, k);
-      hb[n][k] = (int32_t)std::min<int64_t>(b, INT32_MAX);
-    }
-  EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_binom, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, E.stream));
-  // shared-memory capacities of the tiled kernels at 2 CTAs per SM (hxv.cu):
-  //   fast role: tile[range + 32][2] doubles ; slow role: tile[range][8] doubles ; + tables
-  {
-    std::vector<Term> tu, td;
-    build_terms(*p, 0, tu);
-    build_terms(*p, 1, td);
-    const size_t per_cta = (E.smem_per_sm - 2 * 1024) / 2;
-    const int nimp_ = 1 << p->Norb;
-    auto cap_of = [&](size_t nterms, size_t bytes_per_state, int64_t slack) {
-      const size_t tables = 8 * (2 * nterms + 2 + 2 * (size_t)nimp_) + 64;
-      const size_t avail = per_cta > tables ? per_cta - tables : 0;
-      return std::max<int64_t>((int64_t)(avail / bytes_per_state) - slack, 1);
-    };
-    EDGPU_TRY(build_spin(E, *p, 0, nup, S.up, cap_of(tu.size(), 16, 32)));
-    EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw,
-                         E.nranks == 1 ? cap_of(td.size(), 64, 0) : cap_of(td.size(), 16, 32)));
-  }
+  EDGPU_TRY(upload_binom(E));
+  EDGPU_TRY(build_spin(E, *p, 0, nup, S.up));
+  EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw));
   // dw split (ED_HAMILTONIAN_NORMAL.f90:128-142).  The reference shrinks the communicator
   // when DimDw < MpiSize (:98-126); here every rank must own at least one column and one row.
   if (E.nranks > 1 && (S.dw.dim < E.nranks || S.up.dim < E.nranks))

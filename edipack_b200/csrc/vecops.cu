@@ -100,13 +100,16 @@ __global__ void __launch_bounds__(VT) k_axpy(double2 *__restrict__ y, const doub
 // splitmix64 -> uniform(0,1), indexed by the GLOBAL state index so that the start vector
 // does not depend on the number of ranks (the test-side checker regenerates it).
 __global__ void __launch_bounds__(VT) k_random(double *__restrict__ v, int64_t nrow, int64_t ld,
-                                               int64_t ncol, int64_t col_offset, uint64_t seed) {
+                                               int64_t ncol, int64_t col_offset, uint64_t seed,
+                                               const int32_t *__restrict__ refup,
+                                               const int32_t *__restrict__ refdw) {
   const int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x;
   const int64_t c = blockIdx.y;
   if (i >= ld) return;
   double x = 0.0;
   if (i < nrow) {
-    uint64_t z = ((uint64_t)(i + (c + col_offset) * nrow) + seed) * 0x9E3779B97F4A7C15ull;
+    // reference (ascending Fock order) state index: independent of ranks and internal order
+    uint64_t z = ((uint64_t)(refup[i] + (int64_t)refdw[c + col_offset] * nrow) + seed) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z = z ^ (z >> 31);
@@ -139,7 +142,8 @@ int vec_zero(Engine &E, double *d_v, int64_t n) {
 int vec_fill_random(Engine &E, double *d_v, uint64_t seed) {
   Sector &S = E.sec;
   dim3 grid((unsigned)((S.up.ld + VT - 1) / VT), (unsigned)S.qdw);
-  k_random<<<grid, VT, 0, E.stream>>>(d_v, S.up.dim, S.up.ld, S.qdw, S.d0, seed);
+  k_random<<<grid, VT, 0, E.stream>>>(d_v, S.up.dim, S.up.ld, S.qdw, S.d0, seed, S.up.refidx,
+                                      S.dw.refidx);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;

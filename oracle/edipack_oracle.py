@@ -567,6 +567,8 @@ def sigma_matsubara(model: Model, pw, iorb: int, spin: int, Lmats: int):
     invg0_normal.f90:22-28, delta_normal.f90:33-42)."""
     wm = math.pi / model.beta * (2 * np.arange(1, Lmats + 1) - 1)
     z = 1j * wm
+    if model.bath_e is None:
+        model.default_bath()
     e = model.bath_e[spin, iorb if model.bath_type == "normal" else 0]
     v = model.bath_v[spin, iorb]
     delta = (v[None, :] ** 2 / (z[:, None] - e[None, :])).sum(axis=1)
