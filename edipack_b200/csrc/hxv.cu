@@ -126,7 +126,11 @@ k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, i
 // ---------------------------------------------------------------------------------------
 constexpr int FAST_THREADS = 512;
 
-template <int WL4, bool WITH_DIAG, bool ACCUM>
+// WL4 = local entry groups per row (0 = dynamic widths, plain loop), NFAR = far slots per row
+// (all in the first far group).  The per-row metadata (entries, eps, impurity bits) of the
+// thread's next row is prefetched one iteration ahead; far gathers are issued before the local
+// hops and consumed after them.
+template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
 __global__ void __launch_bounds__(FAST_THREADS, 2)
 k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
        int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp) {
@@ -169,34 +173,97 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
   const uint32_t xc_sa = smem_u32(xc);
   // the last range also owns the pad rows [dim, ld): their entries are all padding -> zeros
   const int rend = (blockIdx.x + 1 == gridDim.x) ? (int)F.ld : r1;
-  for (int i = r0 + tid; i < rend; i += FAST_THREADS) {
-    uint4 q[WL4 > 0 ? WL4 : 1];
+
+  if (WL4 > 0) {
+    constexpr int NG = WL4 > 0 ? WL4 : 1;
+    const uint4 *ellf = F.ell4 + (int64_t)F.Wl4 * F.ld;  // first far group
+    uint4 nq[NG], nqf = make_uint4(0, 0, 0, 0);
+    double neu = 0.0;
+    uint32_t nm = 0;
+    int i = r0 + tid;
+    if (i < rend) {
 #pragma unroll
-    for (int g = 0; g < WL4; g++) q[g] = F.ell4[(int64_t)g * F.ld + i];
-    double2 acc = make_double2(0.0, 0.0);
-    if (WITH_DIAG) {
-      const double eu = F.eps[i];
-      const uint32_t m = (uint32_t)F.imp[i];
-      const double2 own = lds128(tile_sa + (uint32_t)i * 16u);
-      acc.x = (eu + lds64(xc_sa + m * 8u)) * own.x;
-      acc.y = (eu + lds64(xc_sa + ((uint32_t)nimp + m) * 8u)) * own.y;
-    }
-    if (ACCUM) {
-      acc.x += h0[i];
-      if (has2) acc.y += h1[i];
-    }
-#pragma unroll
-    for (int g = 0; g < WL4; g++) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t ent = ent_of(q[g], k);
-        const double a = lds64(amp_sa + amp_off(ent));
-        const double2 x = lds128(tile_sa + (ent & HOP_TGT_MASK) * 16u);
-        acc.x += a * x.x;
-        acc.y += a * x.y;
+      for (int g = 0; g < WL4; g++) nq[g] = F.ell4[(int64_t)g * F.ld + i];
+      if (NFAR > 0) nqf = ellf[i];
+      if (WITH_DIAG) {
+        neu = F.eps[i];
+        nm = (uint32_t)F.imp[i];
       }
     }
-    if (WL4 == 0) {  // dynamic width
+    for (; i < rend; i += FAST_THREADS) {
+      uint4 q[NG];
+#pragma unroll
+      for (int g = 0; g < WL4; g++) q[g] = nq[g];
+      const uint4 qf = nqf;
+      const double eu = neu;
+      const uint32_t m = nm;
+      double2 hacc = make_double2(0.0, 0.0);
+      if (ACCUM) {
+        hacc.x = h0[i];
+        if (has2) hacc.y = h1[i];
+      }
+      // far gathers first (L2), consumed after the local hops
+      double2 xf[NFAR > 0 ? NFAR : 1];
+#pragma unroll
+      for (int k = 0; k < NFAR; k++) {
+        const uint32_t ent = ent_of(qf, k);
+        const uint32_t t = ent & HOP_TGT_MASK;  // padding entries point at the row itself
+        xf[k] = make_double2(v0[t], v1[t]);
+      }
+      const int inext = i + FAST_THREADS;
+      if (inext < rend) {
+#pragma unroll
+        for (int g = 0; g < WL4; g++) nq[g] = F.ell4[(int64_t)g * F.ld + inext];
+        if (NFAR > 0) nqf = ellf[inext];
+        if (WITH_DIAG) {
+          neu = F.eps[inext];
+          nm = (uint32_t)F.imp[inext];
+        }
+      }
+      double2 acc = make_double2(0.0, 0.0);
+      if (WITH_DIAG) {
+        const double2 own = lds128(tile_sa + (uint32_t)i * 16u);
+        acc.x = (eu + lds64(xc_sa + m * 8u)) * own.x;
+        acc.y = (eu + lds64(xc_sa + ((uint32_t)nimp + m) * 8u)) * own.y;
+      }
+#pragma unroll
+      for (int g = 0; g < WL4; g++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t ent = ent_of(q[g], k);
+          const double a = lds64(amp_sa + amp_off(ent));
+          const double2 x = lds128(tile_sa + (ent & HOP_TGT_MASK) * 16u);
+          acc.x += a * x.x;
+          acc.y += a * x.y;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NFAR; k++) {
+        const double a = lds64(amp_sa + amp_off(ent_of(qf, k)));  // padding -> amplitude 0
+        acc.x += a * xf[k].x;
+        acc.y += a * xf[k].y;
+      }
+      if (ACCUM) {
+        acc.x += hacc.x;
+        acc.y += hacc.y;
+      }
+      h0[i] = acc.x;
+      if (has2) h1[i] = acc.y;
+    }
+  } else {
+    for (int i = r0 + tid; i < rend; i += FAST_THREADS) {
+      double2 acc = make_double2(0.0, 0.0);
+      if (WITH_DIAG) {
+        const double eu = F.eps[i];
+        const uint32_t m = (uint32_t)F.imp[i];
+        const double2 own = lds128(tile_sa + (uint32_t)i * 16u);
+        acc.x = (eu + lds64(xc_sa + m * 8u)) * own.x;
+        acc.y = (eu + lds64(xc_sa + ((uint32_t)nimp + m) * 8u)) * own.y;
+      }
+      if (ACCUM) {
+        acc.x += h0[i];
+        if (has2) acc.y += h1[i];
+      }
       for (int g = 0; g < F.Wl4; g++) {
         const uint4 qq = F.ell4[(int64_t)g * F.ld + i];
 #pragma unroll
@@ -208,24 +275,24 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
           acc.y += a * x.y;
         }
       }
-    }
-    for (int g = 0; g < F.Wf4; g++) {
-      const uint4 qq = F.ell4[(int64_t)(F.Wl4 + g) * F.ld + i];
+      for (int g = 0; g < F.Wf4; g++) {
+        const uint4 qq = F.ell4[(int64_t)(F.Wl4 + g) * F.ld + i];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (4 * g + k >= F.Wf) break;  // uniform: slots beyond the widest far row
-        const uint32_t ent = ent_of(qq, k);
-        const uint32_t idx = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
-        if (idx != PAD) {
-          const double a = lds64(amp_sa + idx * 8u);
-          const uint32_t t = ent & HOP_TGT_MASK;
-          acc.x += a * v0[t];
-          acc.y += a * v1[t];
+        for (int k = 0; k < 4; k++) {
+          if (4 * g + k >= F.Wf) break;  // uniform: slots beyond the widest far row
+          const uint32_t ent = ent_of(qq, k);
+          const uint32_t idx = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
+          if (idx != PAD) {
+            const double a = lds64(amp_sa + idx * 8u);
+            const uint32_t t = ent & HOP_TGT_MASK;
+            acc.x += a * v0[t];
+            acc.y += a * v1[t];
+          }
         }
       }
+      h0[i] = acc.x;
+      if (has2) h1[i] = acc.y;
     }
-    h0[i] = acc.x;
-    if (has2) h1[i] = acc.y;
   }
 }
 
@@ -288,31 +355,44 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
   const uint32_t amp_sa = smem_u32(amp_s);
   const uint4 *ell = S.ell4 + s0;
   constexpr int NG = W4 > 0 ? W4 : 1;
-  uint4 nq[NG];
-  double2 nh = make_double2(0.0, 0.0);  // Hv of the next column (accumulate mode), prefetched
-  if (jl < len) {
-    if (W4 > 0) {
+
+  if (W4 > 0) {
+    // Software pipeline over the thread's columns j0, j0+CSTEP, ...:
+    //   iteration j : (A) finish column j-CSTEP = consume its deferred loads (far gathers, Hv)
+    //                 (B) issue the deferred loads of column j, prefetch the entries of j+CSTEP
+    //                 (C) local hops of column j from shared memory
+    // so that the L2 / DRAM latency of (B) is covered by a whole iteration.
+    uint4 nq[NG];
+    if (jl < len) {
 #pragma unroll
       for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * S.ld + jl];
     }
-    if (ACCUM) nh = *reinterpret_cast<const double2 *>(hv + (int64_t)(s0 + jl) * ldv + i0 + rp2);
-  }
-  for (int j = jl; j < len; j += CSTEP) {
-    double *o = hv + (int64_t)(s0 + j) * ldv + i0 + rp2;
-    double2 acc = make_double2(0.0, 0.0);
-    const double2 hcur = nh;
-    if (ACCUM && j + CSTEP < len)
-      nh = *reinterpret_cast<const double2 *>(o + (int64_t)CSTEP * ldv);
-    if (W4 > 0) {
+    double2 xf[NF > 0 ? NF : 1];
+    double2 hold = make_double2(0.0, 0.0), accp = make_double2(0.0, 0.0);
+    uint4 q0p = make_uint4(0, 0, 0, 0);
+    double *op = nullptr;
+    for (int j = jl; j < len + CSTEP; j += CSTEP) {
+      // (A)
+      if (j > jl) {
+#pragma unroll
+        for (int e = 0; e < NF; e++) {
+          const double a = lds64(amp_sa + amp_off(ent_of(q0p, e & 3)));
+          accp.x += a * xf[e].x;
+          accp.y += a * xf[e].y;
+        }
+        if (ACCUM) {
+          accp.x += hold.x;
+          accp.y += hold.y;
+        }
+        *reinterpret_cast<double2 *>(op) = accp;
+      }
+      if (j >= len) break;
+      // (B)
       uint4 q[NG];
 #pragma unroll
       for (int g = 0; g < W4; g++) q[g] = nq[g];
-      if (j + CSTEP < len) {
-#pragma unroll
-        for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * S.ld + j + CSTEP];
-      }
-      // leading NF slots: far or local, loads first
-      double2 xf[NF > 0 ? NF : 1];
+      double *o = hv + (int64_t)(s0 + j) * ldv + i0 + rp2;
+      if (ACCUM) hold = *reinterpret_cast<const double2 *>(o);
 #pragma unroll
       for (int e = 0; e < NF; e++) {
         const uint32_t ent = ent_of(q[e >> 2], e & 3);
@@ -322,6 +402,12 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
         else
           xf[e] = lds128(trow_sa + t * (SLOW_R * 8u));
       }
+      if (j + CSTEP < len) {
+#pragma unroll
+        for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * S.ld + j + CSTEP];
+      }
+      // (C)
+      double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
       for (int e = NF; e < 4 * W4; e++) {
         const uint32_t ent = ent_of(q[e >> 2], e & 3);
@@ -330,15 +416,15 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
         acc.x += a * x.x;
         acc.y += a * x.y;
       }
-#pragma unroll
-      for (int e = 0; e < NF; e++) {
-        const uint32_t ent = ent_of(q[e >> 2], e & 3);
-        const double a = lds64(amp_sa + amp_off(ent));
-        acc.x += a * xf[e].x;
-        acc.y += a * xf[e].y;
-      }
-    } else {
+      accp = acc;
+      q0p = q[0];
+      op = o;
+    }
+  } else {
+    for (int j = jl; j < len; j += CSTEP) {
       const int c = s0 + j;
+      double *o = hv + (int64_t)c * ldv + i0 + rp2;
+      double2 acc = ACCUM ? *reinterpret_cast<const double2 *>(o) : make_double2(0.0, 0.0);
       for (int g = 0; g < S.Wl4; g++) {
         const uint4 qq = S.ell4[(int64_t)g * S.ld + c];
 #pragma unroll
@@ -355,12 +441,8 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
           acc.y += a * x.y;
         }
       }
+      *reinterpret_cast<double2 *>(o) = acc;
     }
-    if (ACCUM) {
-      acc.x += hcur.x;
-      acc.y += hcur.y;
-    }
-    *reinterpret_cast<double2 *>(o) = acc;
   }
 }
 
@@ -420,12 +502,12 @@ size_t slow_smem_bytes(int64_t max_range, int nterms) {
   return sizeof(double) * ((size_t)max_range * SLOW_R + 2 * (size_t)nterms + 2);
 }
 
-template <int WL4, bool WITH_DIAG, bool ACCUM>
+template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
 static int launch_fast(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
                        int64_t col_offset, const SpinView &F, const SpinView &S, int64_t max_range,
                        const double *xud, int nimp) {
   const size_t smem = fast_smem_bytes(max_range, F.nterms, nimp);
-  auto kern = k_fast<WL4, WITH_DIAG, ACCUM>;
+  auto kern = k_fast<WL4, NFAR, WITH_DIAG, ACCUM>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)F.nranges, (unsigned)((ncol + 1) / 2));
   kern<<<grid, FAST_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp);
@@ -451,17 +533,25 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
     EDGPU_CUDA(cudaGetLastError());
     return 0;
   }
-#define EDGPU_FAST2(WW, DD, AA) \
-  launch_fast<WW, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_range, xud, nimp)
-#define EDGPU_FAST(WW)                                                              \
-  (with_diag ? (accum ? EDGPU_FAST2(WW, true, true) : EDGPU_FAST2(WW, true, false)) \
-             : (accum ? EDGPU_FAST2(WW, false, true) : EDGPU_FAST2(WW, false, false)))
-  switch (F.Wl4) {
-    case 1: return EDGPU_FAST(1);
-    case 2: return EDGPU_FAST(2);
-    case 3: return EDGPU_FAST(3);
-    default: return EDGPU_FAST(0);
+#define EDGPU_FAST2(WW, FF, DD, AA) \
+  launch_fast<WW, FF, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_range, xud, nimp)
+#define EDGPU_FAST(WW, FF)                                                                  \
+  (with_diag ? (accum ? EDGPU_FAST2(WW, FF, true, true) : EDGPU_FAST2(WW, FF, true, false)) \
+             : (accum ? EDGPU_FAST2(WW, FF, false, true) : EDGPU_FAST2(WW, FF, false, false)))
+  if (F.Wl4 >= 1 && F.Wl4 <= 3 && F.Wf <= 2) {
+    switch (F.Wl4 * 4 + F.Wf) {
+      case 4 + 0: return EDGPU_FAST(1, 0);
+      case 4 + 1: return EDGPU_FAST(1, 1);
+      case 4 + 2: return EDGPU_FAST(1, 2);
+      case 8 + 0: return EDGPU_FAST(2, 0);
+      case 8 + 1: return EDGPU_FAST(2, 1);
+      case 8 + 2: return EDGPU_FAST(2, 2);
+      case 12 + 0: return EDGPU_FAST(3, 0);
+      case 12 + 1: return EDGPU_FAST(3, 1);
+      case 12 + 2: return EDGPU_FAST(3, 2);
+    }
   }
+  return EDGPU_FAST(0, 0);
 #undef EDGPU_FAST2
 #undef EDGPU_FAST
 }
