@@ -266,16 +266,30 @@ def run_ours(args):
     # ---- roofline of the dominant kernel + of the whole product ---------------------------
     peak, peak_kind = peaks()
     stage = [float(ms3[k]) / max(nrec.value, 1) for k in range(3)]  # ms per launch
-    names = ["k_fast_tiled(up+diag)", "k_slow_tiled(dw)" if world == 1 else "transpose+k_fast_tiled(dw)+transpose",
-             "k_nonlocal"]
-    # compulsory bytes per local state and launch: up kernel reads v, writes Hv (16 B);
-    # dw kernel reads v, reads+writes Hv (24 B)
+    if world == 1:
+        names = ["k_fast(diag+up hops)", "k_slow(dw hops)", "k_nonlocal"]
+    else:
+        names = ["k_fast(diag+up hops)", "transpose(v)+k_fast(dw hops on v^T)",
+                 "transpose(Hv^T)+accumulate"]
+    # compulsory bytes per local state and launch (DESIGN.md "Kernels"): pass B k_fast reads v and
+    # writes Hv (16 B); pass A k_slow reads v and read-modify-writes Hv (24 B)
     alg_bytes = [16.0 * ldu * qdw, 24.0 * ldu * qdw, 24.0 * ldu * qdw]
-    dom = int(np.argmax(stage[:2]))
+    dom = int(np.argmax(stage[:2] if world == 1 else stage))
     ach = alg_bytes[dom] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+    # dram__bytes_read+write per launch of that kernel from the committed ncu --set full capture
+    # of the same workload (profiles/traffic.json), else null
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("ns") == ns and world == 1:
+            traffic = tj["kernels"][("k_fast", "k_slow")[dom]]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_kind": peak_kind,
-                "algorithmic_bytes_per_launch": alg_bytes[dom], "ms_per_launch": stage[dom]}
+                "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": alg_bytes[dom], "ms_per_launch": stage[dom],
+                "limiter": "L1TEX/shared-memory data pipe (ncu l1tex__throughput ~90%), see profiles/"}
     hxv_ach = 16.0 * nloc / (ms_per_step * 1e-3) / 1e9
     hxv_roofline = {"bound": "hbm", "achieved": hxv_ach, "peak": peak, "unit": "GB/s",
                     "frac": hxv_ach / peak, "per_gpu_states": nloc,
@@ -344,7 +358,8 @@ def run_ours(args):
                                    f"({dim} states), direct HxV, dw-sharded over {world} GPU(s)",
                        "ns": ns, "dim": dim, "vector_gb": 8 * dim / 1e9,
                        "l2_policy": "inputs larger than L2 (1.3 GB vector per HxV)",
-                       "kernel_variant": args.variant or 2},
+                       "kernel_variant": args.variant or 2,
+                       "kernels": "two tiled passes: k_fast (up range x 2 columns) + k_slow (16 rows x dw range)"},
             "roofline": roofline, "hxv_roofline": hxv_roofline, "kernels": kernels,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "lanczos_gs": lanczos,

@@ -182,6 +182,75 @@ def comm_unique_id() -> bytes:
 
 
 # ------------------------------------------------------------------------------------------
+# dw-split bookkeeping and the rank <-> root vector movers (host side; any torch.distributed
+# backend: NCCL on the GPUs, gloo in the CPU tests)
+# ------------------------------------------------------------------------------------------
+def mpi_split(n: int, nranks: int, rank: int):
+    """Block split with the first (n mod P) ranks one element longer: the dw-column split of
+    build_Hv_sector_normal (ED_HAMILTONIAN_NORMAL.f90:128-142) and the row split of
+    vector_transpose_MPI (ED_HAMILTONIAN_NORMAL_COMMON.f90:104-112).  Returns (count, start)."""
+    base, rem = divmod(n, nranks)
+    return base + (1 if rank < rem else 0), rank * base + min(rank, rem)
+
+
+def chunk_bounds(DimUp: int, DimDw: int, nranks: int, rank: int):
+    """[istart, iend) of this rank's chunk of the sector vector, i = iup + idw*DimUp:
+    mpiIshift / mpiQ of ED_HAMILTONIAN_NORMAL.f90:136-142."""
+    q, d0 = mpi_split(DimDw, nranks, rank)
+    return d0 * DimUp, (d0 + q) * DimUp
+
+
+def scatter_vector_MPI(v_full, DimUp: int, DimDw: int, root: int = 0, group=None):
+    """d_scatter_vector_MPI (ED_AUX_FUNX.f90:598): root's full vector -> every rank's dw chunk."""
+    import torch
+    import torch.distributed as dist
+
+    P, r = dist.get_world_size(group), dist.get_rank(group)
+    bounds = [chunk_bounds(DimUp, DimDw, P, k) for k in range(P)]
+    nmax = max(hi - lo for lo, hi in bounds)  # collectives want equal pieces: pad to the longest
+    lo, hi = bounds[r]
+    dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
+           else torch.device("cpu"))
+    out = torch.empty(nmax, dtype=torch.float64, device=dev)
+    pieces = None
+    if r == root:
+        t = torch.as_tensor(np.ascontiguousarray(v_full, np.float64))
+        pieces = []
+        for a, b in bounds:
+            x = torch.zeros(nmax, dtype=torch.float64)
+            x[: b - a] = t[a:b]
+            pieces.append(x.to(dev))
+    dist.scatter(out, pieces, src=root, group=group)
+    return out[: hi - lo].cpu().numpy()
+
+
+def allgather_vector_MPI(chunk, DimUp: int, DimDw: int, group=None):
+    """d_allgather_vector_MPI (ED_AUX_FUNX.f90:840): every rank's chunk -> full vector."""
+    import torch
+    import torch.distributed as dist
+
+    P = dist.get_world_size(group)
+    dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
+           else torch.device("cpu"))
+    mine = torch.as_tensor(np.ascontiguousarray(chunk, np.float64)).to(dev)
+    sizes = [hi - lo for lo, hi in (chunk_bounds(DimUp, DimDw, P, k) for k in range(P))]
+    nmax = max(sizes)
+    pad = torch.zeros(nmax, dtype=torch.float64, device=dev)
+    pad[: mine.numel()] = mine
+    outs = [torch.empty(nmax, dtype=torch.float64, device=dev) for _ in range(P)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:n] for o, n in zip(outs, sizes)]).cpu().numpy()
+
+
+def gather_vector_MPI(chunk, DimUp: int, DimDw: int, root: int = 0, group=None):
+    """d_gather_vector_MPI (ED_AUX_FUNX.f90:742); the full vector is returned on root only."""
+    import torch.distributed as dist
+
+    full = allgather_vector_MPI(chunk, DimUp, DimDw, group)
+    return full if dist.get_rank(group) == root else None
+
+
+# ------------------------------------------------------------------------------------------
 # sector + H x v
 # ------------------------------------------------------------------------------------------
 def build_Hv_sector_normal(model: EDModel, nup: int, ndw: int):
