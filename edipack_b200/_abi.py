@@ -24,7 +24,8 @@ ABI_SYMBOLS = [
     "edgpu_vec_upload", "edgpu_vec_download", "edgpu_lanczos_gs", "edgpu_lanczos_tridiag",
     "edgpu_state_store", "edgpu_state_free", "edgpu_apply_op", "edgpu_state_observables",
     "edgpu_last_error", "edgpu_launch_count", "edgpu_last_hxv_stage_ms", "edgpu_set_kernel_variant",
-    "edgpu_stream", "edgpu_profile_begin", "edgpu_profile_end",
+    "edgpu_stream", "edgpu_profile_begin", "edgpu_profile_end", "edgpu_csr_open_d",
+    "edgpu_csr_open_z", "edgpu_hxv_z",
 ]
 
 
@@ -82,6 +83,10 @@ def load():
     L.edgpu_sector_get_hops.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.edgpu_hxv_d.restype = None
     L.edgpu_hxv_d.argtypes = [C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
+    L.edgpu_hxv_z.restype = None
+    L.edgpu_hxv_z.argtypes = [C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
+    for f in (L.edgpu_csr_open_d, L.edgpu_csr_open_z):
+        f.argtypes = [i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.edgpu_hxv_dev.argtypes = [C.c_void_p, C.c_void_p]
     L.edgpu_vec_padded_len.restype = i64
     L.edgpu_vec_upload.argtypes = [C.c_void_p, C.c_void_p]

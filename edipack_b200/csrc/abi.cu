@@ -80,6 +80,12 @@ static double *g_stage = nullptr;
 static int64_t g_stage_len = 0;
 
 static int upload(Engine &E, double *d_dst, const double *h_src) {
+  if (E.csr.open) {
+    const int64_t n = (E.csr.cplx ? 2 : 1) * E.csr.nloc, npad = E.csr.padded_len();
+    EDGPU_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double) * n, cudaMemcpyHostToDevice, E.stream));
+    if (npad > n) EDGPU_CUDA(cudaMemsetAsync(d_dst + n, 0, sizeof(double) * (npad - n), E.stream));
+    return 0;
+  }
   Sector &S = E.sec;
   if (S.up.ord.identity && S.dw.ord.identity) {
     EDGPU_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(double) * S.padded_len(), E.stream));
@@ -99,6 +105,12 @@ static int upload(Engine &E, double *d_dst, const double *h_src) {
   return 0;
 }
 static int download(Engine &E, double *h_dst, const double *d_src) {
+  if (E.csr.open) {
+    const int64_t n = (E.csr.cplx ? 2 : 1) * E.csr.nloc;
+    EDGPU_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double) * n, cudaMemcpyDeviceToHost, E.stream));
+    EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+    return 0;
+  }
   Sector &S = E.sec;
   if (S.up.ord.identity && S.dw.ord.identity) {
     EDGPU_CUDA(cudaMemcpy2DAsync(h_dst, sizeof(double) * S.up.dim, d_src, sizeof(double) * S.up.ld,
@@ -219,6 +231,7 @@ int edgpu_init(int device) {
 int edgpu_finalize(void) {
   if (!g.inited) return 0;
   sector_close(g);
+  csr_close(g);
   for (auto &kv : g_states) cudaFree(kv.second.vec);
   g_states.clear();
   cudaFree(g_current);
@@ -255,14 +268,37 @@ int edgpu_comm_size(void) { return g.nranks; }
 int edgpu_sector_open_normal(const edgpu_normal_params *p, int nup, int ndw) {
   clear_error();
   if (!p) return set_error("null params");
+  if (g.csr.open) csr_close(g);
   return sector_open(g, p, nup, ndw);
 }
 int edgpu_sector_close(void) {
   clear_error();
+  csr_close(g);
   return sector_close(g);
 }
-int64_t edgpu_sector_vecdim(void) { return g.sec.open ? g.sec.up.dim * g.sec.qdw : 0; }
-int64_t edgpu_sector_dim(void) { return g.sec.open ? g.sec.up.dim * g.sec.dw.dim : 0; }
+int edgpu_csr_open_d(int64_t nloc, int64_t nglobal, int64_t row_offset, const int64_t *rowptr,
+                     const int32_t *cols, const double *vals) {
+  clear_error();
+  if (!rowptr || (!cols && rowptr[nloc] > 0)) return set_error("null CSR arrays");
+  if (g.sec.open) sector_close(g);
+  return csr_open(g, false, nloc, nglobal, row_offset, rowptr, cols, vals);
+}
+int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const int64_t *rowptr,
+                     const int32_t *cols, const double *vals_re_im) {
+  clear_error();
+  if (!rowptr || (!cols && rowptr[nloc] > 0)) return set_error("null CSR arrays");
+  if (g.sec.open) sector_close(g);
+  return csr_open(g, true, nloc, nglobal, row_offset, rowptr, cols, vals_re_im);
+}
+static bool any_open() { return g.sec.open || g.csr.open; }
+int64_t edgpu_sector_vecdim(void) {
+  if (g.csr.open) return g.csr.nloc;
+  return g.sec.open ? g.sec.up.dim * g.sec.qdw : 0;
+}
+int64_t edgpu_sector_dim(void) {
+  if (g.csr.open) return g.csr.nglobal;
+  return g.sec.open ? g.sec.up.dim * g.sec.dw.dim : 0;
+}
 int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_start) {
   if (!g.sec.open) return set_error("no sector open");
   if (DimUp) *DimUp = g.sec.up.dim;
@@ -342,17 +378,17 @@ int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *va
   return 0;
 }
 
-int64_t edgpu_vec_padded_len(void) { return g.sec.open ? g.sec.padded_len() : 0; }
+int64_t edgpu_vec_padded_len(void) { return any_open() ? g.veclen() : 0; }
 int edgpu_vec_upload(double *d_dst, const double *h_src) {
   clear_error();
-  if (!g.sec.open) return set_error("no sector open");
+  if (!any_open()) return set_error("no sector open");
   EDGPU_TRY(upload(g, d_dst, h_src));
   EDGPU_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
 }
 int edgpu_vec_download(double *h_dst, const double *d_src) {
   clear_error();
-  if (!g.sec.open) return set_error("no sector open");
+  if (!any_open()) return set_error("no sector open");
   return download(g, h_dst, d_src);
 }
 
@@ -364,22 +400,34 @@ int edgpu_hxv_dev(const double *d_v, double *d_Hv) {
 static double *g_hx_in = nullptr, *g_hx_out = nullptr;
 static int64_t g_hx_in_len = 0, g_hx_out_len = 0;
 
-void edgpu_hxv_d(const int32_t *Nloc, const double *v, double *Hv) {
+static void hxv_host(const char *who, bool want_cplx, const int32_t *Nloc, const double *v, double *Hv) {
   clear_error();
-  if (!g.sec.open) {
-    set_error("edgpu_hxv_d: no sector open (spHtimesV_p used outside build/delete_Hv_sector)");
+  if (!any_open()) {
+    set_error("%s: no sector open (spHtimesV_p used outside build/delete_Hv_sector)", who);
+    return;
+  }
+  const bool is_cplx = g.csr.open && g.csr.cplx;
+  if (is_cplx != want_cplx) {
+    set_error("%s: the open sector is %s", who, is_cplx ? "complex (use edgpu_hxv_z)" : "real (use edgpu_hxv_d)");
     return;
   }
   // "if(Nloc/=getdim(isector))stop" (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:52)
   if ((int64_t)*Nloc != edgpu_sector_vecdim()) {
-    set_error("edgpu_hxv_d: Nloc=%d /= vecDim=%lld", (int)*Nloc, (long long)edgpu_sector_vecdim());
+    set_error("%s: Nloc=%d /= vecDim=%lld", who, (int)*Nloc, (long long)edgpu_sector_vecdim());
     return;
   }
-  const int64_t n = g.sec.padded_len();
+  const int64_t n = g.veclen();
   if (ensure_buf(&g_hx_in, &g_hx_in_len, n) || ensure_buf(&g_hx_out, &g_hx_out_len, n)) return;
   if (upload(g, g_hx_in, v)) return;
   if (hxv_device(g, g_hx_in, g_hx_out, false, false)) return;
   download(g, Hv, g_hx_out);
+}
+
+void edgpu_hxv_d(const int32_t *Nloc, const double *v, double *Hv) {
+  hxv_host("edgpu_hxv_d", false, Nloc, v, Hv);
+}
+void edgpu_hxv_z(const int32_t *Nloc, const double *v_re_im, double *Hv_re_im) {
+  hxv_host("edgpu_hxv_z", true, Nloc, v_re_im, Hv_re_im);
 }
 
 int edgpu_status(void) { return g_status; }
@@ -438,8 +486,8 @@ int edgpu_set_kernel_variant(int variant) {
 int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, uint64_t seed,
                      double *egs, double *vec_host, int *niter) {
   clear_error();
-  if (!g.sec.open) return set_error("no sector open");
-  const int64_t n = g.sec.padded_len();
+  if (!any_open()) return set_error("no sector open");
+  const int64_t n = g.veclen();
   EDGPU_TRY(ensure_buf(&g_current, &g_current_len, n));
   double *d_start = nullptr;
   if (use_start) {
@@ -461,8 +509,8 @@ int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, 
 int edgpu_lanczos_tridiag(const double *seed_host, int nlanc, double threshold, double *alanc,
                           double *blanc, int *nused, double *norm2) {
   clear_error();
-  if (!g.sec.open) return set_error("no sector open");
-  const int64_t n = g.sec.padded_len();
+  if (!any_open()) return set_error("no sector open");
+  const int64_t n = g.veclen();
   if (seed_host) {
     EDGPU_TRY(ensure_buf(&g_seed, &g_seed_len, n));
     EDGPU_TRY(upload(g, g_seed, seed_host));
@@ -476,7 +524,7 @@ int edgpu_lanczos_tridiag(const double *seed_host, int nlanc, double threshold, 
   for (int i = 0; i < nlanc; i++) alanc[i] = blanc[i] = 0.0;
   *nused = 0;
   if (n2 == 0.0) return 0;  // "if(norm2/=0d0)" (:355)
-  const int64_t dim_global = g.sec.up.dim * g.sec.dw.dim;
+  const int64_t dim_global = edgpu_sector_dim();
   if (nlanc > dim_global) nlanc = (int)dim_global;
   double *work = nullptr;
   EDGPU_CUDA(cudaMalloc(&work, sizeof(double) * n));

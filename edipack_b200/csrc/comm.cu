@@ -33,6 +33,7 @@ static struct {
   int (*GroupEnd)() = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 } N;
 
@@ -56,6 +57,7 @@ static int nccl_load() {
   EDGPU_SYM(GroupEnd, "ncclGroupEnd");
   EDGPU_SYM(AllReduce, "ncclAllReduce");
   EDGPU_SYM(AllGather, "ncclAllGather");
+  EDGPU_SYM(Broadcast, "ncclBroadcast");
   EDGPU_SYM(GetErrorString, "ncclGetErrorString");
 #undef EDGPU_SYM
   return 0;
@@ -107,6 +109,25 @@ int comm_allreduce_sum(Engine &E, double *d_buf, int n) {
   if (E.nranks == 1) return 0;
   EDGPU_NCCL(N.AllReduce(d_buf, d_buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)E.nccl,
                          E.stream));
+  return 0;
+}
+
+// MPI_Allgatherv of the input vector (ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:256-259): every rank's
+// chunk lands at its offset of the full vector; unequal counts -> one grouped broadcast per rank.
+int comm_allgatherv(Engine &E, const double *d_chunk, double *d_full, const std::vector<int64_t> &counts,
+                    const std::vector<int64_t> &offs) {
+  const int P = E.nranks, me = E.rank;
+  if (P == 1) {
+    EDGPU_CUDA(cudaMemcpyAsync(d_full + offs[0], d_chunk, sizeof(double) * counts[0],
+                               cudaMemcpyDeviceToDevice, E.stream));
+    return 0;
+  }
+  EDGPU_NCCL(N.GroupStart());
+  for (int p = 0; p < P; p++)
+    EDGPU_NCCL(N.Broadcast(p == me ? (const void *)d_chunk : (const void *)(d_full + offs[p]),
+                           d_full + offs[p], (size_t)counts[p], NCCL_FLOAT64, p, (nccl_comm_t)E.nccl,
+                           E.stream));
+  EDGPU_NCCL(N.GroupEnd());
   return 0;
 }
 

@@ -145,6 +145,26 @@ struct Sector {
   int64_t padded_len_t() const { return dw.ld * qup; }
 };
 
+// Stored-H sector (ED_SPARSE_H=T): the host's sparse_matrix_csr (ED_SPARSE_MATRIX.f90:16-41)
+// as device CSR.  Rows = this rank's rows [row0, row0+nloc) of the flat row split
+// (ED_HAMILTONIAN_NONSU2.f90:72-79), columns global.  Vectors are plain contiguous arrays of
+// nloc reals / complex numbers, padded with zeros to a multiple of 16 doubles.
+struct CsrSector {
+  bool open = false;
+  bool cplx = false;
+  int64_t nloc = 0, nglobal = 0, row0 = 0, nnz = 0;
+  int64_t *rowptr = nullptr;  // [nloc+1]
+  int32_t *cols = nullptr;    // [nnz] 0-based global columns
+  double *vals = nullptr;     // [nnz] or [2*nnz] (re,im)
+  int lanes = 8;              // threads per row of the SpMV kernel
+  double *vfull = nullptr;    // nranks>1: all-gathered input vector
+  std::vector<int64_t> counts, offs;  // row split of all ranks
+  int64_t padded_len() const {
+    const int64_t n = cplx ? 2 * nloc : nloc;
+    return (n + 15) / 16 * 16;
+  }
+};
+
 struct Engine {
   bool inited = false;
   int device = -1;
@@ -162,6 +182,9 @@ struct Engine {
   double *d_part = nullptr;   // block partials
   int64_t part_cap = 0;
   Sector sec;
+  CsrSector csr;
+  // length (in doubles) of a device vector of whatever sector is open
+  int64_t veclen() const { return csr.open ? csr.padded_len() : sec.padded_len(); }
   int variant_request = 0;
   float stage_ms[4] = {0, 0, 0, 0};
   // profiling ring (edgpu_profile_begin/end): 4 events per recorded H x v
@@ -185,9 +208,19 @@ void block_split(int64_t n, int P, int r, int64_t *q, int64_t *start);
 
 // hxv.cu
 int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed);
+int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed, double s_acc,
+                  double s_old, double *dot_out);
+
+// csr.cu
+int csr_open(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, const int64_t *rowptr,
+             const int32_t *cols, const double *vals);
+int csr_close(Engine &E);
+int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, double s_acc, double s_old);
 
 // comm.cu
 int comm_unique_id(void *uid);
+int comm_allgatherv(Engine &E, const double *d_chunk, double *d_full, const std::vector<int64_t> &counts,
+                    const std::vector<int64_t> &offs);
 int comm_init(Engine &E, int rank, int nranks, const void *uid);
 int comm_allreduce_sum(Engine &E, double *d_buf, int n);
 int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int64_t qcol,
@@ -196,6 +229,10 @@ int comm_finalize(Engine &E);
 
 // vecops.cu
 int vec_fill_random(Engine &E, double *d_v, uint64_t seed);
+int ensure_partials(Engine &E, int64_t n);                 // E.d_part holds >= n doubles
+int final_sum(Engine &E, int nblocks, double *d_out);      // *d_out = sum(E.d_part[0..n)), on device
+int vec_dot_dev(Engine &E, const double *a, const double *b, double *d_out);  // local, device scalar
+int scalar_to_host(Engine &E, double *d_scalar, double *h_out);  // all-reduce + copy + sync
 int vec_zero(Engine &E, double *d_v, int64_t n);
 int vec_dot(Engine &E, const double *a, const double *b, double *h_out);  // all-reduced
 int vec_scale(Engine &E, double *a, double s);

@@ -85,13 +85,13 @@ template <bool WITH_DIAG, bool WITH_SLOW>
 __global__ void __launch_bounds__(128)
 k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, int64_t ldv,
           int64_t ncol, int64_t col_offset, SpinView F, SpinView S,
-          const double *__restrict__ xud, int nimp, int accum) {
+          const double *__restrict__ xud, int nimp, int accum, double s_acc, double s_old) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t c = blockIdx.y;
   if (i >= nrow) return;
   const int64_t cg = c + col_offset;  // global slow index (for eps / imp / slow hops)
   const double *vc = v + c * ldv;
-  double acc = accum ? hv[c * ldv + i] : 0.0;
+  double acc = 0.0;
   if (WITH_DIAG) {
     double d = F.eps[i] + S.eps[cg] + xud[(int)S.imp[cg] * nimp + (int)F.imp[i]];
     acc += d * vc[i];
@@ -114,7 +114,7 @@ k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, i
       }
     }
   }
-  hv[c * ldv + i] = acc;
+  hv[c * ldv + i] = accum ? s_acc * acc + s_old * hv[c * ldv + i] : s_acc * acc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -133,7 +133,8 @@ constexpr int FAST_THREADS = 512;
 template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
 __global__ void __launch_bounds__(FAST_THREADS, 2)
 k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
-       int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp) {
+       int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
+       double s_acc, double s_old) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int r0 = (int)F.range_start[blockIdx.x], r1 = (int)F.range_start[blockIdx.x + 1];
@@ -243,9 +244,12 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
         acc.x += a * xf[k].x;
         acc.y += a * xf[k].y;
       }
+      // Hv = s_acc * (H v) [+ s_old * Hv_old] : the Lanczos drivers fold 1/|v| and -beta here
+      acc.x *= s_acc;
+      acc.y *= s_acc;
       if (ACCUM) {
-        acc.x += hacc.x;
-        acc.y += hacc.y;
+        acc.x += s_old * hacc.x;
+        acc.y += s_old * hacc.y;
       }
       h0[i] = acc.x;
       if (has2) h1[i] = acc.y;
@@ -260,9 +264,10 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
         acc.x = (eu + lds64(xc_sa + m * 8u)) * own.x;
         acc.y = (eu + lds64(xc_sa + ((uint32_t)nimp + m) * 8u)) * own.y;
       }
+      double2 hacc = make_double2(0.0, 0.0);
       if (ACCUM) {
-        acc.x += h0[i];
-        if (has2) acc.y += h1[i];
+        hacc.x = h0[i];
+        if (has2) hacc.y = h1[i];
       }
       for (int g = 0; g < F.Wl4; g++) {
         const uint4 qq = F.ell4[(int64_t)g * F.ld + i];
@@ -290,6 +295,12 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
           }
         }
       }
+      acc.x *= s_acc;
+      acc.y *= s_acc;
+      if (ACCUM) {
+        acc.x += s_old * hacc.x;
+        acc.y += s_old * hacc.y;
+      }
       h0[i] = acc.x;
       if (has2) h1[i] = acc.y;
     }
@@ -316,13 +327,31 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// deterministic CTA reduction of one double per thread -> dot_part[linear CTA index]
+__device__ __forceinline__ void slow_block_sum(double x, double *__restrict__ dot_part) {
+  __shared__ double red[SLOW_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < SLOW_THREADS / 32; w++) t += red[w];
+    dot_part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
 // W4 = entry groups per column (0 = dynamic, slow generic loop), NF = number of leading slots
 // that may hold far entries (the table is sorted far-first, sector.cu): their loads are issued
 // first and consumed last, so that the L2 latency of the far gathers hides behind the local
 // hops.  Entries of the next column are prefetched into registers.
-template <int W4, int NF, bool ACCUM>
+// DOT: also accumulates <v, Hv_final> over the CTA's states into dot_part[CTA] (fused alpha of
+// the Lanczos recurrence: v is in the tile, Hv_final in registers -> no extra memory traffic).
+template <int W4, int NF, bool ACCUM, bool DOT>
 __global__ void __launch_bounds__(SLOW_THREADS, 2)
-k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinView S) {
+k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinView S,
+       double s_acc, double *__restrict__ dot_part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tile = reinterpret_cast<double *>(smem_raw);
   const int tid = threadIdx.x;
@@ -368,6 +397,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
       for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * S.ld + jl];
     }
     double2 xf[NF > 0 ? NF : 1];
+    double dsum = 0.0;
     double2 hold = make_double2(0.0, 0.0), accp = make_double2(0.0, 0.0);
     uint4 q0p = make_uint4(0, 0, 0, 0);
     double *op = nullptr;
@@ -380,11 +410,17 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
           accp.x += a * xf[e].x;
           accp.y += a * xf[e].y;
         }
+        accp.x *= s_acc;
+        accp.y *= s_acc;
         if (ACCUM) {
           accp.x += hold.x;
           accp.y += hold.y;
         }
         *reinterpret_cast<double2 *>(op) = accp;
+        if (DOT) {
+          const double2 own = lds128(trow_sa + (uint32_t)(s0 + j - CSTEP) * (SLOW_R * 8u));
+          dsum += own.x * accp.x + own.y * accp.y;
+        }
       }
       if (j >= len) break;
       // (B)
@@ -420,11 +456,14 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
       q0p = q[0];
       op = o;
     }
+    if (DOT) slow_block_sum(dsum, dot_part);
   } else {
+    double dsum = 0.0;
     for (int j = jl; j < len; j += CSTEP) {
       const int c = s0 + j;
       double *o = hv + (int64_t)c * ldv + i0 + rp2;
-      double2 acc = ACCUM ? *reinterpret_cast<const double2 *>(o) : make_double2(0.0, 0.0);
+      const double2 hold = ACCUM ? *reinterpret_cast<const double2 *>(o) : make_double2(0.0, 0.0);
+      double2 acc = make_double2(0.0, 0.0);
       for (int g = 0; g < S.Wl4; g++) {
         const uint4 qq = S.ell4[(int64_t)g * S.ld + c];
 #pragma unroll
@@ -441,8 +480,15 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
           acc.y += a * x.y;
         }
       }
+      acc.x = s_acc * acc.x + hold.x;
+      acc.y = s_acc * acc.y + hold.y;
       *reinterpret_cast<double2 *>(o) = acc;
+      if (DOT) {
+        const double2 own = lds128(trow_sa + (uint32_t)c * (SLOW_R * 8u));
+        dsum += own.x * acc.x + own.y * acc.y;
+      }
     }
+    if (DOT) slow_block_sum(dsum, dot_part);
   }
 }
 
@@ -463,7 +509,7 @@ __global__ void __launch_bounds__(128)
 k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nrow, int64_t ldv,
            int64_t ncol, int64_t col_offset, const int32_t *__restrict__ mapu,
            const int32_t *__restrict__ mapd, RankView Lu, RankView Ld, int Norb,
-           const double *__restrict__ jx, const double *__restrict__ jp) {
+           const double *__restrict__ jx, const double *__restrict__ jp, double s_acc) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t c = blockIdx.y;
   if (i >= nrow) return;
@@ -489,7 +535,7 @@ k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nr
         acc += y * sg * vfull[id * ldv + iu];
       }
     }
-  if (acc != 0.0) hv[c * ldv + i] += acc;
+  if (acc != 0.0) hv[c * ldv + i] += s_acc * acc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -505,12 +551,13 @@ size_t slow_smem_bytes(int64_t max_range, int nterms) {
 template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
 static int launch_fast(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
                        int64_t col_offset, const SpinView &F, const SpinView &S, int64_t max_range,
-                       const double *xud, int nimp) {
+                       const double *xud, int nimp, double s_acc, double s_old) {
   const size_t smem = fast_smem_bytes(max_range, F.nterms, nimp);
   auto kern = k_fast<WL4, NFAR, WITH_DIAG, ACCUM>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)F.nranges, (unsigned)((ncol + 1) / 2));
-  kern<<<grid, FAST_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp);
+  kern<<<grid, FAST_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp,
+                                               s_acc, s_old);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
@@ -519,22 +566,25 @@ static int launch_fast(Engine &E, const double *v, double *hv, int64_t ldv, int6
 // Applies (diag +) the fast-index operator F to an [F.ld x ncol] block.
 static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const double *v, double *hv,
                       int64_t ncol, int64_t col_offset, const SpinSpace &Fs, const SpinView &F,
-                      const SpinView &S, const double *xud, int nimp) {
+                      const SpinView &S, const double *xud, int nimp, double s_acc = 1.0,
+                      double s_old = 1.0) {
   if (ncol <= 0) return 0;
   if (!tiled) {
     dim3 grid((unsigned)((F.dim + 127) / 128), (unsigned)ncol);
     if (with_diag)
       k_generic<true, false><<<grid, 128, 0, E.stream>>>(v, hv, F.dim, F.ld, ncol, col_offset, F,
-                                                          S, xud, nimp, (int)accum);
+                                                          S, xud, nimp, (int)accum, s_acc, s_old);
     else
       k_generic<false, false><<<grid, 128, 0, E.stream>>>(v, hv, F.dim, F.ld, ncol, col_offset,
-                                                           F, S, xud, nimp, (int)accum);
+                                                           F, S, xud, nimp, (int)accum, s_acc,
+                                                           s_old);
     EDGPU_COUNT_LAUNCH();
     EDGPU_CUDA(cudaGetLastError());
     return 0;
   }
 #define EDGPU_FAST2(WW, FF, DD, AA) \
-  launch_fast<WW, FF, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_range, xud, nimp)
+  launch_fast<WW, FF, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_range, xud, nimp, \
+                              s_acc, s_old)
 #define EDGPU_FAST(WW, FF)                                                                  \
   (with_diag ? (accum ? EDGPU_FAST2(WW, FF, true, true) : EDGPU_FAST2(WW, FF, true, false)) \
              : (accum ? EDGPU_FAST2(WW, FF, false, true) : EDGPU_FAST2(WW, FF, false, false)))
@@ -556,26 +606,35 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
 #undef EDGPU_FAST
 }
 
-template <int W4, int NF, bool ACCUM>
+template <int W4, int NF, bool ACCUM, bool DOT>
 static int launch_slow(Engine &E, const double *v, double *hv, const SpinSpace &Ss,
-                       const SpinView &Fv, const SpinView &S) {
+                       const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part) {
   const size_t smem = slow_smem_bytes(Ss.max_range, S.nterms);
   dim3 grid((unsigned)S.nranges, (unsigned)((Fv.ld + SLOW_R - 1) / SLOW_R));
-  auto kern = k_slow<W4, NF, ACCUM>;
+  auto kern = k_slow<W4, NF, ACCUM, DOT>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S);
+  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S, s_acc, dot_part);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
 
+// number of CTAs (= dot partials) of the slow pass
+static int64_t slow_grid_size(const SpinView &Fv, const SpinView &S) {
+  return (int64_t)S.nranges * ((Fv.ld + SLOW_R - 1) / SLOW_R);
+}
+
 static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const SpinSpace &Ss,
-                      const SpinView &Fv, const SpinView &S) {
+                      const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part) {
   // the element offset t * ld of a far gather is formed in 32 bits
   const bool small = (uint64_t)Ss.dim * (uint64_t)Fv.ld < (1ull << 32);
   const int W4 = Ss.Wl4, NF = Ss.Wf;  // Wf = largest number of far entries of a column
-#define EDGPU_SLOW(WW, FF) \
-  (accum ? launch_slow<WW, FF, true>(E, v, hv, Ss, Fv, S) : launch_slow<WW, FF, false>(E, v, hv, Ss, Fv, S))
+  const bool dot = dot_part != nullptr;
+#define EDGPU_SLOW(WW, FF)                                                                       \
+  (accum ? (dot ? launch_slow<WW, FF, true, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part)          \
+                : launch_slow<WW, FF, true, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part))        \
+         : (dot ? launch_slow<WW, FF, false, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part)         \
+                : launch_slow<WW, FF, false, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part)))
   if (small && W4 >= 1 && W4 <= 3 && NF <= 4 && NF <= 4 * W4) {
     switch (W4 * 8 + NF) {
       case 8 + 0: return EDGPU_SLOW(1, 0);
@@ -599,7 +658,23 @@ static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const 
 #undef EDGPU_SLOW
 }
 
-int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed) {
+// Hv = s_acc * (H v) [+ s_old * Hv_old when accum].  When `dot_out` is given the device scalar
+// *dot_out receives <v, Hv> of the LOCAL chunk, fused into the last pass when possible
+// (single rank, tiled kernels), else through a separate dot kernel; the caller all-reduces.
+int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed, double s_acc,
+                  double s_old, double *dot_out) {
+  if (E.csr.open) {  // stored-H sector: one SpMV kernel (csr.cu)
+    if (timed) cudaEventRecord(E.ev[0], E.stream);
+    EDGPU_TRY(csr_hxv_device(E, d_v, d_hv, accum, s_acc, s_old));
+    if (dot_out) EDGPU_TRY(vec_dot_dev(E, d_v, d_hv, dot_out));
+    if (timed) {
+      cudaEventRecord(E.ev[1], E.stream);
+      cudaEventSynchronize(E.ev[1]);
+      cudaEventElapsedTime(&E.stage_ms[0], E.ev[0], E.ev[1]);
+      E.stage_ms[1] = E.stage_ms[2] = E.stage_ms[3] = 0.f;
+    }
+    return 0;
+  }
   Sector &S = E.sec;
   if (!S.open) return set_error("no sector open (build_Hv_sector_normal not called)");
   const SpinView U = view_of(S.up), D = view_of(S.dw);
@@ -607,6 +682,7 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
   const int variant = S.variant == 0 ? 2 : S.variant;
   const bool tiled = (variant == 2);
   cudaStream_t st = E.stream;
+  bool dot_done = false;
   // event sink: the profiling ring when armed, else the 4 scratch events (timed calls only)
   cudaEvent_t *evs = E.ev;
   if (E.prof_on && E.prof_n < E.prof_cap) {
@@ -625,7 +701,7 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
       // one fused gather kernel: diagonal + up hops + dw hops
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
       k_generic<true, true><<<grid, 128, 0, st>>>(d_v, d_hv, U.dim, U.ld, S.qdw, 0, U, D, S.xud,
-                                                  nimp, (int)accum);
+                                                  nimp, (int)accum, s_acc, s_old);
       EDGPU_COUNT_LAUNCH();
       EDGPU_CUDA(cudaGetLastError());
       EDGPU_MARK(1);
@@ -633,16 +709,29 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
     } else {
       // pass B (diag + up hops) writes / accumulates first: it is the pass that saturates the
       // shared-memory pipe, so the read-modify-write of Hv is left to pass A (dw hops)
-      EDGPU_TRY(apply_fast(E, true, true, accum, d_v, d_hv, S.qdw, 0, S.up, U, D, S.xud, nimp));
+      EDGPU_TRY(apply_fast(E, true, true, accum, d_v, d_hv, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc,
+                           s_old));
       EDGPU_MARK(1);
-      if ((D.Wl4 + D.Wf4) > 0) EDGPU_TRY(apply_slow(E, true, d_v, d_hv, S.dw, U, D));
+      if ((D.Wl4 + D.Wf4) > 0) {
+        double *part = nullptr;
+        const int64_t nblk = slow_grid_size(U, D);
+        if (dot_out && !S.nonlocal) {
+          EDGPU_TRY(ensure_partials(E, nblk));
+          part = E.d_part;
+        }
+        EDGPU_TRY(apply_slow(E, true, d_v, d_hv, S.dw, U, D, s_acc, part));
+        if (part) {
+          EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
+          dot_done = true;
+        }
+      }
       EDGPU_MARK(2);
     }
     if (S.nonlocal) {
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
       const RankView Lu = rank_view(S.up.lin, S.up.ord), Ld = rank_view(S.dw.lin, S.dw.ord);
       k_nonlocal<<<grid, 128, 0, st>>>(d_v, d_hv, U.dim, U.ld, S.qdw, 0, S.up.map, S.dw.map, Lu, Ld,
-                                       S.Norb, S.jx, S.jp);
+                                       S.Norb, S.jx, S.jp, s_acc);
       EDGPU_COUNT_LAUNCH();
       EDGPU_CUDA(cudaGetLastError());
     }
@@ -653,7 +742,8 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
     //   vt  = transpose(v)                            NCCL all-to-all of tiles
     //   Hvt = Hdw vt                                  dw is now the fast index
     //   Hv += transpose(Hvt)
-    EDGPU_TRY(apply_fast(E, tiled, true, accum, d_v, d_hv, S.qdw, S.d0, S.up, U, D, S.xud, nimp));
+    EDGPU_TRY(apply_fast(E, tiled, true, accum, d_v, d_hv, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
+                         s_old));
     EDGPU_MARK(1);
     const size_t nt = (size_t)S.padded_len_t();
     if (!S.vt) {
@@ -663,13 +753,15 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
       EDGPU_CUDA(cudaMemsetAsync(S.hvt, 0, sizeof(double) * nt, st));
     }
     EDGPU_TRY(comm_transpose(E, d_v, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false));
-    EDGPU_TRY(apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp));
+    EDGPU_TRY(apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
+                         1.0));
     EDGPU_MARK(2);
     EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, d_hv, U.dim, U.ld, S.qdw, true));
     if (S.nonlocal) return set_error("non-local (Jx/Jp) terms with nranks>1 are not implemented yet");
     EDGPU_MARK(3);
   }
 #undef EDGPU_MARK
+  if (dot_out && !dot_done) EDGPU_TRY(vec_dot_dev(E, d_v, d_hv, dot_out));
   if (timed) {
     cudaEventSynchronize(E.ev[3]);
     cudaEventElapsedTime(&E.stage_ms[0], E.ev[0], E.ev[1]);
@@ -678,6 +770,10 @@ int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool time
     E.stage_ms[3] = 0.f;
   }
   return 0;
+}
+
+int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed) {
+  return hxv_device_ex(E, d_v, d_hv, accum, timed, 1.0, 1.0, nullptr);
 }
 
 }  // namespace edgpu

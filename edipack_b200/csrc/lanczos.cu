@@ -84,26 +84,44 @@ int tridiag_eig(int n, const double *diag, const double *sub, double *evals, dou
   return 0;
 }
 
+// Un-normalised three-term recurrence: x = X_j with |X_j| = nx (v_j = X_j / nx), y = X_{j-1}
+// with |X_{j-1}| = ny.  One step costs three passes over the vectors:
+//   T   = (1/nx) H X_j - (beta_{j-1}/ny) X_{j-1}   written over X_{j-1}   (k_fast + k_slow; the
+//         scalings ride in the kernels' epilogues, alfa_j = <X_j,T>/nx is fused into k_slow)
+//   X_{j+1} = T - (alfa_j/nx) X_j ,  beta_j = |X_{j+1}|                   (k_axpy_norm)
+// = 72 B/state instead of the 120 B/state of scale+swap / accumulate / dot / axpy, and the
+// host sees alfa and beta only.
 struct LanczosVecs {
-  double *vin = nullptr, *vout = nullptr;
+  double *x = nullptr, *y = nullptr;
+  double nx = 1.0, ny = 1.0, beta_prev = 0.0;
 };
 
-// One step of the recurrence on device vectors; returns alfa, beta on the host.
+// One step; returns alfa, beta on the host and leaves L advanced (x = X_{j+1}, nx = beta).
+// v_j / nx (the normalised Lanczos vector of this step) is L_before.x: callers that need it
+// (pass 2 of the ground-state driver) read x and nx BEFORE calling.
 static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, double *beta) {
   if (iter == 1) {
     double n2;
-    EDGPU_TRY(vec_dot(E, L.vin, L.vin, &n2));
+    EDGPU_TRY(vec_dot(E, L.x, L.x, &n2));
     if (n2 == 0.0) return set_error("lanczos_iteration: norm = 0");
-    EDGPU_TRY(vec_scale(E, L.vin, 1.0 / std::sqrt(n2)));
-    EDGPU_TRY(vec_zero(E, L.vout, E.sec.padded_len()));
-  } else {
-    EDGPU_TRY(vec_swap_scale(E, L.vin, L.vout, *beta));
+    L.nx = std::sqrt(n2);
+    L.ny = 1.0;
+    L.beta_prev = 0.0;
+    EDGPU_TRY(vec_zero(E, L.y, E.veclen()));
   }
-  EDGPU_TRY(hxv_device(E, L.vin, L.vout, /*accum=*/true, /*timed=*/false));
-  EDGPU_TRY(vec_dot(E, L.vin, L.vout, alfa));
+  double *d_dot = E.d_scal + 1;
+  EDGPU_TRY(hxv_device_ex(E, L.x, L.y, /*accum=*/true, /*timed=*/false, 1.0 / L.nx,
+                          -L.beta_prev / L.ny, d_dot));
+  double xt;
+  EDGPU_TRY(scalar_to_host(E, d_dot, &xt));
+  *alfa = xt / L.nx;
   double b2;
-  EDGPU_TRY(vec_axpy_norm(E, L.vout, L.vin, *alfa, &b2));
+  EDGPU_TRY(vec_axpy_norm(E, L.y, L.x, *alfa / L.nx, &b2));
   *beta = std::sqrt(b2);
+  std::swap(L.x, L.y);
+  L.ny = L.nx;
+  L.nx = *beta;
+  L.beta_prev = *beta;
   return 0;
 }
 
@@ -111,7 +129,9 @@ static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, doubl
 // d_seed is consumed (used as vin).  d_work is a second vector of the same padded length.
 int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, double threshold,
                         double *alanc, double *blanc, int *nused) {
-  LanczosVecs L{d_seed, d_work};
+  LanczosVecs L;
+  L.x = d_seed;
+  L.y = d_work;
   for (int i = 0; i < nlanc; i++) alanc[i] = blanc[i] = 0.0;
   double alfa = 0.0, beta = 0.0;
   *nused = 0;
@@ -132,9 +152,8 @@ int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, do
 // d_vect: output (padded length).  Scratch: two more vectors allocated here.
 int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
                    uint64_t seed, double *egs, double *d_vect, int *niter) {
-  Sector &S = E.sec;
-  const int64_t n = S.padded_len();
-  const int64_t dim_global = S.up.dim * S.dw.dim;
+  const int64_t n = E.veclen();
+  const int64_t dim_global = E.csr.open ? E.csr.nglobal : E.sec.up.dim * E.sec.dw.dim;
   if (nitermax > dim_global) nitermax = (int)dim_global;
   if (nitermax < 1) nitermax = 1;
   if (ncheck < 1) ncheck = 1;
@@ -156,7 +175,9 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   int rc = init_start();
   if (rc) { cleanup(); return rc; }
   std::vector<double> a, b(1, 0.0), ev, esave;
-  LanczosVecs L{vin, vout};
+  LanczosVecs L;
+  L.x = vin;
+  L.y = vout;
   double alfa = 0.0, beta = 0.0;
   int nlanc = 0;
   for (int it = 1; it <= nitermax; it++) {
@@ -186,12 +207,22 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   rc = init_start();
   if (rc) { cleanup(); return rc; }
   vec_zero(E, d_vect, n);
-  L = LanczosVecs{vin, vout};
+  L = LanczosVecs();
+  L.x = vin;
+  L.y = vout;
   beta = 0.0;
   for (int it = 1; it <= nlanc; it++) {
-    rc = lanczos_step(E, it, L, &alfa, &beta);
+    // v_it = x / nx with (x, nx) as they are BEFORE the step (iteration 1 normalises inside)
+    if (it == 1) {
+      double n2s;
+      rc = vec_dot(E, L.x, L.x, &n2s);
+      if (rc) { cleanup(); return rc; }
+      L.nx = std::sqrt(n2s);
+    }
+    rc = vec_axpy(E, d_vect, L.x, Z[it - 1] / L.nx);  // Z(iter,1): component iter of eigenvector 1
     if (rc) { cleanup(); return rc; }
-    rc = vec_axpy(E, d_vect, L.vin, Z[it - 1]);  // Z(iter,1): component iter of eigenvector 1
+    if (it == nlanc) break;  // the last vector needs no further H x v
+    rc = lanczos_step(E, it, L, &alfa, &beta);
     if (rc) { cleanup(); return rc; }
   }
   double n2;

@@ -124,6 +124,38 @@ static int grid_for(Engine &E, int64_t n2) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+int ensure_partials(Engine &E, int64_t n) {
+  if (E.part_cap >= n) return 0;
+  cudaFree(E.d_part);
+  E.d_part = nullptr;
+  EDGPU_CUDA(cudaMalloc(&E.d_part, sizeof(double) * n));
+  E.part_cap = n;
+  return 0;
+}
+
+int final_sum(Engine &E, int nblocks, double *d_out) {
+  k_final_sum<<<1, 1024, 0, E.stream>>>(E.d_part, nblocks, d_out);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vec_dot_dev(Engine &E, const double *a, const double *b, double *d_out) {
+  const int64_t n2 = E.veclen() / 2;
+  int gb = grid_for(E, n2);
+  k_dot<<<gb, VT, 0, E.stream>>>((const double2 *)a, (const double2 *)b, n2, E.d_part);
+  EDGPU_COUNT_LAUNCH();
+  return final_sum(E, gb, d_out);
+}
+
+int scalar_to_host(Engine &E, double *d_scalar, double *h_out) {
+  EDGPU_TRY(comm_allreduce_sum(E, d_scalar, 1));
+  EDGPU_CUDA(cudaMemcpyAsync(E.h_scal, d_scalar, sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  *h_out = E.h_scal[0];
+  return 0;
+}
+
 static int finish_scalar(Engine &E, int nblocks, double *h_out) {
   k_final_sum<<<1, 1024, 0, E.stream>>>(E.d_part, nblocks, E.d_scal);
   EDGPU_COUNT_LAUNCH();
@@ -139,7 +171,32 @@ int vec_zero(Engine &E, double *d_v, int64_t n) {
   return 0;
 }
 
+// CSR sectors: plain vector, entry k of the padded array <- hash(global element index)
+__global__ void __launch_bounds__(VT) k_random_flat(double *__restrict__ v, int64_t n, int64_t npad,
+                                                    int64_t offset, uint64_t seed) {
+  const int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x;
+  if (i >= npad) return;
+  double x = 0.0;
+  if (i < n) {
+    uint64_t z = ((uint64_t)(i + offset) + seed) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    x = ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  v[i] = x;
+}
+
 int vec_fill_random(Engine &E, double *d_v, uint64_t seed) {
+  if (E.csr.open) {
+    const CsrSector &C = E.csr;
+    const int64_t w = C.cplx ? 2 : 1, npad = C.padded_len();
+    k_random_flat<<<(unsigned)((npad + VT - 1) / VT), VT, 0, E.stream>>>(d_v, w * C.nloc, npad,
+                                                                        w * C.row0, seed);
+    EDGPU_COUNT_LAUNCH();
+    EDGPU_CUDA(cudaGetLastError());
+    return 0;
+  }
   Sector &S = E.sec;
   dim3 grid((unsigned)((S.up.ld + VT - 1) / VT), (unsigned)S.qdw);
   k_random<<<grid, VT, 0, E.stream>>>(d_v, S.up.dim, S.up.ld, S.qdw, S.d0, seed, S.up.refidx,
@@ -150,7 +207,7 @@ int vec_fill_random(Engine &E, double *d_v, uint64_t seed) {
 }
 
 int vec_dot(Engine &E, const double *a, const double *b, double *h_out) {
-  const int64_t n2 = E.sec.padded_len() / 2;
+  const int64_t n2 = E.veclen() / 2;
   int gb = grid_for(E, n2);
   k_dot<<<gb, VT, 0, E.stream>>>((const double2 *)a, (const double2 *)b, n2, E.d_part);
   EDGPU_COUNT_LAUNCH();
@@ -158,7 +215,7 @@ int vec_dot(Engine &E, const double *a, const double *b, double *h_out) {
 }
 
 int vec_scale(Engine &E, double *a, double s) {
-  const int64_t n2 = E.sec.padded_len() / 2;
+  const int64_t n2 = E.veclen() / 2;
   k_scale<<<grid_for(E, n2), VT, 0, E.stream>>>((double2 *)a, n2, s);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
@@ -166,7 +223,7 @@ int vec_scale(Engine &E, double *a, double s) {
 }
 
 int vec_swap_scale(Engine &E, double *a, double *b, double beta) {
-  const int64_t n2 = E.sec.padded_len() / 2;
+  const int64_t n2 = E.veclen() / 2;
   k_swap_scale<<<grid_for(E, n2), VT, 0, E.stream>>>((double2 *)a, (double2 *)b, n2, 1.0 / beta,
                                                      -beta);
   EDGPU_COUNT_LAUNCH();
@@ -175,7 +232,7 @@ int vec_swap_scale(Engine &E, double *a, double *b, double beta) {
 }
 
 int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2) {
-  const int64_t n2 = E.sec.padded_len() / 2;
+  const int64_t n2 = E.veclen() / 2;
   int gb = grid_for(E, n2);
   k_axpy_norm<<<gb, VT, 0, E.stream>>>((double2 *)w, (const double2 *)v, n2, alpha, E.d_part);
   EDGPU_COUNT_LAUNCH();
@@ -183,7 +240,7 @@ int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h
 }
 
 int vec_axpy(Engine &E, double *y, const double *x, double a) {
-  const int64_t n2 = E.sec.padded_len() / 2;
+  const int64_t n2 = E.veclen() / 2;
   k_axpy<<<grid_for(E, n2), VT, 0, E.stream>>>((double2 *)y, (const double2 *)x, n2, a);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());

@@ -258,6 +258,8 @@ def build_Hv_sector_normal(model: EDModel, nup: int, ndw: int):
 
 
 def delete_Hv_sector_normal():
+    global _open_is_complex
+    _open_is_complex = False
     check(_abi.load().edgpu_sector_close())
 
 
@@ -305,6 +307,50 @@ def spHtimesV_p(v: np.ndarray) -> np.ndarray:
     return hv
 
 
+# ------------------------------------------------------------------------------------------
+# stored-H sectors (ED_SPARSE_H=T): sparse_matrix_csr -> device CSR
+# ------------------------------------------------------------------------------------------
+_open_is_complex = False
+
+
+def build_Hv_sector_csr(rowptr, cols, vals, nglobal=None, row_offset: int = 0):
+    """Hands the host-built stored Hamiltonian (the reference's spH0, ED_SPARSE_MATRIX.f90:16-41,
+    filled by ed_buildh_*_main) to the device: rowptr (0-based offsets, nloc+1), cols (1-based
+    global columns, any order, duplicates add up), vals real or complex.  Afterwards
+    spHtimesV_p / spHtimesV_cc and the sp_lanc_* drivers act on this matrix."""
+    global _open_is_complex
+    L = _abi.load()
+    rowptr = np.ascontiguousarray(rowptr, np.int64)
+    cols = np.ascontiguousarray(cols, np.int32)
+    nloc = rowptr.size - 1
+    nglobal = nloc if nglobal is None else int(nglobal)
+    if np.iscomplexobj(vals):
+        v = np.ascontiguousarray(vals, np.complex128)
+        check(L.edgpu_csr_open_z(nloc, nglobal, row_offset, ptr(rowptr), ptr(cols), ptr(v)))
+        _open_is_complex = True
+    else:
+        v = np.ascontiguousarray(vals, np.float64)
+        check(L.edgpu_csr_open_d(nloc, nglobal, row_offset, ptr(rowptr), ptr(cols), ptr(v)))
+        _open_is_complex = False
+
+
+def delete_Hv_sector_csr():
+    global _open_is_complex
+    _open_is_complex = False
+    check(_abi.load().edgpu_sector_close())
+
+
+def spHtimesV_cc(v: np.ndarray) -> np.ndarray:
+    """``call spHtimesV_cc(Nloc,v,Hv)`` (cc_sparse_HxV, ED_VARS_GLOBAL.f90:121-132), complex(8)."""
+    L = _abi.load()
+    v = np.ascontiguousarray(v, np.complex128)
+    hv = np.empty_like(v)
+    n = C.c_int32(v.size)
+    L.edgpu_hxv_z(C.byref(n), ptr(v), ptr(hv))
+    check(L.edgpu_status())
+    return hv
+
+
 def set_kernel_variant(variant: int):
     check(_abi.load().edgpu_set_kernel_variant(variant))
 
@@ -317,12 +363,13 @@ def sp_lanc_eigh(nitermax: int, threshold: float = 1e-12, ncheck: int = 10, vect
     """sp_lanc_eigh(MatVec, egs, vect, Nitermax, threshold=): returns (egs, vect, niter)."""
     L = _abi.load()
     n = vecDim_Hv_sector_normal()
+    dt = np.complex128 if _open_is_complex else np.float64  # complex stored-H sector
     use_start = vect is not None
     buf = None
     if use_start:
-        buf = np.ascontiguousarray(vect, np.float64).copy()
+        buf = np.ascontiguousarray(vect, dt).copy()
     elif want_vector:
-        buf = np.zeros(n)
+        buf = np.zeros(n, dt)
     egs, nit = C.c_double(), C.c_int()
     check(L.edgpu_lanczos_gs(nitermax, threshold, ncheck, int(use_start), seed, C.byref(egs),
                              ptr(buf) if buf is not None else None, C.byref(nit)))
@@ -335,7 +382,8 @@ def sp_lanc_tridiag(vin, nlanc: int, threshold: float = 1e-12):
     L = _abi.load()
     a, b = np.zeros(nlanc), np.zeros(nlanc)
     nused, n2 = C.c_int(), C.c_double()
-    seed = None if vin is None else np.ascontiguousarray(vin, np.float64)
+    seed = None if vin is None else np.ascontiguousarray(
+        vin, np.complex128 if _open_is_complex else np.float64)
     check(L.edgpu_lanczos_tridiag(ptr(seed) if seed is not None else None, nlanc, threshold,
                                   ptr(a), ptr(b), C.byref(nused), C.byref(n2)))
     return a, b, nused.value, n2.value

@@ -93,6 +93,25 @@ int edgpu_sector_get_map(int spin, int32_t *map);
 int64_t edgpu_sector_hop_count(int spin);                      /* total entries */
 int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *value);
 
+/* ---------------- stored-H sector (ED_SPARSE_H=T) ---------------- */
+
+/* The host's stored Hamiltonian as CSR.  Replaces the sparse_matrix_csr objects spH0 /
+ * spH0d+spH0ups+spH0dws+spH0nd (ED_SPARSE_MATRIX.f90:16-41, filled by ed_buildh_*_main,
+ * ..._STORED_HxV.f90) and their products spMatVec[_mpi]_{normal,superc,nonsu2}_main
+ * (ED_HAMILTONIAN_NORMAL_STORED_HxV.f90:517-929, ..._NONSU2_STORED_HxV.f90:194-265,
+ * ..._SUPERC_STORED_HxV.f90:312-432): any ed_mode, real (_d) or complex (_z, values as
+ * interleaved re,im).  rowptr[nloc+1] (0-based offsets), cols 1-based GLOBAL column indices as
+ * in the reference's row%cols, unsorted and with duplicates allowed (they add up, like
+ * sp_insert_element).  Rows are this rank's rows [row_offset, row_offset+nloc) of the flat
+ * row split MpiQ = Dim/P, remainder to the last rank (ED_HAMILTONIAN_NONSU2.f90:72-79);
+ * with nranks>1 the input vector is all-gathered on every product like the reference does.
+ * While a stored-H sector is open, edgpu_hxv_d / edgpu_hxv_z and the Lanczos drivers act on
+ * it; vectors are plain arrays of nloc reals / complex numbers. */
+int edgpu_csr_open_d(int64_t nloc, int64_t nglobal, int64_t row_offset, const int64_t *rowptr,
+                     const int32_t *cols, const double *vals);
+int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const int64_t *rowptr,
+                     const int32_t *cols, const double *vals_re_im);
+
 /* ---------------- H x v ---------------- */
 
 /* Signature-compatible with the abstract interface dd_sparse_HxV(Nloc,v,Hv)
@@ -100,6 +119,9 @@ int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *va
  * the local chunk length, Hv fully overwritten, v untouched.  Errors are latched and
  * reported by edgpu_last_error()/edgpu_status(). */
 void edgpu_hxv_d(const int32_t *Nloc, const double *v, double *Hv);
+/* cc_sparse_HxV(Nloc,v,Hv) (ED_VARS_GLOBAL.f90:121-132), complex(8) as interleaved re,im:
+ * `spHtimesV_cc => edgpu_hxv_z` for a complex stored-H sector. */
+void edgpu_hxv_z(const int32_t *Nloc, const double *v_re_im, double *Hv_re_im);
 int edgpu_status(void);
 
 /* Device-resident variant on the engine's internal (padded) layout; d_v/d_Hv are device
