@@ -269,8 +269,8 @@ def run_ours(args):
     if world == 1:
         names = ["k_fast(diag+up hops)", "k_slow(dw hops)", "k_nonlocal"]
     else:
-        names = ["k_fast(diag+up hops)", "transpose(v)+k_fast(dw hops on v^T)",
-                 "transpose(Hv^T)+accumulate"]
+        names = ["k_fast(diag+up hops) overlapped with transpose(v)+k_fast(dw hops on v^T)",
+                 "join of the communication stream", "transpose(Hv^T)+accumulate"]
     # compulsory bytes per local state and launch (DESIGN.md "Kernels"): pass B k_fast reads v and
     # writes Hv (16 B); pass A k_slow reads v and read-modify-writes Hv (24 B)
     alg_bytes = [16.0 * ldu * qdw, 24.0 * ldu * qdw, 24.0 * ldu * qdw]

@@ -217,6 +217,9 @@ int edgpu_init(int device) {
   g.smem_optin = prop.sharedMemPerBlockOptin;
   g.smem_per_sm = prop.sharedMemPerMultiprocessor;
   EDGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  EDGPU_CUDA(cudaStreamCreateWithFlags(&g.comm_stream, cudaStreamNonBlocking));
+  EDGPU_CUDA(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+  EDGPU_CUDA(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
   for (auto &ev : g.ev) EDGPU_CUDA(cudaEventCreate(&ev));
   g.part_cap = (int64_t)g.sm_count * 8;
   EDGPU_CUDA(cudaMalloc(&g.d_part, sizeof(double) * g.part_cap));
@@ -249,6 +252,9 @@ int edgpu_finalize(void) {
   cudaFreeHost(g.h_scal);
   for (auto &ev : g.ev) cudaEventDestroy(ev);
   for (auto &ev : g.prof_ev) cudaEventDestroy(ev);
+  cudaEventDestroy(g.ev_fork);
+  cudaEventDestroy(g.ev_join);
+  cudaStreamDestroy(g.comm_stream);
   cudaStreamDestroy(g.stream);
   g = Engine();
   return 0;

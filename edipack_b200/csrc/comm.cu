@@ -21,7 +21,7 @@ typedef struct {
   char internal[128];
 } nccl_uid_t;
 typedef void *nccl_comm_t;
-enum { NCCL_SUM = 0, NCCL_FLOAT64 = 8 };
+enum { NCCL_SUM = 0, NCCL_CHAR = 0, NCCL_FLOAT64 = 8 };
 static struct {
   void *h = nullptr;
   int (*GetUniqueId)(nccl_uid_t *) = nullptr;
@@ -234,6 +234,197 @@ int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int6
       k_unpack<false><<<grid, 256, 0, st>>>(S.recvbuf + roff[p], d_b + c0, ldb, qrow, qc);
     EDGPU_COUNT_LAUNCH();
   }
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Peer-memory transposes.  Every rank maps the vt / hvt buffers of all ranks (CUDA IPC, handles
+// all-gathered through NCCL) and the two vector_transpose_MPI of one H x v become
+//   push : vt_p[(i - u0_p) * ldD + d0_me + c] = v[c * ldU + i]      for every row i, p = owner(i)
+//   pull : hv[c * ldU + i] += hvt_p[(i - u0_p) * ldD + d0_me + c]
+// one kernel each, 32x32 tiles transposed through shared memory so that both the local and
+// the remote side move 256-byte segments; the NVLink traffic is issued by the kernel itself
+// (st.global / ld.global on mapped peer pointers), no pack / send / recv / unpack passes.
+// Ordering between ranks: in-stream 1-element NCCL all-reduces (comm_barrier).
+// ---------------------------------------------------------------------------------------
+struct PeerTable {
+  double *ptr[EDGPU_MAXRANKS];
+  int32_t row0[EDGPU_MAXRANKS + 1];  // rows [row0[p], row0[p+1]) of the fast index belong to rank p
+  int nranks;
+};
+
+__device__ __forceinline__ int owner_of(const PeerTable &T, int i) {
+  int p = 0;
+#pragma unroll 1
+  while (p + 1 < T.nranks && i >= T.row0[p + 1]) p++;
+  return p;
+}
+
+// grid = (ceil(qcol/32), ceil(nrow/32)); a = [nrow (fast, lda) x qcol] local block of v.
+// Column tiles run fastest: consecutive CTAs then extend the SAME 32 remote rows by consecutive
+// 256-byte pieces.  (Row tiles fastest makes every remote segment land on another 2 MB page of a
+// multi-GB peer buffer: measured 200 ms instead of ~5 ms per transpose at Ns=18 on 8 GPUs.)
+__global__ void __launch_bounds__(256)
+k_push_transpose(const double *__restrict__ a, int64_t lda, int nrow, int qcol, int64_t c_off,
+                 int64_t ldb, PeerTable T) {
+  __shared__ double t[32][33];
+  const int ib = blockIdx.y * 32, jb = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int i = ib + tx, j = jb + ty + k;
+    if (i < nrow && j < qcol) t[ty + k][tx] = a[(int64_t)j * lda + i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int j = jb + tx, i = ib + ty + k;  // the 32 lanes write 32 consecutive columns of row i
+    if (i < nrow && j < qcol) {
+      const int p = owner_of(T, i);
+      T.ptr[p][(int64_t)(i - T.row0[p]) * ldb + c_off + j] = t[tx][ty + k];
+    }
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256)
+k_pull_transpose_acc(double *__restrict__ hv, int64_t lda, int nrow, int qcol, int64_t c_off,
+                     int64_t ldb, PeerTable T) {
+  __shared__ double t[32][33];
+  const int ib = blockIdx.y * 32, jb = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int j = jb + tx, i = ib + ty + k;
+    if (i < nrow && j < qcol) {
+      const int p = owner_of(T, i);
+      t[ty + k][tx] = T.ptr[p][(int64_t)(i - T.row0[p]) * ldb + c_off + j];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int i = ib + tx, j = jb + ty + k;
+    if (i < nrow && j < qcol) hv[(int64_t)j * lda + i] += t[tx][ty + k];
+  }
+}
+
+int comm_barrier(Engine &E) {
+  if (E.nranks == 1) return 0;
+  EDGPU_NCCL(N.AllReduce(E.d_scal + 32, E.d_scal + 32, 1, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)E.nccl,
+                         E.stream));
+  return 0;
+}
+
+static PeerTable peer_table(Engine &E, double *const *ptrs) {
+  PeerTable T;
+  memset(&T, 0, sizeof(T));
+  T.nranks = E.nranks;
+  for (int p = 0; p < E.nranks; p++) {
+    int64_t q, r0;
+    block_split(E.sec.up.dim, E.nranks, p, &q, &r0);
+    T.ptr[p] = ptrs[p];
+    T.row0[p] = (int32_t)r0;
+    T.row0[p + 1] = (int32_t)(r0 + q);
+  }
+  return T;
+}
+
+int comm_p2p_setup(Engine &E) {
+  Sector &S = E.sec;
+  S.p2p = false;
+  const int P = E.nranks, me = E.rank;
+  if (P == 1 || P > EDGPU_MAXRANKS) return 0;
+  const char *off = getenv("EDGPU_NO_P2P");
+  // every rank must take the same decision: all-reduce the local "ok" flags
+  int ok = (off && off[0] == '1') ? 0 : 1;
+  cudaIpcMemHandle_t mine[2];
+  if (ok && (cudaIpcGetMemHandle(&mine[0], S.vt) != cudaSuccess ||
+             cudaIpcGetMemHandle(&mine[1], S.hvt) != cudaSuccess)) {
+    cudaGetLastError();
+    ok = 0;
+  }
+  unsigned char *d_h = nullptr;
+  const size_t hb = 2 * sizeof(cudaIpcMemHandle_t);
+  EDGPU_CUDA(cudaMalloc(&d_h, hb * P));
+  EDGPU_CUDA(cudaMemcpyAsync(d_h + hb * me, mine, hb, cudaMemcpyHostToDevice, E.stream));
+  EDGPU_NCCL(N.AllGather(d_h + hb * me, d_h, hb, NCCL_CHAR, (nccl_comm_t)E.nccl, E.stream));
+  std::vector<cudaIpcMemHandle_t> all(2 * (size_t)P);
+  EDGPU_CUDA(cudaMemcpyAsync(all.data(), d_h, hb * P, cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  cudaFree(d_h);
+  for (int p = 0; p < P && ok; p++) {
+    if (p == me) {
+      S.peer_vt[p] = S.vt;
+      S.peer_hvt[p] = S.hvt;
+      continue;
+    }
+    void *a = nullptr, *b = nullptr;
+    if (cudaIpcOpenMemHandle(&a, all[2 * p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&b, all[2 * p + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    S.peer_vt[p] = (double *)a;
+    S.peer_hvt[p] = (double *)b;
+  }
+  double flag = ok ? 0.0 : 1.0;
+  EDGPU_CUDA(cudaMemcpyAsync(E.d_scal + 33, &flag, sizeof(double), cudaMemcpyHostToDevice, E.stream));
+  EDGPU_NCCL(N.AllReduce(E.d_scal + 33, E.d_scal + 33, 1, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)E.nccl,
+                         E.stream));
+  EDGPU_CUDA(cudaMemcpyAsync(&flag, E.d_scal + 33, sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  S.p2p = (flag == 0.0);
+  if (!S.p2p) {  // someone could not map: everybody unmaps and uses the NCCL path
+    for (int p = 0; p < P; p++) {
+      if (p != me && S.peer_vt[p]) cudaIpcCloseMemHandle(S.peer_vt[p]);
+      if (p != me && S.peer_hvt[p]) cudaIpcCloseMemHandle(S.peer_hvt[p]);
+      S.peer_vt[p] = S.peer_hvt[p] = nullptr;
+    }
+    cudaGetLastError();
+  }
+  return 0;
+}
+
+int comm_p2p_teardown(Engine &E) {
+  Sector &S = E.sec;
+  if (!S.p2p) return 0;
+  // nobody may still be reading / writing a peer's buffer
+  comm_barrier(E);
+  cudaStreamSynchronize(E.stream);
+  for (int p = 0; p < E.nranks; p++) {
+    if (p != E.rank) {
+      cudaIpcCloseMemHandle(S.peer_vt[p]);
+      cudaIpcCloseMemHandle(S.peer_hvt[p]);
+    }
+    S.peer_vt[p] = S.peer_hvt[p] = nullptr;
+  }
+  comm_barrier(E);  // every rank unmapped before anybody frees
+  cudaStreamSynchronize(E.stream);
+  S.p2p = false;
+  return 0;
+}
+
+int comm_push_transpose(Engine &E, const double *d_a) {
+  Sector &S = E.sec;
+  const PeerTable T = peer_table(E, S.peer_vt);
+  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)((S.up.dim + 31) / 32));
+  k_push_transpose<<<grid, 256, 0, E.stream>>>(d_a, S.up.ld, (int)S.up.dim, (int)S.qdw, S.d0, S.dw.ld, T);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_pull_transpose_acc(Engine &E, double *d_hv) {
+  Sector &S = E.sec;
+  const PeerTable T = peer_table(E, S.peer_hvt);
+  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)((S.up.dim + 31) / 32));
+  k_pull_transpose_acc<<<grid, 256, 0, E.stream>>>(d_hv, S.up.ld, (int)S.up.dim, (int)S.qdw, S.d0,
+                                                   S.dw.ld, T);
+  EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }

@@ -41,6 +41,7 @@ extern int64_t g_launches;  // kernels launched by this library (bench "gpu_laun
 // (2*term + sign; amp2[2t] = +h_t, amp2[2t+1] = -h_t, amp2[2*nterms] = 0 for padding),
 // [31] "far" flag (slow-role tables only: the target lies outside the row's range)
 // ---------------------------------------------------------------------------------------
+constexpr int EDGPU_MAXRANKS = 16;
 constexpr uint32_t HOP_TGT_MASK = 0xFFFFFu;
 constexpr int HOP_AMP_SHIFT = 20;
 constexpr uint32_t HOP_AMP_MASK = 0x7FFu;
@@ -141,6 +142,12 @@ struct Sector {
   int variant = 0;
   // scratch for the distributed transposes
   double *vt = nullptr, *hvt = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
+  // peer-memory transposes (comm.cu): vt / hvt of every rank mapped through CUDA IPC
+  bool p2p = false;
+  double *peer_vt[EDGPU_MAXRANKS] = {}, *peer_hvt[EDGPU_MAXRANKS] = {};
+  // all-gathered vector for the non-local terms with nranks>1
+  double *vfull = nullptr;
+  std::vector<int64_t> gcounts, goffs;
   int64_t padded_len() const { return up.ld * qdw; }
   int64_t padded_len_t() const { return dw.ld * qup; }
 };
@@ -172,6 +179,8 @@ struct Engine {
   size_t smem_optin = 0;
   size_t smem_per_sm = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;  // transposes overlapped with the rank-local pass
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[8] = {};
   // communicator
   int rank = 0, nranks = 1;
@@ -226,6 +235,13 @@ int comm_allreduce_sum(Engine &E, double *d_buf, int n);
 int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int64_t qcol,
                    double *d_b, int64_t ncol, int64_t ldb, int64_t qrow, bool accumulate);
 int comm_finalize(Engine &E);
+// peer-memory path of the two transposes of one H x v (falls back to comm_transpose when the
+// peers' buffers cannot be mapped)
+int comm_p2p_setup(Engine &E);     // after S.vt / S.hvt exist: exchange + map IPC handles
+int comm_p2p_teardown(Engine &E);  // before they are freed
+int comm_barrier(Engine &E);       // in-stream barrier over all ranks (1-element all-reduce)
+int comm_push_transpose(Engine &E, const double *d_a);             // v -> every rank's vt
+int comm_pull_transpose_acc(Engine &E, double *d_hv);              // Hv += transpose(hvt of all)
 
 // vecops.cu
 int vec_fill_random(Engine &E, double *d_v, uint64_t seed);

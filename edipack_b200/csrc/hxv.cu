@@ -742,22 +742,60 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
     //   vt  = transpose(v)                            NCCL all-to-all of tiles
     //   Hvt = Hdw vt                                  dw is now the fast index
     //   Hv += transpose(Hvt)
+    // The first transpose only reads v: it runs on the communication stream concurrently with
+    // the rank-local pass (diag + up hops) on the main stream.
+    EDGPU_CUDA(cudaEventRecord(E.ev_fork, st));
+    EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
+    {
+      cudaStream_t keep = E.stream;
+      E.stream = E.comm_stream;  // the comm_* helpers and apply_fast launch on E.stream
+      int rc = 0;
+      if (S.p2p) {
+        // push v^T into every rank's vt over NVLink, barrier, dw hops on the local vt, barrier
+        rc = comm_push_transpose(E, d_v);
+        if (!rc) rc = comm_barrier(E);
+      } else {
+        rc = comm_transpose(E, d_v, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false);
+      }
+      if (!rc)
+        rc = apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
+                        1.0);
+      if (!rc && S.p2p) rc = comm_barrier(E);
+      E.stream = keep;
+      if (rc) return rc;
+    }
+    EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
     EDGPU_TRY(apply_fast(E, tiled, true, accum, d_v, d_hv, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
                          s_old));
     EDGPU_MARK(1);
-    const size_t nt = (size_t)S.padded_len_t();
-    if (!S.vt) {
-      EDGPU_CUDA(cudaMalloc(&S.vt, sizeof(double) * nt));
-      EDGPU_CUDA(cudaMalloc(&S.hvt, sizeof(double) * nt));
-      EDGPU_CUDA(cudaMemsetAsync(S.vt, 0, sizeof(double) * nt, st));
-      EDGPU_CUDA(cudaMemsetAsync(S.hvt, 0, sizeof(double) * nt, st));
-    }
-    EDGPU_TRY(comm_transpose(E, d_v, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false));
-    EDGPU_TRY(apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
-                         1.0));
+    EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
     EDGPU_MARK(2);
-    EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, d_hv, U.dim, U.ld, S.qdw, true));
-    if (S.nonlocal) return set_error("non-local (Jx/Jp) terms with nranks>1 are not implemented yet");
+    if (S.p2p)
+      EDGPU_TRY(comm_pull_transpose_acc(E, d_hv));
+    else
+      EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, d_hv, U.dim, U.ld, S.qdw, true));
+    if (S.nonlocal) {
+      // non-local terms gather from anywhere: all ranks' columns first, like
+      // allgather_vector_MPI (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:355-360)
+      if (!S.vfull) {
+        EDGPU_CUDA(cudaMalloc(&S.vfull, sizeof(double) * (size_t)U.ld * (size_t)D.dim));
+        S.gcounts.assign(E.nranks, 0);
+        S.goffs.assign(E.nranks, 0);
+        for (int p = 0; p < E.nranks; p++) {
+          int64_t q, d0;
+          block_split(D.dim, E.nranks, p, &q, &d0);
+          S.gcounts[p] = q * U.ld;
+          S.goffs[p] = d0 * U.ld;
+        }
+      }
+      EDGPU_TRY(comm_allgatherv(E, d_v, S.vfull, S.gcounts, S.goffs));
+      dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
+      const RankView Lu = rank_view(S.up.lin, S.up.ord), Ld = rank_view(S.dw.lin, S.dw.ord);
+      k_nonlocal<<<grid, 128, 0, st>>>(S.vfull, d_hv, U.dim, U.ld, S.qdw, S.d0, S.up.map, S.dw.map, Lu,
+                                       Ld, S.Norb, S.jx, S.jp, s_acc);
+      EDGPU_COUNT_LAUNCH();
+      EDGPU_CUDA(cudaGetLastError());
+    }
     EDGPU_MARK(3);
   }
 #undef EDGPU_MARK

@@ -498,6 +498,8 @@ int sector_close(Engine &E) {
   Sector &S = E.sec;
   if (!S.open) return 0;
   cudaStreamSynchronize(E.stream);
+  cudaStreamSynchronize(E.comm_stream);
+  if (E.nranks > 1) comm_p2p_teardown(E);
   free_spin(S.up);
   free_spin(S.dw);
   cudaFree(S.xud);
@@ -507,8 +509,9 @@ int sector_close(Engine &E) {
   cudaFree(S.hvt);
   cudaFree(S.sendbuf);
   cudaFree(S.recvbuf);
+  cudaFree(S.vfull);
   S.xud = S.jx = S.jp = nullptr;
-  S.vt = S.hvt = S.sendbuf = S.recvbuf = nullptr;
+  S.vt = S.hvt = S.sendbuf = S.recvbuf = S.vfull = nullptr;
   S.open = false;
   return 0;
 }
@@ -577,6 +580,16 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
   }
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
 
+  if (E.nranks > 1) {
+    // transposed block [DimDw (fast) x qup] for the dw hops, mapped into every peer when possible
+    const size_t nt = (size_t)S.padded_len_t();
+    EDGPU_CUDA(cudaMalloc(&S.vt, sizeof(double) * nt));
+    EDGPU_CUDA(cudaMalloc(&S.hvt, sizeof(double) * nt));
+    EDGPU_CUDA(cudaMemsetAsync(S.vt, 0, sizeof(double) * nt, E.stream));
+    EDGPU_CUDA(cudaMemsetAsync(S.hvt, 0, sizeof(double) * nt, E.stream));
+    EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+    EDGPU_TRY(comm_p2p_setup(E));
+  }
   S.variant = E.variant_request;
   S.open = true;
   return 0;

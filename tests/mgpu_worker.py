@@ -38,6 +38,7 @@ def main():
     cases = [("star7", star_kwargs(7), (4, 4)), ("star9", star_kwargs(9), (5, 5)),
              ("star9_54", star_kwargs(9), (5, 4)), ("star11", star_kwargs(11), (6, 6)),
              ("two_orb_nb3_nojx", two_orb_kwargs(3, with_nd=False), (4, 4)),
+             ("two_orb_nb3_jxjp", two_orb_kwargs(3), (4, 4)), ("two_orb_nb2_jxjp", two_orb_kwargs(2), (3, 2)),
              ("star13", star_kwargs(13), (7, 7))]
     for name, kw, (nup, ndw) in cases:
         m, mo = E.EDModel(**kw), O.Model(**kw)
