@@ -1,0 +1,299 @@
+"""CPU restatement of EDIpack's NONSU2-mode stored Hamiltonian (ED_SPARSE_H=T), numpy.
+
+TEST INFRASTRUCTURE ONLY (see oracle/ed_oracle.h): plays the role of the Fortran host that
+builds ``spH0`` for the stored-H path; the product never imports it.
+
+Follows, per state of the sector:
+  build_sector (nonsu2, Jz_basis=F)   src/singlesite/ED_SECTOR.f90:335-368  (m = iup + idw*2**Ns,
+                                       idw outer / iup inner -> ascending m, popcount = Ntot)
+  c / cdg on the 2*Ns-bit state       src/singlesite/ED_AUX_FUNX.f90:334-384 (sign counts ALL lower bits)
+  stored/Himp.f90                     diagonal :15-21, same-spin hops :38-80, spin-flip :85-110,
+                                       spin_field :243-300 (z on the diagonal, x/y off-diagonal)
+  stored/Hint.f90                     density-density + Hartree shifts :13-52, S-E :63-90, P-H :96-124
+  stored/Hbath.f90                    normal/hybrid diagonal :12-27
+  stored/Himp_bath.f90                spin-conserving hybridisation :10-67, spin-flip u :72-136
+Matrix convention (sp_insert_element(spH0,htmp,i,j)): row i = the state the operators act on,
+column j = the resulting state, value = conjg(amplitude)*sign; duplicates accumulate
+(ED_SPARSE_MATRIX.f90:346-357).
+
+Parity status: pinned to test/src/HYBRID_NONSU2/{evals,dens,docc,magX}.check
+(tests/test_oracle_golden_nonsu2.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class ModelNonsu2:
+    Norb: int = 2
+    Nbath: int = 4
+    bath_type: str = "hybrid"          # normal | hybrid
+    Uloc: tuple = (1.0, 1.0)
+    Ust: float = 0.0
+    Jh: float = 0.0
+    Jx: float = 0.0
+    Jp: float = 0.0
+    xmu: float = 0.0
+    hfmode: bool = True
+    ed_hw_bath: float = 2.0
+    hloc: np.ndarray | None = None     # complex [2,2,Norb,Norb]  impHloc(ispin,jspin,iorb,jorb)
+    bath_e: np.ndarray | None = None   # [2, Nfoo, Nbath]
+    bath_v: np.ndarray | None = None   # [2, Norb, Nbath]
+    bath_u: np.ndarray | None = None   # [2, Norb, Nbath]  spin-flip hybridisation
+    spin_field: np.ndarray | None = None  # [Norb, 3]
+
+    @property
+    def Ns(self):  # ED_SETUP.f90:118-126
+        return self.Nbath + self.Norb if self.bath_type == "hybrid" else (self.Nbath + 1) * self.Norb
+
+    @property
+    def Nfoo(self):
+        return 1 if self.bath_type == "hybrid" else self.Norb
+
+    def stride(self, a, k):  # getBathStride(a+1,k+1), 1-based site (ED_SETUP.f90:605-622)
+        if self.bath_type == "hybrid":
+            return self.Norb + k + 1
+        return self.Norb + a * self.Nbath + k + 1
+
+    def default_bath(self):
+        """init_dmft_bath, ED_BATH_DMFT.f90:211-244 (nonsu2: u = v)."""
+        Nb, hw = self.Nbath, self.ed_hw_bath
+        e = np.zeros(Nb)
+        e[0], e[-1] = -hw, hw
+        Nh = Nb // 2
+        if Nb % 2 == 0 and Nb >= 4:
+            de = hw / max(Nh - 1, 1)
+            e[Nh - 1], e[Nh] = -0.1, 0.1
+            for i in range(2, Nh):
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        elif Nb % 2 != 0 and Nb >= 3:
+            de = hw / Nh
+            e[Nh] = 0.0
+            for i in range(2, Nh + 1):
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        v = max(0.1, 1.0 / math.sqrt(Nb))
+        self.bath_e = np.broadcast_to(e, (2, self.Nfoo, Nb)).copy()
+        self.bath_v = np.full((2, self.Norb, Nb), v)
+        self.bath_u = np.full((2, self.Norb, Nb), v)
+        return self
+
+
+def build_sector(Ns: int, Ntot: int) -> np.ndarray:
+    """Ascending list of m = iup + idw*2**Ns with popcount(m) = Ntot (ED_SECTOR.f90:351-368)."""
+    allm = np.arange(1 << (2 * Ns), dtype=np.int64)
+    pc = np.zeros_like(allm)
+    x = allm.copy()
+    while x.any():
+        pc += x & 1
+        x >>= 1
+    return allm[pc == Ntot]
+
+
+def _c(pos, m):
+    """c(pos,in,out,fsgn) with pos 1-based; returns (out, sign) or None (ED_AUX_FUNX.f90:334-357)."""
+    b = pos - 1
+    if not (m >> b) & 1:
+        return None
+    sgn = -1.0 if bin(m & ((1 << b) - 1)).count("1") & 1 else 1.0
+    return m & ~(1 << b), sgn
+
+
+def _cdg(pos, m):
+    b = pos - 1
+    if (m >> b) & 1:
+        return None
+    sgn = -1.0 if bin(m & ((1 << b) - 1)).count("1") & 1 else 1.0
+    return m | (1 << b), sgn
+
+
+def stored_H(model: ModelNonsu2, Ntot: int):
+    """ed_buildH_nonsu2_main (ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190) for one sector:
+    returns (map, rowptr, cols [1-based], vals [complex]) in list-of-rows insertion order."""
+    if model.bath_e is None:
+        model.default_bath()
+    Ns, No, Nb = model.Ns, model.Norb, model.Nbath
+    smap = build_sector(Ns, Ntot)
+    index = {int(m): i + 1 for i, m in enumerate(smap)}  # binary_search -> 1-based index
+    hloc = np.zeros((2, 2, No, No), complex) if model.hloc is None else np.asarray(model.hloc, complex)
+    U = np.asarray(model.Uloc, float)
+    Ust = np.full((No, No), model.Ust) - np.diag(np.full(No, model.Ust))
+    Jh = np.full((No, No), model.Jh) - np.diag(np.full(No, model.Jh))
+    Jx = np.full((No, No), model.Jx) - np.diag(np.full(No, model.Jx))
+    Jp = np.full((No, No), model.Jp) - np.diag(np.full(No, model.Jp))
+    sf = np.zeros((No, 3)) if model.spin_field is None else np.asarray(model.spin_field, float)
+    rows = []
+    for m_ in smap:
+        m = int(m_)
+        row = {}  # column -> value, insertion-ordered; duplicates accumulate
+
+        def ins(val, j):
+            row[j] = row.get(j, 0.0) + val
+
+        ib = [(m >> k) & 1 for k in range(2 * Ns)]
+        nup = [float(ib[a]) for a in range(No)]
+        ndw = [float(ib[a + Ns]) for a in range(No)]
+        i = index[m]
+
+        def hop(alfa, beta, amp):
+            """c(beta) then cdg(alfa); inserts conjg(amp)*sg1*sg2 at (i, j)."""
+            r1 = _c(beta, m)
+            if r1 is None:
+                return
+            r2 = _cdg(alfa, r1[0])
+            if r2 is None:
+                return
+            ins(np.conj(amp) * r1[1] * r2[1], index[r2[0]])
+
+        # ---- Himp.f90 : local part
+        h = 0.0
+        for a in range(No):
+            h += hloc[0, 0, a, a] * nup[a] + hloc[1, 1, a, a] * ndw[a] - model.xmu * (nup[a] + ndw[a])
+        ins(h, i)
+        for a in range(No):
+            for b in range(No):
+                if hloc[0, 0, a, b] != 0 and ib[b] == 1 and ib[a] == 0:
+                    hop(a + 1, b + 1, hloc[0, 0, a, b])
+                if hloc[1, 1, a, b] != 0 and ib[b + Ns] == 1 and ib[a + Ns] == 0:
+                    hop(a + 1 + Ns, b + 1 + Ns, hloc[1, 1, a, b])
+        for isp in range(2):
+            jsp = 1 - isp
+            for a in range(No):
+                for b in range(No):
+                    ialfa, ibeta = a + 1 + isp * Ns, b + 1 + jsp * Ns
+                    if hloc[isp, jsp, a, b] != 0 and ib[ibeta - 1] == 1 and ib[ialfa - 1] == 0:
+                        hop(ialfa, ibeta, hloc[isp, jsp, a, b])
+        if np.any(sf != 0):
+            # NB the reference reuses the running htmp here (Himp.f90:247-250); it is zero unless a
+            # hop was inserted just before -- restated as the intended F_z term only
+            ins(sum(sf[a, 2] * (nup[a] - ndw[a]) for a in range(No)), i)
+            for a in range(No):
+                for (src, dst, sy) in ((a + 1, a + 1 + Ns, -1j), (a + 1 + Ns, a + 1, 1j)):
+                    r1 = _c(src, m)
+                    if r1 is None:
+                        continue
+                    r2 = _cdg(dst, r1[0])
+                    if r2 is None:
+                        continue
+                    j = index[r2[0]]
+                    ins(sf[a, 0] * r1[1] * r2[1], j)
+                    ins(sy * sf[a, 1] * r1[1] * r2[1], j)
+        # ---- Hint.f90
+        h = 0.0
+        for a in range(No):
+            h += U[a] * nup[a] * ndw[a]
+        for a in range(No):
+            for b in range(a + 1, No):
+                h += Ust[a, b] * (nup[a] * ndw[b] + nup[b] * ndw[a])
+                h += (Ust[a, b] - Jh[a, b]) * (nup[a] * nup[b] + ndw[a] * ndw[b])
+        if model.hfmode:
+            for a in range(No):
+                h += -0.5 * U[a] * (nup[a] + ndw[a]) + 0.25 * U[a]
+            for a in range(No):
+                for b in range(a + 1, No):
+                    nn = nup[a] + ndw[a] + nup[b] + ndw[b]
+                    h += -0.5 * Ust[a, b] * nn + 0.5 * Ust[a, b]
+                    h += -0.5 * (Ust[a, b] - Jh[a, b]) * nn + 0.5 * (Ust[a, b] - Jh[a, b])
+        ins(h, i)
+        if No > 1 and np.any(Jx != 0):
+            for a in range(No):
+                for b in range(No):
+                    if a != b and ib[b] == 1 and ib[a + Ns] == 1 and ib[b + Ns] == 0 and ib[a] == 0:
+                        k, s = m, 1.0
+                        for f, pos in ((_c, b + 1), (_c, a + 1 + Ns), (_cdg, b + 1 + Ns), (_cdg, a + 1)):
+                            k, sg = f(pos, k)
+                            s *= sg
+                        ins(Jx[a, b] * s, index[k])
+        if No > 1 and np.any(Jp != 0):
+            for a in range(No):
+                for b in range(No):
+                    if a != b and ib[b] == 1 and ib[b + Ns] == 1 and ib[a + Ns] == 0 and ib[a] == 0:
+                        k, s = m, 1.0
+                        for f, pos in ((_c, b + 1), (_c, b + 1 + Ns), (_cdg, a + 1 + Ns), (_cdg, a + 1)):
+                            k, sg = f(pos, k)
+                            s *= sg
+                        ins(Jp[a, b] * s, index[k])
+        # ---- Hbath.f90 (normal / hybrid)
+        h = 0.0
+        for a in range(model.Nfoo):
+            for k in range(Nb):
+                s = model.stride(a, k)
+                h += model.bath_e[0, a, k] * ib[s - 1] + model.bath_e[1, a, k] * ib[s - 1 + Ns]
+        ins(h, i)
+        # ---- Himp_bath.f90
+        for a in range(No):
+            for k in range(Nb):
+                ms = model.stride(a, k)
+                for sp in range(2):
+                    v = model.bath_v[sp, a, k]
+                    if v != 0:
+                        hop(ms + sp * Ns, a + 1 + sp * Ns, v)   # imp -> bath
+                        hop(a + 1 + sp * Ns, ms + sp * Ns, v)   # bath -> imp
+        for a in range(No):
+            for k in range(Nb):
+                ms = model.stride(a, k)
+                u1, u2 = model.bath_u[0, a, k], model.bath_u[1, a, k]
+                if u1 != 0:  # IMP UP <--> BATH DW (amplitude inserted without conjg, it is real)
+                    hop(ms + Ns, a + 1, u1)
+                    hop(a + 1, ms + Ns, u1)
+                if u2 != 0:  # IMP DW <--> BATH UP
+                    hop(ms, a + 1 + Ns, u2)
+                    hop(a + 1 + Ns, ms, u2)
+        rows.append(row)
+    rowptr = np.zeros(len(rows) + 1, np.int64)
+    cols, vals = [], []
+    for r, row in enumerate(rows):
+        for j, val in row.items():
+            cols.append(j)
+            vals.append(val)
+        rowptr[r + 1] = len(cols)
+    return smap, rowptr, np.array(cols, np.int32), np.array(vals, complex)
+
+
+def to_dense(rowptr, cols, vals):
+    n = len(rowptr) - 1
+    H = np.zeros((n, n), complex)
+    for i in range(n):
+        for k in range(rowptr[i], rowptr[i + 1]):
+            H[i, cols[k] - 1] += vals[k]
+    return H
+
+
+def csr_matvec(rowptr, cols, vals, v):
+    """sp_matvec_matrix_csr_c (ED_SPARSE_MATRIX.f90:778): Hv(i) = sum_k vals(k) * v(cols(k))."""
+    out = np.zeros(len(rowptr) - 1, complex)
+    for i in range(len(out)):
+        s = slice(rowptr[i], rowptr[i + 1])
+        out[i] = np.dot(vals[s], v[cols[s] - 1])
+    return out
+
+
+def observables(model: ModelNonsu2, smap, vec):
+    """dens, docc, magX of one state (ED_OBSERVABLES_NONSU2.f90: n_up+n_dw, n_up*n_dw,
+    <c+_up c_dw + c+_dw c_up> = |(c_up + c_dw)|gs>|^2 - n_up - n_dw, :265-294)."""
+    Ns, No = model.Ns, model.Norb
+    w = np.abs(vec) ** 2
+    dens, docc, magx = np.zeros(No), np.zeros(No), np.zeros(No)
+    index = {int(m): i for i, m in enumerate(smap)}
+    for a in range(No):
+        nu = ((smap >> a) & 1).astype(float)
+        nd = ((smap >> (a + Ns)) & 1).astype(float)
+        dens[a] = float((w * (nu + nd)).sum())
+        docc[a] = float((w * nu * nd).sum())
+        acc = 0.0 + 0.0j
+        for i, m_ in enumerate(smap):  # <gs| c+_up c_dw |gs> + h.c.
+            m = int(m_)
+            r1 = _c(a + 1 + Ns, m)
+            if r1 is None:
+                continue
+            r2 = _cdg(a + 1, r1[0])
+            if r2 is None:
+                continue
+            acc += np.conj(vec[index[r2[0]]]) * r1[1] * r2[1] * vec[i]
+        magx[a] = 2.0 * acc.real
+    return dens, docc, magx

@@ -27,10 +27,13 @@ def inputs(path):
 
 
 def main():
-    for name in ("NORMAL_NORMAL",):
+    checks = {"NORMAL_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
+              "HYBRID_NONSU2": ("evals", "dens", "docc", "energy", "doubles", "imp", "magX",
+                                "Sigma11_momenta", "Sigma12_momenta")}
+    for name in ("NORMAL_NORMAL", "HYBRID_NONSU2"):
         d = os.path.join(REF, name)
         g = {"source": f"test/src/{name}", "inputs": inputs(os.path.join(d, "inputED.in"))}
-        for chk in ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"):
+        for chk in checks[name]:
             g[chk] = read(os.path.join(d, chk + ".check"))
         with open(os.path.join(HERE, name.lower() + ".json"), "w") as f:
             json.dump(g, f, indent=1)

@@ -78,3 +78,39 @@ def replica_kwargs():
     kw.update(bath_type="replica", hbath=hb, bath_e=np.zeros((2, norb, nbath)),
               bath_v=np.full((2, norb, nbath), 0.6))
     return kw
+
+
+def hybrid_nonsu2_model(oracle_nonsu2):
+    """test/src/HYBRID_NONSU2: inputED.in + Hloc = Mh * Gamma5 (= sigma_0 (x) tau_z in the test's
+    spin-major so2j ordering, ed_hybrid_nonsu2.f90:50,76; COMMON.f90:81-122), default bath."""
+    g = golden("hybrid_nonsu2")["inputs"]
+    norb = int(g["NORB"])
+    mh = _f(g["MH"])
+    hloc = np.zeros((2, 2, norb, norb), complex)
+    for s in range(2):
+        hloc[s, s] = np.diag([mh, -mh])
+    m = oracle_nonsu2.ModelNonsu2(
+        Norb=norb, Nbath=int(g["NBATH"]), bath_type=g["BATH_TYPE"],
+        Uloc=tuple(_f(x) for x in g["ULOC"].split(",")), Ust=_f(g["UST"]), Jh=_f(g["JH"]),
+        Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
+        ed_hw_bath=_f(g["ED_HW_BATH"]), hloc=hloc)
+    return m.default_bath()
+
+
+def soc_nonsu2_model(oracle_nonsu2, nbath=5):
+    """cfg5 family at a size the numpy oracle builds in seconds: nonsu2, hybrid bath, complex
+    spin-orbit-like Hloc (spin-flip, imaginary inter-orbital terms), spin field."""
+    norb = 2
+    hloc = np.zeros((2, 2, norb, norb), complex)
+    lam = 0.3
+    for s in range(2):
+        hloc[s, s] = np.array([[0.2, 1j * lam * (1 - 2 * s)], [-1j * lam * (1 - 2 * s), -0.2]])
+    hloc[0, 1] = np.array([[0.0, lam], [-lam, 0.0]])
+    hloc[1, 0] = hloc[0, 1].conj().T
+    rng = np.random.default_rng(5)
+    m = oracle_nonsu2.ModelNonsu2(Norb=norb, Nbath=nbath, bath_type="hybrid", Uloc=(2.0, 1.7),
+                                  Ust=1.5, Jh=0.25, Jx=0.25, Jp=0.25, xmu=0.1, hfmode=True, hloc=hloc,
+                                  spin_field=np.array([[0.05, 0.02, -0.03], [0.0, 0.04, 0.01]]))
+    m.default_bath()
+    m.bath_u = 0.2 + 0.2 * rng.random(m.bath_u.shape)
+    return m

@@ -111,3 +111,51 @@ def test_csr_error_behaviour(engine):
         assert np.allclose(E.spHtimesV_p(np.array([1.0, 1.0])), [1.0, 2.0])
     finally:
         E.delete_Hv_sector_csr()
+
+
+def test_golden_hybrid_nonsu2_through_gpu(engine):
+    """The reference's HYBRID_NONSU2 fixture: the host (numpy oracle standing in for the Fortran
+    ed_buildH_nonsu2_main) builds spH0, the GPU does the complex stored-H Lanczos (the reference
+    uses ARPACK + spMatVec_nonsu2_main here, LANC_DIM_THRESHOLD=256 < 924) -> evals 1e-9,
+    dens / docc / magX 1e-8 against test/src/HYBRID_NONSU2/*.check."""
+    import edipack_oracle_nonsu2 as N
+    from models import golden, hybrid_nonsu2_model
+
+    E = engine
+    g = golden("hybrid_nonsu2")
+    m = hybrid_nonsu2_model(N)
+    smap, rp, cj, va = N.stored_H(m, 6)
+    E.build_Hv_sector_csr(rp, cj, va)
+    try:
+        e, vec, nit = E.sp_lanc_eigh(512, 1e-14)
+    finally:
+        E.delete_Hv_sector_csr()
+    assert abs(e - g["evals"][0]) < 1e-9
+    dens, docc, magx = N.observables(m, smap, vec)
+    assert np.abs(dens - np.array(g["dens"])).max() < 1e-8
+    assert np.abs(docc - np.array(g["docc"])).max() < 1e-8
+    assert np.abs(magx - np.array(g["magX"])).max() < 1e-8
+
+
+def test_nonsu2_soc_stored_hxv(engine):
+    """cfg5 family (complex Hloc with spin-flip terms, spin field, spin-flip hybridisation) at
+    3432 states: H x v of the complex CSR kernel vs the oracle's sp_matvec, GS energy vs LAPACK."""
+    import edipack_oracle_nonsu2 as N
+    from models import soc_nonsu2_model
+
+    E = engine
+    m = soc_nonsu2_model(N, nbath=5)
+    smap, rp, cj, va = N.stored_H(m, 7)
+    assert len(smap) == 3432
+    rng = np.random.default_rng(9)
+    v = rng.standard_normal(len(smap)) + 1j * rng.standard_normal(len(smap))
+    ref = N.csr_matvec(rp, cj, va, v)
+    E.build_Hv_sector_csr(rp, cj, va)
+    try:
+        hv = E.spHtimesV_cc(v)
+        assert rel_err(hv, ref) < 1e-12
+        e, vec, nit = E.sp_lanc_eigh(600, 1e-14)
+    finally:
+        E.delete_Hv_sector_csr()
+    ev = np.linalg.eigvalsh(N.to_dense(rp, cj, va))
+    assert abs(e - ev[0]) < 1e-10

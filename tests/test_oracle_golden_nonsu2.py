@@ -1,0 +1,58 @@
+"""Pins the nonsu2 stored-H oracle (oracle/edipack_oracle_nonsu2.py) to the reference's golden
+values test/src/HYBRID_NONSU2/{evals,dens,docc,magX}.check at the reference's 1e-9
+(test/src/ASSERTING.f90:78)."""
+import numpy as np
+import pytest
+
+from models import golden, hybrid_nonsu2_model, soc_nonsu2_model
+
+
+@pytest.fixture(scope="module")
+def N():
+    import edipack_oracle_nonsu2 as N
+
+    return N
+
+
+@pytest.fixture(scope="module")
+def solved(N):
+    m = hybrid_nonsu2_model(N)
+    best = None
+    for nt in range(0, 2 * m.Ns + 1):
+        smap, rp, cj, va = N.stored_H(m, nt)
+        H = N.to_dense(rp, cj, va)
+        assert np.abs(H - H.conj().T).max() < 1e-12  # the stored matrix is Hermitian
+        ev, U = np.linalg.eigh(H)
+        if best is None or ev[0] < best[0]:
+            best = (ev[0], nt, smap, U[:, 0], ev)
+    return m, best
+
+
+def test_ground_state_energy(solved):
+    m, (e, nt, smap, vec, ev) = solved
+    g = golden("hybrid_nonsu2")
+    assert nt == 6 and len(smap) == 924
+    assert abs(e - g["evals"][0]) < 1e-9
+    assert ev[1] - ev[0] > 1e-3  # unique ground state: zeta_function = 1
+
+
+def test_dens_docc_magx(N, solved):
+    m, (e, nt, smap, vec, ev) = solved
+    g = golden("hybrid_nonsu2")
+    dens, docc, magx = N.observables(m, smap, vec)
+    assert np.abs(dens - np.array(g["dens"])).max() < 1e-9
+    assert np.abs(docc - np.array(g["docc"])).max() < 1e-9
+    assert np.abs(magx - np.array(g["magX"])).max() < 1e-9
+
+
+def test_sector_map_and_matvec(N):
+    """Map = ascending m = iup + idw*2**Ns with popcount Ntot; CSR product = dense product."""
+    m = soc_nonsu2_model(N, nbath=3)
+    smap, rp, cj, va = N.stored_H(m, 4)
+    assert np.all(np.diff(smap) > 0)
+    assert all(bin(int(x)).count("1") == 4 for x in smap)
+    H = N.to_dense(rp, cj, va)
+    assert np.abs(H - H.conj().T).max() < 1e-12
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(len(smap)) + 1j * rng.standard_normal(len(smap))
+    assert np.abs(N.csr_matvec(rp, cj, va, v) - H @ v).max() < 1e-12
