@@ -29,8 +29,9 @@ def inputs(path):
 def main():
     checks = {"NORMAL_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
               "HYBRID_NONSU2": ("evals", "dens", "docc", "energy", "doubles", "imp", "magX",
-                                "Sigma11_momenta", "Sigma12_momenta")}
-    for name in ("NORMAL_NORMAL", "HYBRID_NONSU2"):
+                                "Sigma11_momenta", "Sigma12_momenta"),
+              "INEQ_NORMAL_NORMAL": ("dens", "docc", "energy", "doubles", "Sigma_momenta")}
+    for name in ("NORMAL_NORMAL", "HYBRID_NONSU2", "INEQ_NORMAL_NORMAL"):
         d = os.path.join(REF, name)
         g = {"source": f"test/src/{name}", "inputs": inputs(os.path.join(d, "inputED.in"))}
         for chk in checks[name]:

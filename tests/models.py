@@ -114,3 +114,28 @@ def soc_nonsu2_model(oracle_nonsu2, nbath=5):
     m.default_bath()
     m.bath_u = 0.2 + 0.2 * rng.random(m.bath_u.shape)
     return m
+
+
+def ineq_site_kwargs(ilat: int):
+    """test/src/INEQ_NORMAL_NORMAL, site ilat (0 or 1): Norb=1, Nbath=7, Nspin=2, Hloc =
+    (sigma_z (x) tau_0) reshaped over (lat,spin,orb) -> +1 on site 1 and -1 on site 2 for both
+    spins (ed_normal_normal_afm2.f90:71-72); default bath, then ed_break_symmetry_bath with
+    sign (-1)**(ilat+1): e_up += sign*SB_FIELD, e_dw -= sign*SB_FIELD (ED_BATH_USER.f90:166-167)."""
+    g = golden("ineq_normal_normal")["inputs"]
+    nbath = int(g["NBATH"])
+    sign = 1.0 if ilat == 0 else -1.0
+    sb = _f(g["SB_FIELD"])
+    hw = _f(g["ED_HW_BATH"])
+    e = np.zeros(nbath)  # init_dmft_bath, odd Nbath (ED_BATH_DMFT.f90:211-244)
+    e[0], e[-1] = -hw, hw
+    nh = nbath // 2
+    de = hw / nh
+    e[nh] = 0.0
+    for i in range(2, nh + 1):
+        e[i - 1] = -hw + (i - 1) * de
+        e[nbath - i] = hw - (i - 1) * de
+    bath_e = np.stack([e + sign * sb, e - sign * sb])[:, None, :]
+    bath_v = np.full((2, 1, nbath), max(0.1, 1.0 / np.sqrt(nbath)))
+    return dict(Norb=1, Nbath=nbath, Nspin=2, bath_type=g["BATH_TYPE"], Uloc=(_f(g["ULOC"]),),
+                xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T", beta=_f(g["BETA"]),
+                ed_hw_bath=hw, hloc=np.full((2, 1, 1), sign), bath_e=bath_e, bath_v=bath_v)

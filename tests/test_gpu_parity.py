@@ -263,3 +263,30 @@ def test_apply_op_matches_oracle(engine, oracle):
                     hv = oracle.direct_hxv(mo, jn[0], jn[1], ref)
                     assert abs(a[0] - (ref @ hv) / n2) < 1e-11
     E.state_free(7)
+
+
+@pytest.mark.parametrize("ilat", [0, 1])
+def test_golden_ineq_normal_normal_through_gpu(engine, oracle, ilat):
+    """test/src/INEQ_NORMAL_NORMAL (Ns=8, Nspin=2, spin-split bath; BASELINE config 1 geometry):
+    device Lanczos over the sectors around half filling, device observables and device GF
+    seeds -> dens/docc 1e-8, Sigma(iw) moments 1e-8 against the reference's *.check."""
+    from models import ineq_site_kwargs
+
+    E = engine
+    g = golden("ineq_normal_normal")
+    kw = ineq_site_kwargs(ilat)
+    m = E.EDModel(**kw)
+    m.lanc_tolerance = 1e-18
+    mo = oracle.Model(**kw)
+    secs = [(a, b) for a in (3, 4, 5) for b in (3, 4, 5)]
+    states = E.ed_diag_d(m, sectors=secs)
+    assert len(states) == 1 and (states[0].nup, states[0].ndw) == (4, 4)
+    dens, docc = E.observables_normal(m, states)
+    assert abs(dens[0] - g["dens"][ilat]) < 1e-8
+    assert abs(docc[0] - g["docc"][ilat]) < 1e-8
+    pw = E.lanc_build_gf_normal_diag(m, states, 0, 0)
+    wm, sig = oracle.sigma_matsubara(mo, pw, 0, 0, int(g["inputs"]["LMATS"]))
+    gold = np.array(g["Sigma_momenta"]).reshape(2, 4)[ilat]
+    assert np.abs(oracle.momenta(wm, sig) / gold - 1.0).max() < 1e-8
+    for s in states:
+        E.state_free(s.slot)
