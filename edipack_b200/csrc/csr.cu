@@ -29,7 +29,36 @@ k_csr_spmv(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ cols,
     k1 = rowptr[row + 1];
   }
   double ar = 0.0, ai = 0.0;
-  for (int64_t k = k0 + lane; k < k1; k += L) {
+  // four entries of this lane per trip: the (col,val) loads and the four gathers of v are
+  // independent and issue back to back (the row's k-range is short: latency, not bandwidth)
+  constexpr int U = 4;
+  int64_t k = k0 + lane;
+  for (; k + (U - 1) * L < k1; k += U * L) {
+    int32_t c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) c[u] = cols[k + u * L];
+    if (CPLX) {
+      double2 a[U], x[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) a[u] = reinterpret_cast<const double2 *>(vals)[k + u * L];
+#pragma unroll
+      for (int u = 0; u < U; u++) x[u] = reinterpret_cast<const double2 *>(vin)[c[u]];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        ar += a[u].x * x[u].x - a[u].y * x[u].y;
+        ai += a[u].x * x[u].y + a[u].y * x[u].x;
+      }
+    } else {
+      double a[U], x[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) a[u] = vals[k + u * L];
+#pragma unroll
+      for (int u = 0; u < U; u++) x[u] = vin[c[u]];
+#pragma unroll
+      for (int u = 0; u < U; u++) ar += a[u] * x[u];
+    }
+  }
+  for (; k < k1; k += L) {
     const int32_t c = cols[k];
     if (CPLX) {
       const double2 a = reinterpret_cast<const double2 *>(vals)[k];
@@ -112,7 +141,8 @@ int csr_open(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, 
   }
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
   const double avg = nloc ? (double)nnz / (double)nloc : 0.0;
-  C.lanes = avg > 24 ? 32 : (avg > 12 ? 16 : (avg > 6 ? 8 : 4));
+  // ~6-8 entries per lane: enough independent loads per lane, few idle lanes in the last trip
+  C.lanes = avg > 160 ? 32 : (avg > 80 ? 16 : (avg > 20 ? 8 : 4));
   if (E.nranks > 1) {
     // row split of every rank: MpiQ = Dim/P, remainder to the LAST rank
     // (ED_HAMILTONIAN_NONSU2.f90:72-79, ED_HAMILTONIAN_SUPERC.f90:76-88)

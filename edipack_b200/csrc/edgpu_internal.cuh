@@ -125,6 +125,9 @@ struct SpinSpace {
   int nterms = 0;
   uint4 *ell4 = nullptr;
   double *amp2 = nullptr;  // [2*nterms+2]
+  // impurity-impurity hop table for the non-local terms (Norb>1): imphop[(a*Norb+b)*ld + row] =
+  // target row of c^+_a c_b | sign << 31, or -1 when the hop is not allowed on that state
+  int32_t *imphop = nullptr;
   std::vector<Term> terms; // host copy
 };
 

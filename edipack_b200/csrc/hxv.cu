@@ -499,40 +499,48 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
 // All four operators act on impurity bits, so signs depend on impurity bits only.
 // vfull is the full (all-gathered) vector with leading dimension ldv.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double pair_sign(uint32_t m, int a, int b) {
-  int lo = min(a, b), hi = max(a, b);
-  uint32_t between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
-  return (__popc(m & between) & 1) ? -1.0 : 1.0;
-}
-
+// upT / dwT: impurity hop tables of the two species (sector.cu, k_imphop_fill).  The dw entries
+// are uniform over a column (= block): columns on which no term can act exit at once.
 __global__ void __launch_bounds__(128)
 k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nrow, int64_t ldv,
-           int64_t ncol, int64_t col_offset, const int32_t *__restrict__ mapu,
-           const int32_t *__restrict__ mapd, RankView Lu, RankView Ld, int Norb,
-           const double *__restrict__ jx, const double *__restrict__ jp, double s_acc) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+           int64_t col_offset, const int32_t *__restrict__ upT, int64_t ldu,
+           const int32_t *__restrict__ dwT, int64_t ldd, int Norb, const double *__restrict__ jx,
+           const double *__restrict__ jp, double s_acc) {
   const int64_t c = blockIdx.y;
+  const int64_t cg = c + col_offset;
+  __shared__ int any_dw;
+  if (threadIdx.x == 0) {
+    int f = 0;
+    for (int io = 0; io < Norb; io++)
+      for (int jo = 0; jo < Norb; jo++) {
+        if (io == jo) continue;
+        if (jx[io * Norb + jo] != 0.0 && dwT[(int64_t)(jo * Norb + io) * ldd + cg] != -1) f = 1;
+        if (jp[io * Norb + jo] != 0.0 && dwT[(int64_t)(io * Norb + jo) * ldd + cg] != -1) f = 1;
+      }
+    any_dw = f;
+  }
+  __syncthreads();
+  if (!any_dw) return;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nrow) return;
-  const uint32_t mu = (uint32_t)mapu[i], md = (uint32_t)mapd[c + col_offset];
   double acc = 0.0;
   for (int io = 0; io < Norb; io++)
     for (int jo = 0; jo < Norb; jo++) {
       if (io == jo) continue;
-      const uint32_t bi = 1u << io, bj = 1u << jo;
+      const int32_t uu = upT[(int64_t)(io * Norb + jo) * ldu + i];  // up: c^+_io c_jo (both terms)
+      if (uu == -1) continue;
+      // S-E: dw c^+_jo c_io, Jx(io,jo) ; P-H: dw c^+_io c_jo, Jp(io,jo)
       const double x = jx[io * Norb + jo];
-      if (x != 0.0 && (mu & bj) && (md & bi) && !(md & bj) && !(mu & bi)) {
-        // dw: c(iorb), cdg(jorb) ; up: c(jorb), cdg(iorb)
-        const uint32_t md2 = (md & ~bi) | bj, mu2 = (mu & ~bj) | bi;
-        const double sg = pair_sign(md, io, jo) * pair_sign(mu, io, jo);
-        const int64_t iu = rank_of(mu2, Lu), id = rank_of(md2, Ld);
-        acc += x * sg * vfull[id * ldv + iu];
+      const int32_t d1 = dwT[(int64_t)(jo * Norb + io) * ldd + cg];
+      if (x != 0.0 && d1 != -1) {
+        const double sg = ((uu ^ d1) < 0) ? -1.0 : 1.0;
+        acc += x * sg * vfull[(int64_t)(d1 & 0x7FFFFFFF) * ldv + (uu & 0x7FFFFFFF)];
       }
       const double y = jp[io * Norb + jo];
-      if (y != 0.0 && (mu & bj) && (md & bj) && !(md & bi) && !(mu & bi)) {
-        const uint32_t md2 = (md & ~bj) | bi, mu2 = (mu & ~bj) | bi;
-        const double sg = pair_sign(md, io, jo) * pair_sign(mu, io, jo);
-        const int64_t iu = rank_of(mu2, Lu), id = rank_of(md2, Ld);
-        acc += y * sg * vfull[id * ldv + iu];
+      const int32_t d2 = dwT[(int64_t)(io * Norb + jo) * ldd + cg];
+      if (y != 0.0 && d2 != -1) {
+        const double sg = ((uu ^ d2) < 0) ? -1.0 : 1.0;
+        acc += y * sg * vfull[(int64_t)(d2 & 0x7FFFFFFF) * ldv + (uu & 0x7FFFFFFF)];
       }
     }
   if (acc != 0.0) hv[c * ldv + i] += s_acc * acc;
@@ -729,9 +737,8 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
     }
     if (S.nonlocal) {
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      const RankView Lu = rank_view(S.up.lin, S.up.ord), Ld = rank_view(S.dw.lin, S.dw.ord);
-      k_nonlocal<<<grid, 128, 0, st>>>(d_v, d_hv, U.dim, U.ld, S.qdw, 0, S.up.map, S.dw.map, Lu, Ld,
-                                       S.Norb, S.jx, S.jp, s_acc);
+      k_nonlocal<<<grid, 128, 0, st>>>(d_v, d_hv, U.dim, U.ld, 0, S.up.imphop, S.up.ld, S.dw.imphop,
+                                       S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
       EDGPU_COUNT_LAUNCH();
       EDGPU_CUDA(cudaGetLastError());
     }
@@ -790,9 +797,8 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
       }
       EDGPU_TRY(comm_allgatherv(E, d_v, S.vfull, S.gcounts, S.goffs));
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      const RankView Lu = rank_view(S.up.lin, S.up.ord), Ld = rank_view(S.dw.lin, S.dw.ord);
-      k_nonlocal<<<grid, 128, 0, st>>>(S.vfull, d_hv, U.dim, U.ld, S.qdw, S.d0, S.up.map, S.dw.map, Lu,
-                                       Ld, S.Norb, S.jx, S.jp, s_acc);
+      k_nonlocal<<<grid, 128, 0, st>>>(S.vfull, d_hv, U.dim, U.ld, S.d0, S.up.imphop, S.up.ld,
+                                       S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
       EDGPU_COUNT_LAUNCH();
       EDGPU_CUDA(cudaGetLastError());
     }

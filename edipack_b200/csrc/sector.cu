@@ -114,6 +114,26 @@ __device__ __forceinline__ uint32_t hop_sign(uint32_t m, int alpha, int beta) {
   return (uint32_t)(__popc(m & between) & 1);
 }
 
+// c^+_a c_b between impurity orbitals, all ordered pairs: the building block of the S-E / P-H
+// terms (direct/HxV_non_local.f90:23-28, 52-56), tabulated once instead of ranked per product
+__global__ void k_imphop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t ld, int Norb,
+                              RankView R, int32_t *__restrict__ out) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= ld) return;
+  for (int a = 0; a < Norb; a++)
+    for (int b = 0; b < Norb; b++) {
+      int32_t val = -1;
+      if (r < dim && a != b) {
+        const uint32_t m = (uint32_t)map[r];
+        if (((m >> b) & 1u) && !((m >> a) & 1u)) {
+          const uint32_t m2 = (m & ~(1u << b)) | (1u << a);
+          val = (int32_t)((uint32_t)rank_of(m2, R) | (hop_sign(m, a, b) << 31));
+        }
+      }
+      out[(int64_t)(a * Norb + b) * ld + r] = val;
+    }
+}
+
 // per-row counts of local / far allowed terms; far = the term touches a bit >= far_bit[r]
 __global__ void k_hop_count(const int32_t *__restrict__ map, int64_t dim,
                             const Term *__restrict__ terms, int nterms,
@@ -255,6 +275,7 @@ static int free_spin(SpinSpace &S) {
   cudaFree(S.imp);
   cudaFree(S.ell4);
   cudaFree(S.amp2);
+  cudaFree(S.imphop);
   cudaFree(S.d_range_start);
   S = SpinSpace();
   return 0;
@@ -434,6 +455,11 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   EDGPU_CUDA(cudaMemsetAsync(S.refidx, 0, sizeof(int32_t) * S.ld, st));
   k_ref_rank<<<gb, T, 0, st>>>(S.map, S.dim, Ns, S.refidx);
   EDGPU_COUNT_LAUNCH();
+  if (p.Norb > 1) {
+    EDGPU_CUDA(cudaMalloc(&S.imphop, sizeof(int32_t) * (size_t)p.Norb * p.Norb * S.ld));
+    k_imphop_fill<<<gl, T, 0, st>>>(S.map, S.dim, S.ld, p.Norb, rank_view(S.lin, S.ord), S.imphop);
+    EDGPU_COUNT_LAUNCH();
+  }
   // diagonal single-spin energies
   EpsCoef c;
   build_eps_coef(p, s, c);
