@@ -375,7 +375,18 @@ int edgpu_sector_get_hops(int spin, int64_t *rowptr, int32_t *target, double *va
         const uint32_t ent = ell[((size_t)gi * S.ld + r) * 4 + k];
         const uint32_t id = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
         if (id == (uint32_t)(2 * S.nterms)) continue;
-        target[n] = ref[(size_t)(ent & HOP_TGT_MASK)] + 1;
+        int64_t t = (int64_t)(ent & HOP_TGT_MASK);
+        if (S.block_mode && gi < S.Wl4) {  // local entries hold tile offsets of the row's work item
+          const BlockItem *it = nullptr;
+          for (const BlockItem &b : S.items)
+            if (r >= b.out0 && r < b.out1) it = &b;
+          int64_t gr = -1;
+          for (int k = 0; it && k < it->nin; k++)
+            if (t >= it->in_off[k] && t < it->in_off[k] + it->in_len[k]) gr = it->in0[k] + (t - it->in_off[k]);
+          if (gr < 0) return set_error("internal: hop entry outside its work item's tile");
+          t = gr;
+        }
+        target[n] = ref[(size_t)t] + 1;
         value[n] = amp[id];
         n++;
       }

@@ -95,6 +95,38 @@ __device__ __forceinline__ int rank_of(uint32_t m, const RankView &R) {
 #endif
 
 enum SpinRole { ROLE_FAST = 0, ROLE_SLOW = 1 };
+
+// Block mode of the fast role: one CTA work item = the states of one range prefix AND one
+// impurity configuration ("block", contiguous in the internal order).  Every one-body term maps
+// a block onto one other block of the same prefix (its impurity bits flip by a fixed mask), so
+// the CTA stages only the blocks its hops read from: for imp<->bath hops that is the other half
+// of the range (bipartite structure) and the tile is half as large as the range.
+constexpr int BLK_MAXIN = 16;
+struct BlockItem {
+  int32_t out0, out1;         // output rows [out0, out1)
+  int32_t nin;                // number of input blocks
+  int32_t tile_rows;          // sum of in_len
+  int32_t in0[BLK_MAXIN];     // first row of input block k
+  int32_t in_len[BLK_MAXIN];
+  int32_t in_off[BLK_MAXIN];  // its offset inside the tile
+};
+#ifdef __CUDACC__
+// tile offset of global row t for work item `it` (-1: not staged)
+__device__ __forceinline__ int block_tile_offset(const BlockItem &it, int t) {
+  for (int k = 0; k < it.nin; k++) {
+    const int d = t - it.in0[k];
+    if ((unsigned)d < (unsigned)it.in_len[k]) return it.in_off[k] + d;
+  }
+  return -1;
+}
+__device__ __forceinline__ int block_global_row(const BlockItem &it, int off) {
+  for (int k = 0; k < it.nin; k++) {
+    const int d = off - it.in_off[k];
+    if ((unsigned)d < (unsigned)it.in_len[k]) return it.in0[k] + d;
+  }
+  return -1;
+}
+#endif
 constexpr int SLOW_ROWS = 16;  // fast-index rows per CTA of the slow-index kernel (128 B segments)
 
 // One spin species of the open sector
@@ -117,6 +149,12 @@ struct SpinSpace {
   std::vector<int64_t> range_start;  // host, nranges+1
   std::vector<int> range_tbits;      // host, prefix length of each range
   int64_t *d_range_start = nullptr;
+  // block mode (fast role): local entries of the hop table hold TILE OFFSETS of their work item
+  bool block_mode = false;
+  std::vector<BlockItem> items;
+  BlockItem *d_items = nullptr;
+  int32_t *d_item_of_row = nullptr;  // [ld]
+  int64_t max_tile = 0;              // largest tile_rows
   // hop table, ELL in groups of 4 entries: ell4[g*ld + row] (uint4).
   //   fast role: groups [0,Wl4) local, [Wl4, Wl4+Wf4) far; unused slots = padding entries
   //   slow role: one list of Wl4 groups (Wf4 = 0), local entries first, far entries flagged

@@ -35,6 +35,10 @@ struct SpinView {
   const uint8_t *imp;
   const int64_t *range_start;
   int nranges;
+  // block mode (fast role): local entries are tile offsets of the row's work item
+  int block_mode, nitems;
+  const BlockItem *items;
+  const int32_t *item_of_row;
 };
 
 static SpinView view_of(const SpinSpace &S) {
@@ -51,6 +55,10 @@ static SpinView view_of(const SpinSpace &S) {
   v.imp = S.imp;
   v.range_start = S.d_range_start;
   v.nranges = S.nranges;
+  v.block_mode = S.block_mode ? 1 : 0;
+  v.nitems = (int)S.items.size();
+  v.items = S.d_items;
+  v.item_of_row = S.d_item_of_row;
   return v;
 }
 
@@ -101,7 +109,13 @@ k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, i
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const uint32_t ent = ent_of(q, k);
-      acc += F.amp2[(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK] * vc[ent & HOP_TGT_MASK];
+      const uint32_t idx = (ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK;
+      uint32_t t = ent & HOP_TGT_MASK;
+      if (F.block_mode && g < F.Wl4) {  // tile offset -> global row (padding: amplitude 0)
+        if (idx == 2u * (uint32_t)F.nterms) continue;
+        t = (uint32_t)block_global_row(F.items[F.item_of_row[i]], (int)t);
+      }
+      acc += F.amp2[idx] * vc[t];
     }
   }
   if (WITH_SLOW) {
@@ -308,6 +322,194 @@ k_fast(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64
 }
 
 // ---------------------------------------------------------------------------------------
+// pass B in block mode.  CTA = one work item (the rows of one range prefix and one impurity
+// configuration) x 4 columns.  Only the blocks the item's hops read from are staged (for
+// imp<->bath hops: the other half of the range), as two planes tile[row][2] of column pairs, so
+// that one 16-byte shared load serves two columns and per-row metadata (entries, amplitudes,
+// eps) are amortised over 4 columns.  The rows' own values (diagonal term) come from global
+// memory.  grid = (nitems, ceil(ncol / 4)), item index fastest (far gathers hit L2).
+// shared layout: planeA[tile_cap] | planeB[tile_cap] (double2) | xc[4][nimp] | amp[2*nterms+2]
+// ---------------------------------------------------------------------------------------
+constexpr int FASTB_THREADS = 512;
+
+template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
+__global__ void __launch_bounds__(FASTB_THREADS, 2)
+k_fastb(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
+        int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
+        double s_acc, double s_old, int tile_cap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  double2 *pa = reinterpret_cast<double2 *>(smem_raw);
+  double2 *pb = pa + tile_cap;
+  double *xc = reinterpret_cast<double *>(pb + tile_cap);
+  double *amp_s = xc + 4 * nimp;
+  const BlockItem &it = F.items[blockIdx.x];
+  const int out0 = it.out0, out1 = it.out1, nin = it.nin;
+
+  const int64_t c0 = (int64_t)blockIdx.y * 4;
+  const int nc = (int)min((int64_t)4, ncol - c0);  // live columns of this CTA
+  // column k of the CTA lives at element offset ko[k] from the first one (CTA-uniform; missing
+  // columns of the last CTA alias column 0 and are never stored)
+  const double *vb = v + c0 * ldv;
+  double *hb = hv + c0 * ldv;
+  const uint32_t ld32 = (uint32_t)ldv;
+  const uint32_t ko[4] = {0u, nc > 1 ? ld32 : 0u, nc > 2 ? 2u * ld32 : 0u, nc > 3 ? 3u * ld32 : 0u};
+  // stage the input blocks: coalesced 8-byte global loads, contiguous 16-byte shared stores
+  for (int b = 0; b < nin; b++) {
+    const int g0 = it.in0[b], len = it.in_len[b], off = it.in_off[b];
+#pragma unroll 2
+    for (int p = tid; p < len; p += FASTB_THREADS) {
+      const uint32_t g = (uint32_t)(g0 + p);
+      pa[off + p] = make_double2(vb[ko[0] + g], vb[ko[1] + g]);
+      pb[off + p] = make_double2(vb[ko[2] + g], vb[ko[3] + g]);
+    }
+  }
+  if (it.tile_rows == 0 && tid == 0) {  // padding entries read slot 0
+    pa[0] = make_double2(0.0, 0.0);
+    pb[0] = make_double2(0.0, 0.0);
+  }
+  // The rows' own values (diagonal term) and, when accumulating, the old Hv are read from
+  // global memory late in each row iteration; pull their lines into L2 now so that those loads
+  // see L2 latency only (they are not kept in registers across the hop loop).
+  {
+    const int l0 = out0 & ~15, nl = ((out1 + 15) & ~15) - l0;  // whole 128-byte lines
+    for (int p = tid * 16; p < nl; p += FASTB_THREADS * 16) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (WITH_DIAG) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + ko[k] + (uint32_t)(l0 + p)));
+        if (ACCUM) asm volatile("prefetch.global.L2 [%0];" ::"l"(hb + ko[k] + (uint32_t)(l0 + p)));
+      }
+    }
+  }
+  for (int t = tid; t < 2 * F.nterms + 2; t += FASTB_THREADS) amp_s[t] = F.amp2[t];
+  if (WITH_DIAG) {
+    // xc[k][m] = eps_S(c) + X[imp_S(c)][m]
+    for (int t = tid; t < 4 * nimp; t += FASTB_THREADS) {
+      const int k = t / nimp, m = t - k * nimp;
+      const int64_t cg = c0 + (k < nc ? k : 0) + col_offset;
+      xc[t] = S.eps[cg] + xud[(int)S.imp[cg] * nimp + m];
+    }
+  }
+  __syncthreads();
+
+  const uint32_t pa_sa = smem_u32(pa), pb_sa = smem_u32(pb);
+  const uint32_t amp_sa = smem_u32(amp_s), xc_sa = smem_u32(xc);
+  // first far group, entry e of row i at far32[4 * i + e]
+  const uint32_t *far32 = reinterpret_cast<const uint32_t *>(F.ell4 + (int64_t)F.Wl4 * F.ld);
+  constexpr int NG = WL4 > 0 ? WL4 : 1;
+  constexpr int NFE = NFAR > 0 ? NFAR : 1;
+  uint4 nq[NG];
+  uint32_t nqf[NFE];
+  double neu = 0.0;
+  uint32_t nm = 0;
+  int i = out0 + tid;
+  if (i < out1) {
+#pragma unroll
+    for (int g = 0; g < WL4; g++) nq[g] = F.ell4[(int64_t)g * F.ld + i];
+#pragma unroll
+    for (int e = 0; e < NFAR; e++) nqf[e] = far32[4 * (int64_t)i + e];
+    if (WITH_DIAG) {
+      neu = F.eps[i];
+      nm = (uint32_t)F.imp[i];
+    }
+  }
+  for (; i < out1; i += FASTB_THREADS) {
+    uint4 q[NG];
+#pragma unroll
+    for (int g = 0; g < WL4; g++) q[g] = nq[g];
+    uint32_t qf[NFE];
+#pragma unroll
+    for (int e = 0; e < NFAR; e++) qf[e] = nqf[e];
+    const double eu = neu;
+    const uint32_t m = nm;
+    const int inext = i + FASTB_THREADS;
+    if (inext < out1) {
+#pragma unroll
+      for (int g = 0; g < WL4; g++) nq[g] = F.ell4[(int64_t)g * F.ld + inext];
+#pragma unroll
+      for (int e = 0; e < NFAR; e++) nqf[e] = far32[4 * (int64_t)inext + e];
+      if (WITH_DIAG) {
+        neu = F.eps[inext];
+        nm = (uint32_t)F.imp[inext];
+      }
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int g = 0; g < WL4; g++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ent_of(q[g], k);
+        const double a = lds64(amp_sa + amp_off(ent));
+        const uint32_t o = (ent & HOP_TGT_MASK) * 16u;
+        const double2 xa = lds128(pa_sa + o), xb = lds128(pb_sa + o);
+        acc[0] += a * xa.x;
+        acc[1] += a * xa.y;
+        acc[2] += a * xb.x;
+        acc[3] += a * xb.y;
+      }
+    }
+    if (WL4 == 0) {  // dynamic widths
+      for (int g = 0; g < F.Wl4; g++) {
+        const uint4 qq = F.ell4[(int64_t)g * F.ld + i];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t ent = ent_of(qq, k);
+          const double a = lds64(amp_sa + amp_off(ent));
+          const uint32_t o = (ent & HOP_TGT_MASK) * 16u;
+          const double2 xa = lds128(pa_sa + o), xb = lds128(pb_sa + o);
+          acc[0] += a * xa.x;
+          acc[1] += a * xa.y;
+          acc[2] += a * xb.x;
+          acc[3] += a * xb.y;
+        }
+      }
+      for (int g = 0; g < F.Wf4; g++) {
+        const uint4 qq = F.ell4[(int64_t)(F.Wl4 + g) * F.ld + i];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (4 * g + k >= F.Wf) break;  // uniform
+          const uint32_t ent = ent_of(qq, k);
+          const double a = lds64(amp_sa + amp_off(ent));  // padding -> amplitude 0, target = row
+          const uint32_t t = ent & HOP_TGT_MASK;
+#pragma unroll
+          for (int c = 0; c < 4; c++) acc[c] += a * vb[ko[c] + t];
+        }
+      }
+    }
+    // far gathers, own values, old Hv: L2 hits (prefetched above / staged by the sibling items)
+    double own[4], hold[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      own[k] = WITH_DIAG ? vb[ko[k] + (uint32_t)i] : 0.0;
+      hold[k] = ACCUM ? hb[ko[k] + (uint32_t)i] : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < NFAR; e++) {
+      const uint32_t t = qf[e] & HOP_TGT_MASK;  // padding entries point at the row itself
+      const double a = lds64(amp_sa + amp_off(qf[e]));
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[k] += a * vb[ko[k] + t];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      double r = acc[k];
+      if (WITH_DIAG) r += (eu + lds64(xc_sa + ((uint32_t)(k * nimp) + m) * 8u)) * own[k];
+      r *= s_acc;
+      if (ACCUM) r += s_old * hold[k];
+      if (k < nc) hb[ko[k] + (uint32_t)i] = r;
+    }
+  }
+  // the last work item also owns the pad rows [dim, ld): zeros (scaled old value when accumulating)
+  if (blockIdx.x + 1 == gridDim.x) {
+    for (int r = (int)F.dim + tid; r < (int)F.ld; r += FASTB_THREADS) {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k < nc) hb[ko[k] + (uint32_t)r] = ACCUM ? s_old * hb[ko[k] + (uint32_t)r] : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // pass A, "slow index" kernel.  CTA = SLOW_ROWS (16) consecutive fast rows x the slow range
 // [s0, s1), staged as tile[j][16] with cp.async (LDGSTS) 16-byte copies.  A thread owns two rows
 // of one column; the 8 threads of a column read one contiguous 128-byte segment per hop
@@ -373,6 +575,13 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
       src += (int64_t)CSTEP * ldv;
       dst += CSTEP * SLOW_R;
     }
+  }
+  if (ACCUM) {
+    // The Hv values this CTA will read-modify-write come from DRAM; their latency does not fit
+    // the one-iteration software pipeline below.  Pull the CTA's whole Hv footprint (one 128-byte
+    // line per column) into L2 now, while the tile loads: costs no registers.
+    for (int j = tid; j < len; j += SLOW_THREADS)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(hv + (int64_t)(s0 + j) * ldv + i0));
   }
   for (int t = tid; t < 2 * S.nterms + 2; t += SLOW_THREADS) amp_s[t] = S.amp2[t];
   cp_async_wait_all();
@@ -552,6 +761,9 @@ k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nr
 size_t fast_smem_bytes(int64_t max_range, int nterms, int nimp) {
   return sizeof(double) * (2 * (size_t)(max_range + 32) + 2 * (size_t)nimp + 2 * (size_t)nterms + 2);
 }
+size_t fastb_smem_bytes(int64_t max_tile, int nterms, int nimp) {
+  return sizeof(double) * (4 * (size_t)std::max<int64_t>(max_tile, 1) + 4 * (size_t)nimp + 2 * (size_t)nterms + 2);
+}
 size_t slow_smem_bytes(int64_t max_range, int nterms) {
   return sizeof(double) * ((size_t)max_range * SLOW_R + 2 * (size_t)nterms + 2);
 }
@@ -566,6 +778,21 @@ static int launch_fast(Engine &E, const double *v, double *hv, int64_t ldv, int6
   dim3 grid((unsigned)F.nranges, (unsigned)((ncol + 1) / 2));
   kern<<<grid, FAST_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp,
                                                s_acc, s_old);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
+static int launch_fastb(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
+                        int64_t col_offset, const SpinView &F, const SpinView &S, int64_t max_tile,
+                        const double *xud, int nimp, double s_acc, double s_old) {
+  const size_t smem = fastb_smem_bytes(max_tile, F.nterms, nimp);
+  auto kern = k_fastb<WL4, NFAR, WITH_DIAG, ACCUM>;
+  EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)F.nitems, (unsigned)((ncol + 3) / 4));
+  kern<<<grid, FASTB_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp, s_acc,
+                                                s_old, (int)std::max<int64_t>(max_tile, 1));
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
@@ -590,9 +817,11 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
     EDGPU_CUDA(cudaGetLastError());
     return 0;
   }
-#define EDGPU_FAST2(WW, FF, DD, AA) \
-  launch_fast<WW, FF, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_range, xud, nimp, \
-                              s_acc, s_old)
+#define EDGPU_FAST2(WW, FF, DD, AA)                                                               \
+  (Fs.block_mode ? launch_fastb<WW, FF, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_tile, \
+                                                xud, nimp, s_acc, s_old)                           \
+                 : launch_fast<WW, FF, DD, AA>(E, v, hv, F.ld, ncol, col_offset, F, S, Fs.max_range, \
+                                               xud, nimp, s_acc, s_old))
 #define EDGPU_FAST(WW, FF)                                                                  \
   (with_diag ? (accum ? EDGPU_FAST2(WW, FF, true, true) : EDGPU_FAST2(WW, FF, true, false)) \
              : (accum ? EDGPU_FAST2(WW, FF, false, true) : EDGPU_FAST2(WW, FF, false, false)))

@@ -163,7 +163,8 @@ __global__ void k_hop_count(const int32_t *__restrict__ map, int64_t dim,
 __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t ld,
                            const Term *__restrict__ terms, int nterms,
                            const uint8_t *__restrict__ far_bit, int merged, int Wl4, int Wf4,
-                           RankView R, uint32_t *__restrict__ ell) {
+                           RankView R, const BlockItem *__restrict__ items,
+                           const int32_t *__restrict__ item_of_row, uint32_t *__restrict__ ell) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= ld) return;
   // slot s of this row lives at ell[((s/4)*ld + r)*4 + s%4]
@@ -192,18 +193,23 @@ __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t
         if (((m >> b) & 1u) && !((m >> a) & 1u)) {
           uint32_t m2 = (m & ~(1u << b)) | (1u << a);
           uint32_t tgt = (uint32_t)rank_of(m2, R);
+          const bool far = (R.ord.pos[a] >= fb || R.ord.pos[b] >= fb);
+          // block mode: a local target is addressed by its offset in the work item's tile
+          if (items && !far) tgt = (uint32_t)block_tile_offset(items[item_of_row[r]], (int)tgt);
           uint32_t val = tgt | ((uint32_t)(2 * t + hop_sign(m, a, b)) << HOP_AMP_SHIFT);
-          if (R.ord.pos[a] >= fb || R.ord.pos[b] >= fb) put(ef++, val); else put(el++, val);
+          if (far) put(ef++, val); else put(el++, val);
         }
       }
     }
   }
-  // padding slots gather the row itself (always inside the row's own tile) with amplitude 0
-  const uint32_t pad = (uint32_t)r | ((uint32_t)(2 * nterms) << HOP_AMP_SHIFT);
+  // padding slots gather the row itself (always inside the row's own tile; block mode: tile
+  // offset 0) with amplitude 0; far padding points at the row itself
+  const uint32_t padamp = (uint32_t)(2 * nterms) << HOP_AMP_SHIFT;
+  const uint32_t pad = (uint32_t)r | padamp;
   if (merged) {
     for (; el < nslots; el++) put(el, pad);
   } else {
-    for (; el < 4 * Wl4; el++) put(el, pad);
+    for (; el < 4 * Wl4; el++) put(el, items ? padamp : pad);
     for (; ef < nslots; ef++) put(ef, pad);
   }
 }
@@ -277,6 +283,8 @@ static int free_spin(SpinSpace &S) {
   cudaFree(S.amp2);
   cudaFree(S.imphop);
   cudaFree(S.d_range_start);
+  cudaFree(S.d_items);
+  cudaFree(S.d_item_of_row);
   S = SpinSpace();
   return 0;
 }
@@ -347,24 +355,116 @@ static int upload_binom(Engine &E) {
   return 0;
 }
 
-// role and tile capacity (in states) of species s in the current communicator
-static void species_role(Engine &E, const edgpu_normal_params &p, int s, int *role, int64_t *cap,
-                         bool *identity) {
+// Everything that fixes the internal enumeration order and the tiling of one species: role,
+// ranges or blocks, number of range bits T, site order.  Depends on (model, nel, communicator)
+// only, so a sector opened later with the same data gets the same order (apply_op relies on it).
+struct SpeciesPlan {
+  int role = ROLE_FAST;
+  bool identity = false;
+  bool block_mode = false;
+  int T = 0;
+  SiteOrder ord;
+  std::vector<int64_t> range_start;  // nranges+1
+  std::vector<int> range_tbits;
+  std::vector<BlockItem> items;
+  int64_t max_range = 0, max_tile = 0;
+};
+
+static void plan_species(Engine &E, const edgpu_normal_params &p, int s, int nel, SpeciesPlan &P) {
+  const int Ns = p.Ns, No = p.Norb;
   std::vector<Term> terms;
   build_terms(p, s, terms);
-  const size_t per_cta = (E.smem_per_sm - 2 * 1024) / 2;
-  const size_t tables = 8 * (2 * terms.size() + 2 + 2 * ((size_t)1 << p.Norb)) + 64;
+  const size_t per_cta = (E.smem_per_sm - 2 * 1024) / 2;  // 2 CTAs per SM
+  const size_t tables = 8 * (2 * terms.size() + 2 + 4 * ((size_t)1 << No)) + 64;
   const size_t avail = per_cta > tables ? per_cta - tables : 0;
-  // shared-memory tiles at 2 CTAs per SM (hxv.cu): fast role tile[range + 32][2] doubles,
-  // slow role tile[range][SLOW_ROWS] doubles
-  if (s == 1 && E.nranks == 1) {
-    *role = ROLE_SLOW;
-    *cap = std::max<int64_t>((int64_t)(avail / (8 * SLOW_ROWS)), 1);
-  } else {
-    *role = ROLE_FAST;
-    *cap = std::max<int64_t>((int64_t)(avail / 16) - 32, 1);
+  P.identity = (s == 1 && E.nranks > 1);
+  P.role = (s == 1 && E.nranks == 1) ? ROLE_SLOW : ROLE_FAST;
+  P.block_mode = false;
+  P.items.clear();
+  // ---- block mode (fast role, permuted order): tile = input blocks x 4 columns (2 planes of
+  // double2 = 32 B per row)
+  if (P.role == ROLE_FAST && !P.identity && !getenv("EDGPU_NO_BLOCKS")) {
+    const int64_t cap = (int64_t)(avail / 32);
+    for (int T = 0; T <= Ns - No && !P.block_mode; T++) {
+      const SiteOrder ord = make_site_order(Ns, No, T, false);
+      const int R = Ns - No - T;
+      std::vector<int> F;  // distinct impurity flip masks of the local terms
+      for (const Term &t : terms) {
+        if (ord.pos[t.alpha] >= Ns - T || ord.pos[t.beta] >= Ns - T) continue;
+        int f = 0;
+        if (t.alpha < No) f ^= 1 << t.alpha;
+        if (t.beta < No) f ^= 1 << t.beta;
+        if (std::find(F.begin(), F.end(), f) == F.end()) F.push_back(f);
+      }
+      std::sort(F.begin(), F.end());
+      if ((int)F.size() > BLK_MAXIN) break;  // more range bits do not help
+      const int nP = 1 << T, nI = 1 << No;
+      std::vector<int64_t> start((size_t)nP * nI + 1, 0);
+      int64_t pos = 0;
+      for (int pr = 0; pr < nP; pr++)
+        for (int im = 0; im < nI; im++) {
+          start[(size_t)pr * nI + im] = pos;
+          pos += host_binomial(R, nel - __builtin_popcount(pr) - __builtin_popcount(im));
+        }
+      start[(size_t)nP * nI] = pos;
+      std::vector<BlockItem> items;
+      int64_t max_tile = 0;
+      bool ok = true;
+      for (int pr = 0; pr < nP && ok; pr++)
+        for (int im = 0; im < nI && ok; im++) {
+          const size_t b = (size_t)pr * nI + im;
+          if (start[b + 1] == start[b]) continue;
+          BlockItem it;
+          memset(&it, 0, sizeof(it));
+          it.out0 = (int32_t)start[b];
+          it.out1 = (int32_t)start[b + 1];
+          for (int f : F) {
+            const size_t bi = (size_t)pr * nI + (im ^ f);
+            const int64_t len = start[bi + 1] - start[bi];
+            if (len <= 0) continue;
+            it.in0[it.nin] = (int32_t)start[bi];
+            it.in_len[it.nin] = (int32_t)len;
+            it.in_off[it.nin] = it.tile_rows;
+            it.tile_rows += (int32_t)len;
+            it.nin++;
+          }
+          if (it.tile_rows > cap) ok = false;
+          max_tile = std::max<int64_t>(max_tile, it.tile_rows);
+          items.push_back(it);
+        }
+      if (!ok) continue;
+      P.block_mode = true;
+      P.T = T;
+      P.ord = ord;
+      P.items = items;
+      P.max_tile = max_tile;
+      P.range_start.clear();
+      P.range_tbits.clear();
+      for (int pr = 0; pr < nP; pr++) {
+        if (start[(size_t)(pr + 1) * nI] == start[(size_t)pr * nI]) continue;
+        P.range_start.push_back(start[(size_t)pr * nI]);
+        P.range_tbits.push_back(T);
+      }
+      P.range_start.push_back(pos);
+    }
   }
-  *identity = (s == 1 && E.nranks > 1);
+  if (!P.block_mode) {
+    // ---- range mode: fast role tile[range + 32][2] doubles, slow role tile[range][SLOW_ROWS]
+    const int64_t cap = P.role == ROLE_SLOW
+                            ? std::max<int64_t>((int64_t)(avail / (8 * SLOW_ROWS)), 1)
+                            : std::max<int64_t>((int64_t)(avail / 16) - 32, 1);
+    P.range_start.clear();
+    P.range_tbits.clear();
+    int64_t pos = 0;
+    split_ranges(Ns, nel, 0, 0, cap, pos, P.range_start, P.range_tbits);
+    P.range_start.push_back(pos);
+    P.T = 0;
+    for (int t : P.range_tbits) P.T = std::max(P.T, t);
+    P.ord = make_site_order(Ns, No, P.T, P.identity);
+  }
+  P.max_range = 0;
+  for (size_t k = 0; k + 1 < P.range_start.size(); k++)
+    P.max_range = std::max(P.max_range, P.range_start[k + 1] - P.range_start[k]);
 }
 
 // map (original Fock integers in internal order) + ranking tables of one species
@@ -397,17 +497,9 @@ static int build_ranking(Engine &E, int Ns, int nel, const SiteOrder &ord, int64
 
 int species_ranking(Engine &E, const edgpu_normal_params &p, int s, int nel, int32_t **map,
                     LinTable *lin, SiteOrder *ord) {
-  int role;
-  int64_t cap;
-  bool identity;
-  species_role(E, p, s, &role, &cap, &identity);
-  std::vector<int64_t> start;
-  std::vector<int> tbits;
-  int64_t pos = 0;
-  split_ranges(p.Ns, nel, 0, 0, cap, pos, start, tbits);
-  int T = 0;
-  for (int t : tbits) T = std::max(T, t);
-  *ord = make_site_order(p.Ns, p.Norb, T, identity);
+  SpeciesPlan P;
+  plan_species(E, p, s, nel, P);
+  *ord = P.ord;
   EDGPU_TRY(upload_binom(E));
   const int64_t dim = host_binomial(p.Ns, nel);
   return build_ranking(E, p.Ns, nel, *ord, dim, (dim + 15) / 16 * 16, map, lin);
@@ -416,10 +508,9 @@ int species_ranking(Engine &E, const edgpu_normal_params &p, int s, int nel, int
 static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, SpinSpace &S) {
   const int Ns = p.Ns;
   cudaStream_t st = E.stream;
-  int role;
-  int64_t cap;
-  bool identity;
-  species_role(E, p, s, &role, &cap, &identity);
+  SpeciesPlan P;
+  plan_species(E, p, s, nel, P);
+  const int role = P.role;
   S.nel = nel;
   S.role = role;
   S.dim = host_binomial(Ns, nel);
@@ -427,28 +518,34 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   if (S.dim > (int64_t)HOP_TGT_MASK) return set_error("sector species dimension %lld too large", (long long)S.dim);
   const int T = 256;
   const unsigned gb = (unsigned)((S.dim + T - 1) / T), gl = (unsigned)((S.ld + T - 1) / T);
-  // ranges (they depend on (Ns, nel, cap) only) -> number of range bits -> site order
+  // ranges / blocks -> per-row far bit (permuted positions >= far_bit are prefix bits)
   std::vector<uint8_t> far_bit((size_t)S.ld, (uint8_t)Ns);
-  {
-    S.range_start.clear();
-    S.range_tbits.clear();
-    int64_t pos = 0;
-    split_ranges(Ns, nel, 0, 0, cap, pos, S.range_start, S.range_tbits);
-    S.range_start.push_back(pos);
-    S.nranges = (int)S.range_start.size() - 1;
-    if (pos != S.dim) return set_error("internal: range partition mismatch");
-    S.max_range = 0;
-    int Tmax = 0;
-    for (int k = 0; k < S.nranges; k++) {
-      S.max_range = std::max(S.max_range, S.range_start[k + 1] - S.range_start[k]);
-      Tmax = std::max(Tmax, S.range_tbits[k]);
-      for (int64_t r = S.range_start[k]; r < S.range_start[k + 1]; r++)
-        far_bit[(size_t)r] = (uint8_t)(Ns - S.range_tbits[k]);
-    }
-    S.ord = make_site_order(Ns, p.Norb, Tmax, identity);
-    EDGPU_CUDA(cudaMalloc(&S.d_range_start, sizeof(int64_t) * S.range_start.size()));
-    EDGPU_CUDA(cudaMemcpyAsync(S.d_range_start, S.range_start.data(),
-                               sizeof(int64_t) * S.range_start.size(), cudaMemcpyHostToDevice, st));
+  S.range_start = P.range_start;
+  S.range_tbits = P.range_tbits;
+  S.nranges = (int)S.range_start.size() - 1;
+  if (S.range_start.back() != S.dim) return set_error("internal: range partition mismatch");
+  S.max_range = P.max_range;
+  for (int k = 0; k < S.nranges; k++)
+    for (int64_t r = S.range_start[k]; r < S.range_start[k + 1]; r++)
+      far_bit[(size_t)r] = (uint8_t)(Ns - S.range_tbits[k]);
+  S.ord = P.ord;
+  EDGPU_CUDA(cudaMalloc(&S.d_range_start, sizeof(int64_t) * S.range_start.size()));
+  EDGPU_CUDA(cudaMemcpyAsync(S.d_range_start, S.range_start.data(),
+                             sizeof(int64_t) * S.range_start.size(), cudaMemcpyHostToDevice, st));
+  S.block_mode = P.block_mode;
+  S.items = P.items;
+  S.max_tile = P.max_tile;
+  if (S.block_mode) {
+    std::vector<int32_t> ior((size_t)S.ld, 0);
+    for (size_t k = 0; k < S.items.size(); k++)
+      for (int32_t r = S.items[k].out0; r < S.items[k].out1; r++) ior[(size_t)r] = (int32_t)k;
+    EDGPU_CUDA(cudaMalloc(&S.d_items, sizeof(BlockItem) * S.items.size()));
+    EDGPU_CUDA(cudaMalloc(&S.d_item_of_row, sizeof(int32_t) * S.ld));
+    EDGPU_CUDA(cudaMemcpyAsync(S.d_items, S.items.data(), sizeof(BlockItem) * S.items.size(),
+                               cudaMemcpyHostToDevice, st));
+    EDGPU_CUDA(cudaMemcpyAsync(S.d_item_of_row, ior.data(), sizeof(int32_t) * S.ld,
+                               cudaMemcpyHostToDevice, st));
+    EDGPU_CUDA(cudaStreamSynchronize(st));  // ior goes out of scope
   }
   EDGPU_TRY(build_ranking(E, Ns, nel, S.ord, S.dim, S.ld, &S.map, &S.lin));
   EDGPU_CUDA(cudaMalloc(&S.refidx, sizeof(int32_t) * S.ld));
@@ -502,7 +599,8 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   const int G = std::max(S.Wl4 + S.Wf4, 1);
   EDGPU_CUDA(cudaMalloc(&S.ell4, sizeof(uint4) * (size_t)G * S.ld));
   k_hop_fill<<<gl, T, 0, st>>>(S.map, S.dim, S.ld, d_terms, S.nterms, d_far, merged, S.Wl4, S.Wf4,
-                               rank_view(S.lin, S.ord), (uint32_t *)S.ell4);
+                               rank_view(S.lin, S.ord), S.d_items, S.d_item_of_row,
+                               (uint32_t *)S.ell4);
   EDGPU_COUNT_LAUNCH();
   std::vector<double> amp(2 * S.nterms + 2, 0.0);
   for (int t = 0; t < S.nterms; t++) {
