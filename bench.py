@@ -39,6 +39,15 @@ def model_kwargs(ns: int):
     return dict(Norb=1, Nbath=ns - 1, Uloc=(2.0,), hfmode=True, xmu=0.0)
 
 
+def workload(ns: int, world: int = 1) -> dict:
+    """`config` of both arms: BASELINE config 2 (or --ns): the half-filled sector of the
+    single-band Anderson impurity with Nbath = ns-1, direct (on-the-fly) H x v."""
+    dim = math.comb(ns, ns // 2) ** 2
+    return {"workload": f"cfg2: Norb=1 Nbath={ns - 1} (Ns={ns}) half-filled sector "
+                        f"({dim} states), direct HxV, dw-sharded over {world} GPU(s)",
+            "ns": ns, "dim": dim, "vector_gb": 8 * dim / 1e9}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -160,9 +169,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg2: Norb=1 Nbath={ns - 1} (Ns={ns}) half-filled sector, "
-                               "direct HxV (ED_SPARSE_H=F), reference MPI algorithm on host cores",
-                   "ns": ns},
+        "config": dict(workload(ns, max(args.gpus, 1)),
+                       arm="reference CPU algorithm (directMatVec_MPI_normal_main port) on the host cores"),
         "cpu_baseline": {"value": value, "unit": "Hxv/s", "cores": cores, "kind": "port",
                          "sample": desc},
         "e2e": {"value": value, "unit": "Hxv/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -267,7 +275,7 @@ def run_ours(args):
     peak, peak_kind = peaks()
     stage = [float(ms3[k]) / max(nrec.value, 1) for k in range(3)]  # ms per launch
     if world == 1:
-        names = ["k_fast(diag+up hops)", "k_slow(dw hops)", "k_nonlocal"]
+        names = ["k_fastb(diag+up hops)", "k_slow(dw hops)", "k_nonlocal"]
     else:
         names = ["k_fast(diag+up hops) overlapped with transpose(v)+k_fast(dw hops on v^T)",
                  "join of the communication stream", "transpose(Hv^T)+accumulate"]
@@ -283,7 +291,7 @@ def run_ours(args):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         if tj.get("ns") == ns and world == 1:
-            traffic = tj["kernels"][("k_fast", "k_slow")[dom]]["dram_bytes_per_launch"]
+            traffic = tj["kernels"][("k_fastb", "k_slow")[dom]]["dram_bytes_per_launch"]
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -357,12 +365,11 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"cfg2: Norb=1 Nbath={ns - 1} (Ns={ns}) half-filled sector "
-                                   f"({dim} states), direct HxV, dw-sharded over {world} GPU(s)",
-                       "ns": ns, "dim": dim, "vector_gb": 8 * dim / 1e9,
-                       "l2_policy": "inputs larger than L2 (1.3 GB vector per HxV)",
-                       "kernel_variant": args.variant or 2,
-                       "kernels": "two tiled passes: k_fast (up range x 2 columns) + k_slow (16 rows x dw range)"},
+            "config": dict(workload(ns, world),
+                           l2_policy=f"inputs larger than L2 ({8 * nloc / 1e9:.2f} GB local vector per HxV)",
+                           kernel_variant=args.variant or 2,
+                           kernels="two tiled passes: k_fastb (up block x 4 columns) + "
+                                   "k_slow (16 rows x dw range)"),
             "roofline": roofline, "hxv_roofline": hxv_roofline, "kernels": kernels,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "lanczos_gs": lanczos,

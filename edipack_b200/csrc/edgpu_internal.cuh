@@ -293,10 +293,6 @@ int scalar_to_host(Engine &E, double *d_scalar, double *h_out);  // all-reduce +
 int vec_zero(Engine &E, double *d_v, int64_t n);
 int vec_dot(Engine &E, const double *a, const double *b, double *h_out);  // all-reduced
 int vec_scale(Engine &E, double *a, double s);
-// (a,b) <- (b/beta, -beta*a)
-int vec_swap_scale(Engine &E, double *a, double *b, double beta);
-// w += t ; alpha = <v,w>
-int vec_add_dot(Engine &E, double *w, const double *t, const double *v, double *h_alpha);
 // w -= alpha v ; beta2 = <w,w>
 int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2);
 int vec_axpy(Engine &E, double *y, const double *x, double a);

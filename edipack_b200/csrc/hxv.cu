@@ -14,12 +14,13 @@
 // Two-pass structure (DESIGN.md "Why two passes"): a tile that is closed under the up hops is a
 // set of full columns, a tile closed under the dw hops is a set of full rows; no 227 KB tile is
 // closed under both, so
-//   pass A  k_slow : CTA = 16 rows x one dw range  (all dw hops of the range from shared memory)
-//   pass B  k_fast : CTA = one up range x 2 columns (diagonal + all up hops from shared memory)
-// A "range" is a maximal run of sector states sharing their top `tbits` bits (contiguous in
-// the ascending map); hops that leave the range ("far", they move an electron into / out of
-// the top bits) are read from global memory (L2: the sibling ranges of the same rows / columns
-// are scheduled next to each other).
+//   pass B  k_fastb / k_fast : diagonal + all up hops; CTA = one work item of the up species x
+//                              4 (block mode) or 2 (range mode) columns, gathers from shared memory
+//   pass A  k_slow           : all dw hops; CTA = 16 rows x one dw range, accumulates onto pass B
+// A "range" is a maximal run of sector states sharing a prefix of top (permuted) bits; a "block"
+// is the part of a range with one impurity configuration (sector.cu).  Hops that leave the
+// range ("far", they move an electron into / out of the prefix bits) are read from global
+// memory (L2: sibling ranges of the same rows / columns are scheduled next to each other).
 #include "edgpu_internal.cuh"
 
 namespace edgpu {

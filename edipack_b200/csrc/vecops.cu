@@ -62,16 +62,6 @@ __global__ void __launch_bounds__(VT) k_scale(double2 *__restrict__ a, int64_t n
   }
 }
 
-// (a,b) <- (b/beta, -beta*a)
-__global__ void __launch_bounds__(VT) k_swap_scale(double2 *__restrict__ a, double2 *__restrict__ b,
-                                                   int64_t n2, double inv_beta, double mbeta) {
-  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
-    double2 x = a[i], y = b[i];
-    a[i] = make_double2(y.x * inv_beta, y.y * inv_beta);
-    b[i] = make_double2(mbeta * x.x, mbeta * x.y);
-  }
-}
-
 // w -= alpha*v ; partial of <w,w>
 __global__ void __launch_bounds__(VT) k_axpy_norm(double2 *__restrict__ w,
                                                   const double2 *__restrict__ v, int64_t n2,
@@ -222,15 +212,6 @@ int vec_scale(Engine &E, double *a, double s) {
   return 0;
 }
 
-int vec_swap_scale(Engine &E, double *a, double *b, double beta) {
-  const int64_t n2 = E.veclen() / 2;
-  k_swap_scale<<<grid_for(E, n2), VT, 0, E.stream>>>((double2 *)a, (double2 *)b, n2, 1.0 / beta,
-                                                     -beta);
-  EDGPU_COUNT_LAUNCH();
-  EDGPU_CUDA(cudaGetLastError());
-  return 0;
-}
-
 int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2) {
   const int64_t n2 = E.veclen() / 2;
   int gb = grid_for(E, n2);
@@ -245,11 +226,6 @@ int vec_axpy(Engine &E, double *y, const double *x, double a) {
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
-}
-
-int vec_add_dot(Engine &E, double *w, const double *t, const double *v, double *h_alpha) {
-  EDGPU_TRY(vec_axpy(E, w, t, 1.0));
-  return vec_dot(E, v, w, h_alpha);
 }
 
 }  // namespace edgpu
