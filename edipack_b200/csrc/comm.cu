@@ -252,8 +252,20 @@ int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int6
 struct PeerTable {
   double *ptr[EDGPU_MAXRANKS];
   int32_t row0[EDGPU_MAXRANKS + 1];  // rows [row0[p], row0[p+1]) of the fast index belong to rank p
-  int nranks;
+  int nranks, me;
 };
+
+// blockIdx.y -> (peer, first row of a 32-row tile of that peer's rows).  Consecutive y rotate over
+// the peers, starting at a different peer on every rank: at any instant each GPU exchanges with a
+// different partner (the all-to-all schedule) instead of all of them hammering the same NVLink
+// endpoint.  Returns false for the padding tiles of peers with fewer rows.
+__device__ __forceinline__ bool peer_tile(const PeerTable &T, int y, int *peer, int *ib) {
+  const int p = (y % T.nranks + T.me) % T.nranks;
+  const int r = T.row0[p] + (y / T.nranks) * 32;
+  *peer = p;
+  *ib = r;
+  return r < T.row0[p + 1];
+}
 
 __device__ __forceinline__ int owner_of(const PeerTable &T, int i) {
   int p = 0;
@@ -267,47 +279,51 @@ __device__ __forceinline__ int owner_of(const PeerTable &T, int i) {
 // 256-byte pieces.  (Row tiles fastest makes every remote segment land on another 2 MB page of a
 // multi-GB peer buffer: measured 200 ms instead of ~5 ms per transpose at Ns=18 on 8 GPUs.)
 __global__ void __launch_bounds__(256)
-k_push_transpose(const double *__restrict__ a, int64_t lda, int nrow, int qcol, int64_t c_off,
-                 int64_t ldb, PeerTable T) {
+k_push_transpose(const double *__restrict__ a, int64_t lda, int qcol, int64_t c_off, int64_t ldb,
+                 PeerTable T) {
   __shared__ double t[32][33];
-  const int ib = blockIdx.y * 32, jb = blockIdx.x * 32;
+  int p, ib;
+  if (!peer_tile(T, blockIdx.y, &p, &ib)) return;
+  const int iend = T.row0[p + 1];
+  const int jb = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
     const int i = ib + tx, j = jb + ty + k;
-    if (i < nrow && j < qcol) t[ty + k][tx] = a[(int64_t)j * lda + i];
+    if (i < iend && j < qcol) t[ty + k][tx] = a[(int64_t)j * lda + i];
   }
   __syncthreads();
+  double *dst = T.ptr[p] + c_off;
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
     const int j = jb + tx, i = ib + ty + k;  // the 32 lanes write 32 consecutive columns of row i
-    if (i < nrow && j < qcol) {
-      const int p = owner_of(T, i);
-      T.ptr[p][(int64_t)(i - T.row0[p]) * ldb + c_off + j] = t[tx][ty + k];
-    }
+    if (i < iend && j < qcol) dst[(int64_t)(i - T.row0[p]) * ldb + j] = t[tx][ty + k];
   }
-  __threadfence_system();
+  // one system-scope fence per CTA (cumulative over the CTA's stores through the barrier)
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
 }
 
 __global__ void __launch_bounds__(256)
-k_pull_transpose_acc(double *__restrict__ hv, int64_t lda, int nrow, int qcol, int64_t c_off,
-                     int64_t ldb, PeerTable T) {
+k_pull_transpose_acc(double *__restrict__ hv, int64_t lda, int qcol, int64_t c_off, int64_t ldb,
+                     PeerTable T) {
   __shared__ double t[32][33];
-  const int ib = blockIdx.y * 32, jb = blockIdx.x * 32;
+  int p, ib;
+  if (!peer_tile(T, blockIdx.y, &p, &ib)) return;
+  const int iend = T.row0[p + 1];
+  const int jb = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const double *src = T.ptr[p] + c_off;
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
     const int j = jb + tx, i = ib + ty + k;
-    if (i < nrow && j < qcol) {
-      const int p = owner_of(T, i);
-      t[ty + k][tx] = T.ptr[p][(int64_t)(i - T.row0[p]) * ldb + c_off + j];
-    }
+    if (i < iend && j < qcol) t[ty + k][tx] = src[(int64_t)(i - T.row0[p]) * ldb + j];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
     const int i = ib + tx, j = jb + ty + k;
-    if (i < nrow && j < qcol) hv[(int64_t)j * lda + i] += t[tx][ty + k];
+    if (i < iend && j < qcol) hv[(int64_t)j * lda + i] += t[tx][ty + k];
   }
 }
 
@@ -322,6 +338,7 @@ static PeerTable peer_table(Engine &E, double *const *ptrs) {
   PeerTable T;
   memset(&T, 0, sizeof(T));
   T.nranks = E.nranks;
+  T.me = E.rank;
   for (int p = 0; p < E.nranks; p++) {
     int64_t q, r0;
     block_split(E.sec.up.dim, E.nranks, p, &q, &r0);
@@ -330,6 +347,13 @@ static PeerTable peer_table(Engine &E, double *const *ptrs) {
     T.row0[p + 1] = (int32_t)(r0 + q);
   }
   return T;
+}
+
+// 32-row tiles of the rank with the most rows of the fast index
+static int peer_row_tiles(Engine &E) {
+  int64_t q, r0;
+  block_split(E.sec.up.dim, E.nranks, 0, &q, &r0);  // rank 0 has the longest share
+  return (int)((q + 31) / 32);
 }
 
 int comm_p2p_setup(Engine &E) {
@@ -411,8 +435,8 @@ int comm_p2p_teardown(Engine &E) {
 int comm_push_transpose(Engine &E, const double *d_a) {
   Sector &S = E.sec;
   const PeerTable T = peer_table(E, S.peer_vt);
-  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)((S.up.dim + 31) / 32));
-  k_push_transpose<<<grid, 256, 0, E.stream>>>(d_a, S.up.ld, (int)S.up.dim, (int)S.qdw, S.d0, S.dw.ld, T);
+  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)(E.nranks * peer_row_tiles(E)));
+  k_push_transpose<<<grid, 256, 0, E.stream>>>(d_a, S.up.ld, (int)S.qdw, S.d0, S.dw.ld, T);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
@@ -421,9 +445,8 @@ int comm_push_transpose(Engine &E, const double *d_a) {
 int comm_pull_transpose_acc(Engine &E, double *d_hv) {
   Sector &S = E.sec;
   const PeerTable T = peer_table(E, S.peer_hvt);
-  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)((S.up.dim + 31) / 32));
-  k_pull_transpose_acc<<<grid, 256, 0, E.stream>>>(d_hv, S.up.ld, (int)S.up.dim, (int)S.qdw, S.d0,
-                                                   S.dw.ld, T);
+  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)(E.nranks * peer_row_tiles(E)));
+  k_pull_transpose_acc<<<grid, 256, 0, E.stream>>>(d_hv, S.up.ld, (int)S.qdw, S.d0, S.dw.ld, T);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
