@@ -596,8 +596,6 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
   if (S.Ns != st.Ns || S.up.nel != tnup || S.dw.nel != tndw)
     return set_error("open sector (%d,%d) is not the target sector (%d,%d) of the operator",
                      S.up.nel, S.dw.nel, tnup, tndw);
-  if (g.nranks > 1 && spin == 1)
-    return set_error("apply_op on the dw species with nranks>1 is not implemented yet");
   // enumeration order + ranking tables of the operated species in the SOURCE sector
   const int nel_src = spin == 0 ? st.nup : st.ndw;
   int32_t *map = nullptr;
@@ -607,13 +605,31 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
   const int64_t n = S.padded_len();
   EDGPU_TRY(ensure_buf(&g_seed, &g_seed_len, n));
   EDGPU_CUDA(cudaMemsetAsync(g_seed, 0, sizeof(double) * n, g.stream));
+  // An operator on the dw species moves amplitude between dw columns, which live on different
+  // ranks in the source and in the target sector (their DimDw differ): gather the stored state
+  // first, like the reference does before apply_op (es_return_dvec, ED_EIGENSPACE.f90:723-793).
+  const double *vsrc = st.vec;
+  double *vfull = nullptr;
+  if (g.nranks > 1 && spin == 1) {
+    std::vector<int64_t> counts(g.nranks), offs(g.nranks);
+    for (int p = 0; p < g.nranks; p++) {
+      int64_t q, d0;
+      block_split(st.dimd, g.nranks, p, &q, &d0);
+      counts[p] = q * st.ldu;
+      offs[p] = d0 * st.ldu;
+    }
+    EDGPU_CUDA(cudaMalloc(&vfull, sizeof(double) * (size_t)st.dimd * (size_t)st.ldu));
+    EDGPU_TRY(comm_allgatherv(g, st.vec, vfull, counts, offs));
+    vsrc = vfull;
+  }
   dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
-  k_apply_op<<<grid, 128, 0, g.stream>>>(st.vec, st.ldu, g_seed, S.up.ld, S.up.dim, S.qdw,
+  k_apply_op<<<grid, 128, 0, g.stream>>>(vsrc, st.ldu, g_seed, S.up.ld, S.up.dim, S.qdw,
                                          spin == 0 ? S.up.map : S.dw.map + S.d0, op, iorb, spin,
                                          rank_view(lin, ord));
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+  cudaFree(vfull);
   cudaFree(map);
   cudaFree(lin.ja);
   cudaFree(lin.jb);

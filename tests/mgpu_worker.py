@@ -77,6 +77,44 @@ def main():
                     failures.append(f"{name}: |gs|^2 = {float(n2loc.item())}")
         finally:
             E.delete_Hv_sector_normal()
+    # Green's-function seeds on the sharded state: c / c^+ of both spins applied to the resident
+    # ground state, read back through norm2 and alpha_1 of the tridiagonalisation
+    # (apply_op_C/CDG, ED_SECTOR.f90:465/654; the dw operators need the gathered state)
+    kw = normal_normal_kwargs()
+    m, mo = E.EDModel(**kw), O.Model(**kw)
+    nup, ndw = 3, 3
+    du, dd = O.sector_dims(m.Ns, nup, ndw)
+    if dd >= world and du >= world:
+        H = O.dense_H(mo, nup, ndw)
+        ev, U = np.linalg.eigh(H)
+        gs = U[:, 0]
+        lo, hi = E.chunk_bounds(du, dd, world, rank)
+        E.build_Hv_sector_normal(m, nup, ndw)
+        try:
+            e, vec, nit = E.sp_lanc_eigh(1, 1e-14, vect=gs[lo:hi].copy())  # current state := gs
+            E.state_store(5)
+        finally:
+            E.delete_Hv_sector_normal()
+        for spin in (0, 1):
+            for iorb in range(m.Norb):
+                for op in (+1, -1):
+                    ref, jn = O.apply_op(mo, op, iorb, spin, nup, ndw, gs)
+                    tdu, tdd = O.sector_dims(m.Ns, jn[0], jn[1])
+                    if tdd < world or tdu < world:
+                        continue
+                    E.build_Hv_sector_normal(m, jn[0], jn[1])
+                    try:
+                        E.apply_op(5, op, iorb, spin)
+                        a, b, nused, n2 = E.sp_lanc_tridiag(None, 1)
+                    finally:
+                        E.delete_Hv_sector_normal()
+                    if abs(n2 - ref @ ref) > 1e-12:
+                        failures.append(f"apply_op spin={spin} orb={iorb} op={op}: norm2 {n2} vs {ref @ ref}")
+                    elif n2 > 0:
+                        hv = O.direct_hxv(mo, jn[0], jn[1], ref)
+                        if abs(a[0] - (ref @ hv) / n2) > 1e-10:
+                            failures.append(f"apply_op spin={spin} orb={iorb} op={op}: alpha1 mismatch")
+        E.state_free(5)
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
     for f in failures:
