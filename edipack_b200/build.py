@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "sector.cu", "hxv.cu", "csr.cu", "vecops.cu", "lanczos.cu", "comm.cu"]
+SOURCES = ["abi.cu", "sector.cu", "hxv.cu", "csr.cu", "vecops.cu", "lanczos.cu", "eigs.cu", "comm.cu"]
 LIB = os.path.join(HERE, "libedgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -28,7 +28,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    hdrs = [os.path.join(CSRC, "edgpu_internal.cuh"),
+    hdrs = [os.path.join(CSRC, "edgpu_internal.cuh"), os.path.join(CSRC, "trlan.hpp"),
             os.path.join(HERE, "..", "include", "edgpu.h")]
     objs = []
     procs = []

@@ -1,4 +1,5 @@
 // extern "C" entry points declared in include/edgpu.h.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -29,6 +30,8 @@ int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, do
                         double *alanc, double *blanc, int *nused);
 int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
                    uint64_t seed, double *egs, double *d_vect, int *niter);
+int eigh_dev(Engine &E, int neigen, int nblock, int nitermax, double tol, uint64_t seed, double *evals,
+             double *resid, std::vector<double *> *vecs, int *nconv, int *nmatvec);
 
 // A state kept on the device (ED_EIGENSPACE state_list entry)
 struct StoredState {
@@ -41,6 +44,11 @@ static double *g_current = nullptr;   // last ground-state vector (device, padde
 static int64_t g_current_len = 0;
 static double *g_seed = nullptr;      // device-resident GF seed for the open sector
 static int64_t g_seed_len = 0;
+static std::vector<double *> g_eigvecs;  // eigenvectors of the last edgpu_eigh (open sector)
+static void free_eigvecs() {
+  for (double *p : g_eigvecs) cudaFree(p);
+  g_eigvecs.clear();
+}
 
 static int ensure_buf(double **p, int64_t *len, int64_t need) {
   if (*p && *len >= need) return 0;
@@ -237,6 +245,7 @@ int edgpu_finalize(void) {
   csr_close(g);
   for (auto &kv : g_states) cudaFree(kv.second.vec);
   g_states.clear();
+  free_eigvecs();
   cudaFree(g_current);
   g_current = nullptr;
   g_current_len = 0;
@@ -279,6 +288,7 @@ int edgpu_sector_open_normal(const edgpu_normal_params *p, int nup, int ndw) {
 }
 int edgpu_sector_close(void) {
   clear_error();
+  free_eigvecs();
   csr_close(g);
   return sector_close(g);
 }
@@ -550,10 +560,8 @@ int edgpu_lanczos_tridiag(const double *seed_host, int nlanc, double threshold, 
   return rc;
 }
 
-int edgpu_state_store(int slot) {
-  clear_error();
-  if (!g.sec.open) return set_error("no sector open");
-  if (!g_current) return set_error("no current state (run edgpu_lanczos_gs first)");
+// es_add_state (ED_EIGENSPACE.f90): keeps a copy of the device vector `src` of the open sector
+static int store_state_from(const double *src, int slot) {
   edgpu_state_free(slot);
   StoredState st;
   Sector &S = g.sec;
@@ -567,10 +575,44 @@ int edgpu_state_store(int slot) {
   st.d0 = S.d0;
   const int64_t n = S.padded_len();
   EDGPU_CUDA(cudaMalloc(&st.vec, sizeof(double) * n));
-  EDGPU_CUDA(cudaMemcpyAsync(st.vec, g_current, sizeof(double) * n, cudaMemcpyDeviceToDevice, g.stream));
+  EDGPU_CUDA(cudaMemcpyAsync(st.vec, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, g.stream));
   EDGPU_CUDA(cudaStreamSynchronize(g.stream));
   g_states[slot] = st;
   return 0;
+}
+
+int edgpu_state_store(int slot) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  if (!g_current) return set_error("no current state (run edgpu_lanczos_gs first)");
+  return store_state_from(g_current, slot);
+}
+
+int edgpu_eigh(int neigen, int nblock, int nitermax, double tol, uint64_t seed, double *evals,
+               double *evecs_host, int *nconv, int *nmatvec) {
+  clear_error();
+  if (!any_open()) return set_error("no sector open");
+  if (!evals) return set_error("edgpu_eigh: evals is NULL");
+  free_eigvecs();
+  std::vector<double> resid((size_t)std::max(neigen, 1));
+  int nc = 0, nm = 0;
+  EDGPU_TRY(eigh_dev(g, neigen, nblock, nitermax, tol, seed, evals, resid.data(), &g_eigvecs, &nc, &nm));
+  if (nconv) *nconv = nc;
+  if (nmatvec) *nmatvec = nm;
+  if (evecs_host) {
+    const int64_t nloc = edgpu_sector_vecdim() * ((g.csr.open && g.csr.cplx) ? 2 : 1);
+    for (size_t i = 0; i < g_eigvecs.size(); i++)
+      EDGPU_TRY(download(g, evecs_host + (int64_t)i * nloc, g_eigvecs[i]));
+  }
+  return 0;
+}
+
+int edgpu_eigh_state_store(int k, int slot) {
+  clear_error();
+  if (!g.sec.open) return set_error("no sector open");
+  if (k < 0 || k >= (int)g_eigvecs.size())
+    return set_error("eigenvector %d not available (last edgpu_eigh kept %d)", k, (int)g_eigvecs.size());
+  return store_state_from(g_eigvecs[k], slot);
 }
 
 int edgpu_state_free(int slot) {

@@ -12,6 +12,7 @@ vecDim_Hv_sector_normal        :func:`vecDim_Hv_sector_normal`  :286
 spHtimesV_p(Nloc,v,Hv)         :func:`spHtimesV_p`              ED_VARS_GLOBAL.f90:111-120,196
 sp_lanc_eigh                   :func:`sp_lanc_eigh`             call site ED_DIAG_NORMAL.f90:206
 sp_lanc_tridiag                :func:`sp_lanc_tridiag`          ED_HAMILTONIAN_NORMAL.f90:360
+sp_eigh (ARPACK)               :func:`sp_eigh`                  call site ED_DIAG_NORMAL.f90:179
 tridiag_Hv_sector_normal       :func:`tridiag_Hv_sector_normal` :321
 ed_diag_d                      :func:`ed_diag_d`                ED_DIAG_NORMAL.f90:76
 lanc_build_gf_normal_diag      :func:`lanc_build_gf_normal_diag` ED_GF_NORMAL.f90:131
@@ -67,6 +68,13 @@ class EDModel:
     lanc_tolerance: float = 1e-12      # LANC_TOLERANCE (reference default 1e-18)
     lanc_dim_threshold: int = 1024     # LANC_DIM_THRESHOLD
     gs_threshold: float = 1e-9         # GS_THRESHOLD
+    lanc_method: str = "arpack"        # LANC_METHOD: "arpack" (default) | "lanczos"
+    lanc_ncv_factor: int = 10          # LANC_NCV_FACTOR
+    lanc_ncv_add: int = 0              # LANC_NCV_ADD
+    ed_finite_temp: bool = False       # ED_FINITE_TEMP
+    lanc_nstates_sector: int = 2       # LANC_NSTATES_SECTOR
+    lanc_nstates_total: int = 2        # LANC_NSTATES_TOTAL
+    cutoff: float = 1e-9               # CUTOFF (spectrum cut-off exp(-beta(E-Egs)) at finite T)
     _params: NormalParams | None = field(default=None, repr=False)
 
     @property
@@ -389,6 +397,30 @@ def sp_lanc_tridiag(vin, nlanc: int, threshold: float = 1e-12):
     return a, b, nused.value, n2.value
 
 
+def sp_eigh(neigen: int, nblock: int, nitermax: int, tol: float = 0.0, seed: int = 4321,
+            want_vectors: bool = True):
+    """sp_eigh(MatVec, eval(Neigen), evec(Nloc,Neigen), Nblock, Nitermax, tol=): the `neigen`
+    lowest eigenpairs of the open sector (thick-restart Lanczos on the device in place of
+    (P-)ARPACK).  Returns (evals[neigen], evecs[Nloc, neigen] or None, nconv, nmatvec); the
+    eigenvectors also stay on the device, see :func:`eigh_state_store`."""
+    L = _abi.load()
+    n = vecDim_Hv_sector_normal()
+    dim = int(L.edgpu_sector_dim())
+    neigen = max(1, min(neigen, dim))
+    dt = np.complex128 if _open_is_complex else np.float64
+    ev = np.zeros(neigen)
+    vec = np.zeros((neigen, n), dt) if want_vectors else None
+    nconv, nmv = C.c_int(), C.c_int()
+    check(L.edgpu_eigh(neigen, nblock, nitermax, tol, seed, ptr(ev),
+                       ptr(vec) if vec is not None else None, C.byref(nconv), C.byref(nmv)))
+    return ev, (vec.T if vec is not None else None), nconv.value, nmv.value
+
+
+def eigh_state_store(k: int, slot: int):
+    """es_add_state of eigenvector `k` (0-based) of the last :func:`sp_eigh` (device copy)."""
+    check(_abi.load().edgpu_eigh_state_store(k, slot))
+
+
 def tridiag_Hv_sector_normal(model: EDModel, nup: int, ndw: int, vvinit, nlanc=None):
     """ED_HAMILTONIAN_NORMAL.f90:321-369: norm2, normalise, build sector, tridiagonalise, delete."""
     build_Hv_sector_normal(model, nup, ndw)
@@ -432,52 +464,101 @@ class EState:
 
 
 def ed_diag_d(model: EDModel, sectors=None):
-    """Sector loop of ``ed_diag_d`` (ED_DIAG_NORMAL.f90:76-296) with LANC_METHOD=lanczos for
-    every sector: plain Lanczos ground state per sector on the device, T=0 state list with the
-    gs_threshold rule (:262-278).  Ground-state vectors stay in HBM (state slots)."""
+    """Sector loop of ``ed_diag_d`` (ED_DIAG_NORMAL.f90:76-296).  Per sector: Neigen / Nblock /
+    Nitermax as at :119-128, then ``sp_eigh`` (LANC_METHOD=arpack, the default) or
+    ``sp_lanc_eigh`` (LANC_METHOD=lanczos) on the device.  State list: T=0 keeps the states within
+    ``gs_threshold`` of the minimum (:267-277); ``ed_finite_temp`` keeps the ``lanc_nstates_total``
+    lowest ones (es_add_state(size=), ED_EIGENSPACE.f90:265-274) and trims those below ``cutoff``
+    (ed_post_diag :489-501).  Eigenvectors never leave HBM (state slots).  Returns the list sorted
+    by energy."""
     Ns = model.Ns
     if sectors is None:
         sectors = [(nu, nd) for nu in range(Ns + 1) for nd in range(Ns + 1)]
+    finiteT = model.ed_finite_temp
+    nst_sector, nst_total = model.lanc_nstates_sector, model.lanc_nstates_total
+    if finiteT:  # ED_SETUP.f90:279-287
+        nst_sector += nst_sector % 2
+        nst_total += nst_total % 2
     states: list[EState] = []
     oldzero = 1000.0
     next_slot = 0
+
+    def drop(st):
+        state_free(st.slot)
+        states.remove(st)
+
     for nup, ndw in sectors:
         dim = binomial(Ns, nup) * binomial(Ns, ndw)
+        nitermax = min(dim, model.lanc_niter)
+        if model.lanc_method == "lanczos":
+            neigen, nblock = 1, 1
+        else:
+            neigen = min(dim, nst_sector)  # neigen_sector, ED_SETUP.f90:554
+            nblock = min(dim, model.lanc_ncv_factor * max(neigen, nst_sector) + model.lanc_ncv_add)
         build_Hv_sector_normal(model, nup, ndw)
         try:
-            e0, _, _ = sp_lanc_eigh(min(dim, model.lanc_niter), model.lanc_tolerance,
-                                    want_vector=False)
-            if e0 < oldzero - 10.0 * model.gs_threshold:
-                oldzero = e0
-                for s in states:
-                    state_free(s.slot)
-                states = []
-                keep = True
-            elif abs(e0 - oldzero) <= model.gs_threshold:
-                oldzero = min(oldzero, e0)
-                keep = True
+            if model.lanc_method == "lanczos":
+                e0, _, _ = sp_lanc_eigh(nitermax, model.lanc_tolerance, want_vector=False)
+                evals = [e0]
             else:
-                keep = False
-            if keep:
-                state_store(next_slot)
-                states.append(EState(e0, nup, ndw, next_slot))
+                ev, _, _, _ = sp_eigh(neigen, nblock, nitermax, model.lanc_tolerance,
+                                      want_vectors=False)
+                evals = list(ev)
+            for i, e in enumerate(evals):
+                if finiteT:
+                    if len(states) >= nst_total:
+                        worst = max(states, key=lambda s: s.e)
+                        if e >= worst.e:
+                            continue
+                        drop(worst)  # es_pop_state
+                elif e < oldzero - 10.0 * model.gs_threshold:
+                    oldzero = e
+                    for st in list(states):
+                        drop(st)
+                elif abs(e - oldzero) <= model.gs_threshold:
+                    oldzero = min(oldzero, e)
+                else:
+                    continue
+                if model.lanc_method == "lanczos":
+                    state_store(next_slot)
+                else:
+                    eigh_state_store(i, next_slot)
+                states.append(EState(float(e), nup, ndw, next_slot))
                 next_slot += 1
         finally:
             delete_Hv_sector_normal()
+    states.sort(key=lambda s: s.e)
+    if finiteT and states:
+        egs = states[0].e
+        while len(states) > 1 and math.exp(-model.beta * (states[-1].e - egs)) <= model.cutoff:
+            drop(states[-1])
     return states
 
 
+def boltzmann_weights(model: EDModel, states):
+    """Weights of the state list: 1/zeta at T=0 (zeta = number of kept states,
+    ED_DIAG_NORMAL.f90:405-414), exp(-beta (E_i - E_gs)) / zeta at finite temperature."""
+    if not states:
+        return []
+    if not model.ed_finite_temp:
+        return [1.0 / len(states)] * len(states)
+    egs = min(s.e for s in states)
+    w = [math.exp(-model.beta * (s.e - egs)) for s in states]
+    z = sum(w)
+    return [x / z for x in w]
+
+
 def observables_normal(model: EDModel, states):
-    """dens/docc of ED_OBSERVABLES_NORMAL.f90:150-215 at T=0."""
+    """dens/docc of ED_OBSERVABLES_NORMAL.f90:150-215 (Boltzmann-weighted over the state list)."""
     dens, docc = np.zeros(model.Norb), np.zeros(model.Norb)
-    for st in states:
+    for st, w in zip(states, boltzmann_weights(model, states)):
         build_Hv_sector_normal(model, st.nup, st.ndw)
         try:
             d, o = state_observables(st.slot, model.Norb)
         finally:
             delete_Hv_sector_normal()
-        dens += d / len(states)
-        docc += o / len(states)
+        dens += d * w
+        docc += o * w
     return dens, docc
 
 
@@ -494,9 +575,8 @@ def lanc_build_gf_normal_diag(model: EDModel, states, iorb: int, ispin: int = 0)
     """ED_GF_NORMAL.f90:131-177 + add_to_lanczos_gf_normal :363-427: list of (weight, pole).
     Seeds c^+|gs>, c|gs> are built on the device from the resident ground states."""
     out = []
-    zeta = len(states)
     Ns = model.Ns
-    for st in states:
+    for st, peso in zip(states, boltzmann_weights(model, states)):
         for op, isign in ((+1, 1), (-1, -1)):
             jn = (st.nup + (op if ispin == 0 else 0), st.ndw + (op if ispin == 1 else 0))
             if min(jn) < 0 or max(jn) > Ns:
@@ -512,5 +592,5 @@ def lanc_build_gf_normal_diag(model: EDModel, states, iorb: int, ispin: int = 0)
                 continue
             ev, Z = tridiag_eigh(a[:nused], b[1:nused])
             for j in range(nused):
-                out.append((norm2 / zeta * Z[0, j] ** 2, isign * (ev[j] - st.e)))
+                out.append((norm2 * peso * Z[0, j] ** 2, isign * (ev[j] - st.e)))
     return out

@@ -153,6 +153,21 @@ int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, 
 int edgpu_lanczos_tridiag(const double *seed_host, int nlanc, double threshold, double *alanc,
                           double *blanc, int *nused, double *norm2);
 
+/* sp_eigh([MpiComm,]MatVec,eval(Neigen),evec(Nloc,Neigen),Nblock,Nitermax,tol=) as called at
+ * ED_DIAG_NORMAL.f90:179-192 (LANC_METHOD=arpack, the reference's default; ED_DIAG_NONSU2.f90:179,
+ * ED_DIAG_SUPERC.f90:161 for complex sectors): the `neigen` lowest eigenpairs of the open sector.
+ * ARPACK (dsaupd/dseupd 'SA', znaupd 'SR') is replaced by a thick-restart Lanczos process with a
+ * fully re-orthogonalised basis of `nblock` (= ARPACK's ncv, <= 128) vectors resident in HBM;
+ * `nitermax` bounds the restarts, `tol` is ARPACK's tolerance on the Ritz estimates
+ * (|beta y_last| <= tol*max(eps^(2/3),|theta|), floored at machine precision).
+ * evals[neigen] ascending; evecs_host = NULL or neigen consecutive local chunks (real: Nloc
+ * doubles each, complex: Nloc (re,im) pairs), orthonormal.  The eigenvectors also stay on the
+ * device until the sector is closed: edgpu_eigh_state_store(k, slot) keeps eigenvector k
+ * (0-based) as state `slot` (es_add_state, ED_DIAG_NORMAL.f90:262-278). */
+int edgpu_eigh(int neigen, int nblock, int nitermax, double tol, uint64_t seed, double *evals,
+               double *evecs_host, int *nconv, int *nmatvec);
+int edgpu_eigh_state_store(int k, int slot);
+
 /* ---------------- state hand-off (ED_EIGENSPACE es_add_state / es_return_dvec) --------- */
 
 /* Keeps the last edgpu_lanczos_gs eigenvector on the device as state `slot` together with

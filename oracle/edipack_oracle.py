@@ -515,15 +515,48 @@ def diagonalize(model: Model, use_lanczos_above: int | None = None, hxv_kind="st
     return states
 
 
-def observables(model: Model, states):
-    """dens / docc of ED_OBSERVABLES_NORMAL.f90:150-215 at T=0 (peso = 1/zeta)."""
+def diagonalize_finite_t(model: Model, beta: float, nstates_sector: int, nstates_total: int,
+                         cutoff: float):
+    """ed_diag_d with ed_finite_temp=T (ED_DIAG_NORMAL.f90:262-266): every sector contributes its
+    Neigen = min(dim, lanc_nstates_sector) lowest eigenpairs (dense LAPACK branch, :222-250), the
+    list keeps the lanc_nstates_total lowest states (es_add_state with size=,
+    ED_EIGENSPACE.f90:265-274; both counts rounded up to even, ED_SETUP.f90:279-287), then
+    ed_post_diag trims the states with exp(-beta (E-Egs)) <= cutoff (:489-501).
+    Returns (states sorted by energy, Boltzmann weights exp(-beta(E-Egs))/zeta, :405-411)."""
+    Ns = model.Ns
+    nstates_sector += nstates_sector % 2
+    nstates_total += nstates_total % 2
+    states: list[GState] = []
+    for isector in range(1, (Ns + 1) ** 2 + 1):
+        nup, ndw = sector_qn(Ns, isector)
+        ev, evec = np.linalg.eigh(dense_H(model, nup, ndw))
+        for i in range(min(len(ev), nstates_sector)):
+            e = float(ev[i])
+            if len(states) >= nstates_total:
+                worst = max(range(len(states)), key=lambda k: states[k].e)
+                if e >= states[worst].e:
+                    continue
+                states.pop(worst)
+            states.append(GState(e, nup, ndw, evec[:, i].copy()))
+    states.sort(key=lambda s: s.e)
+    egs = states[0].e
+    while len(states) > 1 and math.exp(-beta * (states[-1].e - egs)) <= cutoff:
+        states.pop()
+    w = np.array([math.exp(-beta * (s.e - egs)) for s in states])
+    return states, w / w.sum()
+
+
+def observables(model: Model, states, weights=None):
+    """dens / docc of ED_OBSERVABLES_NORMAL.f90:150-215: peso = 1/zeta at T=0, the Boltzmann
+    weights of diagonalize_finite_t otherwise."""
     Ns, No = model.Ns, model.Norb
     dens = np.zeros(No)
     docc = np.zeros(No)
-    zeta = len(states)
-    for st in states:
+    if weights is None:
+        weights = [1.0 / len(states)] * len(states)
+    for st, peso in zip(states, weights):
         mu, md = build_map(Ns, st.nup), build_map(Ns, st.ndw)
-        w = (st.vec ** 2).reshape(len(md), len(mu)) / zeta  # [idw, iup]
+        w = (st.vec ** 2).reshape(len(md), len(mu)) * peso  # [idw, iup]
         for a in range(No):
             nu = ((mu >> a) & 1).astype(float)[None, :]
             nd = ((md >> a) & 1).astype(float)[:, None]
@@ -532,13 +565,15 @@ def observables(model: Model, states):
     return dens, docc
 
 
-def gf_poles_weights(model: Model, states, iorb: int, spin: int = 0, hxv_kind="direct"):
+def gf_poles_weights(model: Model, states, iorb: int, spin: int = 0, hxv_kind="direct",
+                     weights=None):
     """lanc_build_gf_normal_diag + add_to_lanczos_gf_normal (ED_GF_NORMAL.f90:131-177,
-    363-427): list of (weight, pole)."""
+    363-427): list of (weight, pole); peso = exp(-beta(Ei-Egs))/zeta at finite T (:385-389)."""
     fn = stored_hxv if hxv_kind == "stored" else direct_hxv
-    zeta = len(states)
+    if weights is None:
+        weights = [1.0 / len(states)] * len(states)
     out = []
-    for st in states:
+    for st, peso in zip(states, weights):
         for op, isign in ((+1, 1), (-1, -1)):
             seed, jn = apply_op(model, op, iorb, spin, st.nup, st.ndw, st.vec)
             if seed is None:
@@ -551,7 +586,7 @@ def gf_poles_weights(model: Model, states, iorb: int, spin: int = 0, hxv_kind="d
             a, b, nused = lanc_tridiag(lambda x: fn(model, jn[0], jn[1], x), seed, nlanc)
             ev, Z = tridiag_eigh(a[:nused], b[1:nused])
             for j in range(nused):
-                out.append((norm2 / zeta * Z[0, j] ** 2, isign * (ev[j] - st.e)))
+                out.append((norm2 * peso * Z[0, j] ** 2, isign * (ev[j] - st.e)))
     return out
 
 

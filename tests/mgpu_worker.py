@@ -75,6 +75,16 @@ def main():
                 dist.all_reduce(n2loc)
                 if abs(float(n2loc.item()) - 1.0) > 1e-10:
                     failures.append(f"{name}: |gs|^2 = {float(n2loc.item())}")
+            if du * dd <= 5000:
+                # sp_eigh (thick-restart Lanczos, all-reduced projection coefficients) on the shards
+                ref_ev = np.linalg.eigvalsh(O.dense_H(mo, nup, ndw))[:3]
+                ev, vecs, nconv, nmv = E.sp_eigh(3, 24, 300, 1e-14)
+                if nconv < 3 or np.abs(ev - ref_ev).max() > 1e-10:
+                    failures.append(f"{name}: sp_eigh {ev} vs {ref_ev} (nconv {nconv})")
+                g = torch.tensor(vecs.T @ vecs, dtype=torch.float64, device="cuda")
+                dist.all_reduce(g)
+                if np.abs(g.cpu().numpy() - np.eye(3)).max() > 1e-10:
+                    failures.append(f"{name}: sp_eigh vectors not orthonormal across ranks")
         finally:
             E.delete_Hv_sector_normal()
     # Green's-function seeds on the sharded state: c / c^+ of both spins applied to the resident

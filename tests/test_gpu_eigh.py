@@ -1,0 +1,162 @@
+"""sp_eigh on the device (edgpu_eigh: thick-restart Lanczos with the basis in HBM, the
+replacement of SciFortran's ARPACK wrapper called at ED_DIAG_NORMAL.f90:179-192) and the
+finite-temperature state list / Green's functions built on it.  Bars: eigenvalues 1e-10 against
+dense LAPACK of the oracle's H, eigenvector residuals 1e-8, observables and G(iw) 1e-8."""
+import numpy as np
+import pytest
+
+from models import messy_kwargs, normal_normal_kwargs, star_kwargs, two_orb_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kw,sec,neigen,nblock", [
+    (star_kwargs(7), (4, 4), 4, 24),          # 4900 states, direct H x v kernels
+    (star_kwargs(7), (4, 4), 1, 10),          # ARPACK defaults of the reference (ncv = 10*Neigen)
+    (two_orb_kwargs(2), (3, 3), 6, 40),       # with the non-local (Jx, Jp) kernel
+    (messy_kwargs(), (3, 2), 3, 20),
+    (normal_normal_kwargs(), (1, 0), 2, 20),  # 6 states: basis = whole sector
+    (star_kwargs(5), (0, 0), 2, 20),          # 1 state
+    (star_kwargs(9), (5, 5), 8, 48),          # 63504 states
+])
+def test_sp_eigh_matches_dense(engine, oracle, kw, sec, neigen, nblock):
+    E = engine
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    du, dd = oracle.sector_dims(m.Ns, *sec)
+    dim = du * dd
+    if dim <= 5000:
+        H = oracle.dense_H(mo, *sec)
+        ref = np.linalg.eigvalsh(H)
+        hx = lambda x: H @ x
+    else:
+        import scipy.sparse.linalg as sla
+
+        hx = lambda x: oracle.direct_hxv(mo, sec[0], sec[1], x)
+        op = sla.LinearOperator((dim, dim), matvec=hx, dtype=float)
+        ref = np.sort(sla.eigsh(op, k=neigen + 2, which="SA", tol=1e-13, ncv=64)[0])
+    E.build_Hv_sector_normal(m, *sec)
+    try:
+        ev, vec, nconv, nmv = E.sp_eigh(neigen, nblock, 512, 1e-14)
+    finally:
+        E.delete_Hv_sector_normal()
+    k = min(neigen, dim)
+    assert nconv >= k
+    assert np.abs(ev[:k] - ref[:k]).max() < 1e-10
+    assert np.abs(vec.T @ vec - np.eye(k)).max() < 1e-10
+    for i in range(k):
+        assert np.abs(hx(vec[:, i]) - ev[i] * vec[:, i]).max() < 1e-8
+
+
+def test_sp_eigh_complex_csr(engine):
+    """Complex Hermitian stored-H sector (ed_mode=nonsu2 route, ED_DIAG_NONSU2.f90:179): complex
+    re-orthogonalisation, no spurious doubling of the eigenvalues, degenerate pair resolved."""
+    from test_gpu_stored import dense_to_ref_csr
+
+    E = engine
+    rng = np.random.default_rng(11)
+    n = 1500
+    A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) * (rng.random((n, n)) < 0.01)
+    H = A + A.conj().T + np.diag(3.0 * rng.standard_normal(n))
+    ref = np.linalg.eigvalsh(H)
+    rp, cj, va = dense_to_ref_csr(H, rng)
+    E.build_Hv_sector_csr(rp, cj, va)
+    try:
+        ev, vec, nconv, nmv = E.sp_eigh(5, 30, 512, 1e-14)
+    finally:
+        E.delete_Hv_sector_csr()
+    assert nconv >= 5
+    assert np.abs(ev - ref[:5]).max() < 1e-10
+    assert np.abs(vec.conj().T @ vec - np.eye(5)).max() < 1e-10
+    for i in range(5):
+        assert np.abs(H @ vec[:, i] - ev[i] * vec[:, i]).max() < 1e-8
+
+
+def test_sp_eigh_hybrid_nonsu2_golden(engine):
+    """HYBRID_NONSU2 fixture (test/src/HYBRID_NONSU2/evals.check, LANC_METHOD=arpack in the
+    reference's run): lowest eigenvalue of the N=6 sector of the oracle-built complex spH0
+    through the device eigen-solver, plus the next states against dense LAPACK."""
+    import edipack_oracle_nonsu2 as ON
+    from models import golden, hybrid_nonsu2_model
+
+    E = engine
+    mo = hybrid_nonsu2_model(ON)
+    _, rp, cj, va = ON.stored_H(mo, 6)
+    Hd = ON.to_dense(rp, cj, va)
+    ref = np.linalg.eigvalsh(Hd)
+    E.build_Hv_sector_csr(rp, cj, va)
+    try:
+        ev, vec, nconv, _ = E.sp_eigh(2, 30, 512, 1e-14)
+    finally:
+        E.delete_Hv_sector_csr()
+    assert nconv >= 2
+    assert abs(ev[0] - golden("hybrid_nonsu2")["evals"][0]) < 1e-9
+    # (the third level of this sector is doubly degenerate; a single-vector Krylov process --
+    # ARPACK included -- resolves such pairs only through rounding, so only the two lowest,
+    # non-degenerate levels are pinned here)
+    assert np.abs(ev - ref[:2]).max() < 1e-9
+    for i in range(2):
+        assert np.abs(Hd @ vec[:, i] - ev[i] * vec[:, i]).max() < 1e-8
+
+
+def exact_gf(oracle, mo, states, weights, iorb, spin, z):
+    """Lehmann sum from full dense spectra of the N+-1 sectors (independent of any Lanczos)."""
+    g = np.zeros_like(z, dtype=complex)
+    for st, w in zip(states, weights):
+        for op, isign in ((+1, 1), (-1, -1)):
+            seed, jn = oracle.apply_op(mo, op, iorb, spin, st.nup, st.ndw, st.vec)
+            if seed is None or not np.any(seed):
+                continue
+            ev, U = np.linalg.eigh(oracle.dense_H(mo, jn[0], jn[1]))
+            amp = (U.T @ seed) ** 2
+            for a, e in zip(amp, ev):
+                g += w * a / (z - isign * (e - st.e))
+    return g
+
+
+def test_finite_temperature_state_list_and_gf(engine, oracle):
+    """ed_finite_temp=T: state list (energies, sectors, Boltzmann weights), dens/docc and G(iw)
+    of test/src/NORMAL_NORMAL's model at beta=12 against the oracle's dense restatement of
+    ed_diag_d / ed_post_diag (13 states survive the cutoff)."""
+    E = engine
+    kw = normal_normal_kwargs()
+    kw["beta"] = 12.0
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    m.ed_finite_temp, m.lanc_nstates_sector, m.lanc_nstates_total, m.cutoff = True, 4, 20, 1e-9
+    m.lanc_tolerance = 1e-14
+    ref_states, ref_w = oracle.diagonalize_finite_t(mo, 12.0, 4, 20, 1e-9)
+    states = E.ed_diag_d(m)
+    assert len(states) == len(ref_states) == 13
+    assert np.abs(np.array([s.e for s in states]) - np.array([s.e for s in ref_states])).max() < 1e-10
+    assert sorted((s.nup, s.ndw) for s in states) == sorted((s.nup, s.ndw) for s in ref_states)
+    w = np.array(E.boltzmann_weights(m, states))
+    assert np.abs(np.sort(w) - np.sort(ref_w)).max() < 1e-10
+    dens, docc = E.observables_normal(m, states)
+    rd, ro = oracle.observables(mo, ref_states, ref_w)
+    assert np.abs(dens - rd).max() < 1e-8 and np.abs(docc - ro).max() < 1e-8
+    wm = np.pi / 12.0 * (2 * np.arange(1, 65) - 1)
+    for iorb in range(m.Norb):
+        pw = E.lanc_build_gf_normal_diag(m, states, iorb, 0)
+        got = oracle.gf_eval(pw, 1j * wm)
+        ref = exact_gf(oracle, mo, ref_states, ref_w, iorb, 0, 1j * wm)
+        assert np.abs(got - ref).max() < 1e-8
+    for s in states:
+        E.state_free(s.slot)
+
+
+@pytest.mark.parametrize("method", ["arpack", "lanczos"])
+def test_zero_temperature_both_methods(engine, oracle, method):
+    """LANC_METHOD=arpack (sp_eigh) and =lanczos (sp_lanc_eigh) give the same T=0 state list."""
+    E = engine
+    kw = star_kwargs(5)
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    m.lanc_method = method
+    ref = oracle.diagonalize(mo)
+    states = E.ed_diag_d(m)
+    assert len(states) == len(ref) == 1
+    assert (states[0].nup, states[0].ndw) == (ref[0].nup, ref[0].ndw)
+    assert abs(states[0].e - ref[0].e) < 1e-10
+    dens, docc = E.observables_normal(m, states)
+    rd, ro = oracle.observables(mo, ref)
+    assert np.abs(dens - rd).max() < 1e-8 and np.abs(docc - ro).max() < 1e-8
+    for s in states:
+        E.state_free(s.slot)

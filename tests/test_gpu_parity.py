@@ -203,8 +203,10 @@ def test_lanczos_ground_state(engine, oracle, name, sec):
     assert np.abs(H @ v - e * v).max() < 1e-6
 
 
-def test_golden_normal_normal_end_to_end(engine, oracle):
-    """The reference's own fixture through the GPU path: sector scan with device Lanczos,
+@pytest.mark.parametrize("method", ["arpack", "lanczos"])
+def test_golden_normal_normal_end_to_end(engine, oracle, method):
+    """The reference's own fixture through the GPU path: sector scan with the device eigen-solver
+    (LANC_METHOD=arpack -> sp_eigh, the reference's default, or =lanczos -> sp_lanc_eigh),
     device-resident ground state, device seeds c/c^+, device tridiagonalisation ->
     evals / dens / docc (1e-9) and Sigma(iw) moments (1e-8), test/src/NORMAL_NORMAL/*.check."""
     E = engine
@@ -212,6 +214,7 @@ def test_golden_normal_normal_end_to_end(engine, oracle):
     kw = normal_normal_kwargs()
     m = E.EDModel(**kw)
     m.lanc_tolerance = 1e-18  # the reference's LANC_TOLERANCE default (ED_INPUT_VARS.f90:726)
+    m.lanc_method = method
     mo = oracle.Model(**kw)
     states = E.ed_diag_d(m)
     assert len(states) == 1 and (states[0].nup, states[0].ndw) == (3, 3)
