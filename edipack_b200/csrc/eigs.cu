@@ -184,7 +184,12 @@ struct DeviceOps {
     nblk = (int)std::max<int64_t>(1, std::min(want, cap));
     EDGPU_TRY(ensure_partials(E, (int64_t)(2 * EIG_LD + 2) * nblk));
     V.assign(nslots, nullptr);
-    for (auto &p : V) EDGPU_CUDA(cudaMalloc(&p, sizeof(double) * n));
+    for (auto &p : V) {
+      EDGPU_CUDA(cudaMalloc(&p, sizeof(double) * n));
+      // the pad entries of a vector must be exactly zero and stay so: the stored-H product does not
+      // write them, every other kernel maps zero pads to zero pads
+      EDGPU_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * n, E.stream));
+    }
     EDGPU_CUDA(cudaMalloc(&d_coef, sizeof(double) * (2 * EIG_LD + 2)));
     EDGPU_CUDA(cudaMemsetAsync(d_coef, 0, sizeof(double) * (2 * EIG_LD + 2), E.stream));
     EDGPU_CUDA(cudaMallocHost(&h_coef, sizeof(double) * (2 * EIG_LD + 2)));

@@ -71,6 +71,27 @@ def test_sp_eigh_complex_csr(engine):
         assert np.abs(H @ vec[:, i] - ev[i] * vec[:, i]).max() < 1e-8
 
 
+def test_sp_eigh_real_csr(engine, oracle):
+    """Real stored-H sector (ED_SPARSE_H=T) whose length is not a multiple of the 16-double pad."""
+    from test_gpu_stored import dense_to_ref_csr
+
+    E = engine
+    kw = messy_kwargs()
+    mo = oracle.Model(**kw)
+    H = oracle.dense_H(mo, 3, 2)
+    assert H.shape[0] % 16 != 0
+    rp, cj, va = dense_to_ref_csr(H, np.random.default_rng(5))
+    ref = np.linalg.eigvalsh(H)
+    E.build_Hv_sector_csr(rp, cj, va)
+    try:
+        ev, vec, nconv, _ = E.sp_eigh(3, 20, 512, 1e-14)
+    finally:
+        E.delete_Hv_sector_csr()
+    assert nconv >= 3 and np.abs(ev - ref[:3]).max() < 1e-10
+    for i in range(3):
+        assert np.abs(H @ vec[:, i] - ev[i] * vec[:, i]).max() < 1e-8
+
+
 def test_sp_eigh_hybrid_nonsu2_golden(engine):
     """HYBRID_NONSU2 fixture (test/src/HYBRID_NONSU2/evals.check, LANC_METHOD=arpack in the
     reference's run): lowest eigenvalue of the N=6 sector of the oracle-built complex spH0
@@ -150,6 +171,7 @@ def test_zero_temperature_both_methods(engine, oracle, method):
     kw = star_kwargs(5)
     m, mo = E.EDModel(**kw), oracle.Model(**kw)
     m.lanc_method = method
+    m.lanc_tolerance = 1e-18  # the reference's LANC_TOLERANCE default (ED_INPUT_VARS.f90:726)
     ref = oracle.diagonalize(mo)
     states = E.ed_diag_d(m)
     assert len(states) == len(ref) == 1
