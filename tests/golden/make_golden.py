@@ -30,8 +30,11 @@ def main():
     checks = {"NORMAL_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
               "HYBRID_NONSU2": ("evals", "dens", "docc", "energy", "doubles", "imp", "magX",
                                 "Sigma11_momenta", "Sigma12_momenta"),
-              "INEQ_NORMAL_NORMAL": ("dens", "docc", "energy", "doubles", "Sigma_momenta")}
-    for name in ("NORMAL_NORMAL", "HYBRID_NONSU2", "INEQ_NORMAL_NORMAL"):
+              "INEQ_NORMAL_NORMAL": ("dens", "docc", "energy", "doubles", "Sigma_momenta"),
+              "HYBRID_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
+              "REPLICA_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
+              "GENERAL_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta")}
+    for name in checks:
         d = os.path.join(REF, name)
         g = {"source": f"test/src/{name}", "inputs": inputs(os.path.join(d, "inputED.in"))}
         for chk in checks[name]:

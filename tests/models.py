@@ -139,3 +139,41 @@ def ineq_site_kwargs(ilat: int):
     return dict(Norb=1, Nbath=nbath, Nspin=2, bath_type=g["BATH_TYPE"], Uloc=(_f(g["ULOC"]),),
                 xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T", beta=_f(g["BETA"]),
                 ed_hw_bath=hw, hloc=np.full((2, 1, 1), sign), bath_e=bath_e, bath_v=bath_v)
+
+
+def hybrid_normal_kwargs():
+    """test/src/HYBRID_NORMAL: Norb=2, hybrid bath of 4 shared levels (default init_dmft_bath),
+    Hloc = Delta*sigma_z(orbital) (ed_hybrid_normal.f90:57-63)."""
+    g = golden("hybrid_normal")["inputs"]
+    norb = int(g["NORB"])
+    delta = _f(g["DELTA"])
+    hloc = np.zeros((2, norb, norb))
+    for s in range(2):
+        hloc[s] = np.diag([delta, -delta])
+    return dict(Norb=norb, Nbath=int(g["NBATH"]), Nspin=int(g["NSPIN"]), bath_type="hybrid",
+                Uloc=tuple(_f(x) for x in g["ULOC"].split(",")), Ust=_f(g["UST"]), Jh=_f(g["JH"]),
+                Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
+                beta=_f(g["BETA"]), ed_hw_bath=_f(g["ED_HW_BATH"]), hloc=hloc)
+
+
+def replica_normal_kwargs(kind="replica"):
+    """test/src/REPLICA_NORMAL and GENERAL_NORMAL: Norb=2, Nbath=2 replicas with
+    H_k = lambda_k1 * 1 + 0.1 * tau_x, lambda_k1 = -1 + 2(k-1)/(Nbath-1)
+    (ed_replica_normal.f90:71-86; the offsets of init_dmft_bath do not apply: the lambdas of the
+    diagonal symmetry differ, ED_BATH_DMFT.f90:268-276), V = max(0.1, 1/sqrt(Nbath)) (:251-257)."""
+    g = golden(f"{kind}_normal")["inputs"]
+    norb, nb = int(g["NORB"]), int(g["NBATH"])
+    delta = _f(g["DELTA"])
+    hloc = np.zeros((2, norb, norb))
+    for s in range(2):
+        hloc[s] = np.diag([delta, -delta])
+    hb = np.zeros((2, norb, norb, nb))
+    for k in range(nb):
+        lam = -1.0 + 2.0 * k / (nb - 1)
+        for s in range(2):
+            hb[s, :, :, k] = lam * np.eye(norb) + 0.1 * (np.ones((norb, norb)) - np.eye(norb))
+    return dict(Norb=norb, Nbath=nb, Nspin=int(g["NSPIN"]), bath_type=kind,
+                Uloc=tuple(_f(x) for x in g["ULOC"].split(",")), Ust=_f(g["UST"]), Jh=_f(g["JH"]),
+                Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
+                beta=_f(g["BETA"]), hloc=hloc, hbath=hb, bath_e=np.zeros((2, norb, nb)),
+                bath_v=np.full((2, norb, nb), max(0.1, 1.0 / np.sqrt(nb))))

@@ -232,6 +232,27 @@ def test_golden_normal_normal_end_to_end(engine, oracle, method):
         E.state_free(s.slot)
 
 
+@pytest.mark.parametrize("name", ["hybrid_normal", "replica_normal", "general_normal"])
+def test_golden_bath_types_through_gpu(engine, oracle, name):
+    """test/src/{HYBRID,REPLICA,GENERAL}_NORMAL/{evals,dens,docc}.check through the GPU path
+    (sector scan with sp_eigh on the device, device observables): 1e-9 / 1e-8."""
+    from models import hybrid_normal_kwargs, replica_normal_kwargs
+
+    E = engine
+    g = golden(name)
+    kw = hybrid_normal_kwargs() if name == "hybrid_normal" else replica_normal_kwargs(name.split("_")[0])
+    m = E.EDModel(**kw)
+    m.lanc_tolerance = 1e-18
+    states = E.ed_diag_d(m)
+    assert len(states) == 1 and (states[0].nup, states[0].ndw) == (3, 3)
+    assert abs(states[0].e - g["evals"][0]) < 1e-9
+    dens, docc = E.observables_normal(m, states)
+    assert np.abs(dens - np.array(g["dens"])).max() < 1e-8
+    assert np.abs(docc - np.array(g["docc"])).max() < 1e-8
+    for s in states:
+        E.state_free(s.slot)
+
+
 def test_apply_op_matches_oracle(engine, oracle):
     E = engine
     kw = normal_normal_kwargs()
