@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "edgpu_last_error", "edgpu_launch_count", "edgpu_last_hxv_stage_ms", "edgpu_set_kernel_variant",
     "edgpu_stream", "edgpu_profile_begin", "edgpu_profile_end", "edgpu_csr_open_d",
     "edgpu_csr_open_z", "edgpu_hxv_z", "edgpu_eigh", "edgpu_eigh_state_store",
+    "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get",
 ]
 
 
@@ -51,6 +52,27 @@ class NormalParams(C.Structure):
         ("diag_hybr", C.c_double * (2 * MAXORB * MAXBATH)),
         ("bath_diag", C.c_double * (2 * MAXORB * MAXBATH)),
         ("hbath", C.c_double * (2 * MAXORB * MAXORB * MAXBATH)),
+        ("stride", C.c_int32 * (MAXORB * MAXBATH)),
+    ]
+
+
+class Nonsu2Params(C.Structure):
+    """``edgpu_nonsu2_params`` (include/edgpu.h)."""
+
+    _fields_ = [
+        ("Ns", C.c_int32), ("Norb", C.c_int32), ("Nbath", C.c_int32), ("bath_type", C.c_int32),
+        ("hfmode", C.c_int32), ("Nfoo", C.c_int32), ("pad0", C.c_int32), ("pad1", C.c_int32),
+        ("xmu", C.c_double),
+        ("hloc", C.c_double * (2 * 2 * MAXORB * MAXORB * 2)),
+        ("spin_field", C.c_double * (MAXORB * 3)),
+        ("Uloc", C.c_double * MAXORB),
+        ("Ust", C.c_double * (MAXORB * MAXORB)),
+        ("Jh", C.c_double * (MAXORB * MAXORB)),
+        ("Jx", C.c_double * (MAXORB * MAXORB)),
+        ("Jp", C.c_double * (MAXORB * MAXORB)),
+        ("bath_e", C.c_double * (2 * MAXORB * MAXBATH)),
+        ("bath_v", C.c_double * (2 * MAXORB * MAXBATH)),
+        ("bath_u", C.c_double * (2 * MAXORB * MAXBATH)),
         ("stride", C.c_int32 * (MAXORB * MAXBATH)),
     ]
 
@@ -87,6 +109,9 @@ def load():
     L.edgpu_hxv_z.argtypes = [C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
     for f in (L.edgpu_csr_open_d, L.edgpu_csr_open_z):
         f.argtypes = [i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.edgpu_sector_open_nonsu2.argtypes = [C.POINTER(Nonsu2Params), C.c_int]
+    L.edgpu_csr_nnz.restype = i64
+    L.edgpu_csr_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.edgpu_hxv_dev.argtypes = [C.c_void_p, C.c_void_p]
     L.edgpu_vec_padded_len.restype = i64
     L.edgpu_vec_upload.argtypes = [C.c_void_p, C.c_void_p]

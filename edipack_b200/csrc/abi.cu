@@ -324,8 +324,35 @@ int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_
   return 0;
 }
 
+int edgpu_sector_open_nonsu2(const edgpu_nonsu2_params *p, int ntot) {
+  clear_error();
+  if (!p) return set_error("null params");
+  if (g.sec.open) sector_close(g);
+  free_eigvecs();
+  return nonsu2_open(g, p, ntot);
+}
+
+int64_t edgpu_csr_nnz(void) { return g.csr.open ? g.csr.nnz : -1; }
+
+int edgpu_csr_get(int64_t *rowptr, int32_t *cols, double *vals) {
+  clear_error();
+  CsrSector &C = g.csr;
+  if (!C.open) return set_error("no stored-H sector open");
+  EDGPU_CUDA(cudaMemcpy(rowptr, C.rowptr, sizeof(int64_t) * (C.nloc + 1), cudaMemcpyDeviceToHost));
+  if (C.nnz) {
+    EDGPU_CUDA(cudaMemcpy(cols, C.cols, sizeof(int32_t) * C.nnz, cudaMemcpyDeviceToHost));
+    EDGPU_CUDA(cudaMemcpy(vals, C.vals, sizeof(double) * (C.cplx ? 2 : 1) * C.nnz, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < C.nnz; k++) cols[k] += 1;  // the reference's 1-based columns
+  }
+  return 0;
+}
+
 int edgpu_sector_get_map(int spin, int32_t *map) {
   clear_error();
+  if (g.csr.open && g.csr.map) {  // device-built nonsu2 sector: H(1)%map(DimEl), packed states
+    EDGPU_CUDA(cudaMemcpy(map, g.csr.map, sizeof(int32_t) * g.csr.nglobal, cudaMemcpyDeviceToHost));
+    return 0;
+  }
   if (!g.sec.open) return set_error("no sector open");
   SpinSpace &S = spin == 0 ? g.sec.up : g.sec.dw;
   // the device map is in the internal enumeration order; report the reference's ascending one

@@ -100,8 +100,63 @@ int csr_close(Engine &E) {
   cudaFree(C.cols);
   cudaFree(C.vals);
   cudaFree(C.vfull);
+  cudaFree(C.map);
   C = CsrSector();
   return 0;
+}
+
+// lanes per row + the row split of all ranks; marks the sector open
+static int csr_finish(Engine &E) {
+  CsrSector &C = E.csr;
+  const int64_t nloc = C.nloc, nglobal = C.nglobal, nnz = C.nnz, row0 = C.row0;
+  const size_t w = C.cplx ? 2 : 1;
+  const double avg = nloc ? (double)nnz / (double)nloc : 0.0;
+  // ~6-8 entries per lane: enough independent loads per lane, few idle lanes in the last trip
+  C.lanes = avg > 160 ? 32 : (avg > 80 ? 16 : (avg > 20 ? 8 : 4));
+  if (E.nranks > 1) {
+    // row split of every rank: MpiQ = Dim/P, remainder to the LAST rank
+    // (ED_HAMILTONIAN_NONSU2.f90:72-79, ED_HAMILTONIAN_SUPERC.f90:76-88)
+    const int P = E.nranks;
+    const int64_t q = nglobal / P;
+    C.counts.assign(P, 0);
+    C.offs.assign(P, 0);
+    for (int p = 0; p < P; p++) {
+      const int64_t qp = q + (p == P - 1 ? nglobal % P : 0);
+      C.counts[p] = (int64_t)w * qp;
+      C.offs[p] = (int64_t)w * q * p;
+    }
+    if (C.offs[E.rank] != (int64_t)w * row0 || C.counts[E.rank] != (int64_t)w * nloc)
+      return set_error("csr_open: (row0=%lld,nloc=%lld) is not rank %d's chunk of the reference row split",
+                       (long long)row0, (long long)nloc, E.rank);
+    EDGPU_CUDA(cudaMalloc(&C.vfull, sizeof(double) * w * nglobal));
+  }
+  C.open = true;
+  return 0;
+}
+
+int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
+                     int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map) {
+  if (E.csr.open) csr_close(E);
+  CsrSector &C = E.csr;
+  C.cplx = cplx;
+  C.nloc = nloc;
+  C.nglobal = nglobal;
+  C.row0 = row0;
+  C.nnz = nnz;
+  C.rowptr = d_rowptr;
+  C.cols = d_cols;
+  C.vals = d_vals;
+  C.map = d_map;
+  int rc = csr_finish(E);
+  if (rc) {  // the caller keeps ownership on failure
+    C.rowptr = nullptr;
+    C.cols = nullptr;
+    C.vals = nullptr;
+    C.map = nullptr;
+    cudaFree(C.vfull);
+    C = CsrSector();
+  }
+  return rc;
 }
 
 int csr_open(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, const int64_t *rowptr,
@@ -140,28 +195,7 @@ int csr_open(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, 
     EDGPU_CUDA(cudaMemcpyAsync(C.vals, vals, sizeof(double) * w * nnz, cudaMemcpyHostToDevice, E.stream));
   }
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
-  const double avg = nloc ? (double)nnz / (double)nloc : 0.0;
-  // ~6-8 entries per lane: enough independent loads per lane, few idle lanes in the last trip
-  C.lanes = avg > 160 ? 32 : (avg > 80 ? 16 : (avg > 20 ? 8 : 4));
-  if (E.nranks > 1) {
-    // row split of every rank: MpiQ = Dim/P, remainder to the LAST rank
-    // (ED_HAMILTONIAN_NONSU2.f90:72-79, ED_HAMILTONIAN_SUPERC.f90:76-88)
-    const int P = E.nranks;
-    const int64_t q = nglobal / P;
-    C.counts.assign(P, 0);
-    C.offs.assign(P, 0);
-    for (int p = 0; p < P; p++) {
-      const int64_t qp = q + (p == P - 1 ? nglobal % P : 0);
-      C.counts[p] = (int64_t)w * qp;
-      C.offs[p] = (int64_t)w * q * p;
-    }
-    if (C.offs[E.rank] != (int64_t)w * row0 || C.counts[E.rank] != (int64_t)w * nloc)
-      return set_error("csr_open: (row0=%lld,nloc=%lld) is not rank %d's chunk of the reference row split",
-                       (long long)row0, (long long)nloc, E.rank);
-    EDGPU_CUDA(cudaMalloc(&C.vfull, sizeof(double) * w * nglobal));
-  }
-  C.open = true;
-  return 0;
+  return csr_finish(E);
 }
 
 template <int L>

@@ -206,6 +206,7 @@ struct CsrSector {
   double *vals = nullptr;     // [nnz] or [2*nnz] (re,im)
   int lanes = 8;              // threads per row of the SpMV kernel
   double *vfull = nullptr;    // nranks>1: all-gathered input vector
+  int32_t *map = nullptr;     // device-built sectors (nonsu2.cu): packed Fock states of the WHOLE sector
   std::vector<int64_t> counts, offs;  // row split of all ranks
   int64_t padded_len() const {
     const int64_t n = cplx ? 2 * nloc : nloc;
@@ -265,6 +266,12 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
 int csr_open(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, const int64_t *rowptr,
              const int32_t *cols, const double *vals);
 int csr_close(Engine &E);
+// takes ownership of device-built CSR arrays (0-based columns) and of the sector map
+int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
+                     int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map);
+
+// nonsu2.cu
+int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot);
 int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, double s_acc, double s_old);
 
 // comm.cu

@@ -13,6 +13,7 @@ spHtimesV_p(Nloc,v,Hv)         :func:`spHtimesV_p`              ED_VARS_GLOBAL.f
 sp_lanc_eigh                   :func:`sp_lanc_eigh`             call site ED_DIAG_NORMAL.f90:206
 sp_lanc_tridiag                :func:`sp_lanc_tridiag`          ED_HAMILTONIAN_NORMAL.f90:360
 sp_eigh (ARPACK)               :func:`sp_eigh`                  call site ED_DIAG_NORMAL.f90:179
+build_Hv_sector_nonsu2         :func:`build_Hv_sector_nonsu2`   ED_HAMILTONIAN_NONSU2.f90:31
 tridiag_Hv_sector_normal       :func:`tridiag_Hv_sector_normal` :321
 ed_diag_d                      :func:`ed_diag_d`                ED_DIAG_NORMAL.f90:76
 lanc_build_gf_normal_diag      :func:`lanc_build_gf_normal_diag` ED_GF_NORMAL.f90:131
@@ -30,7 +31,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _abi
-from ._abi import EdgpuError, MAXBATH, MAXORB, NormalParams, check, ptr
+from ._abi import EdgpuError, MAXBATH, MAXORB, NormalParams, Nonsu2Params, check, ptr
 
 BATH_CODES = {"normal": 0, "hybrid": 1, "replica": 2, "general": 3}
 
@@ -357,6 +358,115 @@ def spHtimesV_cc(v: np.ndarray) -> np.ndarray:
     L.edgpu_hxv_z(C.byref(n), ptr(v), ptr(hv))
     check(L.edgpu_status())
     return hv
+
+
+@dataclass
+class EDModelNonsu2:
+    """Module globals read by ``ed_buildH_nonsu2_main`` (ed_mode=nonsu2, normal / hybrid bath)."""
+
+    Norb: int = 2
+    Nbath: int = 4
+    bath_type: str = "hybrid"
+    Uloc: tuple = (1.0, 1.0)
+    Ust: float = 0.0
+    Jh: float = 0.0
+    Jx: float = 0.0
+    Jp: float = 0.0
+    xmu: float = 0.0
+    hfmode: bool = True
+    ed_hw_bath: float = 2.0
+    hloc: np.ndarray | None = None        # complex [2, 2, Norb, Norb]  impHloc(is, js, a, b)
+    bath_e: np.ndarray | None = None      # [2, Nfoo, Nbath]
+    bath_v: np.ndarray | None = None      # [2, Norb, Nbath]
+    bath_u: np.ndarray | None = None      # [2, Norb, Nbath]
+    spin_field: np.ndarray | None = None  # [Norb, 3]
+
+    @property
+    def Ns(self) -> int:
+        return self.Nbath + self.Norb if self.bath_type == "hybrid" else (self.Nbath + 1) * self.Norb
+
+    @property
+    def Nfoo(self) -> int:
+        return 1 if self.bath_type == "hybrid" else self.Norb
+
+    def init_dmft_bath(self):
+        """init_dmft_bath for nonsu2 (ED_BATH_DMFT.f90:211-244): e and v as NORMAL mode, u = v."""
+        tmp = EDModel(Norb=self.Norb, Nbath=self.Nbath, bath_type=self.bath_type,
+                      ed_hw_bath=self.ed_hw_bath).init_dmft_bath()
+        self.bath_e, self.bath_v, self.bath_u = tmp.bath_e, tmp.bath_v, tmp.bath_v.copy()
+        return self
+
+    def params(self) -> Nonsu2Params:
+        if self.bath_e is None:
+            self.init_dmft_bath()
+        No, Nb = self.Norb, self.Nbath
+        if No > MAXORB or Nb > MAXBATH or 2 * self.Ns > 31:
+            raise EdgpuError("model too large for edgpu_nonsu2_params")
+        p = Nonsu2Params()
+        p.Ns, p.Norb, p.Nbath = self.Ns, No, Nb
+        p.bath_type = BATH_CODES[self.bath_type]
+        p.hfmode, p.Nfoo, p.xmu = int(self.hfmode), self.Nfoo, self.xmu
+        hl = np.zeros((2, 2, MAXORB, MAXORB, 2))
+        if self.hloc is not None:
+            h = np.asarray(self.hloc, complex)
+            hl[:, :, :No, :No, 0], hl[:, :, :No, :No, 1] = h.real, h.imag
+        p.hloc[:] = hl.ravel().tolist()
+        sf = np.zeros((MAXORB, 3))
+        if self.spin_field is not None:
+            sf[:No] = self.spin_field
+        p.spin_field[:] = sf.ravel().tolist()
+        U = np.zeros(MAXORB)
+        U[:No] = np.asarray(self.Uloc, float)[:No]
+        p.Uloc[:] = U.tolist()
+        off = np.zeros((MAXORB, MAXORB))
+        off[:No, :No] = 1.0 - np.eye(No)
+        for name, val in (("Ust", self.Ust), ("Jh", self.Jh), ("Jx", self.Jx), ("Jp", self.Jp)):
+            getattr(p, name)[:] = (val * off).ravel().tolist()
+        for name, arr, n0 in (("bath_e", self.bath_e, self.Nfoo), ("bath_v", self.bath_v, No),
+                              ("bath_u", self.bath_u, No)):
+            buf = np.zeros((2, MAXORB, MAXBATH))
+            buf[:, :n0, :Nb] = arr
+            getattr(p, name)[:] = buf.ravel().tolist()
+        st = np.zeros((MAXORB, MAXBATH), np.int32)
+        for a in range(No):
+            for k in range(Nb):
+                st[a, k] = (No + k + 1) if self.bath_type == "hybrid" else (No + a * Nb + k + 1)
+        p.stride[:] = st.ravel().tolist()
+        return p
+
+
+def build_Hv_sector_nonsu2(model: EDModelNonsu2, ntot: int):
+    """build_Hv_sector_nonsu2 + ed_buildH_nonsu2_main on the device (sector map and complex spH0
+    generated by kernels); afterwards spHtimesV_cc / sp_lanc_* / sp_eigh act on it."""
+    global _open_is_complex
+    check(_abi.load().edgpu_sector_open_nonsu2(C.byref(model.params()), ntot))
+    _open_is_complex = True
+
+
+def delete_Hv_sector_nonsu2():
+    delete_Hv_sector_csr()
+
+
+def sector_map_nonsu2() -> np.ndarray:
+    """H(1)%map(DimEl) of the open device-built nonsu2 sector (packed states iup + idw*2^Ns)."""
+    L = _abi.load()
+    m = np.empty(int(L.edgpu_sector_dim()), np.int32)
+    check(L.edgpu_sector_get_map(0, ptr(m)))
+    return m
+
+
+def stored_csr():
+    """Downloads the device CSR of the open stored-H sector: (rowptr, cols 1-based, vals)."""
+    L = _abi.load()
+    nnz = int(L.edgpu_csr_nnz())
+    if nnz < 0:
+        raise EdgpuError("no stored-H sector open")
+    nloc = vecDim_Hv_sector_normal()
+    rp = np.zeros(nloc + 1, np.int64)
+    cj = np.zeros(max(nnz, 1), np.int32)
+    va = np.zeros(max(nnz, 1), np.complex128 if _open_is_complex else np.float64)
+    check(L.edgpu_csr_get(ptr(rp), ptr(cj), ptr(va)))
+    return rp, cj[:nnz], va[:nnz]
 
 
 def set_kernel_variant(variant: int):

@@ -59,6 +59,27 @@ typedef struct edgpu_normal_params {
   int32_t stride[EDGPU_MAXORB][EDGPU_MAXBATH];                  /* getBathStride(a,k), 1-based */
 } edgpu_normal_params;
 
+/*
+ * Everything ed_buildH_nonsu2_main reads from module globals
+ * (ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190 and ED_NONSU2/stored/*.f90), normal / hybrid bath.
+ * Spin index 0 = up, 1 = dw; complex numbers as (re, im).
+ */
+typedef struct edgpu_nonsu2_params {
+  int32_t Ns, Norb, Nbath, bath_type, hfmode, Nfoo, pad0, pad1;
+  double xmu;
+  double hloc[2][2][EDGPU_MAXORB][EDGPU_MAXORB][2]; /* impHloc(ispin,jspin,iorb,jorb) */
+  double spin_field[EDGPU_MAXORB][3];               /* spin_field(iorb, x|y|z) */
+  double Uloc[EDGPU_MAXORB];
+  double Ust[EDGPU_MAXORB][EDGPU_MAXORB];
+  double Jh[EDGPU_MAXORB][EDGPU_MAXORB];
+  double Jx[EDGPU_MAXORB][EDGPU_MAXORB];
+  double Jp[EDGPU_MAXORB][EDGPU_MAXORB];
+  double bath_e[2][EDGPU_MAXORB][EDGPU_MAXBATH];    /* dmft_bath%e(ispin, iorb|1, k) */
+  double bath_v[2][EDGPU_MAXORB][EDGPU_MAXBATH];    /* dmft_bath%v(ispin, iorb, k)   */
+  double bath_u[2][EDGPU_MAXORB][EDGPU_MAXBATH];    /* dmft_bath%u(ispin, iorb, k): spin-flip hybridisation */
+  int32_t stride[EDGPU_MAXORB][EDGPU_MAXBATH];      /* getBathStride(a,k), 1-based */
+} edgpu_nonsu2_params;
+
 /* ---------------- engine / communicator ---------------- */
 
 /* Selects the CUDA device and creates the engine's stream.  Replaces nothing in the
@@ -111,6 +132,20 @@ int edgpu_csr_open_d(int64_t nloc, int64_t nglobal, int64_t row_offset, const in
                      const int32_t *cols, const double *vals);
 int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const int64_t *rowptr,
                      const int32_t *cols, const double *vals_re_im);
+
+/* build_Hv_sector_nonsu2(isector) + ed_buildH_nonsu2_main (ED_HAMILTONIAN_NONSU2.f90:31-130,
+ * ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190) entirely on the device: the sector map
+ * H(1)%map(DimEl) of packed states m = iup + idw*2^Ns with Ntot electrons (build_sector,
+ * ED_SECTOR.f90:351-368), this rank's rows of the flat split (:72-79) and the complex stored
+ * Hamiltonian spH0 (element generators ED_NONSU2/stored/Himp.f90, Hint.f90, Hbath.f90,
+ * Himp_bath.f90) are generated by kernels; afterwards the sector behaves like one opened with
+ * edgpu_csr_open_z (edgpu_hxv_z, Lanczos drivers, edgpu_eigh).  Normal and hybrid baths.
+ * Parity hooks: edgpu_sector_get_map(0, map) returns the DimEl packed states;
+ * edgpu_csr_nnz / edgpu_csr_get download the device CSR (rowptr 0-based offsets, cols 1-based
+ * global, vals (re,im) pairs for complex sectors), duplicates within a row add up. */
+int edgpu_sector_open_nonsu2(const edgpu_nonsu2_params *p, int ntot);
+int64_t edgpu_csr_nnz(void);
+int edgpu_csr_get(int64_t *rowptr, int32_t *cols, double *vals);
 
 /* ---------------- H x v ---------------- */
 

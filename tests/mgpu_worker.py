@@ -125,6 +125,34 @@ def main():
                         if abs(a[0] - (ref @ hv) / n2) > 1e-10:
                             failures.append(f"apply_op spin={spin} orb={iorb} op={op}: alpha1 mismatch")
         E.state_free(5)
+    # ed_mode=nonsu2 built on the device: every rank generates its rows of the flat row split
+    # (ED_HAMILTONIAN_NONSU2.f90:72-79), the product all-gathers the input vector
+    import edipack_oracle_nonsu2 as N
+    from models import soc_nonsu2_model
+
+    mo2 = soc_nonsu2_model(N, nbath=4)
+    m2 = E.EDModelNonsu2(**vars(mo2))
+    smap, rp, cj, va = N.stored_H(mo2, 6)
+    dim = len(smap)
+    q = dim // world
+    lo, hi = q * rank, (dim if rank == world - 1 else q * (rank + 1))
+    rng = np.random.default_rng(31)
+    vfull = rng.standard_normal(dim) + 1j * rng.standard_normal(dim)
+    ref = N.csr_matvec(rp, cj, va, vfull)
+    E.build_Hv_sector_nonsu2(m2, 6)
+    try:
+        if E.vecDim_Hv_sector_normal() != hi - lo:
+            failures.append(f"nonsu2: vecDim {E.vecDim_Hv_sector_normal()} vs {hi - lo}")
+        hv = E.spHtimesV_cc(vfull[lo:hi].copy())
+        err = np.abs(hv - ref[lo:hi]).max() / np.abs(ref).max()
+        if not err < 1e-12:
+            failures.append(f"nonsu2: HxV rel err {err:.3e} on rank {rank}")
+        ev, _, nconv, _ = E.sp_eigh(2, 24, 300, 1e-14, want_vectors=False)
+        ev_ref = np.linalg.eigvalsh(N.to_dense(rp, cj, va))[:2]
+        if np.abs(ev - ev_ref).max() > 1e-10:
+            failures.append(f"nonsu2: sp_eigh {ev} vs {ev_ref}")
+    finally:
+        E.delete_Hv_sector_nonsu2()
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
     for f in failures:
