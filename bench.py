@@ -331,16 +331,24 @@ def run_ours(args):
     if args.lanczos:
         del hv
         torch.cuda.empty_cache()
-        # untimed warm-up of the Lanczos-only kernel variants (lazy module loading, first-use
-        # allocations): 3 iterations
-        E.sp_lanc_eigh(3, 1e-12, want_vector=False)
+        # first solve: pays lazy module loading of the Lanczos-only kernel variants and the
+        # allocation of the pooled Lanczos-vector buffers (reported, not the headline); the
+        # second, identical solve is the warm time-to-solution every later solve of a DMFT run sees
+        barrier()
+        t0 = time.perf_counter()
+        E.sp_lanc_eigh(args.lanczos_niter, 1e-12, want_vector=False)
+        barrier()
+        t_first = max_over_ranks(time.perf_counter() - t0)
         barrier()
         t0 = time.perf_counter()
         egs, _, nit = E.sp_lanc_eigh(args.lanczos_niter, 1e-12, want_vector=False)
         barrier()
         t_l = max_over_ranks(time.perf_counter() - t0)
-        lanczos = {"egs": egs, "niter": nit, "seconds": t_l, "hxv": 2 * nit,
-                   "threshold": 1e-12, "nitermax": args.lanczos_niter}
+        nstored, nhxv = E.lanczos_last_info()
+        lanczos = {"egs": egs, "niter": nit, "seconds": t_l, "seconds_first_solve": t_first,
+                   "hxv": nhxv,
+                   "vectors_kept_in_hbm": nstored, "threshold": 1e-12,
+                   "nitermax": args.lanczos_niter}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -------------------------
     cpu = None

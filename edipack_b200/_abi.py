@@ -26,7 +26,8 @@ ABI_SYMBOLS = [
     "edgpu_last_error", "edgpu_launch_count", "edgpu_last_hxv_stage_ms", "edgpu_set_kernel_variant",
     "edgpu_stream", "edgpu_profile_begin", "edgpu_profile_end", "edgpu_csr_open_d",
     "edgpu_csr_open_z", "edgpu_hxv_z", "edgpu_eigh", "edgpu_eigh_state_store",
-    "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get",
+    "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
+    "edgpu_release_cache",
 ]
 
 
@@ -123,6 +124,7 @@ def load():
     L.edgpu_eigh.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_void_p,
                              C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.edgpu_eigh_state_store.argtypes = [C.c_int, C.c_int]
+    L.edgpu_lanczos_last_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.edgpu_state_store.argtypes = [C.c_int]
     L.edgpu_state_free.argtypes = [C.c_int]
     L.edgpu_apply_op.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]

@@ -30,6 +30,7 @@ int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, do
                         double *alanc, double *blanc, int *nused);
 int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
                    uint64_t seed, double *egs, double *d_vect, int *niter);
+extern int g_lanczos_last_stored, g_lanczos_last_hxv;
 int eigh_dev(Engine &E, int neigen, int nblock, int nitermax, double tol, uint64_t seed, double *evals,
              double *resid, std::vector<double *> *vecs, int *nconv, int *nmatvec);
 
@@ -239,8 +240,14 @@ int edgpu_init(int device) {
   return 0;
 }
 
+int edgpu_release_cache(void) {
+  lanczos_release(g);
+  return 0;
+}
+
 int edgpu_finalize(void) {
   if (!g.inited) return 0;
+  lanczos_release(g);
   sector_close(g);
   csr_close(g);
   for (auto &kv : g_states) cudaFree(kv.second.vec);
@@ -557,6 +564,12 @@ int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, 
   cudaFree(d_start);
   if (rc) return rc;
   if (vec_host) EDGPU_TRY(download(g, vec_host, g_current));
+  return 0;
+}
+
+int edgpu_lanczos_last_info(int *nstored, int *nhxv) {
+  if (nstored) *nstored = g_lanczos_last_stored;
+  if (nhxv) *nhxv = g_lanczos_last_hxv;
   return 0;
 }
 

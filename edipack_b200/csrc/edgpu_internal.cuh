@@ -237,6 +237,12 @@ struct Engine {
   // length (in doubles) of a device vector of whatever sector is open
   int64_t veclen() const { return csr.open ? csr.padded_len() : sec.padded_len(); }
   int variant_request = 0;
+  // Pool of device chunks holding the Lanczos vectors of the ground-state driver (lanczos.cu).
+  // Allocating HBM costs ~4 ms/GB, more than re-running the recurrence saves on a single solve,
+  // so the chunks are kept across solves and sectors (a DMFT run solves dozens of sectors per
+  // iteration) and are given back as soon as any other allocation of the library runs short
+  // (dev_malloc) or on edgpu_release_cache / edgpu_finalize.
+  std::vector<std::pair<double *, size_t>> lz_chunks;  // (pointer, bytes)
   float stage_ms[4] = {0, 0, 0, 0};
   // profiling ring (edgpu_profile_begin/end): 4 events per recorded H x v
   std::vector<cudaEvent_t> prof_ev;
@@ -245,6 +251,15 @@ struct Engine {
 };
 
 extern Engine g;
+
+// Every device allocation of the library goes through dev_malloc: when device memory is short
+// the cached Lanczos vector pool is given back first and the allocation is retried.
+cudaError_t dev_malloc(void **p, size_t bytes);
+template <class T>
+inline cudaError_t dev_malloc_t(T **p, size_t bytes) {
+  return dev_malloc((void **)p, bytes);
+}
+#define cudaMalloc(p, n) ::edgpu::dev_malloc_t((p), (n))
 
 // sector.cu
 int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw);
@@ -300,11 +315,14 @@ int scalar_to_host(Engine &E, double *d_scalar, double *h_out);  // all-reduce +
 int vec_zero(Engine &E, double *d_v, int64_t n);
 int vec_dot(Engine &E, const double *a, const double *b, double *h_out);  // all-reduced
 int vec_scale(Engine &E, double *a, double s);
-// w -= alpha v ; beta2 = <w,w>
-int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2);
+// w -= alpha v ; beta2 = <w,w> ; store (optional) receives a copy of the new w
+int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2,
+                  double *store = nullptr);
+int vec_lincomb(Engine &E, double *out, const std::vector<double *> &vecs, const std::vector<double> &coef);
 int vec_axpy(Engine &E, double *y, const double *x, double a);
 
 // lanczos.cu
+void lanczos_release(Engine &E);  // frees the Lanczos vector pool
 int tridiag_eig(int n, const double *diag, const double *sub, double *evals, double *evecs,
                 bool want_vecs);
 

@@ -9,6 +9,7 @@
 // All Lanczos vectors stay in HBM; per iteration the host only sees alfa and beta.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "edgpu_internal.cuh"
 
@@ -91,6 +92,25 @@ int tridiag_eig(int n, const double *diag, const double *sub, double *evals, dou
 //   X_{j+1} = T - (alfa_j/nx) X_j ,  beta_j = |X_{j+1}|                   (k_axpy_norm)
 // = 72 B/state instead of the 120 B/state of scale+swap / accumulate / dot / axpy, and the
 // host sees alfa and beta only.
+int g_lanczos_last_stored = 0, g_lanczos_last_hxv = 0;  // edgpu_lanczos_last_info
+
+void lanczos_release(Engine &E) {
+  if (E.lz_chunks.empty()) return;
+  cudaStreamSynchronize(E.stream);
+  for (auto &c : E.lz_chunks) cudaFree(c.first);
+  E.lz_chunks.clear();
+}
+
+cudaError_t dev_malloc(void **p, size_t bytes) {
+  cudaError_t e = (cudaMalloc)(p, bytes);  // the runtime's cudaMalloc, not the macro
+  if (e == cudaErrorMemoryAllocation && !g.lz_chunks.empty()) {
+    cudaGetLastError();
+    lanczos_release(g);
+    e = (cudaMalloc)(p, bytes);
+  }
+  return e;
+}
+
 struct LanczosVecs {
   double *x = nullptr, *y = nullptr;
   double nx = 1.0, ny = 1.0, beta_prev = 0.0;
@@ -99,7 +119,8 @@ struct LanczosVecs {
 // One step; returns alfa, beta on the host and leaves L advanced (x = X_{j+1}, nx = beta).
 // v_j / nx (the normalised Lanczos vector of this step) is L_before.x: callers that need it
 // (pass 2 of the ground-state driver) read x and nx BEFORE calling.
-static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, double *beta) {
+static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, double *beta,
+                        double *store = nullptr) {
   if (iter == 1) {
     double n2;
     EDGPU_TRY(vec_dot(E, L.x, L.x, &n2));
@@ -116,7 +137,7 @@ static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, doubl
   EDGPU_TRY(scalar_to_host(E, d_dot, &xt));
   *alfa = xt / L.nx;
   double b2;
-  EDGPU_TRY(vec_axpy_norm(E, L.y, L.x, *alfa / L.nx, &b2));
+  EDGPU_TRY(vec_axpy_norm(E, L.y, L.x, *alfa / L.nx, &b2, store));  // store <- X_{j+1}
   *beta = std::sqrt(b2);
   std::swap(L.x, L.y);
   L.ny = L.nx;
@@ -146,10 +167,18 @@ int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, do
 }
 
 // sp_lanc_eigh: pass 1 builds T until the lowest Ritz value is stationary (checked every
-// iteration once nlanc >= ncheck) or beta -> 0 or nitermax; pass 2 replays the recurrence
-// from the same start vector accumulating vect += Z(iter,1) * v_iter; vect normalised.
+// iteration once nlanc >= ncheck) or beta -> 0 or nitermax; pass 2 forms
+// vect = sum_iter Z(iter,1) * v_iter, normalised.
+// SciFortran's driver keeps two vectors and therefore re-runs the whole recurrence for pass 2
+// (twice the H x v count).  With 180 GB of HBM per GPU the Lanczos vectors of pass 1 are kept
+// instead (written by the same kernel that produces them, +8 B/state per iteration) as long as
+// device memory lasts: pass 2 is then one streaming linear combination, and only the iterations
+// whose vectors no longer fitted are replayed, restarting the recurrence from the last two stored
+// vectors.  The result equals a full replay up to the summation order of the final combination
+// (the replay regenerates exactly the stored vectors).  EDGPU_LANCZOS_STORE=0 disables the store
+// (two-vector mode).
 // d_start: start vector (kept intact, copied) or nullptr for the seeded random start.
-// d_vect: output (padded length).  Scratch: two more vectors allocated here.
+// d_vect: output (padded length).
 int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
                    uint64_t seed, double *egs, double *d_vect, int *niter) {
   const int64_t n = E.veclen();
@@ -158,31 +187,71 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   if (nitermax < 1) nitermax = 1;
   if (ncheck < 1) ncheck = 1;
   double *vin = nullptr, *vout = nullptr;
+  std::vector<double *> store;  // store[j] = X_{j+1} (un-normalised Lanczos vector j+1)
   EDGPU_CUDA(cudaMalloc(&vin, sizeof(double) * n));
   EDGPU_CUDA(cudaMalloc(&vout, sizeof(double) * n));
   auto cleanup = [&]() {
     cudaFree(vin);
     cudaFree(vout);
+    store.clear();  // slots of the pooled chunks (E.lz_chunks), kept for the next solve
   };
-  auto init_start = [&]() -> int {
-    if (d_start) {
-      EDGPU_CUDA(cudaMemcpyAsync(vin, d_start, sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream));
-    } else {
-      EDGPU_TRY(vec_fill_random(E, vin, seed));
+  const char *env = getenv("EDGPU_LANCZOS_STORE");
+  bool storing = !(env && env[0] == '0');
+  // Vector slots are carved from the pooled chunks; new chunks (8 vectors, at least 256 MB) are
+  // added on demand while device memory lasts, keeping a reserve for everything else that is
+  // allocated while sectors are open (stored states, seeds, transposes, the callers' buffers).
+  const size_t vbytes = sizeof(double) * (size_t)n;
+  size_t chunk_i = 0, chunk_used = 0;  // carving position
+  auto try_store_slot = [&]() -> double * {
+    if (!storing || (int)store.size() > nitermax) {
+      storing = false;
+      return nullptr;
     }
-    return 0;
+    while (chunk_i < E.lz_chunks.size() && chunk_used + vbytes > E.lz_chunks[chunk_i].second) {
+      chunk_i++;
+      chunk_used = 0;
+    }
+    if (chunk_i == E.lz_chunks.size()) {
+      size_t fr = 0, tot = 0;
+      const size_t reserve = std::max<size_t>((size_t)4 << 30, 6 * vbytes);
+      const size_t left = (size_t)nitermax + 1 - store.size();
+      const size_t want = std::min(left * vbytes, std::max<size_t>(8 * vbytes, (size_t)256 << 20));
+      void *p = nullptr;
+      if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr < reserve + want ||
+          (cudaMalloc)(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        storing = false;
+        return nullptr;
+      }
+      E.lz_chunks.emplace_back((double *)p, want);
+      chunk_used = 0;
+    }
+    double *slot = (double *)((char *)E.lz_chunks[chunk_i].first + chunk_used);
+    chunk_used += vbytes;
+    store.push_back(slot);
+    return slot;
   };
-  int rc = init_start();
-  if (rc) { cleanup(); return rc; }
-  std::vector<double> a, b(1, 0.0), ev, esave;
+  if (d_start) {
+    EDGPU_CUDA(cudaMemcpyAsync(vin, d_start, sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream));
+  } else {
+    int rc0 = vec_fill_random(E, vin, seed);
+    if (rc0) { cleanup(); return rc0; }
+  }
+  if (double *p0 = try_store_slot())  // X_1
+    cudaMemcpyAsync(p0, vin, sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream);
+  std::vector<double> a, b(1, 0.0), ev, esave, nrm;  // nrm[j] = |X_{j+1}|
   LanczosVecs L;
   L.x = vin;
   L.y = vout;
   double alfa = 0.0, beta = 0.0;
-  int nlanc = 0;
+  int nlanc = 0, rc = 0;
   for (int it = 1; it <= nitermax; it++) {
-    rc = lanczos_step(E, it, L, &alfa, &beta);
+    // X_{it+1} is only worth keeping while the chain of stored vectors is unbroken
+    double *slot = (int)store.size() == it ? try_store_slot() : nullptr;
+    rc = lanczos_step(E, it, L, &alfa, &beta, slot);
     if (rc) { cleanup(); return rc; }
+    if (it == 1) nrm.push_back(L.ny);  // |X_1| (the step normalised with it)
+    nrm.push_back(beta);               // |X_{it+1}|
     a.push_back(alfa);
     nlanc = it;
     if (std::fabs(beta) < threshold && it > 1) break;
@@ -203,27 +272,59 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   if (rc) { cleanup(); return rc; }
   *egs = ev[0];
   *niter = nlanc;
-  // pass 2
-  rc = init_start();
-  if (rc) { cleanup(); return rc; }
-  vec_zero(E, d_vect, n);
-  L = LanczosVecs();
-  L.x = vin;
-  L.y = vout;
-  beta = 0.0;
-  for (int it = 1; it <= nlanc; it++) {
-    // v_it = x / nx with (x, nx) as they are BEFORE the step (iteration 1 normalises inside)
-    if (it == 1) {
-      double n2s;
-      rc = vec_dot(E, L.x, L.x, &n2s);
-      if (rc) { cleanup(); return rc; }
-      L.nx = std::sqrt(n2s);
+  // pass 2: vect = sum_j Z(j,1) X_j / |X_j|
+  const int ns = std::min((int)store.size(), nlanc);  // stored: X_1 .. X_ns
+  g_lanczos_last_stored = ns;
+  g_lanczos_last_hxv = nlanc + ((ns >= 2 || ns >= nlanc) ? nlanc - ns : nlanc - 1);
+  if (ns >= 2 || ns >= nlanc) {
+    std::vector<double *> vs(store.begin(), store.begin() + ns);
+    std::vector<double> cf(ns);
+    for (int j = 0; j < ns; j++) cf[j] = Z[j] / nrm[j];
+    rc = vec_lincomb(E, d_vect, vs, cf);
+    if (rc) { cleanup(); return rc; }
+    if (ns < nlanc) {
+      // replay the tail: recurrence state after step ns-1 is x = X_ns, y = X_{ns-1}
+      EDGPU_CUDA(cudaMemcpyAsync(vin, store[ns - 1], sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream));
+      EDGPU_CUDA(cudaMemcpyAsync(vout, store[ns - 2], sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream));
+      L = LanczosVecs();
+      L.x = vin;
+      L.y = vout;
+      L.nx = nrm[ns - 1];
+      L.ny = nrm[ns - 2];
+      L.beta_prev = nrm[ns - 1];  // beta_{ns-1} = |X_ns|
+      for (int it = ns; it < nlanc; it++) {
+        rc = lanczos_step(E, it, L, &alfa, &beta);  // -> x = X_{it+1}
+        if (rc) { cleanup(); return rc; }
+        rc = vec_axpy(E, d_vect, L.x, Z[it] / L.nx);
+        if (rc) { cleanup(); return rc; }
+      }
     }
-    rc = vec_axpy(E, d_vect, L.x, Z[it - 1] / L.nx);  // Z(iter,1): component iter of eigenvector 1
-    if (rc) { cleanup(); return rc; }
-    if (it == nlanc) break;  // the last vector needs no further H x v
-    rc = lanczos_step(E, it, L, &alfa, &beta);
-    if (rc) { cleanup(); return rc; }
+  } else {
+    // two-vector mode: replay the recurrence from the same start vector
+    if (d_start) {
+      EDGPU_CUDA(cudaMemcpyAsync(vin, d_start, sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream));
+    } else {
+      rc = vec_fill_random(E, vin, seed);
+      if (rc) { cleanup(); return rc; }
+    }
+    vec_zero(E, d_vect, n);
+    L = LanczosVecs();
+    L.x = vin;
+    L.y = vout;
+    for (int it = 1; it <= nlanc; it++) {
+      // v_it = x / nx with (x, nx) as they are BEFORE the step (iteration 1 normalises inside)
+      if (it == 1) {
+        double n2s;
+        rc = vec_dot(E, L.x, L.x, &n2s);
+        if (rc) { cleanup(); return rc; }
+        L.nx = std::sqrt(n2s);
+      }
+      rc = vec_axpy(E, d_vect, L.x, Z[it - 1] / L.nx);  // Z(iter,1): component iter of eigenvector 1
+      if (rc) { cleanup(); return rc; }
+      if (it == nlanc) break;  // the last vector needs no further H x v
+      rc = lanczos_step(E, it, L, &alfa, &beta);
+      if (rc) { cleanup(); return rc; }
+    }
   }
   double n2;
   rc = vec_dot(E, d_vect, d_vect, &n2);

@@ -2,6 +2,8 @@
 // lanczos_iteration does with Fortran array syntax + MPI_Allreduce): every kernel streams
 // its operands once with 16-byte accesses and reduces through warp shuffles -> per-block
 // partials -> one fixed-order final block (deterministic), then NCCL all-reduce of the scalar.
+#include <algorithm>
+
 #include "edgpu_internal.cuh"
 
 namespace edgpu {
@@ -62,19 +64,45 @@ __global__ void __launch_bounds__(VT) k_scale(double2 *__restrict__ a, int64_t n
   }
 }
 
-// w -= alpha*v ; partial of <w,w>
+// w -= alpha*v ; partial of <w,w>; optionally a second copy of the new w (the Lanczos vector
+// store of the ground-state driver: 8 B/state more, written while the value is in registers)
+template <bool STORE>
 __global__ void __launch_bounds__(VT) k_axpy_norm(double2 *__restrict__ w,
                                                   const double2 *__restrict__ v, int64_t n2,
-                                                  double alpha, double *__restrict__ part) {
+                                                  double alpha, double *__restrict__ part,
+                                                  double2 *__restrict__ store) {
   double s = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
     double2 x = w[i], y = v[i];
     x.x -= alpha * y.x;
     x.y -= alpha * y.y;
     w[i] = x;
+    if (STORE) store[i] = x;
     s += x.x * x.x + x.y * x.y;
   }
   block_partial(s, part);
+}
+
+// out = [out +] sum_b c_b V_b for a batch of up to 8 vectors (second pass of the ground-state
+// driver when the Lanczos vectors were kept in HBM)
+struct LcBatch {
+  const double2 *p[8];
+  double c[8];
+};
+template <bool ACC>
+__global__ void __launch_bounds__(VT) k_lincomb(double2 *__restrict__ out, LcBatch B, int nb, int64_t n2) {
+  for (int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) {
+    double2 a = ACC ? out[i] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      if (b < nb) {
+        const double2 x = B.p[b][i];
+        a.x += B.c[b] * x.x;
+        a.y += B.c[b] * x.y;
+      }
+    }
+    out[i] = a;
+  }
 }
 
 __global__ void __launch_bounds__(VT) k_axpy(double2 *__restrict__ y, const double2 *__restrict__ x,
@@ -212,12 +240,38 @@ int vec_scale(Engine &E, double *a, double s) {
   return 0;
 }
 
-int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2) {
+int vec_axpy_norm(Engine &E, double *w, const double *v, double alpha, double *h_beta2, double *store) {
   const int64_t n2 = E.veclen() / 2;
   int gb = grid_for(E, n2);
-  k_axpy_norm<<<gb, VT, 0, E.stream>>>((double2 *)w, (const double2 *)v, n2, alpha, E.d_part);
+  if (store)
+    k_axpy_norm<true><<<gb, VT, 0, E.stream>>>((double2 *)w, (const double2 *)v, n2, alpha, E.d_part,
+                                               (double2 *)store);
+  else
+    k_axpy_norm<false><<<gb, VT, 0, E.stream>>>((double2 *)w, (const double2 *)v, n2, alpha, E.d_part,
+                                                nullptr);
   EDGPU_COUNT_LAUNCH();
   return finish_scalar(E, gb, h_beta2);
+}
+
+// out = sum_j coef[j] * vecs[j]  (overwrites out)
+int vec_lincomb(Engine &E, double *out, const std::vector<double *> &vecs, const std::vector<double> &coef) {
+  const int64_t n2 = E.veclen() / 2;
+  const int gb = grid_for(E, n2);
+  const int m = (int)vecs.size();
+  if (m == 0) return vec_zero(E, out, E.veclen());
+  for (int f = 0; f < m; f += 8) {
+    LcBatch B;
+    const int nb = std::min(8, m - f);
+    for (int b = 0; b < 8; b++) {
+      B.p[b] = (const double2 *)vecs[f + (b < nb ? b : 0)];
+      B.c[b] = b < nb ? coef[f + b] : 0.0;
+    }
+    if (f == 0) k_lincomb<false><<<gb, VT, 0, E.stream>>>((double2 *)out, B, nb, n2);
+    else k_lincomb<true><<<gb, VT, 0, E.stream>>>((double2 *)out, B, nb, n2);
+    EDGPU_COUNT_LAUNCH();
+  }
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int vec_axpy(Engine &E, double *y, const double *x, double a) {

@@ -494,6 +494,18 @@ def sp_lanc_eigh(nitermax: int, threshold: float = 1e-12, ncheck: int = 10, vect
     return egs.value, buf, nit.value
 
 
+def lanczos_last_info():
+    """(Lanczos vectors kept in HBM, H x v products) of the last :func:`sp_lanc_eigh`."""
+    a, b = C.c_int(), C.c_int()
+    check(_abi.load().edgpu_lanczos_last_info(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def release_cache():
+    """Returns the pooled Lanczos-vector buffers to the device allocator."""
+    check(_abi.load().edgpu_release_cache())
+
+
 def sp_lanc_tridiag(vin, nlanc: int, threshold: float = 1e-12):
     """sp_lanc_tridiag(MatVec, vin, alanc, blanc); vin=None uses the device-resident seed
     left by :func:`apply_op`.  Returns (alanc, blanc, nused, norm2)."""

@@ -180,6 +180,15 @@ int edgpu_vec_download(double *h_dst, const double *d_src);
 int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, uint64_t seed,
                      double *egs, double *vec_host, int *niter);
 
+/* Diagnostics of the last edgpu_lanczos_gs: Lanczos vectors that were kept in HBM during pass 1
+ * (all of them when device memory allows: pass 2 is then a linear combination instead of a
+ * second run of the recurrence) and the number of H x v products spent in both passes. */
+int edgpu_lanczos_last_info(int *nstored, int *nhxv);
+/* The buffers holding those vectors are pooled across solves and sectors (allocating HBM costs
+ * more than a second run of the recurrence saves on a single solve).  The library gives the pool
+ * back by itself when one of its own allocations runs short; call this to return it earlier. */
+int edgpu_release_cache(void);
+
 /* sp_lanc_tridiag([MpiComm,]MatVec,vin,alanc,blanc) as called from
  * tridiag_Hv_sector_normal (ED_HAMILTONIAN_NORMAL.f90:321-369).  seed_host = local chunk of
  * the (un-normalised) start vector, or NULL to use the device-resident seed produced by
