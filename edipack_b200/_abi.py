@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "edgpu_stream", "edgpu_profile_begin", "edgpu_profile_end", "edgpu_csr_open_d",
     "edgpu_csr_open_z", "edgpu_hxv_z", "edgpu_eigh", "edgpu_eigh_state_store",
     "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
-    "edgpu_release_cache",
+    "edgpu_release_cache", "edgpu_sector_open_superc",
 ]
 
 
@@ -78,6 +78,28 @@ class Nonsu2Params(C.Structure):
     ]
 
 
+class SupercParams(C.Structure):
+    """``edgpu_superc_params`` (include/edgpu.h)."""
+
+    _fields_ = [
+        ("Ns", C.c_int32), ("Norb", C.c_int32), ("Nbath", C.c_int32), ("bath_type", C.c_int32),
+        ("hfmode", C.c_int32), ("Nfoo", C.c_int32), ("pad0", C.c_int32), ("pad1", C.c_int32),
+        ("xmu", C.c_double),
+        ("hloc", C.c_double * (2 * MAXORB * MAXORB * 2)),
+        ("hloc_anomalous", C.c_double * (MAXORB * MAXORB * 2)),
+        ("pair_field", C.c_double * MAXORB),
+        ("Uloc", C.c_double * MAXORB),
+        ("Ust", C.c_double * (MAXORB * MAXORB)),
+        ("Jh", C.c_double * (MAXORB * MAXORB)),
+        ("Jx", C.c_double * (MAXORB * MAXORB)),
+        ("Jp", C.c_double * (MAXORB * MAXORB)),
+        ("bath_e", C.c_double * (2 * MAXORB * MAXBATH)),
+        ("bath_d", C.c_double * (MAXORB * MAXBATH)),
+        ("bath_v", C.c_double * (2 * MAXORB * MAXBATH)),
+        ("stride", C.c_int32 * (MAXORB * MAXBATH)),
+    ]
+
+
 _lib = None
 
 
@@ -111,6 +133,7 @@ def load():
     for f in (L.edgpu_csr_open_d, L.edgpu_csr_open_z):
         f.argtypes = [i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.edgpu_sector_open_nonsu2.argtypes = [C.POINTER(Nonsu2Params), C.c_int]
+    L.edgpu_sector_open_superc.argtypes = [C.POINTER(SupercParams), C.c_int]
     L.edgpu_csr_nnz.restype = i64
     L.edgpu_csr_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.edgpu_hxv_dev.argtypes = [C.c_void_p, C.c_void_p]

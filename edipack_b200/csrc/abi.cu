@@ -339,6 +339,14 @@ int edgpu_sector_open_nonsu2(const edgpu_nonsu2_params *p, int ntot) {
   return nonsu2_open(g, p, ntot);
 }
 
+int edgpu_sector_open_superc(const edgpu_superc_params *p, int sz) {
+  clear_error();
+  if (!p) return set_error("null params");
+  if (g.sec.open) sector_close(g);
+  free_eigvecs();
+  return superc_open(g, p, sz);
+}
+
 int64_t edgpu_csr_nnz(void) { return g.csr.open ? g.csr.nnz : -1; }
 
 int edgpu_csr_get(int64_t *rowptr, int32_t *cols, double *vals) {

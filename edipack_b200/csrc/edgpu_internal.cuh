@@ -285,8 +285,9 @@ int csr_close(Engine &E);
 int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
                      int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map);
 
-// nonsu2.cu
+// packed.cu
 int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot);
+int superc_open(Engine &E, const edgpu_superc_params *p, int sz);
 int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, double s_acc, double s_old);
 
 // comm.cu

@@ -1,36 +1,53 @@
-// ed_mode=nonsu2 on the device: sector map and stored Hamiltonian built by kernels, replacing
-//   build_sector (nonsu2 branch)      ED_SECTOR.f90:335-368   m = iup + idw*2^Ns, popcount = Ntot,
-//                                                             ascending m (idw outer, iup inner)
-//   build_Hv_sector_nonsu2            ED_HAMILTONIAN_NONSU2.f90:31-130 (row split :72-79)
+// ed_mode=nonsu2 and ed_mode=superc on the device: sector map and stored Hamiltonian built by
+// kernels, replacing
+//   build_sector (nonsu2 branch)      ED_SECTOR.f90:335-368   m = iup + idw*2^Ns, popcount = Ntot
+//   build_sector (superc branch)      ED_SECTOR.f90:244-281   m = iup + idw*2^Ns, popcnt(iup)-popcnt(idw) = Sz
+//                                     (both: idw outer / iup inner -> ascending m)
+//   build_Hv_sector_nonsu2 / _superc  ED_HAMILTONIAN_NONSU2.f90:31-130, ED_HAMILTONIAN_SUPERC.f90:31-140
+//                                     (flat row split, remainder to the last rank)
 //   ed_buildH_nonsu2_main             ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190 with the element
 //                                     generators ED_NONSU2/stored/Himp.f90, Hint.f90, Hbath.f90,
 //                                     Himp_bath.f90 (normal / hybrid bath)
+//   ed_buildH_superc_main             ED_HAMILTONIAN_SUPERC_STORED_HxV.f90:29-260 with
+//                                     ED_SUPERC/stored/Himp.f90 (incl. anomalous local pairing :86-125),
+//                                     Hint.f90, Hbath.f90 (bath pairing d :97-133), Himp_bath.f90
 // The reference inserts element by element into a list of rows (`sp_insert_element`, O(row) search
 // + realloc per element, ED_SPARSE_MATRIX.f90:346-357) after a recursive binary search of the
 // target state.  Here one thread per row enumerates the same terms in the same order twice
-// (count, then fill) straight into flat CSR arrays in HBM; the target index is the combinadic
-// rank of the packed 2*Ns-bit state (the sector is the set of all Ntot-subsets in ascending
-// integer order), fermionic signs are popc of a bit window over ALL lower bits (up and dw),
-// as c/cdg do on the packed state (ED_AUX_FUNX.f90:334-384 called with pos+Ns, Himp.f90:62).
-// The diagonal contributions (Himp, spin_field z, Hint, Hbath) are summed in the reference's
-// order into one entry; off-diagonal entries that hit the same column stay separate entries
-// (they add up in the product, like sp_insert_element's accumulation).
-// The product itself is the CSR SpMV of csr.cu (complex).
+// (count, then fill) straight into flat CSR arrays in HBM.  The target index is computed, not
+// searched: nonsu2 sectors are all Ntot-subsets of 2*Ns bits in ascending integer order
+// (combinadic rank); superc sectors are, for each dw integer in ascending order, the up integers
+// with popcnt(idw)+Sz electrons (a prefix table over idw + the combinadic rank of iup).
+// Fermionic signs are popc of a bit window over ALL lower bits (up and dw), as c/cdg do on the
+// packed state (ED_AUX_FUNX.f90:334-384 called with pos+Ns, Himp.f90:62).
+// The diagonal contributions are summed in the reference's order into one entry; off-diagonal
+// entries that hit the same column stay separate entries (they add up in the product, like
+// sp_insert_element's accumulation).  The product itself is the complex CSR SpMV of csr.cu.
 #include <algorithm>
+#include <cstring>
 
 #include "edgpu_internal.cuh"
 
 namespace edgpu {
 
+enum { MODE_NONSU2 = 0, MODE_SUPERC = 1 };
+
 struct Nonsu2Dev {
-  edgpu_nonsu2_params p;
+  edgpu_nonsu2_params p;  // superc sectors reuse the fields they share (hloc spin-diagonal)
+  // superc only
+  double anom[EDGPU_MAXORB][EDGPU_MAXORB][2];  // impHloc_anomalous(1,1,a,b)
+  double pair_field[EDGPU_MAXORB];
+  double bath_d[EDGPU_MAXORB][EDGPU_MAXBATH];  // dmft_bath%d(1,a,k)
+  const int32_t *off;                          // [2^Ns + 1] first sector index of each idw
   int32_t binom[33][33];  // C(n,k), n,k <= 32 (entries that overflow int32 are never used)
-  int32_t ntot;
+  int32_t mode;
+  int32_t ntot;   // nonsu2: electrons; superc: Sz
   int32_t nbits;  // 2*Ns
 };
 __constant__ Nonsu2Dev c_n2;
 
-__device__ __forceinline__ int64_t n2_rank(uint32_t m) {
+// combinadic rank of a bit pattern among the patterns with the same popcount (ascending order)
+__device__ __forceinline__ int64_t comb_rank(uint32_t m) {
   int64_t r = 0;
   int k = 0;
   while (m) {
@@ -41,17 +58,36 @@ __device__ __forceinline__ int64_t n2_rank(uint32_t m) {
   }
   return r;
 }
-
-__device__ __forceinline__ uint32_t n2_unrank(int64_t r) {
+// pattern number r (ascending) among those of `nbits` bits with k ones
+__device__ __forceinline__ uint32_t comb_unrank(int64_t r, int nbits, int k) {
   uint32_t m = 0;
-  int p = c_n2.nbits - 1;
-  for (int k = c_n2.ntot; k >= 1; k--) {
+  int p = nbits - 1;
+  for (; k >= 1; k--) {
     while (c_n2.binom[p][k] > r) p--;
     m |= 1u << p;
     r -= c_n2.binom[p][k];
     p--;
   }
   return m;
+}
+
+// sector index (0-based) of the packed state m
+__device__ __forceinline__ int64_t n2_rank(uint32_t m) {
+  if (c_n2.mode == MODE_NONSU2) return comb_rank(m);
+  const int Ns = c_n2.nbits >> 1;
+  return (int64_t)c_n2.off[m >> Ns] + comb_rank(m & ((1u << Ns) - 1u));
+}
+
+__device__ __forceinline__ uint32_t n2_unrank(int64_t r) {
+  if (c_n2.mode == MODE_NONSU2) return comb_unrank(r, c_n2.nbits, c_n2.ntot);
+  const int Ns = c_n2.nbits >> 1;
+  int lo = 0, hi = 1 << Ns;  // largest idw with off[idw] <= r among non-empty slots
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (c_n2.off[mid] <= r) lo = mid; else hi = mid;
+  }
+  const uint32_t iup = comb_unrank(r - c_n2.off[lo], Ns, __popc((uint32_t)lo) + c_n2.ntot);
+  return iup | ((uint32_t)lo << Ns);
 }
 
 __global__ void __launch_bounds__(256) k_n2_map(int32_t *__restrict__ map, int64_t dim) {
@@ -99,6 +135,18 @@ __device__ __forceinline__ void n2_chain(uint32_t m, int p1, int p2, int p3, int
   s.emit(n2_rank(m), (par & 1) ? -amp : amp, 0.0);
 }
 
+// pair annihilation c(p2) c(p1) (p1 applied first) / pair creation cdg(p2) cdg(p1); the caller
+// checked the occupations (Himp.f90:90-121, Hbath.f90:101-131 of ED_SUPERC/stored)
+template <class Sink>
+__device__ __forceinline__ void n2_pair(uint32_t m, int p1, int p2, bool create, double re, double im, Sink &s) {
+  int par = __popc(m & ((1u << p1) - 1u));
+  m = create ? (m | (1u << p1)) : (m & ~(1u << p1));
+  par += __popc(m & ((1u << p2) - 1u));
+  m = create ? (m | (1u << p2)) : (m & ~(1u << p2));
+  const double sg = (par & 1) ? -1.0 : 1.0;
+  s.emit(n2_rank(m), re * sg, im * sg);
+}
+
 template <class Sink>
 __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
   const edgpu_nonsu2_params &P = c_n2.p;
@@ -116,9 +164,11 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
     dre += HL(0, 0, a, a, 0) * nup[a] + HL(1, 1, a, a, 0) * ndw[a] - P.xmu * (nup[a] + ndw[a]);
     dim_ += HL(0, 0, a, a, 1) * nup[a] + HL(1, 1, a, a, 1) * ndw[a];
   }
+  const bool superc = c_n2.mode == MODE_SUPERC;
   bool any_sf = false;
   for (int a = 0; a < No; a++)
     any_sf = any_sf || P.spin_field[a][0] != 0.0 || P.spin_field[a][1] != 0.0 || P.spin_field[a][2] != 0.0;
+  if (superc) any_sf = false;
   if (any_sf) {
     double h = 0.0;
     for (int a = 0; a < No; a++) h += P.spin_field[a][2] * (nup[a] - ndw[a]);
@@ -161,8 +211,24 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
       if (HL(1, 1, a, b, 0) != 0.0 || HL(1, 1, a, b, 1) != 0.0)
         n2_hop(m, a + Ns, b + Ns, HL(1, 1, a, b, 0), HL(1, 1, a, b, 1), s);
     }
-  // spin-flip local terms :85-110
-  for (int is = 0; is < 2; is++) {
+  if (superc) {
+    // anomalous local pairing: impHloc_anomalous + pair_field (ED_SUPERC/stored/Himp.f90:86-125)
+    bool any_an = false;
+    for (int a = 0; a < No; a++) {
+      any_an = any_an || c_n2.pair_field[a] != 0.0;
+      for (int b = 0; b < No; b++) any_an = any_an || c_n2.anom[a][b][0] != 0.0 || c_n2.anom[a][b][1] != 0.0;
+    }
+    if (any_an)
+      for (int a = 0; a < No; a++)
+        for (int b = 0; b < No; b++) {
+          const double pf = a == b ? c_n2.pair_field[a] : 0.0;
+          const bool ua = (m >> a) & 1u, db = (m >> (b + Ns)) & 1u;
+          if (ua && db) n2_pair(m, a, b + Ns, false, c_n2.anom[a][b][0] + pf, c_n2.anom[a][b][1], s);
+          if (!ua && !db) n2_pair(m, b + Ns, a, true, c_n2.anom[a][b][0] + pf, -c_n2.anom[a][b][1], s);
+        }
+  }
+  // spin-flip local terms :85-110 (nonsu2 only)
+  for (int is = 0; is < 2 && !superc; is++) {
     const int js = 1 - is;
     for (int a = 0; a < No; a++)
       for (int b = 0; b < No; b++)
@@ -196,6 +262,18 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
       for (int b = 0; b < No; b++)
         if (a != b && ((m >> b) & 1u) && ((m >> (b + Ns)) & 1u) && !((m >> (a + Ns)) & 1u) && !((m >> a) & 1u))
           n2_chain(m, b, b + Ns, a + Ns, a, P.Jp[a][b], s);
+  if (superc) {
+    // bath pairing Delta_l (c_dw c_up + h.c.) on every bath level (ED_SUPERC/stored/Hbath.f90:97-133)
+    for (int a = 0; a < P.Nfoo; a++)
+      for (int k = 0; k < Nb; k++) {
+        const int ms = P.stride[a][k] - 1;
+        const double d = c_n2.bath_d[a][k];
+        if (d == 0.0) continue;
+        const bool u = (m >> ms) & 1u, w = (m >> (ms + Ns)) & 1u;
+        if (u && w) n2_pair(m, ms, ms + Ns, false, d, 0.0, s);
+        if (!u && !w) n2_pair(m, ms + Ns, ms, true, d, 0.0, s);
+      }
+  }
   // ---- Himp_bath.f90: spin-conserving hybridisation :10-67
   for (int a = 0; a < No; a++)
     for (int k = 0; k < Nb; k++) {
@@ -208,8 +286,8 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
         }
       }
     }
-  // spin-flip hybridisation u :72-136
-  for (int a = 0; a < No; a++)
+  // spin-flip hybridisation u :72-136 (nonsu2 only)
+  for (int a = 0; a < No && !superc; a++)
     for (int k = 0; k < Nb; k++) {
       const int ms = P.stride[a][k] - 1;
       const double u1 = P.bath_u[0][a][k], u2 = P.bath_u[1][a][k];
@@ -246,31 +324,52 @@ k_n2_fill(const int32_t *__restrict__ map, int64_t row0, int64_t nloc, const int
 int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
                      int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map);
 
-int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot) {
+// mode/quantum number are in h; builds map + CSR of this rank's rows and opens the stored-H sector
+static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
   if (!E.inited) return set_error("edgpu_init was not called");
-  if (E.sec.open) return set_error("close the direct-H sector before opening a nonsu2 one");
+  if (E.sec.open) return set_error("close the direct-H sector before opening a %s one", who);
   if (E.csr.open) csr_close(E);
-  const int nbits = 2 * p->Ns;
-  if (p->Ns < 1 || nbits > 31) return set_error("nonsu2: 2*Ns = %d exceeds the 31-bit packed state", nbits);
+  const edgpu_nonsu2_params *p = &h.p;
+  const int nbits = 2 * p->Ns, Ns = p->Ns;
+  if (p->Ns < 1 || nbits > 31) return set_error("%s: 2*Ns = %d exceeds the 31-bit packed state", who, nbits);
   if (p->Norb < 1 || p->Norb > EDGPU_MAXORB || p->Nbath < 0 || p->Nbath > EDGPU_MAXBATH)
-    return set_error("nonsu2: Norb/Nbath out of range");
+    return set_error("%s: Norb/Nbath out of range", who);
   if (p->bath_type != EDGPU_BATH_NORMAL && p->bath_type != EDGPU_BATH_HYBRID)
-    return set_error("nonsu2: only normal / hybrid baths are generated on the device "
-                     "(replica / general: hand the host-built spH0 to edgpu_csr_open_z)");
-  if (ntot < 0 || ntot > nbits) return set_error("nonsu2: Ntot = %d outside [0, %d]", ntot, nbits);
-  static Nonsu2Dev h;  // 10 KB: not on the stack
-  h.p = *p;
-  h.ntot = ntot;
+    return set_error("%s: only normal / hybrid baths are generated on the device "
+                     "(replica / general: hand the host-built spH0 to edgpu_csr_open_z)", who);
   h.nbits = nbits;
   for (int n = 0; n <= 32; n++)
     for (int k = 0; k <= 32; k++) {
       int64_t c = k > n ? 0 : (k == 0 || k == n ? 1 : (int64_t)h.binom[n - 1][k - 1] + h.binom[n - 1][k]);
       h.binom[n][k] = (int32_t)std::min<int64_t>(c, INT32_MAX);
     }
-  const int64_t dim = host_binomial(nbits, ntot);
-  if (dim > INT32_MAX) return set_error("nonsu2: sector dimension %lld exceeds 32-bit columns", (long long)dim);
+  int64_t dim = 0;
+  int32_t *d_off = nullptr;
+  if (h.mode == MODE_NONSU2) {
+    if (h.ntot < 0 || h.ntot > nbits) return set_error("nonsu2: Ntot = %d outside [0, %d]", h.ntot, nbits);
+    dim = host_binomial(nbits, h.ntot);
+  } else {
+    if (h.ntot < -Ns || h.ntot > Ns) return set_error("superc: Sz = %d outside [%d, %d]", h.ntot, -Ns, Ns);
+    // first sector index of every dw integer (ED_SECTOR.f90:262-281: idw outer, iup inner)
+    std::vector<int32_t> off(((size_t)1 << Ns) + 1, 0);
+    for (uint32_t idw = 0; idw < (1u << Ns); idw++) {
+      const int k = __builtin_popcount(idw) + h.ntot;
+      const int64_t c = (k < 0 || k > Ns) ? 0 : host_binomial(Ns, k);
+      dim += c;
+      if (dim > INT32_MAX) return set_error("superc: sector dimension exceeds 32-bit columns");
+      off[(size_t)idw + 1] = (int32_t)dim;
+    }
+    EDGPU_CUDA(cudaMalloc(&d_off, sizeof(int32_t) * off.size()));
+    EDGPU_CUDA(cudaMemcpy(d_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));
+  }
+  h.off = d_off;
+  if (dim > INT32_MAX) {
+    cudaFree(d_off);
+    return set_error("%s: sector dimension %lld exceeds 32-bit columns", who, (long long)dim);
+  }
   EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_n2, &h, sizeof(h), 0, cudaMemcpyHostToDevice, E.stream));
-  // row split MpiQ = Dim/P, remainder to the last rank (ED_HAMILTONIAN_NONSU2.f90:72-79)
+  // row split MpiQ = Dim/P, remainder to the last rank (ED_HAMILTONIAN_NONSU2.f90:72-79,
+  // ED_HAMILTONIAN_SUPERC.f90:76-88)
   const int P = E.nranks;
   const int64_t q = dim / P;
   const int64_t row0 = q * E.rank, nloc = q + (E.rank == P - 1 ? dim % P : 0);
@@ -283,6 +382,7 @@ int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot) {
     cudaFree(d_cols);
     cudaFree(d_rowptr);
     cudaFree(d_vals);
+    cudaFree(d_off);
     return rc;
   };
 #define N2_CUDA(call)                                                                         \
@@ -292,8 +392,10 @@ int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot) {
       return fail(set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__)); \
   } while (0)
   N2_CUDA(cudaMalloc(&d_map, sizeof(int32_t) * std::max<int64_t>(dim, 1)));
-  k_n2_map<<<(unsigned)((dim + 255) / 256), 256, 0, E.stream>>>(d_map, dim);
-  EDGPU_COUNT_LAUNCH();
+  if (dim > 0) {
+    k_n2_map<<<(unsigned)((dim + 255) / 256), 256, 0, E.stream>>>(d_map, dim);
+    EDGPU_COUNT_LAUNCH();
+  }
   N2_CUDA(cudaMalloc(&d_cnt, sizeof(int32_t) * std::max<int64_t>(nloc, 1)));
   const unsigned grid = (unsigned)std::max<int64_t>(1, (nloc + 127) / 128);
   k_n2_count<<<grid, 128, 0, E.stream>>>(d_map, row0, nloc, d_cnt);
@@ -316,9 +418,53 @@ int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot) {
 #undef N2_CUDA
   cudaFree(d_cnt);
   d_cnt = nullptr;
+  cudaFree(d_off);  // only the builder kernels rank states
+  d_off = nullptr;
   int rc = csr_adopt_device(E, true, nloc, dim, row0, d_rowptr, d_cols, d_vals, nnz, d_map);
   if (rc) return fail(rc);
   return 0;
+}
+
+static Nonsu2Dev g_host_dev;  // ~14 KB: not on the stack
+
+int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot) {
+  Nonsu2Dev &h = g_host_dev;
+  h = Nonsu2Dev();
+  h.p = *p;
+  h.mode = MODE_NONSU2;
+  h.ntot = ntot;
+  return packed_open(E, h, "nonsu2");
+}
+
+int superc_open(Engine &E, const edgpu_superc_params *p, int sz) {
+  Nonsu2Dev &h = g_host_dev;
+  h = Nonsu2Dev();
+  edgpu_nonsu2_params &q = h.p;
+  q.Ns = p->Ns;
+  q.Norb = p->Norb;
+  q.Nbath = p->Nbath;
+  q.bath_type = p->bath_type;
+  q.hfmode = p->hfmode;
+  q.Nfoo = p->Nfoo;
+  q.xmu = p->xmu;
+  for (int s = 0; s < 2; s++)
+    for (int a = 0; a < EDGPU_MAXORB; a++)
+      for (int b = 0; b < EDGPU_MAXORB; b++)
+        for (int c = 0; c < 2; c++) q.hloc[s][s][a][b][c] = p->hloc[s][a][b][c];
+  memcpy(q.Uloc, p->Uloc, sizeof(q.Uloc));
+  memcpy(q.Ust, p->Ust, sizeof(q.Ust));
+  memcpy(q.Jh, p->Jh, sizeof(q.Jh));
+  memcpy(q.Jx, p->Jx, sizeof(q.Jx));
+  memcpy(q.Jp, p->Jp, sizeof(q.Jp));
+  memcpy(q.bath_e, p->bath_e, sizeof(q.bath_e));
+  memcpy(q.bath_v, p->bath_v, sizeof(q.bath_v));
+  memcpy(q.stride, p->stride, sizeof(q.stride));
+  memcpy(h.anom, p->hloc_anomalous, sizeof(h.anom));
+  memcpy(h.pair_field, p->pair_field, sizeof(h.pair_field));
+  memcpy(h.bath_d, p->bath_d, sizeof(h.bath_d));
+  h.mode = MODE_SUPERC;
+  h.ntot = sz;
+  return packed_open(E, h, "superc");
 }
 
 }  // namespace edgpu

@@ -14,6 +14,7 @@ sp_lanc_eigh                   :func:`sp_lanc_eigh`             call site ED_DIA
 sp_lanc_tridiag                :func:`sp_lanc_tridiag`          ED_HAMILTONIAN_NORMAL.f90:360
 sp_eigh (ARPACK)               :func:`sp_eigh`                  call site ED_DIAG_NORMAL.f90:179
 build_Hv_sector_nonsu2         :func:`build_Hv_sector_nonsu2`   ED_HAMILTONIAN_NONSU2.f90:31
+build_Hv_sector_superc         :func:`build_Hv_sector_superc`   ED_HAMILTONIAN_SUPERC.f90:31
 tridiag_Hv_sector_normal       :func:`tridiag_Hv_sector_normal` :321
 ed_diag_d                      :func:`ed_diag_d`                ED_DIAG_NORMAL.f90:76
 lanc_build_gf_normal_diag      :func:`lanc_build_gf_normal_diag` ED_GF_NORMAL.f90:131
@@ -31,7 +32,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _abi
-from ._abi import EdgpuError, MAXBATH, MAXORB, NormalParams, Nonsu2Params, check, ptr
+from ._abi import (EdgpuError, MAXBATH, MAXORB, NormalParams, Nonsu2Params, SupercParams, check,
+                   ptr)
 
 BATH_CODES = {"normal": 0, "hybrid": 1, "replica": 2, "general": 3}
 
@@ -433,6 +435,101 @@ class EDModelNonsu2:
                 st[a, k] = (No + k + 1) if self.bath_type == "hybrid" else (No + a * Nb + k + 1)
         p.stride[:] = st.ravel().tolist()
         return p
+
+
+@dataclass
+class EDModelSuperc:
+    """Module globals read by ``ed_buildH_superc_main`` (ed_mode=superc, normal / hybrid bath)."""
+
+    Norb: int = 2
+    Nbath: int = 2
+    bath_type: str = "normal"
+    Uloc: tuple = (-2.0, -2.0)
+    Ust: float = 0.0
+    Jh: float = 0.0
+    Jx: float = 0.0
+    Jp: float = 0.0
+    xmu: float = 0.0
+    hfmode: bool = True
+    ed_hw_bath: float = 2.0
+    deltasc: float = 0.02
+    hloc: np.ndarray | None = None            # complex [2, Norb, Norb]  impHloc(s, s, a, b)
+    hloc_anomalous: np.ndarray | None = None  # complex [Norb, Norb]
+    pair_field: tuple = ()
+    bath_e: np.ndarray | None = None          # [2, Nfoo, Nbath]
+    bath_d: np.ndarray | None = None          # [Nfoo, Nbath]
+    bath_v: np.ndarray | None = None          # [2, Norb, Nbath]
+
+    @property
+    def Ns(self) -> int:
+        return self.Nbath + self.Norb if self.bath_type == "hybrid" else (self.Nbath + 1) * self.Norb
+
+    @property
+    def Nfoo(self) -> int:
+        return 1 if self.bath_type == "hybrid" else self.Norb
+
+    def init_dmft_bath(self):
+        """init_dmft_bath for superc (ED_BATH_DMFT.f90:211-244): e and v as NORMAL mode, d = deltasc."""
+        tmp = EDModel(Norb=self.Norb, Nbath=self.Nbath, bath_type=self.bath_type,
+                      ed_hw_bath=self.ed_hw_bath).init_dmft_bath()
+        self.bath_e, self.bath_v = tmp.bath_e, tmp.bath_v
+        self.bath_d = np.full((self.Nfoo, self.Nbath), self.deltasc)
+        return self
+
+    def params(self) -> SupercParams:
+        if self.bath_e is None:
+            self.init_dmft_bath()
+        No, Nb = self.Norb, self.Nbath
+        if No > MAXORB or Nb > MAXBATH or 2 * self.Ns > 31:
+            raise EdgpuError("model too large for edgpu_superc_params")
+        p = SupercParams()
+        p.Ns, p.Norb, p.Nbath = self.Ns, No, Nb
+        p.bath_type = BATH_CODES[self.bath_type]
+        p.hfmode, p.Nfoo, p.xmu = int(self.hfmode), self.Nfoo, self.xmu
+        hl = np.zeros((2, MAXORB, MAXORB, 2))
+        if self.hloc is not None:
+            h = np.asarray(self.hloc, complex)
+            hl[:, :No, :No, 0], hl[:, :No, :No, 1] = h.real, h.imag
+        p.hloc[:] = hl.ravel().tolist()
+        an = np.zeros((MAXORB, MAXORB, 2))
+        if self.hloc_anomalous is not None:
+            h = np.asarray(self.hloc_anomalous, complex)
+            an[:No, :No, 0], an[:No, :No, 1] = h.real, h.imag
+        p.hloc_anomalous[:] = an.ravel().tolist()
+        pf = np.zeros(MAXORB)
+        pf[: len(self.pair_field)] = self.pair_field
+        p.pair_field[:] = pf.tolist()
+        U = np.zeros(MAXORB)
+        U[:No] = np.asarray(self.Uloc, float)[:No]
+        p.Uloc[:] = U.tolist()
+        off = np.zeros((MAXORB, MAXORB))
+        off[:No, :No] = 1.0 - np.eye(No)
+        for name, val in (("Ust", self.Ust), ("Jh", self.Jh), ("Jx", self.Jx), ("Jp", self.Jp)):
+            getattr(p, name)[:] = (val * off).ravel().tolist()
+        for name, arr, n0 in (("bath_e", self.bath_e, self.Nfoo), ("bath_v", self.bath_v, No)):
+            buf = np.zeros((2, MAXORB, MAXBATH))
+            buf[:, :n0, :Nb] = arr
+            getattr(p, name)[:] = buf.ravel().tolist()
+        bd = np.zeros((MAXORB, MAXBATH))
+        bd[: self.Nfoo, :Nb] = self.bath_d
+        p.bath_d[:] = bd.ravel().tolist()
+        st = np.zeros((MAXORB, MAXBATH), np.int32)
+        for a in range(No):
+            for k in range(Nb):
+                st[a, k] = (No + k + 1) if self.bath_type == "hybrid" else (No + a * Nb + k + 1)
+        p.stride[:] = st.ravel().tolist()
+        return p
+
+
+def build_Hv_sector_superc(model: EDModelSuperc, sz: int):
+    """build_Hv_sector_superc + ed_buildH_superc_main on the device for the sector Sz = Nup - Ndw."""
+    global _open_is_complex
+    check(_abi.load().edgpu_sector_open_superc(C.byref(model.params()), sz))
+    _open_is_complex = True
+
+
+def delete_Hv_sector_superc():
+    delete_Hv_sector_csr()
 
 
 def build_Hv_sector_nonsu2(model: EDModelNonsu2, ntot: int):

@@ -80,6 +80,29 @@ typedef struct edgpu_nonsu2_params {
   int32_t stride[EDGPU_MAXORB][EDGPU_MAXBATH];      /* getBathStride(a,k), 1-based */
 } edgpu_nonsu2_params;
 
+/*
+ * Everything ed_buildH_superc_main reads from module globals
+ * (ED_HAMILTONIAN_SUPERC_STORED_HxV.f90:29-260 and ED_SUPERC/stored/*.f90), normal / hybrid bath.
+ * With Nspin=1 the caller stores the same numbers in both spin slots (the reference's index
+ * `Nspin`, stored/Himp.f90:18).
+ */
+typedef struct edgpu_superc_params {
+  int32_t Ns, Norb, Nbath, bath_type, hfmode, Nfoo, pad0, pad1;
+  double xmu;
+  double hloc[2][EDGPU_MAXORB][EDGPU_MAXORB][2];         /* impHloc(s,s,a,b)+mfHloc(s,s,a,b) */
+  double hloc_anomalous[EDGPU_MAXORB][EDGPU_MAXORB][2];  /* impHloc_anomalous(1,1,a,b) */
+  double pair_field[EDGPU_MAXORB];
+  double Uloc[EDGPU_MAXORB];
+  double Ust[EDGPU_MAXORB][EDGPU_MAXORB];
+  double Jh[EDGPU_MAXORB][EDGPU_MAXORB];
+  double Jx[EDGPU_MAXORB][EDGPU_MAXORB];
+  double Jp[EDGPU_MAXORB][EDGPU_MAXORB];
+  double bath_e[2][EDGPU_MAXORB][EDGPU_MAXBATH];   /* dmft_bath%e(ispin, iorb|1, k) */
+  double bath_d[EDGPU_MAXORB][EDGPU_MAXBATH];      /* dmft_bath%d(1, iorb|1, k): bath pairing */
+  double bath_v[2][EDGPU_MAXORB][EDGPU_MAXBATH];   /* dmft_bath%v(ispin, iorb, k) */
+  int32_t stride[EDGPU_MAXORB][EDGPU_MAXBATH];     /* getBathStride(a,k), 1-based */
+} edgpu_superc_params;
+
 /* ---------------- engine / communicator ---------------- */
 
 /* Selects the CUDA device and creates the engine's stream.  Replaces nothing in the
@@ -144,6 +167,11 @@ int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const in
  * edgpu_csr_nnz / edgpu_csr_get download the device CSR (rowptr 0-based offsets, cols 1-based
  * global, vals (re,im) pairs for complex sectors), duplicates within a row add up. */
 int edgpu_sector_open_nonsu2(const edgpu_nonsu2_params *p, int ntot);
+/* build_Hv_sector_superc(isector) + ed_buildH_superc_main (ED_HAMILTONIAN_SUPERC.f90:31-140,
+ * ED_HAMILTONIAN_SUPERC_STORED_HxV.f90:29-260) on the device, sector Sz = Nup - Ndw
+ * (build_sector, ED_SECTOR.f90:244-281): same contract as edgpu_sector_open_nonsu2, with the
+ * anomalous local terms (impHloc_anomalous, pair_field) and the bath pairing amplitudes d. */
+int edgpu_sector_open_superc(const edgpu_superc_params *p, int sz);
 int64_t edgpu_csr_nnz(void);
 int edgpu_csr_get(int64_t *rowptr, int32_t *cols, double *vals);
 

@@ -1,0 +1,253 @@
+"""CPU restatement of EDIpack's SUPERC-mode stored Hamiltonian (ED_SPARSE_H=T), numpy.
+
+TEST INFRASTRUCTURE ONLY (see oracle/ed_oracle.h): the checker for the device-side builder of
+``edgpu_sector_open_superc``; the product never imports it.
+
+Follows, per state of the sector (normal / hybrid bath, Nspin=1 or 2):
+  build_sector (superc)        src/singlesite/ED_SECTOR.f90:244-281  m = iup + idw*2**Ns, idw outer /
+                               iup inner, popcnt(iup) - popcnt(idw) = Sz
+  c / cdg on the 2*Ns-bit state  src/singlesite/ED_AUX_FUNX.f90:334-384
+  ED_SUPERC/stored/Himp.f90    diagonal :11-27, same-spin hops :31-80, anomalous local pairing
+                               impHloc_anomalous + pair_field :86-125
+  ED_SUPERC/stored/Hint.f90    = ED_NONSU2/stored/Hint.f90 (density-density, Hartree shifts, S-E, P-H)
+  ED_SUPERC/stored/Hbath.f90   normal/hybrid diagonal :12-27, bath pairing d :97-133
+  ED_SUPERC/stored/Himp_bath.f90  spin-conserving hybridisation :10-67
+  ED_OBSERVABLES_SUPERC.f90    dens/docc :150-165, phisc :204-248 through
+                               apply_Cops(v,[1,1],[-1,+1],[a,b],[dw,up]) (ED_SECTOR.f90)
+Matrix convention as in the reference: sp_insert_element(spH0,htmp,i,j), row i = the state the
+operators act on, column j = the resulting state; duplicates accumulate.
+
+Parity status: pinned to test/src/NORMAL_SUPERC/{evals,dens,docc,phisc}.check and
+test/src/HYBRID_SUPERC/{evals,dens,docc}.check (tests/test_oracle_golden_superc.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from edipack_oracle_nonsu2 import _c, _cdg
+
+
+@dataclass
+class ModelSuperc:
+    Norb: int = 2
+    Nbath: int = 2
+    bath_type: str = "normal"          # normal | hybrid
+    Uloc: tuple = (-2.0, -2.0)
+    Ust: float = 0.0
+    Jh: float = 0.0
+    Jx: float = 0.0
+    Jp: float = 0.0
+    xmu: float = 0.0
+    hfmode: bool = True
+    ed_hw_bath: float = 2.0
+    deltasc: float = 0.02
+    hloc: np.ndarray | None = None       # complex [2, Norb, Norb]  impHloc(s,s,a,b)
+    hloc_anomalous: np.ndarray | None = None  # complex [Norb, Norb]  impHloc_anomalous(1,1,a,b)
+    pair_field: tuple = ()               # [Norb]
+    bath_e: np.ndarray | None = None     # [2, Nfoo, Nbath]
+    bath_d: np.ndarray | None = None     # [Nfoo, Nbath]   dmft_bath%d(1,:,:)
+    bath_v: np.ndarray | None = None     # [2, Norb, Nbath]
+
+    @property
+    def Ns(self):  # ED_SETUP.f90:118-126
+        return self.Nbath + self.Norb if self.bath_type == "hybrid" else (self.Nbath + 1) * self.Norb
+
+    @property
+    def Nfoo(self):
+        return 1 if self.bath_type == "hybrid" else self.Norb
+
+    def stride(self, a, k):  # getBathStride(a+1,k+1), 1-based site (ED_SETUP.f90:605-622)
+        if self.bath_type == "hybrid":
+            return self.Norb + k + 1
+        return self.Norb + a * self.Nbath + k + 1
+
+    def default_bath(self):
+        """init_dmft_bath, ED_BATH_DMFT.f90:211-244 (superc: d = deltasc)."""
+        Nb, hw = self.Nbath, self.ed_hw_bath
+        e = np.zeros(Nb)
+        e[0], e[-1] = -hw, hw
+        Nh = Nb // 2
+        if Nb % 2 == 0 and Nb >= 4:
+            de = hw / max(Nh - 1, 1)
+            e[Nh - 1], e[Nh] = -0.1, 0.1
+            for i in range(2, Nh):
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        elif Nb % 2 != 0 and Nb >= 3:
+            de = hw / Nh
+            e[Nh] = 0.0
+            for i in range(2, Nh + 1):
+                e[i - 1] = -hw + (i - 1) * de
+                e[Nb - i] = hw - (i - 1) * de
+        self.bath_e = np.broadcast_to(e, (2, self.Nfoo, Nb)).copy()
+        self.bath_d = np.full((self.Nfoo, Nb), self.deltasc)
+        self.bath_v = np.full((2, self.Norb, Nb), max(0.1, 1.0 / math.sqrt(Nb)))
+        return self
+
+
+def build_sector(Ns: int, Sz: int) -> np.ndarray:
+    """List of m = iup + idw*2**Ns with popcnt(iup) - popcnt(idw) = Sz, idw outer / iup inner
+    (ED_SECTOR.f90:262-281): ascending in m."""
+    one = np.arange(1 << Ns, dtype=np.int64)
+    pc = np.array([bin(int(x)).count("1") for x in one])
+    out = []
+    for idw in one:
+        ups = one[pc - pc[idw] == Sz]
+        out.append(ups + (idw << Ns))
+    return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+
+def stored_H(model: ModelSuperc, Sz: int):
+    """ed_buildH_superc_main (ED_HAMILTONIAN_SUPERC_STORED_HxV.f90:29-260) for one sector:
+    returns (map, rowptr, cols [1-based], vals [complex]) in list-of-rows insertion order."""
+    if model.bath_e is None:
+        model.default_bath()
+    Ns, No, Nb = model.Ns, model.Norb, model.Nbath
+    smap = build_sector(Ns, Sz)
+    index = {int(m): i + 1 for i, m in enumerate(smap)}
+    hloc = np.zeros((2, No, No), complex) if model.hloc is None else np.asarray(model.hloc, complex)
+    anom = (np.zeros((No, No), complex) if model.hloc_anomalous is None
+            else np.asarray(model.hloc_anomalous, complex))
+    pf = np.zeros(No)
+    pf[: len(model.pair_field)] = model.pair_field
+    U = np.asarray(model.Uloc, float)
+    offd = 1.0 - np.eye(No)
+    Ust, Jh, Jx, Jp = model.Ust * offd, model.Jh * offd, model.Jx * offd, model.Jp * offd
+    rows = []
+    for m_ in smap:
+        m = int(m_)
+        row = {}
+
+        def ins(val, j):
+            row[j] = row.get(j, 0.0) + val
+
+        ib = [(m >> k) & 1 for k in range(2 * Ns)]
+        nup = [float(ib[a]) for a in range(No)]
+        ndw = [float(ib[a + Ns]) for a in range(No)]
+        i = index[m]
+
+        def chain(ops, amp):
+            """ops applied left to right: list of (fn, pos 1-based); inserts amp*signs at (i, j)."""
+            k, s = m, 1.0
+            for f, pos in ops:
+                r = f(pos, k)
+                if r is None:
+                    return
+                k, sg = r
+                s *= sg
+            ins(amp * s, index[k])
+
+        # ---- Himp.f90
+        h = 0.0
+        for a in range(No):
+            h += hloc[0, a, a] * nup[a] + hloc[1, a, a] * ndw[a] - model.xmu * (nup[a] + ndw[a])
+        ins(h, i)
+        for a in range(No):
+            for b in range(No):
+                if hloc[0, a, b] != 0 and ib[b] == 1 and ib[a] == 0:
+                    chain([(_c, b + 1), (_cdg, a + 1)], np.conj(hloc[0, a, b]))
+                if hloc[1, a, b] != 0 and ib[b + Ns] == 1 and ib[a + Ns] == 0:
+                    chain([(_c, b + 1 + Ns), (_cdg, a + 1 + Ns)], np.conj(hloc[1, a, b]))
+        if np.any(pf != 0) or np.any(np.abs(anom) != 0):
+            for a in range(No):
+                for b in range(No):
+                    if ib[a] == 1 and ib[b + Ns] == 1:
+                        chain([(_c, a + 1), (_c, b + 1 + Ns)], anom[a, b] + (pf[a] if a == b else 0.0))
+                    if ib[a] == 0 and ib[b + Ns] == 0:
+                        chain([(_cdg, b + 1 + Ns), (_cdg, a + 1)],
+                              np.conj(anom[a, b]) + (pf[a] if a == b else 0.0))
+        # ---- Hint.f90 (identical to nonsu2)
+        h = 0.0
+        for a in range(No):
+            h += U[a] * nup[a] * ndw[a]
+        for a in range(No):
+            for b in range(a + 1, No):
+                h += Ust[a, b] * (nup[a] * ndw[b] + nup[b] * ndw[a])
+                h += (Ust[a, b] - Jh[a, b]) * (nup[a] * nup[b] + ndw[a] * ndw[b])
+        if model.hfmode:
+            for a in range(No):
+                h += -0.5 * U[a] * (nup[a] + ndw[a]) + 0.25 * U[a]
+            for a in range(No):
+                for b in range(a + 1, No):
+                    nn = nup[a] + ndw[a] + nup[b] + ndw[b]
+                    h += -0.5 * Ust[a, b] * nn + 0.5 * Ust[a, b]
+                    h += -0.5 * (Ust[a, b] - Jh[a, b]) * nn + 0.5 * (Ust[a, b] - Jh[a, b])
+        ins(h, i)
+        if No > 1 and np.any(Jx != 0):
+            for a in range(No):
+                for b in range(No):
+                    if a != b and ib[b] == 1 and ib[a + Ns] == 1 and ib[b + Ns] == 0 and ib[a] == 0:
+                        chain([(_c, b + 1), (_c, a + 1 + Ns), (_cdg, b + 1 + Ns), (_cdg, a + 1)], Jx[a, b])
+        if No > 1 and np.any(Jp != 0):
+            for a in range(No):
+                for b in range(No):
+                    if a != b and ib[b] == 1 and ib[b + Ns] == 1 and ib[a + Ns] == 0 and ib[a] == 0:
+                        chain([(_c, b + 1), (_c, b + 1 + Ns), (_cdg, a + 1 + Ns), (_cdg, a + 1)], Jp[a, b])
+        # ---- Hbath.f90 (normal / hybrid)
+        h = 0.0
+        for a in range(model.Nfoo):
+            for k in range(Nb):
+                s = model.stride(a, k)
+                h += model.bath_e[0, a, k] * ib[s - 1] + model.bath_e[1, a, k] * ib[s - 1 + Ns]
+        ins(h, i)
+        for a in range(model.Nfoo):
+            for k in range(Nb):
+                ms = model.stride(a, k)
+                d = model.bath_d[a, k]
+                if d != 0 and ib[ms - 1] == 1 and ib[ms - 1 + Ns] == 1:
+                    chain([(_c, ms), (_c, ms + Ns)], d)
+                if d != 0 and ib[ms - 1] == 0 and ib[ms - 1 + Ns] == 0:
+                    chain([(_cdg, ms + Ns), (_cdg, ms)], d)
+        # ---- Himp_bath.f90
+        for a in range(No):
+            for k in range(Nb):
+                ms = model.stride(a, k)
+                for sp in range(2):
+                    v = model.bath_v[sp, a, k]
+                    if v != 0:
+                        chain([(_c, a + 1 + sp * Ns), (_cdg, ms + sp * Ns)], np.conj(v))  # imp -> bath
+                        chain([(_c, ms + sp * Ns), (_cdg, a + 1 + sp * Ns)], np.conj(v))  # bath -> imp
+        rows.append(row)
+    rowptr = np.zeros(len(rows) + 1, np.int64)
+    cols, vals = [], []
+    for r, row in enumerate(rows):
+        for j, val in row.items():
+            cols.append(j)
+            vals.append(val)
+        rowptr[r + 1] = len(cols)
+    return smap, rowptr, np.array(cols, np.int32), np.array(vals, complex)
+
+
+def observables(model: ModelSuperc, Sz: int, smap, vec):
+    """dens, docc, phisc of one state with weight 1 (ED_OBSERVABLES_SUPERC.f90:150-165, 204-248):
+    RePhi(a,b) = ( |(c_{a,dw} + c^+_{b,up})|gs>|^2 - <n_{a,dw}> - (1 - <n_{b,up}>) ) / 2."""
+    Ns, No = model.Ns, model.Norb
+    w = np.abs(vec) ** 2
+    dens, docc = np.zeros(No), np.zeros(No)
+    dup, ddw = np.zeros(No), np.zeros(No)
+    for a in range(No):
+        nu = ((smap >> a) & 1).astype(float)
+        nd = ((smap >> (a + Ns)) & 1).astype(float)
+        dens[a] = float((w * (nu + nd)).sum())
+        docc[a] = float((w * nu * nd).sum())
+        dup[a], ddw[a] = float((w * nu).sum()), float((w * nd).sum())
+    phi = np.zeros((No, No))
+    if Sz < Ns:
+        tmap = build_sector(Ns, Sz + 1)
+        tindex = {int(m): i for i, m in enumerate(tmap)}
+        for a in range(No):
+            for b in range(No):
+                eta = np.zeros(len(tmap), complex)
+                for i, m_ in enumerate(smap):
+                    m = int(m_)
+                    r = _c(a + 1 + Ns, m)
+                    if r is not None:
+                        eta[tindex[r[0]]] += r[1] * vec[i]
+                    r = _cdg(b + 1, m)
+                    if r is not None:
+                        eta[tindex[r[0]]] += r[1] * vec[i]
+                phi[a, b] = 0.5 * (float(np.vdot(eta, eta).real) - ddw[a] - (1.0 - dup[b]))
+    return dens, docc, phi

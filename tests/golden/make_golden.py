@@ -33,7 +33,9 @@ def main():
               "INEQ_NORMAL_NORMAL": ("dens", "docc", "energy", "doubles", "Sigma_momenta"),
               "HYBRID_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
               "REPLICA_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
-              "GENERAL_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta")}
+              "GENERAL_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
+              "NORMAL_SUPERC": ("evals", "dens", "docc", "phisc", "energy", "doubles", "imp"),
+              "HYBRID_SUPERC": ("evals", "dens", "docc", "phisc", "energy", "doubles", "imp")}
     for name in checks:
         d = os.path.join(REF, name)
         g = {"source": f"test/src/{name}", "inputs": inputs(os.path.join(d, "inputED.in"))}

@@ -177,3 +177,20 @@ def replica_normal_kwargs(kind="replica"):
                 Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
                 beta=_f(g["BETA"]), hloc=hloc, hbath=hb, bath_e=np.zeros((2, norb, nb)),
                 bath_v=np.full((2, norb, nb), max(0.1, 1.0 / np.sqrt(nb))))
+
+
+def superc_model(oracle_superc, name):
+    """test/src/NORMAL_SUPERC / HYBRID_SUPERC: attractive two-orbital model, default bath with
+    d = DELTASC, Hloc = Delta*sigma_z(orbital) (ed_normal_superc.f90:57-63)."""
+    g = golden(name)["inputs"]
+    norb = int(g["NORB"])
+    delta = _f(g["DELTA"])
+    hloc = np.zeros((2, norb, norb), complex)
+    for s in range(2):
+        hloc[s] = np.diag([delta, -delta])
+    m = oracle_superc.ModelSuperc(
+        Norb=norb, Nbath=int(g["NBATH"]), bath_type=g["BATH_TYPE"],
+        Uloc=tuple(_f(x) for x in g["ULOC"].split(",")), Ust=_f(g["UST"]), Jh=_f(g["JH"]),
+        Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
+        ed_hw_bath=_f(g["ED_HW_BATH"]), deltasc=_f(g["DELTASC"]), hloc=hloc)
+    return m.default_bath()

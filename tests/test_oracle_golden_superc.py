@@ -1,0 +1,45 @@
+"""Pins the SUPERC-mode oracle (oracle/edipack_oracle_superc.py) to the reference's golden vectors
+test/src/NORMAL_SUPERC and HYBRID_SUPERC {evals,dens,docc,phisc}.check (reference tolerance 1e-9
+on evals; its dens/docc/phisc were produced from an ARPACK vector and are themselves consistent
+only to ~2e-8 -- e.g. HYBRID_SUPERC dens sums to 1.99999998693 -- hence 5e-8 there)."""
+import numpy as np
+import pytest
+
+from models import golden, superc_model
+
+
+@pytest.mark.parametrize("name", ["normal_superc", "hybrid_superc"])
+def test_superc_fixture(name):
+    import edipack_oracle_nonsu2 as N
+    import edipack_oracle_superc as S
+
+    g = golden(name)
+    m = superc_model(S, name)
+    best = None
+    for sz in range(-2, 3):
+        smap, rp, cj, va = S.stored_H(m, sz)
+        H = N.to_dense(rp, cj, va)
+        assert np.abs(H - H.conj().T).max() < 1e-13
+        ev, U = np.linalg.eigh(H)
+        if best is None or ev[0] < best[0]:
+            best = (ev[0], sz, smap, U[:, 0])
+    e, sz, smap, v = best
+    assert sz == 0
+    assert abs(e - g["evals"][0]) < 1e-9
+    dens, docc, phi = S.observables(m, sz, smap, v)
+    assert np.abs(dens - np.array(g["dens"])).max() < 5e-8
+    assert np.abs(docc - np.array(g["docc"])).max() < 5e-8
+    assert np.abs(phi.ravel() - np.array(g["phisc"])).max() < 5e-8
+
+
+def test_superc_sector_map_order():
+    import edipack_oracle_superc as S
+
+    for ns, sz in ((3, 0), (4, 1), (4, -2), (5, 5), (3, -3)):
+        smap = S.build_sector(ns, sz)
+        assert np.all(np.diff(smap) > 0)
+        iup, idw = smap & ((1 << ns) - 1), smap >> ns
+        pc = lambda x: np.array([bin(int(t)).count("1") for t in x])
+        assert np.all(pc(iup) - pc(idw) == sz)
+        from math import comb
+        assert len(smap) == sum(comb(ns, k) * comb(ns, k - sz) for k in range(ns + 1) if 0 <= k - sz <= ns)
