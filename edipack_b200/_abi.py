@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "edgpu_stream", "edgpu_profile_begin", "edgpu_profile_end", "edgpu_csr_open_d",
     "edgpu_csr_open_z", "edgpu_hxv_z", "edgpu_eigh", "edgpu_eigh_state_store",
     "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
-    "edgpu_release_cache", "edgpu_sector_open_superc",
+    "edgpu_release_cache", "edgpu_sector_open_superc", "edgpu_apply_ops_packed", "edgpu_seed_norm2",
 ]
 
 
@@ -151,6 +151,8 @@ def load():
     L.edgpu_state_store.argtypes = [C.c_int]
     L.edgpu_state_free.argtypes = [C.c_int]
     L.edgpu_apply_op.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.edgpu_apply_ops_packed.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.edgpu_seed_norm2.argtypes = [dp]
     L.edgpu_state_observables.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     L.edgpu_last_error.restype = C.c_char_p
     L.edgpu_launch_count.restype = i64

@@ -36,6 +36,9 @@ int eigh_dev(Engine &E, int neigen, int nblock, int nitermax, double tol, uint64
 
 // A state kept on the device (ED_EIGENSPACE state_list entry)
 struct StoredState {
+  // packed-state sectors (nonsu2 / superc, device-built): kind = 1, vector = this rank's rows
+  int kind = 0, pk_mode = -1, pk_qn = 0;
+  int64_t nglobal = 0, row0 = 0, nloc = 0, padded = 0;
   int Ns = 0, nup = 0, ndw = 0;
   int64_t dimu = 0, dimd = 0, ldu = 0, qdw = 0, d0 = 0;
   double *vec = nullptr;
@@ -612,6 +615,23 @@ int edgpu_lanczos_tridiag(const double *seed_host, int nlanc, double threshold, 
 static int store_state_from(const double *src, int slot) {
   edgpu_state_free(slot);
   StoredState st;
+  if (g.csr.open) {
+    CsrSector &C = g.csr;
+    if (C.pk_mode < 0) return set_error("states of host-supplied stored-H sectors are not kept on the device");
+    st.kind = 1;
+    st.pk_mode = C.pk_mode;
+    st.pk_qn = C.pk_qn;
+    st.Ns = C.pk_Ns;
+    st.nglobal = C.nglobal;
+    st.row0 = C.row0;
+    st.nloc = C.nloc;
+    st.padded = C.padded_len();
+    EDGPU_CUDA(cudaMalloc(&st.vec, sizeof(double) * st.padded));
+    EDGPU_CUDA(cudaMemcpyAsync(st.vec, src, sizeof(double) * st.padded, cudaMemcpyDeviceToDevice, g.stream));
+    EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+    g_states[slot] = st;
+    return 0;
+  }
   Sector &S = g.sec;
   st.Ns = S.Ns;
   st.nup = S.up.nel;
@@ -631,7 +651,7 @@ static int store_state_from(const double *src, int slot) {
 
 int edgpu_state_store(int slot) {
   clear_error();
-  if (!g.sec.open) return set_error("no sector open");
+  if (!any_open()) return set_error("no sector open");
   if (!g_current) return set_error("no current state (run edgpu_lanczos_gs first)");
   return store_state_from(g_current, slot);
 }
@@ -657,7 +677,7 @@ int edgpu_eigh(int neigen, int nblock, int nitermax, double tol, uint64_t seed, 
 
 int edgpu_eigh_state_store(int k, int slot) {
   clear_error();
-  if (!g.sec.open) return set_error("no sector open");
+  if (!any_open()) return set_error("no sector open");
   if (k < 0 || k >= (int)g_eigvecs.size())
     return set_error("eigenvector %d not available (last edgpu_eigh kept %d)", k, (int)g_eigvecs.size());
   return store_state_from(g_eigvecs[k], slot);
@@ -672,12 +692,73 @@ int edgpu_state_free(int slot) {
   return 0;
 }
 
+int edgpu_apply_ops_packed(int slot, int nops, const double *coef_re_im, const int *op, const int *iorb,
+                           const int *spin) {
+  clear_error();
+  CsrSector &C = g.csr;
+  if (!C.open || C.pk_mode < 0) return set_error("no device-built nonsu2/superc sector open");
+  auto it = g_states.find(slot);
+  if (it == g_states.end()) return set_error("state slot %d is empty", slot);
+  StoredState &st = it->second;
+  if (st.kind != 1 || st.pk_mode != C.pk_mode || st.Ns != C.pk_Ns)
+    return set_error("state %d does not belong to the open sector's mode / model", slot);
+  if (nops < 1 || nops > 4) return set_error("apply_ops: 1..4 operators");
+  PackedOps ops;
+  ops.n = nops;
+  const int No = C.pk_Ns;  // bound check below uses Norb through iorb < Ns only; model-level check is the host's
+  for (int k = 0; k < nops; k++) {
+    if (op[k] != 1 && op[k] != -1) return set_error("op must be +1 (CDG) or -1 (C)");
+    if (spin[k] != 0 && spin[k] != 1) return set_error("spin must be 0 or 1");
+    if (iorb[k] < 0 || iorb[k] >= No) return set_error("iorb out of range");
+    ops.bit[k] = iorb[k] + spin[k] * C.pk_Ns;
+    ops.create[k] = op[k] > 0;
+    ops.cre[k] = coef_re_im[2 * k];
+    ops.cim[k] = coef_re_im[2 * k + 1];
+    // quantum number of the target: Ntot +- 1 (nonsu2), Sz +- 1 with the sign of the spin (superc)
+    const int dq = C.pk_mode == 0 ? op[k] : (spin[k] == 0 ? op[k] : -op[k]);
+    if (st.pk_qn + dq != C.pk_qn)
+      return set_error("operator %d maps the state's sector (%d) to %d, not to the open sector (%d)", k,
+                       st.pk_qn, st.pk_qn + dq, C.pk_qn);
+  }
+  const int64_t n = C.padded_len();
+  EDGPU_TRY(ensure_buf(&g_seed, &g_seed_len, n));
+  // the whole source vector is needed (es_return_cvec gathers it in the reference)
+  const double *vsrc = st.vec;
+  double *vfull = nullptr;
+  if (g.nranks > 1) {
+    std::vector<int64_t> counts(g.nranks), offs(g.nranks);
+    const int64_t q = st.nglobal / g.nranks;
+    for (int p = 0; p < g.nranks; p++) {
+      counts[p] = 2 * (q + (p == g.nranks - 1 ? st.nglobal % g.nranks : 0));
+      offs[p] = 2 * q * p;
+    }
+    EDGPU_CUDA(cudaMalloc(&vfull, sizeof(double) * 2 * (size_t)st.nglobal));
+    EDGPU_TRY(comm_allgatherv(g, st.vec, vfull, counts, offs));
+    vsrc = vfull;
+  }
+  int rc = packed_apply_ops(g, ops, st.pk_mode, st.pk_qn, vsrc, g_seed);
+  cudaFree(vfull);
+  return rc;
+}
+
+int edgpu_seed_norm2(double *norm2) {
+  clear_error();
+  if (!any_open()) return set_error("no sector open");
+  if (!g_seed || g_seed_len < g.veclen()) return set_error("no device-resident seed");
+  return vec_dot(g, g_seed, g_seed, norm2);
+}
+
 int edgpu_apply_op(int slot, int op, int iorb, int spin) {
   clear_error();
+  if (g.csr.open && g.csr.pk_mode >= 0) {
+    const double one[2] = {1.0, 0.0};
+    return edgpu_apply_ops_packed(slot, 1, one, &op, &iorb, &spin);
+  }
   if (!g.sec.open) return set_error("no sector open");
   auto it = g_states.find(slot);
   if (it == g_states.end()) return set_error("state slot %d is empty", slot);
   StoredState &st = it->second;
+  if (st.kind != 0) return set_error("state %d belongs to a nonsu2/superc sector", slot);
   Sector &S = g.sec;
   if (op != 1 && op != -1) return set_error("op must be +1 (CDG) or -1 (C)");
   if (spin != 0 && spin != 1) return set_error("spin must be 0 or 1");
@@ -731,6 +812,12 @@ int edgpu_state_observables(int slot, double *dens, double *docc) {
   auto it = g_states.find(slot);
   if (it == g_states.end()) return set_error("state slot %d is empty", slot);
   StoredState &st = it->second;
+  if (st.kind == 1) {
+    CsrSector &C = g.csr;
+    if (!C.open || C.pk_mode != st.pk_mode || C.pk_qn != st.pk_qn || C.pk_Ns != st.Ns)
+      return set_error("the state's own sector must be open for observables");
+    return packed_observables(g, st.vec, dens, docc);
+  }
   Sector &S = g.sec;
   if (!S.open || S.up.nel != st.nup || S.dw.nel != st.ndw || S.Ns != st.Ns)
     return set_error("the state's own sector must be open for observables");

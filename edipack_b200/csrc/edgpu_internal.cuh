@@ -206,7 +206,9 @@ struct CsrSector {
   double *vals = nullptr;     // [nnz] or [2*nnz] (re,im)
   int lanes = 8;              // threads per row of the SpMV kernel
   double *vfull = nullptr;    // nranks>1: all-gathered input vector
-  int32_t *map = nullptr;     // device-built sectors (nonsu2.cu): packed Fock states of the WHOLE sector
+  int32_t *map = nullptr;     // device-built sectors (packed.cu): packed Fock states of the WHOLE sector
+  int pk_mode = -1;           // -1: host-supplied CSR; 0: nonsu2 (qn = Ntot); 1: superc (qn = Sz)
+  int pk_qn = 0, pk_Ns = 0;
   std::vector<int64_t> counts, offs;  // row split of all ranks
   int64_t padded_len() const {
     const int64_t n = cplx ? 2 * nloc : nloc;
@@ -288,6 +290,19 @@ int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_
 // packed.cu
 int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot);
 int superc_open(Engine &E, const edgpu_superc_params *p, int sz);
+// apply_COps (ED_SECTOR.f90) on packed-state sectors: out (this rank's rows of the OPEN sector) =
+// sum_k coef_k O_k |src>, O_k = c (create=0) / c^+ (create=1) on bit_k; vsrc = FULL source vector
+// (complex) of the sector (src_mode, src_qn)
+struct PackedOps {
+  int n;
+  int bit[4], create[4];
+  double cre[4], cim[4];
+};
+int packed_apply_ops(Engine &E, const PackedOps &ops, int src_mode, int src_qn, const double *d_vsrc_full,
+                     double *d_out);
+int64_t packed_sector_dim(int mode, int Ns, int qn);
+// dens(a), docc(a) partial sums over this rank's rows of a packed-state vector
+int packed_observables(Engine &E, const double *d_vec, double *h_dens, double *h_docc);
 int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, double s_acc, double s_old);
 
 // comm.cu

@@ -324,6 +324,8 @@ k_n2_fill(const int32_t *__restrict__ map, int64_t row0, int64_t nloc, const int
 int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
                      int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map);
 
+static Nonsu2Dev g_host_dev;  // host copy of the open sector's constants (~17 KB: not on the stack)
+
 // mode/quantum number are in h; builds map + CSR of this rank's rows and opens the stored-H sector
 static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
   if (!E.inited) return set_error("edgpu_init was not called");
@@ -422,10 +424,124 @@ static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
   d_off = nullptr;
   int rc = csr_adopt_device(E, true, nloc, dim, row0, d_rowptr, d_cols, d_vals, nnz, d_map);
   if (rc) return fail(rc);
+  E.csr.pk_mode = h.mode;
+  E.csr.pk_qn = h.ntot;
+  E.csr.pk_Ns = Ns;
   return 0;
 }
 
-static Nonsu2Dev g_host_dev;  // ~14 KB: not on the stack
+int64_t packed_sector_dim(int mode, int Ns, int qn) {
+  if (mode == MODE_NONSU2) return host_binomial(2 * Ns, qn);
+  int64_t dim = 0;
+  for (int k = 0; k <= Ns; k++)
+    if (k - qn >= 0 && k - qn <= Ns) dim += host_binomial(Ns, k) * host_binomial(Ns, k - qn);
+  return dim;
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply_COps / apply_op_C / apply_op_CDG on packed states (ED_SECTOR.f90:465-1140, nonsu2 and
+// superc branches), gather form on the target sector: out(j) = sum_k coef_k sgn_k V(i_k) with
+// |j> = O_k |i_k>.  The source index is ranked, not searched.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_pk_apply(const int32_t *__restrict__ map_t, int64_t row0, int64_t nloc, const double2 *__restrict__ vsrc,
+           double2 *__restrict__ out, PackedOps ops, int src_mode, const int32_t *__restrict__ src_off,
+           int Ns) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nloc) return;
+  const uint32_t m = (uint32_t)map_t[row0 + i];
+  double2 acc = make_double2(0.0, 0.0);
+  for (int k = 0; k < ops.n; k++) {
+    const int bit = ops.bit[k];
+    const bool occ = (m >> bit) & 1u;
+    if (ops.create[k] ? !occ : occ) continue;  // c^+ leaves the bit set, c leaves it empty
+    const uint32_t ms = m ^ (1u << bit);
+    const double sg = (__popc(ms & ((1u << bit) - 1u)) & 1) ? -1.0 : 1.0;
+    const int64_t idx = src_mode == MODE_NONSU2
+                            ? comb_rank(ms)
+                            : (int64_t)src_off[ms >> Ns] + comb_rank(ms & ((1u << Ns) - 1u));
+    const double2 x = vsrc[idx];
+    acc.x += sg * (ops.cre[k] * x.x - ops.cim[k] * x.y);
+    acc.y += sg * (ops.cre[k] * x.y + ops.cim[k] * x.x);
+  }
+  out[i] = acc;
+}
+
+int packed_apply_ops(Engine &E, const PackedOps &ops, int src_mode, int src_qn, const double *d_vsrc_full,
+                     double *d_out) {
+  CsrSector &C = E.csr;
+  if (!C.open || C.pk_mode < 0 || !C.map) return set_error("apply_ops: no device-built nonsu2/superc sector open");
+  const int Ns = C.pk_Ns;
+  int32_t *d_off = nullptr;
+  if (src_mode == MODE_SUPERC) {
+    std::vector<int32_t> off(((size_t)1 << Ns) + 1, 0);
+    int64_t dim = 0;
+    for (uint32_t idw = 0; idw < (1u << Ns); idw++) {
+      const int k = __builtin_popcount(idw) + src_qn;
+      dim += (k < 0 || k > Ns) ? 0 : host_binomial(Ns, k);
+      off[(size_t)idw + 1] = (int32_t)dim;
+    }
+    EDGPU_CUDA(cudaMalloc(&d_off, sizeof(int32_t) * off.size()));
+    EDGPU_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, E.stream));
+    EDGPU_CUDA(cudaStreamSynchronize(E.stream));  // `off` is a local
+  }
+  EDGPU_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * C.padded_len(), E.stream));
+  if (C.nloc > 0) {
+    k_pk_apply<<<(unsigned)((C.nloc + 127) / 128), 128, 0, E.stream>>>(
+        C.map, C.row0, C.nloc, (const double2 *)d_vsrc_full, (double2 *)d_out, ops, src_mode, d_off, Ns);
+    EDGPU_COUNT_LAUNCH();
+  }
+  EDGPU_CUDA(cudaGetLastError());
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  cudaFree(d_off);
+  return 0;
+}
+
+// dens / docc of a packed-state vector (ED_OBSERVABLES_NONSU2.f90 / _SUPERC.f90:150-165)
+__global__ void __launch_bounds__(256)
+k_pk_observables(const int32_t *__restrict__ map, int64_t row0, int64_t nloc, const double2 *__restrict__ v,
+                 int Ns, int Norb, double *__restrict__ out) {
+  double acc[2 * EDGPU_MAXORB];
+#pragma unroll
+  for (int k = 0; k < 2 * EDGPU_MAXORB; k++) acc[k] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nloc; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t m = (uint32_t)map[row0 + i];
+    const double2 x = v[i];
+    const double w = x.x * x.x + x.y * x.y;
+#pragma unroll
+    for (int a = 0; a < EDGPU_MAXORB; a++)
+      if (a < Norb) {
+        const int nu = (m >> a) & 1u, nd = (m >> (a + Ns)) & 1u;
+        acc[a] += w * (nu + nd);
+        acc[EDGPU_MAXORB + a] += w * (nu * nd);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 2 * EDGPU_MAXORB; k++) {
+    double x = acc[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(out + k, x);
+  }
+}
+
+int packed_observables(Engine &E, const double *d_vec, double *h_dens, double *h_docc) {
+  CsrSector &C = E.csr;
+  if (!C.open || C.pk_mode < 0 || !C.map) return set_error("observables: no device-built nonsu2/superc sector open");
+  double *d_out = E.d_scal + 8;
+  EDGPU_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * EDGPU_MAXORB, E.stream));
+  const int Norb = g_host_dev.p.Norb;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((C.nloc + 255) / 256, 1024));
+  k_pk_observables<<<grid, 256, 0, E.stream>>>(C.map, C.row0, C.nloc, (const double2 *)d_vec, C.pk_Ns, Norb, d_out);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_TRY(comm_allreduce_sum(E, d_out, 2 * EDGPU_MAXORB));
+  EDGPU_CUDA(cudaMemcpyAsync(E.h_scal + 8, d_out, sizeof(double) * 2 * EDGPU_MAXORB, cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  for (int a = 0; a < Norb; a++) {
+    h_dens[a] = E.h_scal[8 + a];
+    h_docc[a] = E.h_scal[8 + EDGPU_MAXORB + a];
+  }
+  return 0;
+}
 
 int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot) {
   Nonsu2Dev &h = g_host_dev;

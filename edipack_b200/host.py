@@ -665,6 +665,22 @@ def apply_op(slot: int, op: int, iorb: int, spin: int):
     check(_abi.load().edgpu_apply_op(slot, op, iorb, spin))
 
 
+def apply_Cops(slot: int, coefs, ops, iorbs, spins):
+    """apply_COps (ED_SECTOR.f90): device seed sum_k coefs[k] * O_k |state(slot)> in the open
+    device-built nonsu2 / superc sector; ops[k] = +1 (c^+) / -1 (c), spins[k] = 0 up / 1 dw."""
+    cf = np.ascontiguousarray(np.asarray(coefs, np.complex128))
+    o = np.ascontiguousarray(ops, np.int32)
+    a = np.ascontiguousarray(iorbs, np.int32)
+    sp = np.ascontiguousarray(spins, np.int32)
+    check(_abi.load().edgpu_apply_ops_packed(slot, len(o), ptr(cf), ptr(o), ptr(a), ptr(sp)))
+
+
+def seed_norm2() -> float:
+    n2 = C.c_double()
+    check(_abi.load().edgpu_seed_norm2(C.byref(n2)))
+    return n2.value
+
+
 def state_observables(slot: int, Norb: int):
     dens, docc = np.zeros(Norb), np.zeros(Norb)
     check(_abi.load().edgpu_state_observables(slot, ptr(dens), ptr(docc)))

@@ -250,7 +250,18 @@ int edgpu_state_free(int slot);
  * builds c_{iorb,spin}|state> (iorb 0-based, spin 0 up / 1 dw) directly in the layout of the
  * CURRENTLY OPEN sector, which must be the target sector getCsector/getCDGsector. */
 int edgpu_apply_op(int slot, int op, int iorb, int spin);
-/* dens(a), docc(a) of ED_OBSERVABLES_NORMAL.f90:150-215 for the stored state (weight 1). */
+/* apply_COps (ED_SECTOR.f90, nonsu2 / superc branches; used by ED_GF_NONSU2.f90:159-301,
+ * ED_GF_SUPERC.f90 and the order-parameter observables ED_OBSERVABLES_SUPERC.f90:204-232): the seed
+ * sum_k coef_k O_k |state>, O_k = c^+ (op=+1) / c (op=-1) on (iorb_k, spin_k), 1 <= nops <= 4, built on
+ * the device in the layout of the open device-built sector, which must be the common target sector
+ * of all operators (Ntot +- 1 for nonsu2; Sz +- 1 for superc).  coef = nops (re,im) pairs.
+ * edgpu_apply_op works on these sectors too (nops = 1, coef = 1).  edgpu_seed_norm2 returns
+ * <seed|seed> (all-reduced) of the device-resident seed. */
+int edgpu_apply_ops_packed(int slot, int nops, const double *coef_re_im, const int *op, const int *iorb,
+                           const int *spin);
+int edgpu_seed_norm2(double *norm2);
+/* dens(a), docc(a) of ED_OBSERVABLES_NORMAL.f90:150-215 (ED_OBSERVABLES_NONSU2 / _SUPERC :150-165
+ * for packed-state sectors) for the stored state (weight 1). */
 int edgpu_state_observables(int slot, double *dens, double *docc);
 
 /* ---------------- diagnostics ---------------- */
