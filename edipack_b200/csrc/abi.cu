@@ -28,9 +28,6 @@ void clear_error() {
 
 int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, double threshold,
                         double *alanc, double *blanc, int *nused);
-int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
-                   uint64_t seed, double *egs, double *d_vect, int *niter);
-extern int g_lanczos_last_stored, g_lanczos_last_hxv;
 int eigh_dev(Engine &E, int neigen, int nblock, int nitermax, double tol, uint64_t seed, double *evals,
              double *resid, std::vector<double *> *vecs, int *nconv, int *nmatvec);
 

@@ -340,6 +340,10 @@ int vec_axpy(Engine &E, double *y, const double *x, double a);
 // lanczos.cu
 void lanczos_release(Engine &E);  // frees the Lanczos vector pool
 int tridiag_eig(int n, const double *diag, const double *sub, double *evals, double *evecs,
-                bool want_vecs);
+                bool want_vecs, int track_row = 0);
+int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
+                   uint64_t seed, double *egs, double *d_vect, int *niter, double resid_tol = 0.0);
+extern int g_lanczos_last_stored, g_lanczos_last_hxv;
+extern double g_lanczos_last_resid;
 
 }  // namespace edgpu

@@ -10,6 +10,7 @@
 //            between the dots and the update), |w|^2 of the result accumulated in the last batch
 //   k_rotate V[:, 0..k) = V[:, 0..m) Y  in place (restart / final Ritz vectors), Y in shared memory
 #include <cmath>
+#include <cstdlib>
 
 #include "edgpu_internal.cuh"
 #include "trlan.hpp"
@@ -288,6 +289,31 @@ int eigh_dev(Engine &E, int neigen, int nblock, int nitermax, double tol, uint64
   if (nblock > EIG_MAXCV) nblock = EIG_MAXCV;
   if ((int64_t)nblock > dim) nblock = (int)dim;
   if (nblock < neigen) return set_error("edgpu_eigh: Nblock=%d < Neigen=%d", nblock, neigen);
+  // A single eigenpair does not need a re-orthogonalised basis: the plain Lanczos recurrence
+  // converges to the lowest pair regardless of the loss of orthogonality, at 1/5 of the memory
+  // traffic per step.  Same stopping rule as below (Ritz estimate against tol), vectors of
+  // pass 1 kept in HBM.  EDGPU_EIGH_FULL=1 forces the thick-restart path.
+  const char *env_full = getenv("EDGPU_EIGH_FULL");
+  if (neigen == 1 && dim > 1 && !(env_full && env_full[0] == '1')) {
+    const int64_t n = E.veclen();
+    double *vec = nullptr;
+    EDGPU_CUDA(cudaMalloc(&vec, sizeof(double) * n));
+    int nit = 0;
+    const double eps = 2.220446049250313e-16;
+    const int nmax = (int)std::min<int64_t>(dim, std::max(nitermax, 64));
+    int rc = lanczos_gs_dev(E, nmax, 0.0, 2, nullptr, seed, evals, vec, &nit, std::max(tol, eps));
+    if (rc) {
+      cudaFree(vec);
+      return rc;
+    }
+    const bool ok = g_lanczos_last_resid <= std::max(tol, eps) * std::max(3.666852862501036e-11, std::fabs(evals[0]))
+                    || nit >= dim;
+    if (resid) resid[0] = g_lanczos_last_resid;
+    if (nconv) *nconv = ok ? 1 : 0;
+    if (nmatvec) *nmatvec = g_lanczos_last_hxv;
+    vecs->push_back(vec);
+    return 0;
+  }
   DeviceOps ops(E);
   int rc = ops.init(nblock + 1);
   if (rc) {

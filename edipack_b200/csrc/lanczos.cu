@@ -18,16 +18,21 @@ namespace edgpu {
 // Symmetric tridiagonal eigen-solver (implicit QL with Wilkinson shifts), the role of
 // SciFortran's tql2 / LAPACK dstev used at ED_GF_NORMAL.f90:416.
 // diag[n], sub[n-1] (sub[i] couples i,i+1).  evals ascending.  evecs: column-major n x n
-// (evecs[j*n+i] = component i of eigenvector j) when want_vecs, else only the FIRST ROW
-// Z(1,j) is returned in evecs[0..n-1].
+// (evecs[j*n+i] = component i of eigenvector j) when want_vecs, else only ONE ROW of Z
+// (track_row: 0 = Z(1,j), the weights of ED_GF_NORMAL.f90:416; n-1 = Z(n,j), the Ritz residual
+// estimates) is returned in evecs[0..n-1].
 int tridiag_eig(int n, const double *diag, const double *sub, double *evals, double *evecs,
-                bool want_vecs) {
+                bool want_vecs, int track_row) {
   if (n <= 0) return 0;
   std::vector<double> d(diag, diag + n), e(n, 0.0);
   for (int i = 0; i + 1 < n; i++) e[i] = sub[i];
   const int zr = want_vecs ? n : 1;  // rows of Z that are tracked
   std::vector<double> z((size_t)zr * n, 0.0);  // z[r*n + j] : row r, eigenvector j
-  for (int r = 0; r < zr; r++) z[(size_t)r * n + r] = 1.0;
+  if (want_vecs) {
+    for (int r = 0; r < zr; r++) z[(size_t)r * n + r] = 1.0;
+  } else {
+    z[track_row] = 1.0;  // the single tracked row starts as row `track_row` of the identity
+  }
   for (int l = 0; l < n; l++) {
     int iter = 0, m;
     do {
@@ -93,6 +98,7 @@ int tridiag_eig(int n, const double *diag, const double *sub, double *evals, dou
 // = 72 B/state instead of the 120 B/state of scale+swap / accumulate / dot / axpy, and the
 // host sees alfa and beta only.
 int g_lanczos_last_stored = 0, g_lanczos_last_hxv = 0;  // edgpu_lanczos_last_info
+double g_lanczos_last_resid = 0.0;  // Ritz estimate |beta z_last| at exit (resid_tol mode)
 
 void lanczos_release(Engine &E) {
   if (E.lz_chunks.empty()) return;
@@ -179,8 +185,10 @@ int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, do
 // (two-vector mode).
 // d_start: start vector (kept intact, copied) or nullptr for the seeded random start.
 // d_vect: output (padded length).
+// resid_tol > 0 replaces the stationarity test by ARPACK's test on the Ritz estimate of the lowest
+// pair, |beta_j Z(j,1)| <= resid_tol * max(eps^(2/3), |theta_1|) (the Neigen=1 route of edgpu_eigh).
 int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,
-                   uint64_t seed, double *egs, double *d_vect, int *niter) {
+                   uint64_t seed, double *egs, double *d_vect, int *niter, double resid_tol) {
   const int64_t n = E.veclen();
   const int64_t dim_global = E.csr.open ? E.csr.nglobal : E.sec.up.dim * E.sec.dw.dim;
   if (nitermax > dim_global) nitermax = (int)dim_global;
@@ -239,7 +247,8 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   }
   if (double *p0 = try_store_slot())  // X_1
     cudaMemcpyAsync(p0, vin, sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream);
-  std::vector<double> a, b(1, 0.0), ev, esave, nrm;  // nrm[j] = |X_{j+1}|
+  std::vector<double> a, b(1, 0.0), ev, esave, nrm, zlast;  // nrm[j] = |X_{j+1}|
+  g_lanczos_last_resid = 0.0;
   LanczosVecs L;
   L.x = vin;
   L.y = vout;
@@ -258,12 +267,20 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
     b.push_back(beta);
     if (nlanc >= ncheck) {
       ev.resize(nlanc);
-      rc = tridiag_eig(nlanc, a.data(), b.data() + 1, ev.data(), nullptr, false);
-      if (rc) { cleanup(); return rc; }
-      esave.push_back(ev[0]);
-      if (esave.size() >= 2 &&
-          std::fabs(esave[esave.size() - 1] - esave[esave.size() - 2]) <= threshold)
-        break;
+      if (resid_tol > 0.0) {
+        zlast.resize(nlanc);
+        rc = tridiag_eig(nlanc, a.data(), b.data() + 1, ev.data(), zlast.data(), false, nlanc - 1);
+        if (rc) { cleanup(); return rc; }
+        g_lanczos_last_resid = std::fabs(beta * zlast[0]);
+        if (g_lanczos_last_resid <= resid_tol * std::max(3.666852862501036e-11, std::fabs(ev[0]))) break;
+      } else {
+        rc = tridiag_eig(nlanc, a.data(), b.data() + 1, ev.data(), nullptr, false);
+        if (rc) { cleanup(); return rc; }
+        esave.push_back(ev[0]);
+        if (esave.size() >= 2 &&
+            std::fabs(esave[esave.size() - 1] - esave[esave.size() - 2]) <= threshold)
+          break;
+      }
     }
   }
   ev.resize(nlanc);

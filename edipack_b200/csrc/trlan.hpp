@@ -126,9 +126,12 @@ int trlan_solve(Ops &ops, int64_t dim, int nev, int ncv, int maxiter, double tol
       double nb, na;
       if ((rc = ops.project_out(j + 1, j + 1, h.data(), &nb, &na))) return rc;
       double alpha = h[j];
-      // "twice is enough" (Kahan/Parlett; ARPACK's DGKS refinement): repeat when the projection
-      // removed most of the vector
-      if (na < 0.5 * nb) {
+      // "twice is enough" (Kahan/Parlett; the DGKS refinement of ARPACK's dsaitr): repeat the
+      // projection when it removed most of the vector.  eta^2 = 0.1: a Lanczos step legitimately
+      // removes alpha v_j + beta v_{j-1}, typically half of |H v_j|^2, which DGKS's eta = 1/sqrt(2)
+      // would answer with a second pass over the whole basis on every other step; the rounding
+      // error of one pass is amplified by at most 1/eta ~ 3.2, i.e. orthogonality stays at a few eps.
+      if (na < 0.1 * nb) {
         double nb2;
         if ((rc = ops.project_out(j + 1, j + 1, h2.data(), &nb2, &na))) return rc;
         alpha += h2[j];

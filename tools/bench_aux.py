@@ -109,6 +109,93 @@ def csr_cfg5_shape():
                       "GBps_warm": alg / warm / 1e6, "rel_err_vs_scipy": float(err)}))
 
 
+def cfg5_device_built():
+    """BASELINE config 5 itself: ed_mode=nonsu2, Norb=3, hybrid bath Nbath=8 (Ns=11, 22 levels),
+    on-site spin-orbit coupling lambda L.S + crystal field (complex Hermitian Hloc with spin-flip
+    terms), U=2, U'=1.5, J=0.25, sector N=11 (705 432 states).  Sector map and stored H are
+    generated on the device (edgpu_sector_open_nonsu2)."""
+    lam, cf = 0.2, 0.1
+    # t2g-like L=1 matrices in the (yz, zx, xy) basis and spin-1/2 matrices
+    Lx = np.array([[0, 0, 0], [0, 0, -1j], [0, 1j, 0]])
+    Ly = np.array([[0, 0, 1j], [0, 0, 0], [-1j, 0, 0]])
+    Lz = np.array([[0, -1j, 0], [1j, 0, 0], [0, 0, 0]])
+    sx = 0.5 * np.array([[0, 1], [1, 0]])
+    sy = 0.5 * np.array([[0, -1j], [1j, 0]])
+    sz = 0.5 * np.array([[1, 0], [0, -1]])
+    hloc = np.zeros((2, 2, 3, 3), complex)
+    for s in range(2):
+        for t in range(2):
+            hloc[s, t] = lam * (Lx * sx[s, t] + Ly * sy[s, t] + Lz * sz[s, t])
+        hloc[s, s] += np.diag([cf, 0.0, -cf])
+    m = E.EDModelNonsu2(Norb=3, Nbath=8, bath_type="hybrid", Uloc=(2.0, 2.0, 2.0), Ust=1.5, Jh=0.25,
+                        Jx=0.25, Jp=0.25, hfmode=True, hloc=hloc)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    E.build_Hv_sector_nonsu2(m, 11)
+    t_build = time.perf_counter() - t0
+    n = E.vecDim_Hv_sector_normal()
+    nnz = int(L.edgpu_csr_nnz())
+    npad = int(L.edgpu_vec_padded_len())
+    v = torch.randn(npad, dtype=torch.float64, device="cuda")
+    v[2 * n:] = 0
+    hv = torch.zeros_like(v)
+    flush = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device="cuda")
+    warm = time_hxv(v, hv)
+    cold = time_hxv(v, hv, steps=10, flush=flush)
+    # Hermiticity as a size-independent property: <x|Hy> = conj(<y|Hx>)
+    x = torch.randn(npad, dtype=torch.float64, device="cuda")
+    x[2 * n:] = 0
+    hx = torch.zeros_like(x)
+    _abi.check(L.edgpu_hxv_dev(x.data_ptr(), hx.data_ptr()))
+    _abi.check(L.edgpu_hxv_dev(v.data_ptr(), hv.data_ptr()))
+    torch.cuda.synchronize()
+    xc, vc = torch.view_as_complex(x[: 2 * n].view(-1, 2)), torch.view_as_complex(v[: 2 * n].view(-1, 2))
+    hxc, hvc = torch.view_as_complex(hx[: 2 * n].view(-1, 2)), torch.view_as_complex(hv[: 2 * n].view(-1, 2))
+    herm = abs(complex(torch.vdot(xc, hvc)) - complex(torch.vdot(vc, hxc)).conjugate()) / abs(complex(torch.vdot(xc, hvc)))
+    t0 = time.perf_counter()
+    e_l, _, nit = E.sp_lanc_eigh(512, 1e-12, want_vector=False)
+    t_l = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ev, _, nconv, nmv = E.sp_eigh(2, 20, 512, 1e-12, want_vectors=False)
+    t_e = time.perf_counter() - t0
+    E.delete_Hv_sector_nonsu2()
+    alg = nnz * (16 + 4) + n * (16 + 16) + (n + 1) * 8  # SURVEY 8d
+    print(json.dumps({"config": "cfg5 nonsu2 Norb=3 hybrid Nbath=8 SOC, sector N=11, device-built spH0",
+                      "rows": n, "nnz": nnz, "nnz_per_row": nnz / n, "build_seconds(map+count+fill)": t_build,
+                      "ms_warm_L2": warm, "ms_L2_flushed": cold, "algorithmic_bytes": alg,
+                      "GBps_flushed": alg / cold / 1e6, "frac_of_measured_hbm": alg / cold / 1e6 / PEAK,
+                      "hermiticity_defect": float(herm),
+                      "lanczos_gs": {"egs": e_l, "niter": nit, "seconds": t_l},
+                      "sp_eigh(neigen=2,ncv=20)": {"evals": list(ev), "nconv": nconv, "hxv": nmv, "seconds": t_e}}))
+
+
+def cfg2_eigh():
+    """sp_eigh (thick-restart Lanczos, ARPACK's role) at BASELINE config 2 next to the plain
+    Lanczos ground state: Neigen=1 with the reference's default basis Nblock = 10*max(Neigen,2)."""
+    m = E.EDModel(Norb=1, Nbath=15, Uloc=(2.0,), hfmode=True)
+    E.build_Hv_sector_normal(m, 8, 8)
+    out = {"config": "cfg2 Ns=16 sector (8,8), 165636900 states"}
+    E.sp_lanc_eigh(300, 1e-12, want_vector=False)
+    t0 = time.perf_counter()
+    e_l, _, nit = E.sp_lanc_eigh(300, 1e-12, want_vector=False)
+    out["sp_lanc_eigh"] = {"egs": e_l, "niter": nit, "seconds_warm_pool": time.perf_counter() - t0}
+    E.release_cache()
+    for neigen, ncv in ((1, 20), (2, 20)):
+        t0 = time.perf_counter()
+        ev, _, nconv, nmv = E.sp_eigh(neigen, ncv, 512, 1e-12, want_vectors=False)
+        out[f"sp_eigh(neigen={neigen},ncv={ncv})"] = {"evals": list(ev), "nconv": nconv, "hxv": nmv,
+                                                       "seconds": time.perf_counter() - t0}
+    E.delete_Hv_sector_normal()
+    print(json.dumps(out))
+
+
 if __name__ == "__main__":
-    cfg3()
-    csr_cfg5_shape()
+    which = sys.argv[1:] or ["cfg3", "csr", "cfg5", "eigh"]
+    if "cfg3" in which:
+        cfg3()
+    if "csr" in which:
+        csr_cfg5_shape()
+    if "cfg5" in which:
+        cfg5_device_built()
+    if "eigh" in which:
+        cfg2_eigh()
