@@ -770,6 +770,63 @@ def ed_diag_d(model: EDModel, sectors=None):
     return states
 
 
+def ed_diag_c(model, qns=None, neigen: int = 2, ncv_factor: int = 10, ncv_add: int = 0,
+              nitermax: int = 512, tol: float = 1e-18, gs_threshold: float = 1e-9):
+    """Sector loop of ``ed_diag_c`` (ED_DIAG_NONSU2.f90:72-296, ED_DIAG_SUPERC.f90:73-277) at T=0
+    for the packed-state modes: sectors are Ntot = 0..2Ns (:class:`EDModelNonsu2`) or
+    Sz = -Ns..Ns (:class:`EDModelSuperc`), built on the device; ``sp_eigh`` with Neigen / Nblock as
+    at ED_DIAG_NONSU2.f90:119-124; state list with the ``gs_threshold`` rule (:262-278).  The
+    returned :class:`EState` carries the quantum number in ``nup`` (``ndw`` = 0)."""
+    Ns = model.Ns
+    superc = isinstance(model, EDModelSuperc)
+    if qns is None:
+        qns = range(-Ns, Ns + 1) if superc else range(0, 2 * Ns + 1)
+    build = build_Hv_sector_superc if superc else build_Hv_sector_nonsu2
+    states: list[EState] = []
+    oldzero = 1000.0
+    next_slot = 0
+    for q in qns:
+        build(model, q)
+        try:
+            dim = int(_abi.load().edgpu_sector_dim())
+            ne = min(dim, neigen)
+            nblock = min(dim, ncv_factor * max(ne, neigen) + ncv_add)
+            ev, _, _, _ = sp_eigh(ne, nblock, min(dim, nitermax), tol, want_vectors=False)
+            for i, e in enumerate(ev):
+                if e < oldzero - 10.0 * gs_threshold:
+                    oldzero = e
+                    for st in states:
+                        state_free(st.slot)
+                    states = []
+                elif abs(e - oldzero) <= gs_threshold:
+                    oldzero = min(oldzero, e)
+                else:
+                    continue
+                eigh_state_store(i, next_slot)
+                states.append(EState(float(e), q, 0, next_slot))
+                next_slot += 1
+        finally:
+            delete_Hv_sector_csr()
+    states.sort(key=lambda s: s.e)
+    return states
+
+
+def observables_packed(model, states):
+    """dens / docc averaged over the T=0 state list (ED_OBSERVABLES_NONSU2 / _SUPERC :150-165)."""
+    superc = isinstance(model, EDModelSuperc)
+    build = build_Hv_sector_superc if superc else build_Hv_sector_nonsu2
+    dens, docc = np.zeros(model.Norb), np.zeros(model.Norb)
+    for st in states:
+        build(model, st.nup)
+        try:
+            d, o = state_observables(st.slot, model.Norb)
+        finally:
+            delete_Hv_sector_csr()
+        dens += d / len(states)
+        docc += o / len(states)
+    return dens, docc
+
+
 def boltzmann_weights(model: EDModel, states):
     """Weights of the state list: 1/zeta at T=0 (zeta = number of kept states,
     ED_DIAG_NORMAL.f90:405-414), exp(-beta (E_i - E_gs)) / zeta at finite temperature."""

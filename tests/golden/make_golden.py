@@ -34,6 +34,7 @@ def main():
               "HYBRID_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
               "REPLICA_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
               "GENERAL_NORMAL": ("evals", "dens", "docc", "energy", "doubles", "imp", "Sigma_momenta"),
+              "NORMAL_NONSU2": ("evals", "dens", "docc", "energy", "doubles", "imp", "magX"),
               "NORMAL_SUPERC": ("evals", "dens", "docc", "phisc", "energy", "doubles", "imp"),
               "HYBRID_SUPERC": ("evals", "dens", "docc", "phisc", "energy", "doubles", "imp")}
     for name in checks:

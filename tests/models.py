@@ -80,10 +80,11 @@ def replica_kwargs():
     return kw
 
 
-def hybrid_nonsu2_model(oracle_nonsu2):
-    """test/src/HYBRID_NONSU2: inputED.in + Hloc = Mh * Gamma5 (= sigma_0 (x) tau_z in the test's
-    spin-major so2j ordering, ed_hybrid_nonsu2.f90:50,76; COMMON.f90:81-122), default bath."""
-    g = golden("hybrid_nonsu2")["inputs"]
+def hybrid_nonsu2_model(oracle_nonsu2, name="hybrid_nonsu2"):
+    """test/src/HYBRID_NONSU2 (or NORMAL_NONSU2: same driver with a normal bath): inputED.in +
+    Hloc = Mh * Gamma5 (= sigma_0 (x) tau_z in the test's spin-major so2j ordering,
+    ed_hybrid_nonsu2.f90:50,76; COMMON.f90:81-122), default bath."""
+    g = golden(name)["inputs"]
     norb = int(g["NORB"])
     mh = _f(g["MH"])
     hloc = np.zeros((2, 2, norb, norb), complex)

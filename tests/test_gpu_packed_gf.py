@@ -128,3 +128,32 @@ def test_nonsu2_seeds_and_gf(engine):
         got = ((n2 * Z[0, :] ** 2)[None, :] / (z[:, None] - (tev[None, :] - e0))).sum(axis=1)
         assert np.abs(got - exact).max() < 1e-8
     E.state_free(3)
+
+
+@pytest.mark.parametrize("name", ["normal_superc", "normal_nonsu2"])
+def test_ed_diag_c_golden(engine, name):
+    """Whole sector scan of ed_diag_c on the device (every Sz / Ntot sector built, solved with
+    sp_eigh, state list by the gs_threshold rule) -> evals / dens / docc of the reference fixture."""
+    from models import golden, hybrid_nonsu2_model, superc_model
+
+    E = engine
+    g = golden(name)
+    if name.endswith("superc"):
+        import edipack_oracle_superc as S
+
+        m = E.EDModelSuperc(**vars(superc_model(S, name)))
+        tol = 5e-8
+    else:
+        import edipack_oracle_nonsu2 as N
+
+        m = E.EDModelNonsu2(**vars(hybrid_nonsu2_model(N, name)))
+        tol = 1e-8
+    states = E.ed_diag_c(m)
+    assert len(states) == 1
+    assert states[0].nup == (0 if name.endswith("superc") else 6)
+    assert abs(states[0].e - g["evals"][0]) < 1e-9
+    dens, docc = E.observables_packed(m, states)
+    assert np.abs(dens - np.array(g["dens"])).max() < tol
+    assert np.abs(docc - np.array(g["docc"])).max() < tol
+    for s in states:
+        E.state_free(s.slot)

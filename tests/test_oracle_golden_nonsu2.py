@@ -56,3 +56,25 @@ def test_sector_map_and_matvec(N):
     rng = np.random.default_rng(0)
     v = rng.standard_normal(len(smap)) + 1j * rng.standard_normal(len(smap))
     assert np.abs(N.csr_matvec(rp, cj, va, v) - H @ v).max() < 1e-12
+
+
+def test_normal_nonsu2_golden():
+    """test/src/NORMAL_NONSU2/{evals,dens,docc,magX}.check: the normal-bath branch of the nonsu2
+    generators (one bath chain per orbital, spin-flip hybridisation u = v)."""
+    import edipack_oracle_nonsu2 as N
+
+    g = golden("normal_nonsu2")
+    m = hybrid_nonsu2_model(N, "normal_nonsu2")
+    assert m.bath_type == "normal" and m.Ns == 6
+    best = None
+    for nt in (5, 6, 7):
+        smap, rp, cj, va = N.stored_H(m, nt)
+        ev, U = np.linalg.eigh(N.to_dense(rp, cj, va))
+        if best is None or ev[0] < best[0]:
+            best = (ev[0], nt, smap, U[:, 0])
+    e, nt, smap, v = best
+    assert nt == 6 and abs(e - g["evals"][0]) < 1e-9
+    dens, docc, magx = N.observables(m, smap, v)
+    assert np.abs(dens - np.array(g["dens"])).max() < 1e-8
+    assert np.abs(docc - np.array(g["docc"])).max() < 1e-8
+    assert np.abs(magx - np.array(g["magX"])).max() < 1e-8
