@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "edgpu_csr_open_z", "edgpu_hxv_z", "edgpu_eigh", "edgpu_eigh_state_store",
     "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
     "edgpu_release_cache", "edgpu_sector_open_superc", "edgpu_apply_ops_packed", "edgpu_seed_norm2",
+    "edgpu_set_coulomb_sundry", "edgpu_set_phonons",
 ]
 
 
@@ -55,6 +56,14 @@ class NormalParams(C.Structure):
         ("hbath", C.c_double * (2 * MAXORB * MAXORB * MAXBATH)),
         ("stride", C.c_int32 * (MAXORB * MAXBATH)),
     ]
+
+
+class SundryTerm(C.Structure):
+    """``edgpu_sundry_term`` = coulomb_matrix_element (ED_VARS_GLOBAL.f90:24-31): every operator
+    as (orbital 1-based, spin 1 up / 2 dw)."""
+
+    _fields_ = [("cd_i", C.c_int32 * 2), ("cd_j", C.c_int32 * 2), ("c_k", C.c_int32 * 2),
+                ("c_l", C.c_int32 * 2), ("U", C.c_double)]
 
 
 class Nonsu2Params(C.Structure):
@@ -119,6 +128,8 @@ def load():
     L.edgpu_comm_unique_id.argtypes = [C.c_void_p]
     L.edgpu_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.edgpu_sector_open_normal.argtypes = [C.POINTER(NormalParams), C.c_int, C.c_int]
+    L.edgpu_set_coulomb_sundry.argtypes = [C.c_int, C.c_void_p]
+    L.edgpu_set_phonons.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int]
     L.edgpu_sector_vecdim.restype = i64
     L.edgpu_sector_dim.restype = i64
     L.edgpu_sector_dims.argtypes = [C.POINTER(i64)] * 4

@@ -38,6 +38,7 @@ struct StoredState {
   int64_t nglobal = 0, row0 = 0, nloc = 0, padded = 0;
   int Ns = 0, nup = 0, ndw = 0;
   int64_t dimu = 0, dimd = 0, ldu = 0, qdw = 0, d0 = 0;
+  int dimph = 1;  // phonon slices, each [qdw][ldu]
   double *vec = nullptr;
 };
 static std::map<int, StoredState> g_states;
@@ -96,20 +97,23 @@ static int upload(Engine &E, double *d_dst, const double *h_src) {
     return 0;
   }
   Sector &S = E.sec;
+  const int64_t n = S.up.dim * S.qdw, slice = S.slice_len();  // per phonon slice
   if (S.up.ord.identity && S.dw.ord.identity) {
     EDGPU_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(double) * S.padded_len(), E.stream));
-    EDGPU_CUDA(cudaMemcpy2DAsync(d_dst, sizeof(double) * S.up.ld, h_src, sizeof(double) * S.up.dim,
-                                 sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyHostToDevice,
-                                 E.stream));
+    for (int iph = 0; iph < S.DimPh; iph++)
+      EDGPU_CUDA(cudaMemcpy2DAsync(d_dst + iph * slice, sizeof(double) * S.up.ld, h_src + iph * n,
+                                   sizeof(double) * S.up.dim, sizeof(double) * S.up.dim, (size_t)S.qdw,
+                                   cudaMemcpyHostToDevice, E.stream));
     return 0;
   }
-  const int64_t n = S.up.dim * S.qdw;
-  EDGPU_TRY(ensure_buf(&g_stage, &g_stage_len, n));
-  EDGPU_CUDA(cudaMemcpyAsync(g_stage, h_src, sizeof(double) * n, cudaMemcpyHostToDevice, E.stream));
+  EDGPU_TRY(ensure_buf(&g_stage, &g_stage_len, n * S.DimPh));
+  EDGPU_CUDA(cudaMemcpyAsync(g_stage, h_src, sizeof(double) * n * S.DimPh, cudaMemcpyHostToDevice, E.stream));
   dim3 grid((unsigned)((S.up.ld + 255) / 256), (unsigned)S.qdw);
-  k_permute_in<<<grid, 256, 0, E.stream>>>(d_dst, S.up.ld, g_stage, S.up.dim, S.d0, S.up.refidx,
-                                           S.dw.refidx);
-  EDGPU_COUNT_LAUNCH();
+  for (int iph = 0; iph < S.DimPh; iph++) {
+    k_permute_in<<<grid, 256, 0, E.stream>>>(d_dst + iph * slice, S.up.ld, g_stage + iph * n, S.up.dim,
+                                             S.d0, S.up.refidx, S.dw.refidx);
+    EDGPU_COUNT_LAUNCH();
+  }
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
@@ -121,21 +125,24 @@ static int download(Engine &E, double *h_dst, const double *d_src) {
     return 0;
   }
   Sector &S = E.sec;
+  const int64_t n = S.up.dim * S.qdw, slice = S.slice_len();  // per phonon slice
   if (S.up.ord.identity && S.dw.ord.identity) {
-    EDGPU_CUDA(cudaMemcpy2DAsync(h_dst, sizeof(double) * S.up.dim, d_src, sizeof(double) * S.up.ld,
-                                 sizeof(double) * S.up.dim, (size_t)S.qdw, cudaMemcpyDeviceToHost,
-                                 E.stream));
+    for (int iph = 0; iph < S.DimPh; iph++)
+      EDGPU_CUDA(cudaMemcpy2DAsync(h_dst + iph * n, sizeof(double) * S.up.dim, d_src + iph * slice,
+                                   sizeof(double) * S.up.ld, sizeof(double) * S.up.dim, (size_t)S.qdw,
+                                   cudaMemcpyDeviceToHost, E.stream));
     EDGPU_CUDA(cudaStreamSynchronize(E.stream));
     return 0;
   }
-  const int64_t n = S.up.dim * S.qdw;
-  EDGPU_TRY(ensure_buf(&g_stage, &g_stage_len, n));
+  EDGPU_TRY(ensure_buf(&g_stage, &g_stage_len, n * S.DimPh));
   dim3 grid((unsigned)((S.up.dim + 255) / 256), (unsigned)S.qdw);
-  k_permute_out<<<grid, 256, 0, E.stream>>>(g_stage, d_src, S.up.ld, S.up.dim, S.d0, S.up.refidx,
-                                            S.dw.refidx);
-  EDGPU_COUNT_LAUNCH();
+  for (int iph = 0; iph < S.DimPh; iph++) {
+    k_permute_out<<<grid, 256, 0, E.stream>>>(g_stage + iph * n, d_src + iph * slice, S.up.ld, S.up.dim,
+                                              S.d0, S.up.refidx, S.dw.refidx);
+    EDGPU_COUNT_LAUNCH();
+  }
   EDGPU_CUDA(cudaGetLastError());
-  EDGPU_CUDA(cudaMemcpyAsync(h_dst, g_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaMemcpyAsync(h_dst, g_stage, sizeof(double) * n * S.DimPh, cudaMemcpyDeviceToHost, E.stream));
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
   return 0;
 }
@@ -293,6 +300,43 @@ int edgpu_sector_open_normal(const edgpu_normal_params *p, int nup, int ndw) {
   if (g.csr.open) csr_close(g);
   return sector_open(g, p, nup, ndw);
 }
+int edgpu_set_coulomb_sundry(int nterms, const edgpu_sundry_term *terms) {
+  clear_error();
+  if (nterms < 0 || nterms > EDGPU_MAXSUNDRY) return set_error("coulomb_sundry: %d terms (max %d)", nterms, EDGPU_MAXSUNDRY);
+  if (nterms > 0 && !terms) return set_error("coulomb_sundry: null terms");
+  for (int t = 0; t < nterms; t++) {
+    const int32_t *ops[4] = {terms[t].cd_i, terms[t].cd_j, terms[t].c_k, terms[t].c_l};
+    for (int k = 0; k < 4; k++) {
+      if (ops[k][1] != 1 && ops[k][1] != 2) return set_error("coulomb_sundry term %d: spin must be 1 or 2", t);
+      if (ops[k][0] < 1 || ops[k][0] > EDGPU_MAXORB) return set_error("coulomb_sundry term %d: orbital out of range", t);
+    }
+    // spin balance, direct/HxV_sundry.f90:24-35
+    int sc = 0;
+    sc += terms[t].c_l[1] == 1 ? 1 : -1;
+    sc -= terms[t].cd_j[1] == 1 ? 1 : -1;
+    sc += terms[t].c_k[1] == 1 ? 1 : -1;
+    sc -= terms[t].cd_i[1] == 1 ? 1 : -1;
+    if (sc != 0)
+      return set_error("In NORMAL mode, operators that change the total spin are forbidden. Check your umatrix file (term %d)", t);
+  }
+  g.sundry_terms.assign(terms, terms + nterms);
+  return 0;
+}
+
+int edgpu_set_phonons(int Nph, double w0_ph, double A_ph, const double *g_ph, int Norb) {
+  clear_error();
+  if (Nph < 0 || Nph > 4096) return set_error("Nph=%d out of range", Nph);
+  if (Norb < 1 || Norb > EDGPU_MAXORB) return set_error("Norb=%d out of range", Norb);
+  if (Nph > 0 && !g_ph) return set_error("g_ph is NULL");
+  g.Nph = Nph;
+  g.w0_ph = w0_ph;
+  g.A_ph = A_ph;
+  for (int a = 0; a < EDGPU_MAXORB; a++)
+    for (int b = 0; b < EDGPU_MAXORB; b++)
+      g.g_ph[a][b] = (Nph > 0 && a < Norb && b < Norb) ? g_ph[a * Norb + b] : 0.0;
+  return 0;
+}
+
 int edgpu_sector_close(void) {
   clear_error();
   free_eigvecs();
@@ -316,11 +360,11 @@ int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const in
 static bool any_open() { return g.sec.open || g.csr.open; }
 int64_t edgpu_sector_vecdim(void) {
   if (g.csr.open) return g.csr.nloc;
-  return g.sec.open ? g.sec.up.dim * g.sec.qdw : 0;
+  return g.sec.open ? g.sec.up.dim * g.sec.qdw * g.sec.DimPh : 0;
 }
 int64_t edgpu_sector_dim(void) {
   if (g.csr.open) return g.csr.nglobal;
-  return g.sec.open ? g.sec.up.dim * g.sec.dw.dim : 0;
+  return g.sec.open ? g.sec.up.dim * g.sec.dw.dim * g.sec.DimPh : 0;
 }
 int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_start) {
   if (!g.sec.open) return set_error("no sector open");
@@ -638,6 +682,7 @@ static int store_state_from(const double *src, int slot) {
   st.ldu = S.up.ld;
   st.qdw = S.qdw;
   st.d0 = S.d0;
+  st.dimph = S.DimPh;
   const int64_t n = S.padded_len();
   EDGPU_CUDA(cudaMalloc(&st.vec, sizeof(double) * n));
   EDGPU_CUDA(cudaMemcpyAsync(st.vec, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, g.stream));
@@ -764,6 +809,8 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
   if (S.Ns != st.Ns || S.up.nel != tnup || S.dw.nel != tndw)
     return set_error("open sector (%d,%d) is not the target sector (%d,%d) of the operator",
                      S.up.nel, S.dw.nel, tnup, tndw);
+  if (st.dimph != S.DimPh)
+    return set_error("state %d has %d phonon slices, the open sector %d", slot, st.dimph, S.DimPh);
   // enumeration order + ranking tables of the operated species in the SOURCE sector
   const int nel_src = spin == 0 ? st.nup : st.ndw;
   int32_t *map = nullptr;
@@ -776,8 +823,10 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
   // An operator on the dw species moves amplitude between dw columns, which live on different
   // ranks in the source and in the target sector (their DimDw differ): gather the stored state
   // first, like the reference does before apply_op (es_return_dvec, ED_EIGENSPACE.f90:723-793).
+  // Electronic operators act on every phonon slice alike (ED_SECTOR.f90:489-491: iph loop).
   const double *vsrc = st.vec;
   double *vfull = nullptr;
+  int64_t src_slice = st.ldu * st.qdw;
   if (g.nranks > 1 && spin == 1) {
     std::vector<int64_t> counts(g.nranks), offs(g.nranks);
     for (int p = 0; p < g.nranks; p++) {
@@ -786,15 +835,21 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
       counts[p] = q * st.ldu;
       offs[p] = d0 * st.ldu;
     }
-    EDGPU_CUDA(cudaMalloc(&vfull, sizeof(double) * (size_t)st.dimd * (size_t)st.ldu));
-    EDGPU_TRY(comm_allgatherv(g, st.vec, vfull, counts, offs));
+    const int64_t full_slice = st.dimd * st.ldu;
+    EDGPU_CUDA(cudaMalloc(&vfull, sizeof(double) * (size_t)full_slice * (size_t)st.dimph));
+    for (int iph = 0; iph < st.dimph; iph++)
+      EDGPU_TRY(comm_allgatherv(g, st.vec + iph * src_slice, vfull + iph * full_slice, counts, offs));
     vsrc = vfull;
+    src_slice = full_slice;
   }
   dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
-  k_apply_op<<<grid, 128, 0, g.stream>>>(vsrc, st.ldu, g_seed, S.up.ld, S.up.dim, S.qdw,
-                                         spin == 0 ? S.up.map : S.dw.map + S.d0, op, iorb, spin,
-                                         rank_view(lin, ord));
-  EDGPU_COUNT_LAUNCH();
+  for (int iph = 0; iph < S.DimPh; iph++) {
+    k_apply_op<<<grid, 128, 0, g.stream>>>(vsrc + iph * src_slice, st.ldu, g_seed + iph * S.slice_len(),
+                                           S.up.ld, S.up.dim, S.qdw,
+                                           spin == 0 ? S.up.map : S.dw.map + S.d0, op, iorb, spin,
+                                           rank_view(lin, ord));
+    EDGPU_COUNT_LAUNCH();
+  }
   EDGPU_CUDA(cudaGetLastError());
   EDGPU_CUDA(cudaStreamSynchronize(g.stream));
   cudaFree(vfull);
@@ -822,9 +877,11 @@ int edgpu_state_observables(int slot, double *dens, double *docc) {
   EDGPU_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * EDGPU_MAXORB, g.stream));
   dim3 grid((unsigned)std::min<int64_t>((S.up.dim + 255) / 256, 64),
             (unsigned)std::min<int64_t>(S.qdw, 1024));
-  k_observables<<<grid, 256, 0, g.stream>>>(st.vec, st.ldu, S.up.dim, S.qdw, S.d0, S.up.imp,
-                                            S.dw.imp, S.Norb, d_out);
-  EDGPU_COUNT_LAUNCH();
+  for (int iph = 0; iph < st.dimph; iph++) {  // the occupations do not see the phonon index
+    k_observables<<<grid, 256, 0, g.stream>>>(st.vec + iph * st.ldu * st.qdw, st.ldu, S.up.dim, S.qdw, S.d0,
+                                              S.up.imp, S.dw.imp, S.Norb, d_out);
+    EDGPU_COUNT_LAUNCH();
+  }
   EDGPU_TRY(comm_allreduce_sum(g, d_out, 2 * EDGPU_MAXORB));
   EDGPU_CUDA(cudaMemcpyAsync(g.h_scal + 8, d_out, sizeof(double) * 2 * EDGPU_MAXORB,
                              cudaMemcpyDeviceToHost, g.stream));

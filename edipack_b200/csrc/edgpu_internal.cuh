@@ -169,6 +169,14 @@ struct SpinSpace {
   std::vector<Term> terms; // host copy
 };
 
+// one coulomb_sundry line in application order (c_l, cd_j, c_k, cd_i): bit of the species
+// integer, species (0 up / 1 dw), creation flag
+struct SundryDev {
+  int8_t bit[4], dw[4], create[4];
+  int32_t pad;
+  double U;
+};
+
 struct Sector {
   bool open = false;
   edgpu_normal_params prm;
@@ -189,7 +197,15 @@ struct Sector {
   // all-gathered vector for the non-local terms with nranks>1
   double *vfull = nullptr;
   std::vector<int64_t> gcounts, goffs;
-  int64_t padded_len() const { return up.ld * qdw; }
+  // a10: user two-body terms (direct/HxV_sundry.f90) and phonons (HxV_ph.f90, HxV_eph.f90)
+  int nsundry = 0;
+  SundryDev *sundry = nullptr;
+  int DimPh = 1;
+  double w0_ph = 0.0, A_ph = 0.0;
+  double *gph = nullptr;     // [Norb*Norb] device
+  bool eph_offdiag = false;  // some g_ph(a,b) != 0 with a != b
+  int64_t slice_len() const { return up.ld * qdw; }  // one phonon slice (electronic chunk)
+  int64_t padded_len() const { return up.ld * qdw * DimPh; }
   int64_t padded_len_t() const { return dw.ld * qup; }
 };
 
@@ -246,6 +262,11 @@ struct Engine {
   // (dev_malloc) or on edgpu_release_cache / edgpu_finalize.
   std::vector<std::pair<double *, size_t>> lz_chunks;  // (pointer, bytes)
   float stage_ms[4] = {0, 0, 0, 0};
+  // module globals coulomb_sundry / Nph, w0_ph, A_ph, g_ph: copied into the sector at open
+  std::vector<edgpu_sundry_term> sundry_terms;
+  int Nph = 0;
+  double w0_ph = 0.0, A_ph = 0.0;
+  double g_ph[EDGPU_MAXORB][EDGPU_MAXORB] = {};
   // profiling ring (edgpu_profile_begin/end): 4 events per recorded H x v
   std::vector<cudaEvent_t> prof_ev;
   int prof_cap = 0, prof_n = 0;
@@ -278,6 +299,12 @@ void block_split(int64_t n, int P, int r, int64_t *q, int64_t *start);
 int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed);
 int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed, double s_acc,
                   double s_old, double *dot_out);
+
+// extra.cu (a10): sundry two-body terms and phonons, applied after the electronic passes.
+// vfull = all dw columns of every phonon slice ([DimPh][DimDw][ld]; the local vector itself on
+// one rank); hv += s_acc * (H_sundry + H_ph + H_eph) v
+int extra_setup(Engine &E);   // sector_open: copies the engine-global settings to the device
+int extra_hxv(Engine &E, const double *d_v, const double *d_vfull, double *d_hv, double s_acc);
 
 // csr.cu
 int csr_open(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, const int64_t *rowptr,

@@ -930,15 +930,37 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
   } else if (!timed) {
     evs = nullptr;
   }
+  // a10: DimPh > 1 phonon slices (each an electronic chunk: HxV_local / HxV_up / HxV_dw act on
+  // every slice, direct/HxV_local.f90:2-4) and the terms applied after the electronic passes
+  const int DimPh = S.DimPh;
+  const int64_t slice = S.slice_len(), slice_full = U.ld * D.dim;
+  const bool extras = (DimPh > 1) || (S.nsundry > 0);
+  // nranks>1: terms that change the dw index gather from the columns of every rank, like
+  // allgather_vector_MPI (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:355-360)
+  const bool need_full = E.nranks > 1 && (S.nonlocal || S.nsundry > 0 || (DimPh > 1 && S.eph_offdiag));
+  if (need_full && !S.vfull) {
+    EDGPU_CUDA(cudaMalloc(&S.vfull, sizeof(double) * (size_t)slice_full * (size_t)DimPh));
+    S.gcounts.assign(E.nranks, 0);
+    S.goffs.assign(E.nranks, 0);
+    for (int p = 0; p < E.nranks; p++) {
+      int64_t q, d0;
+      block_split(D.dim, E.nranks, p, &q, &d0);
+      S.gcounts[p] = q * U.ld;
+      S.goffs[p] = d0 * U.ld;
+    }
+  }
 #define EDGPU_MARK(k) \
-  if (evs) cudaEventRecord(evs[k], st)
+  if (evs && (k == 0 ? iph == 0 : iph == DimPh - 1)) cudaEventRecord(evs[k], st)
+  for (int iph = 0; iph < DimPh; iph++) {
+  const double *v_s = d_v + iph * slice;
+  double *hv_s = d_hv + iph * slice;
   EDGPU_MARK(0);
 
   if (E.nranks == 1) {
     if (!tiled) {
       // one fused gather kernel: diagonal + up hops + dw hops
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      k_generic<true, true><<<grid, 128, 0, st>>>(d_v, d_hv, U.dim, U.ld, S.qdw, 0, U, D, S.xud,
+      k_generic<true, true><<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, S.qdw, 0, U, D, S.xud,
                                                   nimp, (int)accum, s_acc, s_old);
       EDGPU_COUNT_LAUNCH();
       EDGPU_CUDA(cudaGetLastError());
@@ -947,17 +969,17 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
     } else {
       // pass B (diag + up hops) writes / accumulates first: it is the pass that saturates the
       // shared-memory pipe, so the read-modify-write of Hv is left to pass A (dw hops)
-      EDGPU_TRY(apply_fast(E, true, true, accum, d_v, d_hv, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc,
+      EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc,
                            s_old));
       EDGPU_MARK(1);
       if ((D.Wl4 + D.Wf4) > 0) {
         double *part = nullptr;
         const int64_t nblk = slow_grid_size(U, D);
-        if (dot_out && !S.nonlocal) {
+        if (dot_out && !S.nonlocal && !extras) {
           EDGPU_TRY(ensure_partials(E, nblk));
           part = E.d_part;
         }
-        EDGPU_TRY(apply_slow(E, true, d_v, d_hv, S.dw, U, D, s_acc, part));
+        EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part));
         if (part) {
           EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
           dot_done = true;
@@ -967,12 +989,12 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
     }
     if (S.nonlocal) {
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      k_nonlocal<<<grid, 128, 0, st>>>(d_v, d_hv, U.dim, U.ld, 0, S.up.imphop, S.up.ld, S.dw.imphop,
+      k_nonlocal<<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, 0, S.up.imphop, S.up.ld, S.dw.imphop,
                                        S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
       EDGPU_COUNT_LAUNCH();
       EDGPU_CUDA(cudaGetLastError());
     }
-    EDGPU_MARK(3);
+    if (!extras) EDGPU_MARK(3);
   } else {
     // dw-split over ranks (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:236-375):
     //   Hv  = (Hd + 1 (x) Hup) v                      local columns
@@ -980,7 +1002,8 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
     //   Hvt = Hdw vt                                  dw is now the fast index
     //   Hv += transpose(Hvt)
     // The first transpose only reads v: it runs on the communication stream concurrently with
-    // the rank-local pass (diag + up hops) on the main stream.
+    // the rank-local pass (diag + up hops) on the main stream.  Phonon slices are processed one
+    // after the other like the reference's `do iph=1,DimPh` (:322-337).
     EDGPU_CUDA(cudaEventRecord(E.ev_fork, st));
     EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
     {
@@ -989,10 +1012,10 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
       int rc = 0;
       if (S.p2p) {
         // push v^T into every rank's vt over NVLink, barrier, dw hops on the local vt, barrier
-        rc = comm_push_transpose(E, d_v);
+        rc = comm_push_transpose(E, v_s);
         if (!rc) rc = comm_barrier(E);
       } else {
-        rc = comm_transpose(E, d_v, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false);
+        rc = comm_transpose(E, v_s, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false);
       }
       if (!rc)
         rc = apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
@@ -1002,36 +1025,29 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
       if (rc) return rc;
     }
     EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
-    EDGPU_TRY(apply_fast(E, tiled, true, accum, d_v, d_hv, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
+    EDGPU_TRY(apply_fast(E, tiled, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
                          s_old));
     EDGPU_MARK(1);
     EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
     EDGPU_MARK(2);
     if (S.p2p)
-      EDGPU_TRY(comm_pull_transpose_acc(E, d_hv));
+      EDGPU_TRY(comm_pull_transpose_acc(E, hv_s));
     else
-      EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, d_hv, U.dim, U.ld, S.qdw, true));
+      EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, hv_s, U.dim, U.ld, S.qdw, true));
+    if (need_full) EDGPU_TRY(comm_allgatherv(E, v_s, S.vfull + iph * slice_full, S.gcounts, S.goffs));
     if (S.nonlocal) {
-      // non-local terms gather from anywhere: all ranks' columns first, like
-      // allgather_vector_MPI (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:355-360)
-      if (!S.vfull) {
-        EDGPU_CUDA(cudaMalloc(&S.vfull, sizeof(double) * (size_t)U.ld * (size_t)D.dim));
-        S.gcounts.assign(E.nranks, 0);
-        S.goffs.assign(E.nranks, 0);
-        for (int p = 0; p < E.nranks; p++) {
-          int64_t q, d0;
-          block_split(D.dim, E.nranks, p, &q, &d0);
-          S.gcounts[p] = q * U.ld;
-          S.goffs[p] = d0 * U.ld;
-        }
-      }
-      EDGPU_TRY(comm_allgatherv(E, d_v, S.vfull, S.gcounts, S.goffs));
       dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      k_nonlocal<<<grid, 128, 0, st>>>(S.vfull, d_hv, U.dim, U.ld, S.d0, S.up.imphop, S.up.ld,
-                                       S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
+      k_nonlocal<<<grid, 128, 0, st>>>(S.vfull + iph * slice_full, hv_s, U.dim, U.ld, S.d0, S.up.imphop,
+                                       S.up.ld, S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
       EDGPU_COUNT_LAUNCH();
       EDGPU_CUDA(cudaGetLastError());
     }
+    if (!extras) EDGPU_MARK(3);
+  }
+  }  // phonon slices
+  if (extras) {
+    EDGPU_TRY(extra_hxv(E, d_v, need_full ? S.vfull : d_v, d_hv, s_acc));
+    const int iph = DimPh - 1;
     EDGPU_MARK(3);
   }
 #undef EDGPU_MARK

@@ -634,6 +634,12 @@ int sector_close(Engine &E) {
   cudaFree(S.sendbuf);
   cudaFree(S.recvbuf);
   cudaFree(S.vfull);
+  cudaFree(S.sundry);
+  cudaFree(S.gph);
+  S.sundry = nullptr;
+  S.gph = nullptr;
+  S.nsundry = 0;
+  S.DimPh = 1;
   S.xud = S.jx = S.jp = nullptr;
   S.vt = S.hvt = S.sendbuf = S.recvbuf = S.vfull = nullptr;
   S.open = false;
@@ -714,6 +720,7 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
     EDGPU_CUDA(cudaStreamSynchronize(E.stream));
     EDGPU_TRY(comm_p2p_setup(E));
   }
+  EDGPU_TRY(extra_setup(E));  // coulomb_sundry + phonons (a10)
   S.variant = E.variant_request;
   S.open = true;
   return 0;

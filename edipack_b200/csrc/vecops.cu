@@ -120,14 +120,15 @@ __global__ void __launch_bounds__(VT) k_axpy(double2 *__restrict__ y, const doub
 __global__ void __launch_bounds__(VT) k_random(double *__restrict__ v, int64_t nrow, int64_t ld,
                                                int64_t ncol, int64_t col_offset, uint64_t seed,
                                                const int32_t *__restrict__ refup,
-                                               const int32_t *__restrict__ refdw) {
+                                               const int32_t *__restrict__ refdw, int64_t dimel) {
   const int64_t i = blockIdx.x * (int64_t)VT + threadIdx.x;
   const int64_t c = blockIdx.y;
   if (i >= ld) return;
   double x = 0.0;
+  v += blockIdx.z * (ld * ncol);  // phonon slice
   if (i < nrow) {
     // reference (ascending Fock order) state index: independent of ranks and internal order
-    uint64_t z = ((uint64_t)(refup[i] + (int64_t)refdw[c + col_offset] * nrow) + seed) * 0x9E3779B97F4A7C15ull;
+    uint64_t z = ((uint64_t)(refup[i] + (int64_t)refdw[c + col_offset] * nrow + blockIdx.z * dimel) + seed) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z = z ^ (z >> 31);
@@ -216,9 +217,9 @@ int vec_fill_random(Engine &E, double *d_v, uint64_t seed) {
     return 0;
   }
   Sector &S = E.sec;
-  dim3 grid((unsigned)((S.up.ld + VT - 1) / VT), (unsigned)S.qdw);
+  dim3 grid((unsigned)((S.up.ld + VT - 1) / VT), (unsigned)S.qdw, (unsigned)S.DimPh);
   k_random<<<grid, VT, 0, E.stream>>>(d_v, S.up.dim, S.up.ld, S.qdw, S.d0, seed, S.up.refidx,
-                                      S.dw.refidx);
+                                      S.dw.refidx, S.up.dim * S.dw.dim);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;

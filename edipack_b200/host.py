@@ -268,6 +268,28 @@ def build_Hv_sector_normal(model: EDModel, nup: int, ndw: int):
     check(_abi.load().edgpu_sector_open_normal(C.byref(model.params()), nup, ndw))
 
 
+def set_coulomb_sundry(terms=()):
+    """The module global ``coulomb_sundry`` (user two-body terms of a umatrix file, applied by
+    direct/HxV_sundry.f90): terms = iterable of (cd_i, cd_j, c_k, c_l, U), every operator an
+    (orbital 1-based, spin 1|2) pair.  Applies to NORMAL sectors opened afterwards; () clears."""
+    terms = list(terms)
+    arr = (_abi.SundryTerm * max(len(terms), 1))()
+    for t, (ci, cj, ck, cl, U) in enumerate(terms):
+        arr[t].cd_i[:] = ci
+        arr[t].cd_j[:] = cj
+        arr[t].c_k[:] = ck
+        arr[t].c_l[:] = cl
+        arr[t].U = U
+    check(_abi.load().edgpu_set_coulomb_sundry(len(terms), C.cast(arr, C.c_void_p)))
+
+
+def set_phonons(Nph: int = 0, w0: float = 0.0, g=None, A: float = 0.0):
+    """Nph, w0_ph, g_ph(Norb,Norb), A_ph (ED_INPUT_VARS.f90:184-198): NORMAL sectors opened
+    afterwards carry DimPh = Nph+1 phonon slices (direct/HxV_ph.f90, HxV_eph.f90)."""
+    g = np.ascontiguousarray(np.atleast_2d(np.zeros((1, 1)) if g is None else np.asarray(g, float)))
+    check(_abi.load().edgpu_set_phonons(int(Nph), float(w0), float(A), ptr(g), g.shape[0]))
+
+
 def delete_Hv_sector_normal():
     global _open_is_complex
     _open_is_complex = False

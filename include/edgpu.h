@@ -103,6 +103,18 @@ typedef struct edgpu_superc_params {
   int32_t stride[EDGPU_MAXORB][EDGPU_MAXBATH];     /* getBathStride(a,k), 1-based */
 } edgpu_superc_params;
 
+/*
+ * One user two-body operator  U cd_i cd_j c_k c_l  = type coulomb_matrix_element
+ * (ED_VARS_GLOBAL.f90:24-31), the entries of the module global `coulomb_sundry` read by
+ * direct/HxV_sundry.f90:16-21: element [0] of every operator is the impurity orbital (1-based),
+ * element [1] the spin (1 = up, 2 = dw), exactly as the reference stores them.
+ */
+typedef struct edgpu_sundry_term {
+  int32_t cd_i[2], cd_j[2], c_k[2], c_l[2];
+  double U;
+} edgpu_sundry_term;
+#define EDGPU_MAXSUNDRY 1024
+
 /* ---------------- engine / communicator ---------------- */
 
 /* Selects the CUDA device and creates the engine's stream.  Replaces nothing in the
@@ -125,6 +137,21 @@ int edgpu_comm_size(void);
  * (:128-142), the per-spin hop tables and diagonal tables, and selects the H x v kernels.
  * The sector is addressed by (nup,ndw) = get_Nup/get_Ndw(isector). */
 int edgpu_sector_open_normal(const edgpu_normal_params *p, int nup, int ndw);
+/* The module global `coulomb_sundry` (filled by ED_PARSE_UMATRIX from a umatrix file): the
+ * user-defined two-body terms applied by direct/HxV_sundry.f90:1-109 (direct_mpi twin) as
+ * Hv(j) += U sg1 sg2 sg3 sg4 vin(i), operators applied right to left as c_l, cd_j, c_k, cd_i on
+ * the row state.  Engine-global like the reference's: applies to every NORMAL sector opened
+ * AFTER the call; nterms = 0 deallocates it.  A term that changes the total spin is refused
+ * (the reference STOPs, HxV_sundry.f90:35). */
+int edgpu_set_coulomb_sundry(int nterms, const edgpu_sundry_term *terms);
+/* Phonon inputs Nph, w0_ph, A_ph, g_ph(Norb,Norb) (ED_INPUT_VARS.f90:184-198), read by
+ * direct/HxV_ph.f90:1-6 and direct/HxV_eph.f90:1-81: DimPh = Nph+1 (ED_SETUP.f90:137), every
+ * vector of a NORMAL sector opened afterwards holds DimPh consecutive electronic chunks,
+ * i = i_el + (iph-1)*DimUp*mpiQdw (direct_mpi/HxV_eph.f90:3-4), and H gains
+ * w0 b^+b + sum_ab g(a,b) c^+_a c_b (b + b^+) [+ A_ph (b + b^+) as the STORED path has it,
+ * stored/H_ph.f90:6-17 -- the direct path has no A_ph term; pass 0 to reproduce it].
+ * g_ph is row-major g_ph[a*Norb + b]; Nph = 0 switches phonons off. */
+int edgpu_set_phonons(int Nph, double w0_ph, double A_ph, const double *g_ph, int Norb);
 int edgpu_sector_close(void);           /* delete_Hv_sector_normal, :212-279 */
 int64_t edgpu_sector_vecdim(void);      /* vecDim_Hv_sector_normal, :286-313 (local chunk) */
 int64_t edgpu_sector_dim(void);         /* getDim(isector) */

@@ -286,17 +286,11 @@ static void emit_scatter(void *c, int64_t i, double h) {
   g->hv[g->off + (i - 1) * g->stride] += h * g->vin[g->self];
 }
 
-/* ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:23-130 (serial, DimPh=1) */
-int ora_direct_hxv(const ora_params *p, int nup_el, int ndw_el, const double *v, double *Hv) {
+/* electronic part of one phonon slice: HxV_local + HxV_up + HxV_dw + HxV_non_local */
+static void direct_hxv_slice(const ora_params *p, const int32_t *mapu, int64_t DimUp,
+                             const int32_t *mapd, int64_t DimDw, const double *v, double *Hv) {
   const int Ns = p->Ns;
-  const int64_t DimUp = ora_binomial(Ns, nup_el), DimDw = ora_binomial(Ns, ndw_el);
   const int64_t Dim = DimUp * DimDw;
-  int32_t *mapu = (int32_t *)malloc(sizeof(int32_t) * DimUp);
-  int32_t *mapd = (int32_t *)malloc(sizeof(int32_t) * DimDw);
-  if (!mapu || !mapd) return -1;
-  ora_build_map(Ns, nup_el, mapu);
-  ora_build_map(Ns, ndw_el, mapd);
-  memset(Hv, 0, sizeof(double) * Dim); /* Hv=zero (:98) */
   int nu[32], nd[32];
   /* direct/HxV_local.f90 */
   for (int64_t i = 1; i <= Dim; i++) {
@@ -327,6 +321,120 @@ int ora_direct_hxv(const ora_params *p, int nup_el, int ndw_el, const double *v,
       int64_t jdw = (j - 1) / DimUp + 1;
       gather_ctx g = {v, Hv, 0, 1, j - 1};
       nonlocal_moves(p, mapu[jup - 1], mapd[jdw - 1], mapu, DimUp, mapd, DimDw, emit_gather, &g);
+    }
+  }
+}
+
+/* ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:23-130 (serial, DimPh=1) */
+int ora_direct_hxv(const ora_params *p, int nup_el, int ndw_el, const double *v, double *Hv) {
+  return ora_direct_hxv_ext(p, nup_el, ndw_el, 0, NULL, NULL, v, Hv);
+}
+
+/* one fermionic operator of a sundry chain on (mup, mdw): spin 1 -> up integer, 2 -> dw */
+static int sundry_op(int create, int orb, int spin, int32_t *mup, int32_t *mdw, double *sg) {
+  int32_t *m = (spin == 1) ? mup : mdw, out;
+  int ok = create ? ora_cdg(orb, *m, &out, sg) : ora_c(orb, *m, &out, sg);
+  if (ok) *m = out;
+  return ok;
+}
+
+int ora_direct_hxv_ext(const ora_params *p, int nup_el, int ndw_el, int nsundry,
+                       const ora_sundry_term *terms, const ora_phonons *ph, const double *v,
+                       double *Hv) {
+  const int Ns = p->Ns, Norb = p->Norb;
+  const int64_t DimUp = ora_binomial(Ns, nup_el), DimDw = ora_binomial(Ns, ndw_el);
+  const int64_t DimEl = DimUp * DimDw;
+  const int DimPh = (ph ? ph->Nph : 0) + 1;
+  const int64_t Dim = DimEl * DimPh;
+  /* spin balance of every sundry term (HxV_sundry.f90:24-35) */
+  for (int t = 0; t < nsundry; t++) {
+    int sc = 0;
+    sc += (terms[t].c_l[1] == 1) ? 1 : -1;
+    sc -= (terms[t].cd_j[1] == 1) ? 1 : -1;
+    sc += (terms[t].c_k[1] == 1) ? 1 : -1;
+    sc -= (terms[t].cd_i[1] == 1) ? 1 : -1;
+    if (sc != 0) return -2;
+  }
+  int32_t *mapu = (int32_t *)malloc(sizeof(int32_t) * DimUp);
+  int32_t *mapd = (int32_t *)malloc(sizeof(int32_t) * DimDw);
+  if (!mapu || !mapd) return -1;
+  ora_build_map(Ns, nup_el, mapu);
+  ora_build_map(Ns, ndw_el, mapd);
+  memset(Hv, 0, sizeof(double) * Dim); /* Hv=zero (:98) */
+  /* HxV_local / HxV_up / HxV_dw act on every phonon slice (their loops run over the whole
+   * vector with j_el = mod(j-1,DimUp*DimDw)+1, e.g. HxV_local.f90:2-4) */
+  for (int iph = 0; iph < DimPh; iph++)
+    direct_hxv_slice(p, mapu, DimUp, mapd, DimDw, v + iph * DimEl, Hv + iph * DimEl);
+  if (DimPh > 1) {
+    /* direct/HxV_ph.f90:1-6 (+ A_ph(b+b^dag) of stored/H_ph.f90:6-17) */
+    for (int64_t i = 1; i <= Dim; i++) {
+      int64_t iph = (i - 1) / DimEl + 1;
+      Hv[i - 1] += ph->w0 * (double)(iph - 1) * v[i - 1];
+      if (ph->A != 0.0) {
+        if (iph < DimPh) Hv[i - 1 + DimEl] += ph->A * sqrt((double)iph) * v[i - 1];
+        if (iph > 1) Hv[i - 1 - DimEl] += ph->A * sqrt((double)(iph - 1)) * v[i - 1];
+      }
+    }
+    /* direct/HxV_eph.f90:1-81, scatter form Hv(j) += h*vin(i) */
+    int nu[32], nd[32];
+    for (int64_t i = 1; i <= Dim; i++) {
+      int64_t i_el = (i - 1) % DimEl + 1, iph = (i - 1) / DimEl + 1;
+      int64_t iup = i_el % DimUp;
+      if (iup == 0) iup = DimUp;
+      int64_t idw = (i_el - 1) / DimUp + 1;
+      int32_t mup = mapu[iup - 1], mdw = mapd[idw - 1], k1, k2;
+      double sg1, sg2;
+      bdecomp(mup, Ns, nu);
+      bdecomp(mdw, Ns, nd);
+      double htmp = 0.0;
+      for (int a = 0; a < Norb; a++) htmp += ph->g[a][a] * (nu[a] + nd[a]);
+      if (iph < DimPh) Hv[i_el - 1 + iph * DimEl] += htmp * sqrt((double)iph) * v[i - 1];
+      if (iph > 1) Hv[i_el - 1 + (iph - 2) * DimEl] += htmp * sqrt((double)(iph - 1)) * v[i - 1];
+      for (int s = 0; s < 2; s++) {
+        const int *n = s == 0 ? nu : nd;
+        for (int io = 0; io < Norb; io++)
+          for (int jo = 0; jo < Norb; jo++) {
+            if (!(ph->g[io][jo] != 0.0 && n[jo] == 1 && n[io] == 0)) continue;
+            ora_c(jo + 1, s == 0 ? mup : mdw, &k1, &sg1);
+            ora_cdg(io + 1, k1, &k2, &sg2);
+            int64_t jup = iup, jdw = idw;
+            if (s == 0)
+              jup = ora_binary_search(mapu, DimUp, k2);
+            else
+              jdw = ora_binary_search(mapd, DimDw, k2);
+            double h = ph->g[io][jo] * sg1 * sg2;
+            int64_t j_el = jup + (jdw - 1) * DimUp;
+            if (iph < DimPh) Hv[j_el - 1 + iph * DimEl] += h * sqrt((double)iph) * v[i - 1];
+            if (iph > 1) Hv[j_el - 1 + (iph - 2) * DimEl] += h * sqrt((double)(iph - 1)) * v[i - 1];
+          }
+      }
+    }
+  }
+  /* direct/HxV_sundry.f90:1-109, gather form Hv(j) += U*sg*vin(i), operators applied right to
+   * left as c_l, cd_j, c_k, cd_i on the row state j */
+  if (nsundry > 0) {
+    for (int64_t j = 1; j <= Dim; j++) {
+      int64_t j_el = (j - 1) % DimEl + 1, iph = (j - 1) / DimEl + 1;
+      int64_t jup = j_el % DimUp;
+      if (jup == 0) jup = DimUp;
+      int64_t jdw = (j_el - 1) / DimUp + 1;
+      for (int t = 0; t < nsundry; t++) {
+        const ora_sundry_term *T = &terms[t];
+        int32_t mu = mapu[jup - 1], md = mapd[jdw - 1];
+        double s1, s2, s3, s4;
+        if (!sundry_op(0, T->c_l[0], T->c_l[1], &mu, &md, &s1)) continue;
+        if (!sundry_op(1, T->cd_j[0], T->cd_j[1], &mu, &md, &s2)) continue;
+        if (!sundry_op(0, T->c_k[0], T->c_k[1], &mu, &md, &s3)) continue;
+        if (!sundry_op(1, T->cd_i[0], T->cd_i[1], &mu, &md, &s4)) continue;
+        int64_t idw = ora_binary_search(mapd, DimDw, md), iup = ora_binary_search(mapu, DimUp, mu);
+        if (idw == 0 || iup == 0) { /* "H_sundry: impossible operator" */
+          free(mapu);
+          free(mapd);
+          return -3;
+        }
+        int64_t i = iup + (idw - 1) * DimUp + (iph - 1) * DimEl;
+        Hv[j - 1] += T->U * s1 * s2 * s3 * s4 * v[i - 1];
+      }
     }
   }
   free(mapu);

@@ -72,6 +72,30 @@ int64_t ora_build_map(int Ns, int nel, int32_t *map); /* returns dim; map may be
 /* ---- direct H x v, serial (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:23 + direct/ *.f90) ---- */
 int ora_direct_hxv(const ora_params *p, int nup, int ndw, const double *v, double *Hv);
 
+/* ---- a10: user two-body terms and phonons of the direct path ----
+ * coulomb_matrix_element (ED_VARS_GLOBAL.f90:24-31): U cd_i cd_j c_k c_l, every operator as
+ * (orbital 1-based, spin 1 = up / 2 = dw) -- element (1) is the orbital and (2) the spin in
+ * direct/HxV_sundry.f90:18-21. */
+typedef struct {
+  int32_t cd_i[2], cd_j[2], c_k[2], c_l[2];
+  double U;
+} ora_sundry_term;
+/* Nph, w0_ph, A_ph, g_ph (ED_INPUT_VARS.f90:184-198); DimPh = Nph+1 (ED_SETUP.f90:137).
+ * The direct path has no A_ph term (direct/HxV_ph.f90:1-6), the stored one has
+ * (stored/H_ph.f90:6-17): A_ph is applied here as the stored path does, 0 reproduces both. */
+typedef struct {
+  int32_t Nph, pad;
+  double w0, A;
+  double g[ORA_MAXORB][ORA_MAXORB];
+} ora_phonons;
+/* directMatVec_normal_main with DimPh>=1 and coulomb_sundry
+ * (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:23-130; direct/HxV_ph.f90, HxV_eph.f90:1-81,
+ * HxV_sundry.f90:1-109).  v/Hv: DimUp*DimDw*(Nph+1), i = iup+(idw-1)DimUp+(iph-1)DimUp*DimDw.
+ * terms may be NULL (nsundry=0), ph may be NULL (Nph=0).  Returns -2 for a spin-unbalanced
+ * sundry term (the reference STOPs, HxV_sundry.f90:35). */
+int ora_direct_hxv_ext(const ora_params *p, int nup, int ndw, int nsundry, const ora_sundry_term *terms,
+                       const ora_phonons *ph, const double *v, double *Hv);
+
 /* ---- direct H x v, MPI algorithm with P emulated ranks
  *      (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:236 + direct_mpi/ *.f90,
  *       dw split ED_HAMILTONIAN_NORMAL.f90:128-142, transposes ..._COMMON.f90:66-178).

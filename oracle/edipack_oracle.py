@@ -56,6 +56,20 @@ class OraParams(C.Structure):
     ]
 
 
+class OraSundryTerm(C.Structure):
+    """Mirror of ``ora_sundry_term``: U cd_i cd_j c_k c_l, each operator (orbital 1-based, spin 1|2)."""
+
+    _fields_ = [("cd_i", C.c_int32 * 2), ("cd_j", C.c_int32 * 2), ("c_k", C.c_int32 * 2),
+                ("c_l", C.c_int32 * 2), ("U", C.c_double)]
+
+
+class OraPhonons(C.Structure):
+    """Mirror of ``ora_phonons``."""
+
+    _fields_ = [("Nph", C.c_int32), ("pad", C.c_int32), ("w0", C.c_double), ("A", C.c_double),
+                ("g", C.c_double * (MAXORB * MAXORB))]
+
+
 def build_library(force: bool = False) -> str:
     """Compile ed_oracle.c -> libed_oracle.so (gcc, reference release flags)."""
     so = os.path.join(_HERE, "libed_oracle.so")
@@ -90,6 +104,7 @@ def lib():
         L.ora_c.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
         L.ora_cdg.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
         L.ora_direct_hxv.argtypes = [PP, C.c_int, C.c_int, dp, dp]
+        L.ora_direct_hxv_ext.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, dp, dp]
         L.ora_direct_hxv_mpi.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]
         L.ora_direct_hxv_mpi_sample.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp,
                                                 dp, C.POINTER(C.c_double)]
@@ -273,6 +288,45 @@ def direct_hxv(model: Model, nup, ndw, v):
     v = np.ascontiguousarray(v, np.float64)
     hv = np.empty_like(v)
     rc = lib().ora_direct_hxv(C.byref(model.params()), nup, ndw, v, hv)
+    assert rc == 0
+    return hv
+
+
+def sundry_array(terms):
+    """terms: iterable of ((orb,spin) cd_i, (orb,spin) cd_j, (orb,spin) c_k, (orb,spin) c_l, U) with
+    1-based orbitals and spin 1 = up / 2 = dw, like one line of coulomb_sundry."""
+    arr = (OraSundryTerm * max(len(terms), 1))()
+    for t, (ci, cj, ck, cl, U) in enumerate(terms):
+        arr[t].cd_i[:] = ci
+        arr[t].cd_j[:] = cj
+        arr[t].c_k[:] = ck
+        arr[t].c_l[:] = cl
+        arr[t].U = U
+    return arr
+
+
+def phonon_struct(Nph, w0, g, A=0.0):
+    ph = OraPhonons()
+    ph.Nph, ph.w0, ph.A = int(Nph), float(w0), float(A)
+    gg = np.zeros((MAXORB, MAXORB))
+    g = np.atleast_2d(np.asarray(g, float))
+    gg[: g.shape[0], : g.shape[1]] = g
+    ph.g[:] = gg.ravel().tolist()
+    return ph
+
+
+def direct_hxv_ext(model: Model, nup, ndw, v, sundry=(), phonons=None):
+    """directMatVec_normal_main with coulomb_sundry and DimPh = Nph+1 phonon slices
+    (direct/HxV_sundry.f90, HxV_ph.f90, HxV_eph.f90).  phonons = dict(Nph=, w0=, g=, A=0)."""
+    v = np.ascontiguousarray(v, np.float64)
+    hv = np.empty_like(v)
+    sundry = list(sundry)
+    arr = sundry_array(sundry)
+    ph = phonon_struct(**phonons) if phonons else None
+    rc = lib().ora_direct_hxv_ext(C.byref(model.params()), nup, ndw, len(sundry),
+                                  C.cast(arr, C.c_void_p), C.byref(ph) if ph else None, v, hv)
+    if rc == -2:
+        raise ValueError("In NORMAL mode, operators that change the total spin are forbidden")
     assert rc == 0
     return hv
 

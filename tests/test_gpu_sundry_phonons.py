@@ -1,0 +1,162 @@
+"""SURVEY 8a row a10 through the C ABI: coulomb_sundry (direct/HxV_sundry.f90) and phonons
+(direct/HxV_ph.f90, HxV_eph.f90) against the oracle's restatement (itself pinned to an independent
+Jordan-Wigner construction in tests/test_oracle_sundry_phonons.py).  H x v 1e-12 relative, Lanczos
+ground state 1e-10, seeds / observables 1e-8."""
+import numpy as np
+import pytest
+
+from models import messy_kwargs, star_kwargs, two_orb_kwargs
+from test_oracle_sundry_phonons import SUNDRY
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+PH2 = dict(Nph=3, w0=0.37, g=[[0.5, 0.2], [0.2, -0.3]])
+PH2_NS = dict(Nph=2, w0=0.1, g=[[0.3, 0.4], [-0.15, 0.0]], A=0.2)
+PH1 = dict(Nph=4, w0=0.5, g=[[0.7]])
+
+CASES = {
+    "sundry_2orb": (lambda: two_orb_kwargs(2), SUNDRY, None),
+    "sundry_messy": (messy_kwargs, SUNDRY, None),
+    "phonons_1orb": (lambda: star_kwargs(5), [], PH1),
+    "phonons_2orb_offdiag": (lambda: two_orb_kwargs(2), [], PH2),
+    "phonons_nonsym_A": (lambda: two_orb_kwargs(1), [], PH2_NS),
+    "both_2orb": (lambda: two_orb_kwargs(2, with_nd=True), SUNDRY, PH2),
+    "both_nb3": (lambda: two_orb_kwargs(3), SUNDRY[:3], dict(Nph=1, w0=0.2, g=[[0.1, 0.0], [0.0, 0.25]])),
+}
+
+
+@pytest.fixture
+def ext(engine):
+    """Clears the engine-global coulomb_sundry / phonon settings after each test."""
+    yield engine
+    try:
+        engine.delete_Hv_sector_normal()
+    except Exception:
+        pass
+    engine.set_coulomb_sundry(())
+    engine.set_phonons(0)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("name", list(CASES))
+def test_hxv_ext_parity(ext, oracle, name, variant):
+    E = ext
+    mk, sundry, ph = CASES[name]
+    kw = mk()
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    ns = m.Ns
+    E.set_coulomb_sundry(sundry)
+    E.set_phonons(**(ph or dict(Nph=0)))
+    nph = (ph["Nph"] if ph else 0) + 1
+    rng = np.random.default_rng(21)
+    h = ns // 2
+    for nup, ndw in [(h, h), (h + 1, h - 1), (1, ns - 1), (0, 2), (ns, ns), (0, 0)]:
+        E.build_Hv_sector_normal(m, nup, ndw)
+        E.set_kernel_variant(variant)
+        try:
+            du, dd = oracle.sector_dims(ns, nup, ndw)
+            assert E.vecDim_Hv_sector_normal() == du * dd * nph
+            v = rng.standard_normal(du * dd * nph)
+            got = E.spHtimesV_p(v)
+        finally:
+            E.set_kernel_variant(0)
+            E.delete_Hv_sector_normal()
+        ref = oracle.direct_hxv_ext(mo, nup, ndw, v, sundry, ph)
+        assert rel_err(got, ref) < 1e-12, (name, nup, ndw)
+
+
+def test_kanamori_lines_equal_builtin_nonlocal(ext, oracle):
+    """Jx / Jp written as coulomb_sundry lines == the built-in k_nonlocal path (two device code paths)."""
+    E = ext
+    kw = two_orb_kwargs(3)
+    J = 0.125
+    lines = []
+    for a in (1, 2):
+        for b in (1, 2):
+            if a != b:
+                lines.append(((a, 1), (b, 2), (b, 1), (a, 2), J))
+                lines.append(((a, 1), (a, 2), (b, 1), (b, 2), J))
+    ns = E.EDModel(**kw).Ns
+    du, dd = oracle.sector_dims(ns, ns // 2, ns // 2)
+    v = np.random.default_rng(3).standard_normal(du * dd)
+    E.build_Hv_sector_normal(E.EDModel(**kw), ns // 2, ns // 2)
+    a = E.spHtimesV_p(v)
+    E.delete_Hv_sector_normal()
+    E.set_coulomb_sundry(lines)
+    E.build_Hv_sector_normal(E.EDModel(**{**kw, "Jx": 0.0, "Jp": 0.0}), ns // 2, ns // 2)
+    b = E.spHtimesV_p(v)
+    E.delete_Hv_sector_normal()
+    assert rel_err(b, a) < 1e-13
+
+
+def test_spin_unbalanced_term_refused(ext):
+    E = ext
+    with pytest.raises(E.EdgpuError, match="total spin"):
+        E.set_coulomb_sundry([((1, 1), (2, 1), (1, 2), (2, 2), 1.0)])
+
+
+def test_phonon_ground_state_and_seed(ext, oracle):
+    """Holstein impurity: Lanczos ground state of the sector with phonons against dense LAPACK of the
+    oracle H (1e-10), dens/docc and |c v|^2 + |c^+ v|^2 = 1 on the device-resident state (1e-8)."""
+    E = ext
+    kw = star_kwargs(3)
+    ph = dict(Nph=5, w0=0.4, g=[[0.6]])
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    ns, nup, ndw = m.Ns, 2, 2
+    du, dd = oracle.sector_dims(ns, nup, ndw)
+    n = du * dd * (ph["Nph"] + 1)
+    H = np.column_stack([oracle.direct_hxv_ext(mo, nup, ndw, e, [], ph) for e in np.eye(n)])
+    assert np.abs(H - H.T).max() < 1e-14
+    w, V = np.linalg.eigh(H)
+    E.set_phonons(**ph)
+    E.build_Hv_sector_normal(m, nup, ndw)
+    try:
+        egs, vec, niter = E.sp_lanc_eigh(300, 1e-14)
+        assert abs(egs - w[0]) < 1e-10
+        assert abs(abs(vec @ V[:, 0]) - 1.0) < 1e-8
+        E.state_store(0)
+        dens, docc = E.state_observables(0, 1)
+        gs = V[:, 0].reshape(ph["Nph"] + 1, dd, du)
+        mu, md = oracle.build_map(ns, nup), oracle.build_map(ns, ndw)
+        nu, nd = (mu & 1).astype(float), (md & 1).astype(float)
+        p = (gs ** 2).sum(0)
+        assert abs(dens[0] - (p * (nu[None, :] + nd[:, None])).sum()) < 1e-8
+        assert abs(docc[0] - (p * (nu[None, :] * nd[:, None])).sum()) < 1e-8
+    finally:
+        E.delete_Hv_sector_normal()
+    tot = 0.0
+    for op in (-1, +1):
+        E.build_Hv_sector_normal(m, nup + op, ndw)
+        try:
+            E.apply_op(0, op, 0, 0)
+            tot += E.seed_norm2()
+        finally:
+            E.delete_Hv_sector_normal()
+    E.state_free(0)
+    assert abs(tot - 1.0) < 1e-10
+
+
+def test_phonon_eigh_two_states(ext, oracle):
+    """sp_eigh (thick-restart Lanczos) on a sector with phonon slices: lowest two eigenvalues 1e-10."""
+    E = ext
+    kw = two_orb_kwargs(1)
+    ph = dict(Nph=2, w0=0.3, g=[[0.4, 0.1], [0.1, 0.2]])
+    m, mo = E.EDModel(**kw), oracle.Model(**kw)
+    ns, nup, ndw = m.Ns, 2, 2
+    du, dd = oracle.sector_dims(ns, nup, ndw)
+    n = du * dd * 3
+    H = np.column_stack([oracle.direct_hxv_ext(mo, nup, ndw, e, [], ph) for e in np.eye(n)])
+    w = np.linalg.eigvalsh(H)
+    E.set_phonons(**ph)
+    E.build_Hv_sector_normal(m, nup, ndw)
+    try:
+        ev, vecs, nconv, _ = E.sp_eigh(2, 20, 300, 0.0)
+    finally:
+        E.delete_Hv_sector_normal()
+    assert nconv >= 2
+    assert np.abs(np.asarray(ev[:2]) - w[:2]).max() < 1e-10
