@@ -42,6 +42,102 @@ def binomial(n: int, k: int) -> int:
     return math.comb(n, k) if 0 <= k <= n else 0
 
 
+
+# ------------------------------------------------------------------------------------------
+# two-body operators: ED_PARSE_UMATRIX.f90 (read_umatrix_file :353-449, parse_umatrix_line
+# :452-634, set_umatrix :88-165)
+# ------------------------------------------------------------------------------------------
+def read_umatrix_file(path: str):
+    """read_umatrix_file: '#'/'!'/'%' comment preamble, '<Norb> BANDS', then one operator per line
+    'oi si oj sj ok sk ol sl U' (orbitals 1-based, spins u|d); malformed lines are skipped.
+    Returns (Norb, [(oi, si, oj, sj, ok, sk, ol, sl, U), ...])."""
+    norb, lines = None, []
+    with open(path) as f:
+        for raw in f:
+            tok = raw.split()
+            if not tok:
+                continue
+            if norb is None:
+                if tok[0][0] in "#!%":
+                    continue
+                norb = int(tok[0])
+                continue
+            try:
+                oi, si, oj, sj, ok, sk, ol, sl = (int(tok[0]), tok[1], int(tok[2]), tok[3], int(tok[4]),
+                                                  tok[5], int(tok[6]), tok[7])
+                U = float(tok[8].replace("d", "e").replace("D", "e"))
+            except (ValueError, IndexError):
+                continue
+            lines.append((oi, si, oj, sj, ok, sk, ol, sl, U))
+    return norb, lines
+
+
+def parse_umatrix(Norb: int, lines, use_kanamori=False, Uloc=(), Ust=0.0, Jh=0.0, Jx=0.0, Jp=0.0):
+    """set_umatrix: every line goes through parse_umatrix_line (1/2 prefactor and sign of the
+    w2dynamics convention, canonical ordering of the creation / annihilation pairs, mean-field
+    term of the anticommutator into mfHloc, re-swap to the c->cd->c->cd application order,
+    classification into Uloc / Ust / Ust-Jh / Jx / Jp, everything else into coulomb_sundry); then
+    the symmetrisations of :124-133 and the ED_USE_KANAMORI additions of :139-146.
+    Returns dict(Uloc[Norb], Ust, Jh, Jx, Jp [Norb,Norb], mfHloc[2,2,Norb,Norb],
+    sundry=[((orb,spin) cd_i, cd_j, c_k, c_l, U)] with spin 1 = up / 2 = dw)."""
+    No = Norb
+    U_in = np.zeros(No)
+    Ust_in, Jh_in, Jx_in, Jp_in = (np.zeros((No, No)) for _ in range(4))
+    mf = np.zeros((2, 2, No, No))
+    sundry = []
+    for (oi, si, oj, sj, ok, sk, ol, sl, U) in lines:
+        if max(oi, oj, ok, ol) > No or min(oi, oj, ok, ol) < 1:
+            raise ValueError("two-body operator: orbital index outside 1..Norb")
+        if any(s not in ("u", "d") for s in (si, sj, sk, sl)):
+            raise ValueError("two-body operator: spin index malformed")
+        ci, cj = [oi, 1 if si == "u" else 2], [oj, 1 if sj == "u" else 2]
+        ck, cl = [ok, 1 if sk == "u" else 2], [ol, 1 if sl == "u" else 2]
+        if abs(U) < 1e-10:
+            continue
+        U = -0.5 * U
+        if ci[0] > cj[0]:   # creation pair: increasing orbital ...
+            ci, cj, U = cj, ci, -U
+        if ci[1] > cj[1]:   # ... overridden by increasing spin
+            ci, cj, U = cj, ci, -U
+        if ck[0] > cl[0]:   # annihilation pair likewise
+            ck, cl, U = cl, ck, -U
+        if ck[1] > cl[1]:
+            ck, cl, U = cl, ck, -U
+        if cj == ck:        # anticommutator {c^+_j, c_k} = 1 leaves a one-body term
+            mf[ci[1] - 1, ck[1] - 1, ci[0] - 1, ck[0] - 1] += U
+        U = -U              # second and third operator are swapped at application time
+        if ci[0] == ck[0] and cj[0] == cl[0]:
+            if ci[1] != cj[1]:
+                if ci[0] == cj[0]:
+                    U_in[ci[0] - 1] += U
+                else:
+                    Ust_in[ci[0] - 1, cj[0] - 1] += U
+                continue
+            if ci[0] != cj[0]:
+                Jh_in[ci[0] - 1, cj[0] - 1] += U   # holds Ust-Jh until the end
+                continue
+        if (ci[0] != cj[0] and ci[1] != cj[1] and ci[0] == cl[0] and ci[1] == ck[1]
+                and cj[0] == ck[0] and cj[1] == cl[1]):
+            Jx_in[ci[0] - 1, ck[0] - 1] += U
+            continue
+        if (ci[0] == cj[0] and ci[1] != cj[1] and ci[0] != ck[0] and ci[1] == ck[1]
+                and cj[0] != cl[0] and cj[1] == cl[1]):
+            Jp_in[ci[0] - 1, ck[0] - 1] += U
+            continue
+        sundry.append((tuple(ci), tuple(cj), tuple(ck), tuple(cl), U))
+    Ust_in = (Ust_in + Ust_in.T) / 2.0
+    Jh_in = (Jh_in + Jh_in.T) / 2.0
+    Jh_in = Ust_in - Jh_in
+    if use_kanamori:
+        off = 1.0 - np.eye(No)
+        U_in = U_in + np.asarray(Uloc, float)[:No]
+        Ust_in = Ust_in + Ust * off
+        Jh_in = Jh_in + Jh * off
+        Jx_in = Jx_in + Jx * off
+        Jp_in = Jp_in + Jp * off
+    return dict(Uloc=U_in, Ust=Ust_in, Jh=Jh_in, Jx=Jx_in, Jp=Jp_in, mfHloc=mf, sundry=sundry)
+
+
 @dataclass
 class EDModel:
     """What ``ed_read_input`` + ``ed_init_solver`` + ``ed_set_Hloc`` + ``set_umatrix`` leave in
@@ -78,7 +174,23 @@ class EDModel:
     lanc_nstates_sector: int = 2       # LANC_NSTATES_SECTOR
     lanc_nstates_total: int = 2        # LANC_NSTATES_TOTAL
     cutoff: float = 1e-9               # CUTOFF (spectrum cut-off exp(-beta(E-Egs)) at finite T)
+    ed_use_kanamori: bool = True       # ED_USE_KANAMORI
+    umatrix_lines: tuple = ()          # ED_READ_UMATRIX file lines + ed_add_twobody_operator calls
     _params: NormalParams | None = field(default=None, repr=False)
+
+    def umatrix(self):
+        """set_umatrix (ED_PARSE_UMATRIX.f90:88-165) for this model."""
+        return parse_umatrix(self.Norb, self.umatrix_lines, self.ed_use_kanamori, self.Uloc, self.Ust,
+                             self.Jh, self.Jx, self.Jp)
+
+    @property
+    def coulomb_sundry(self):
+        return self.umatrix()["sundry"]
+
+    def add_twobody_operator(self, oi, si, oj, sj, ok, sk, ol, sl, Uijkl):
+        """ed_add_twobody_operator (ED_PARSE_UMATRIX.f90:44-86)."""
+        self.umatrix_lines = tuple(self.umatrix_lines) + ((oi, si, oj, sj, ok, sk, ol, sl, Uijkl),)
+        self._params = None
 
     @property
     def Ns(self) -> int:  # ED_SETUP.f90:118-126
@@ -131,22 +243,25 @@ class EDModel:
         p.Ns, p.Norb, p.Nbath = self.Ns, No, Nb
         p.bath_type = BATH_CODES[self.bath_type]
         p.hfmode, p.Nfoo, p.xmu = int(self.hfmode), self.Nfoo, self.xmu
+        um = self.umatrix()
         eloc = np.zeros((2, MAXORB, MAXORB))
         if self.hloc is not None:
             eloc[:, :No, :No] = self.hloc
+        for s_ in range(2):  # impHloc + mfHloc, spin-diagonal blocks (direct/HxV_local.f90:17-20)
+            eloc[s_, :No, :No] += um["mfHloc"][s_, s_]
         p.eloc[:] = eloc.ravel().tolist()
         sf = np.zeros(MAXORB)
         sf[: len(self.spin_field_z)] = self.spin_field_z
         p.spin_field_z[:] = sf.tolist()
         p.exc_field[:] = list(self.exc_field)
-        # ED_USE_KANAMORI=T branch of set_umatrix (ED_PARSE_UMATRIX.f90:136-143)
+        # internal interaction matrices left by set_umatrix (ED_PARSE_UMATRIX.f90:88-165)
         U = np.zeros(MAXORB)
-        U[:No] = np.asarray(self.Uloc, float)[:No]
+        U[:No] = um["Uloc"]
         p.Uloc[:] = U.tolist()
-        off = np.zeros((MAXORB, MAXORB))
-        off[:No, :No] = 1.0 - np.eye(No)
-        for name, val in (("Ust", self.Ust), ("Jh", self.Jh), ("Jx", self.Jx), ("Jp", self.Jp)):
-            getattr(p, name)[:] = (val * off).ravel().tolist()
+        for name in ("Ust", "Jh", "Jx", "Jp"):
+            mat = np.zeros((MAXORB, MAXORB))
+            mat[:No, :No] = um[name]
+            getattr(p, name)[:] = mat.ravel().tolist()
         dh = np.zeros((2, MAXORB, MAXBATH))
         dh[:, :No, :Nb] = self.bath_v
         bd = np.zeros((2, MAXORB, MAXBATH))
@@ -281,6 +396,13 @@ def set_coulomb_sundry(terms=()):
         arr[t].c_l[:] = cl
         arr[t].U = U
     check(_abi.load().edgpu_set_coulomb_sundry(len(terms), C.cast(arr, C.c_void_p)))
+
+
+def set_umatrix(model: "EDModel"):
+    """The engine-side half of set_umatrix (ED_PARSE_UMATRIX.f90:88-165, called from
+    ed_init_solver): hands the model's coulomb_sundry list to the engine (the Kanamori matrices and
+    mfHloc travel in edgpu_normal_params)."""
+    set_coulomb_sundry(model.coulomb_sundry)
 
 
 def set_phonons(Nph: int = 0, w0: float = 0.0, g=None, A: float = 0.0):

@@ -120,6 +120,102 @@ def lib():
     return _lib
 
 
+
+# --------------------------------------------------------------------------------------
+# two-body operators: ED_PARSE_UMATRIX.f90 (read_umatrix_file :353-449, parse_umatrix_line
+# :452-634, set_umatrix :88-165)
+# --------------------------------------------------------------------------------------
+def read_umatrix_file(path: str):
+    """read_umatrix_file: '#'/'!'/'%' comment preamble, '<Norb> BANDS', then one operator per line
+    'oi si oj sj ok sk ol sl U' (orbitals 1-based, spins u|d); malformed lines are skipped.
+    Returns (Norb, [(oi, si, oj, sj, ok, sk, ol, sl, U), ...])."""
+    norb, lines = None, []
+    with open(path) as f:
+        for raw in f:
+            tok = raw.split()
+            if not tok:
+                continue
+            if norb is None:
+                if tok[0][0] in "#!%":
+                    continue
+                norb = int(tok[0])
+                continue
+            try:
+                oi, si, oj, sj, ok, sk, ol, sl = (int(tok[0]), tok[1], int(tok[2]), tok[3], int(tok[4]),
+                                                  tok[5], int(tok[6]), tok[7])
+                U = float(tok[8].replace("d", "e").replace("D", "e"))
+            except (ValueError, IndexError):
+                continue
+            lines.append((oi, si, oj, sj, ok, sk, ol, sl, U))
+    return norb, lines
+
+
+def parse_umatrix(Norb: int, lines, use_kanamori=False, Uloc=(), Ust=0.0, Jh=0.0, Jx=0.0, Jp=0.0):
+    """set_umatrix: every line goes through parse_umatrix_line (1/2 prefactor and sign of the
+    w2dynamics convention, canonical ordering of the creation / annihilation pairs, mean-field
+    term of the anticommutator into mfHloc, re-swap to the c->cd->c->cd application order,
+    classification into Uloc / Ust / Ust-Jh / Jx / Jp, everything else into coulomb_sundry); then
+    the symmetrisations of :124-133 and the ED_USE_KANAMORI additions of :139-146.
+    Returns dict(Uloc[Norb], Ust, Jh, Jx, Jp [Norb,Norb], mfHloc[2,2,Norb,Norb],
+    sundry=[((orb,spin) cd_i, cd_j, c_k, c_l, U)] with spin 1 = up / 2 = dw)."""
+    No = Norb
+    U_in = np.zeros(No)
+    Ust_in, Jh_in, Jx_in, Jp_in = (np.zeros((No, No)) for _ in range(4))
+    mf = np.zeros((2, 2, No, No))
+    sundry = []
+    for (oi, si, oj, sj, ok, sk, ol, sl, U) in lines:
+        if max(oi, oj, ok, ol) > No or min(oi, oj, ok, ol) < 1:
+            raise ValueError("two-body operator: orbital index outside 1..Norb")
+        if any(s not in ("u", "d") for s in (si, sj, sk, sl)):
+            raise ValueError("two-body operator: spin index malformed")
+        ci, cj = [oi, 1 if si == "u" else 2], [oj, 1 if sj == "u" else 2]
+        ck, cl = [ok, 1 if sk == "u" else 2], [ol, 1 if sl == "u" else 2]
+        if abs(U) < 1e-10:
+            continue
+        U = -0.5 * U
+        if ci[0] > cj[0]:   # creation pair: increasing orbital ...
+            ci, cj, U = cj, ci, -U
+        if ci[1] > cj[1]:   # ... overridden by increasing spin
+            ci, cj, U = cj, ci, -U
+        if ck[0] > cl[0]:   # annihilation pair likewise
+            ck, cl, U = cl, ck, -U
+        if ck[1] > cl[1]:
+            ck, cl, U = cl, ck, -U
+        if cj == ck:        # anticommutator {c^+_j, c_k} = 1 leaves a one-body term
+            mf[ci[1] - 1, ck[1] - 1, ci[0] - 1, ck[0] - 1] += U
+        U = -U              # second and third operator are swapped at application time
+        if ci[0] == ck[0] and cj[0] == cl[0]:
+            if ci[1] != cj[1]:
+                if ci[0] == cj[0]:
+                    U_in[ci[0] - 1] += U
+                else:
+                    Ust_in[ci[0] - 1, cj[0] - 1] += U
+                continue
+            if ci[0] != cj[0]:
+                Jh_in[ci[0] - 1, cj[0] - 1] += U   # holds Ust-Jh until the end
+                continue
+        if (ci[0] != cj[0] and ci[1] != cj[1] and ci[0] == cl[0] and ci[1] == ck[1]
+                and cj[0] == ck[0] and cj[1] == cl[1]):
+            Jx_in[ci[0] - 1, ck[0] - 1] += U
+            continue
+        if (ci[0] == cj[0] and ci[1] != cj[1] and ci[0] != ck[0] and ci[1] == ck[1]
+                and cj[0] != cl[0] and cj[1] == cl[1]):
+            Jp_in[ci[0] - 1, ck[0] - 1] += U
+            continue
+        sundry.append((tuple(ci), tuple(cj), tuple(ck), tuple(cl), U))
+    Ust_in = (Ust_in + Ust_in.T) / 2.0
+    Jh_in = (Jh_in + Jh_in.T) / 2.0
+    Jh_in = Ust_in - Jh_in
+    if use_kanamori:
+        off = 1.0 - np.eye(No)
+        U_in = U_in + np.asarray(Uloc, float)[:No]
+        Ust_in = Ust_in + Ust * off
+        Jh_in = Jh_in + Jh * off
+        Jx_in = Jx_in + Jx * off
+        Jp_in = Jp_in + Jp * off
+    return dict(Uloc=U_in, Ust=Ust_in, Jh=Jh_in, Jx=Jx_in, Jp=Jp_in, mfHloc=mf, sundry=sundry)
+
+
 # --------------------------------------------------------------------------------------
 # model description (what ed_read_input + ed_init_solver + ed_set_Hloc + set_umatrix leave
 # in the reference's module globals)
@@ -150,7 +246,18 @@ class Model:
     lanc_tolerance: float = 1e-18
     lanc_dim_threshold: int = 1024
     gs_threshold: float = 1e-9
+    ed_use_kanamori: bool = True        # ED_USE_KANAMORI
+    umatrix_lines: tuple = ()           # umatrix file lines + ed_add_twobody_operator calls
     _params: OraParams | None = field(default=None, repr=False)
+
+    def umatrix(self):
+        """set_umatrix (ED_PARSE_UMATRIX.f90:88-165) for this model."""
+        return parse_umatrix(self.Norb, self.umatrix_lines, self.ed_use_kanamori, self.Uloc, self.Ust,
+                             self.Jh, self.Jx, self.Jp)
+
+    @property
+    def coulomb_sundry(self):
+        return self.umatrix()["sundry"]
 
     @property
     def Ns(self) -> int:
@@ -211,23 +318,24 @@ class Model:
         if self.bath_e is None:
             self.default_bath()
         hloc = np.zeros((2, No, No)) if self.hloc is None else np.asarray(self.hloc, float)
+        um = self.umatrix()
         eloc = np.zeros((2, MAXORB, MAXORB))
         eloc[:, :No, :No] = hloc
+        for s_ in range(2):  # impHloc + mfHloc, spin-diagonal blocks (direct/HxV_local.f90:17-20)
+            eloc[s_, :No, :No] += um["mfHloc"][s_, s_]
         p.eloc[:] = eloc.ravel().tolist()
         sf = np.zeros(MAXORB)
         sf[: len(self.spin_field_z)] = self.spin_field_z
         p.spin_field_z[:] = sf.tolist()
         p.exc_field[:] = list(self.exc_field)
-        # set_umatrix with ED_USE_KANAMORI=T (ED_PARSE_UMATRIX.f90:136-143)
+        # internal interaction matrices left by set_umatrix (ED_PARSE_UMATRIX.f90:88-165)
         U = np.zeros(MAXORB)
-        U[:No] = np.asarray(self.Uloc, float)[:No]
+        U[:No] = um["Uloc"]
         p.Uloc[:] = U.tolist()
-        off = np.zeros((MAXORB, MAXORB))
-        off[:No, :No] = 1.0 - np.eye(No)
-        p.Ust[:] = (self.Ust * off).ravel().tolist()
-        p.Jh[:] = (self.Jh * off).ravel().tolist()
-        p.Jx[:] = (self.Jx * off).ravel().tolist()
-        p.Jp[:] = (self.Jp * off).ravel().tolist()
+        for name in ("Ust", "Jh", "Jx", "Jp"):
+            mat = np.zeros((MAXORB, MAXORB))
+            mat[:No, :No] = um[name]
+            getattr(p, name)[:] = mat.ravel().tolist()
         dh = np.zeros((2, MAXORB, MAXBATH))
         dh[:, :No, :Nb] = self.bath_v
         bd = np.zeros((2, MAXORB, MAXBATH))
