@@ -10,14 +10,16 @@ Follows, per state of the sector:
   stored/Himp.f90                     diagonal :15-21, same-spin hops :38-80, spin-flip :85-110,
                                        spin_field :243-300 (z on the diagonal, x/y off-diagonal)
   stored/Hint.f90                     density-density + Hartree shifts :13-52, S-E :63-90, P-H :96-124
-  stored/Hbath.f90                    normal/hybrid diagonal :12-27
+  stored/Hbath.f90                    normal/hybrid diagonal :12-27; replica/general diagonal :30-45,
+                                       same-spin bath hops :49-100, spin-flip bath hops :103-133
   stored/Himp_bath.f90                spin-conserving hybridisation :10-67, spin-flip u :72-136
+                                       (normal/hybrid only)
 Matrix convention (sp_insert_element(spH0,htmp,i,j)): row i = the state the operators act on,
 column j = the resulting state, value = conjg(amplitude)*sign; duplicates accumulate
 (ED_SPARSE_MATRIX.f90:346-357).
 
-Parity status: pinned to test/src/HYBRID_NONSU2/{evals,dens,docc,magX}.check
-(tests/test_oracle_golden_nonsu2.py).
+Parity status: pinned to test/src/{HYBRID,NORMAL,REPLICA,GENERAL}_NONSU2/{evals,dens,docc}.check
+(+ magX / exciton) (tests/test_oracle_golden_nonsu2.py).
 """
 from __future__ import annotations
 
@@ -31,7 +33,7 @@ import numpy as np
 class ModelNonsu2:
     Norb: int = 2
     Nbath: int = 4
-    bath_type: str = "hybrid"          # normal | hybrid
+    bath_type: str = "hybrid"          # normal | hybrid | replica | general
     Uloc: tuple = (1.0, 1.0)
     Ust: float = 0.0
     Jh: float = 0.0
@@ -45,6 +47,7 @@ class ModelNonsu2:
     bath_v: np.ndarray | None = None   # [2, Norb, Nbath]
     bath_u: np.ndarray | None = None   # [2, Norb, Nbath]  spin-flip hybridisation
     spin_field: np.ndarray | None = None  # [Norb, 3]
+    hbath: np.ndarray | None = None    # replica/general: complex [2,2,Norb,Norb,Nbath] Hbath_tmp
 
     @property
     def Ns(self):  # ED_SETUP.f90:118-126
@@ -57,6 +60,8 @@ class ModelNonsu2:
     def stride(self, a, k):  # getBathStride(a+1,k+1), 1-based site (ED_SETUP.f90:605-622)
         if self.bath_type == "hybrid":
             return self.Norb + k + 1
+        if self.bath_type in ("replica", "general"):
+            return (a + 1) + (k + 1) * self.Norb
         return self.Norb + a * self.Nbath + k + 1
 
     def default_bath(self):
@@ -218,13 +223,40 @@ def stored_H(model: ModelNonsu2, Ntot: int):
                             k, sg = f(pos, k)
                             s *= sg
                         ins(Jp[a, b] * s, index[k])
-        # ---- Hbath.f90 (normal / hybrid)
-        h = 0.0
-        for a in range(model.Nfoo):
+        replica = model.bath_type in ("replica", "general")
+        if not replica:
+            # ---- Hbath.f90 (normal / hybrid)
+            h = 0.0
+            for a in range(model.Nfoo):
+                for k in range(Nb):
+                    s = model.stride(a, k)
+                    h += model.bath_e[0, a, k] * ib[s - 1] + model.bath_e[1, a, k] * ib[s - 1 + Ns]
+            ins(h, i)
+        else:
+            # ---- Hbath.f90 (replica / general): bath_diag(s,a,k) = Hbath_tmp(s,s,a,a,k)
+            hb = np.asarray(model.hbath, complex)
+            h = 0.0
             for k in range(Nb):
-                s = model.stride(a, k)
-                h += model.bath_e[0, a, k] * ib[s - 1] + model.bath_e[1, a, k] * ib[s - 1 + Ns]
-        ins(h, i)
+                for a in range(No):
+                    s = model.stride(a, k)
+                    h += hb[0, 0, a, a, k] * ib[s - 1] + hb[1, 1, a, a, k] * ib[s - 1 + Ns]
+            ins(h, i)
+            for k in range(Nb):          # same-spin bath hops
+                for a in range(No):
+                    for b in range(No):
+                        ia, ibt = model.stride(a, k), model.stride(b, k)
+                        if hb[0, 0, a, b, k] != 0 and ib[ibt - 1] == 1 and ib[ia - 1] == 0:
+                            hop(ia, ibt, hb[0, 0, a, b, k])
+                        if hb[1, 1, a, b, k] != 0 and ib[ibt - 1 + Ns] == 1 and ib[ia - 1 + Ns] == 0:
+                            hop(ia + Ns, ibt + Ns, hb[1, 1, a, b, k])
+            for k in range(Nb):          # spin-flip bath hops
+                for isp in range(2):
+                    jsp = 1 - isp
+                    for a in range(No):
+                        for b in range(No):
+                            ia, ibt = model.stride(a, k) + isp * Ns, model.stride(b, k) + jsp * Ns
+                            if hb[isp, jsp, a, b, k] != 0 and ib[ibt - 1] == 1 and ib[ia - 1] == 0:
+                                hop(ia, ibt, hb[isp, jsp, a, b, k])
         # ---- Himp_bath.f90
         for a in range(No):
             for k in range(Nb):
@@ -235,6 +267,8 @@ def stored_H(model: ModelNonsu2, Ntot: int):
                         hop(ms + sp * Ns, a + 1 + sp * Ns, v)   # imp -> bath
                         hop(a + 1 + sp * Ns, ms + sp * Ns, v)   # bath -> imp
         for a in range(No):
+            if replica:                  # no spin-flip hybridisation (Himp_bath.f90:72)
+                break
             for k in range(Nb):
                 ms = model.stride(a, k)
                 u1, u2 = model.bath_u[0, a, k], model.bath_u[1, a, k]

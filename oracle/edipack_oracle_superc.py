@@ -10,7 +10,9 @@ Follows, per state of the sector (normal / hybrid bath, Nspin=1 or 2):
   ED_SUPERC/stored/Himp.f90    diagonal :11-27, same-spin hops :31-80, anomalous local pairing
                                impHloc_anomalous + pair_field :86-125
   ED_SUPERC/stored/Hint.f90    = ED_NONSU2/stored/Hint.f90 (density-density, Hartree shifts, S-E, P-H)
-  ED_SUPERC/stored/Hbath.f90   normal/hybrid diagonal :12-27, bath pairing d :97-133
+  ED_SUPERC/stored/Hbath.f90   normal/hybrid diagonal :12-27, bath pairing d :97-133; replica/general:
+                               Nambu diagonal :29-45, particle (1,1) / hole (2,2) block hops :48-92,
+                               anomalous (1,2) / (2,1) blocks :135-177
   ED_SUPERC/stored/Himp_bath.f90  spin-conserving hybridisation :10-67
   ED_OBSERVABLES_SUPERC.f90    dens/docc :150-165, phisc :204-248 through
                                apply_Cops(v,[1,1],[-1,+1],[a,b],[dw,up]) (ED_SECTOR.f90)
@@ -18,7 +20,8 @@ Matrix convention as in the reference: sp_insert_element(spH0,htmp,i,j), row i =
 operators act on, column j = the resulting state; duplicates accumulate.
 
 Parity status: pinned to test/src/NORMAL_SUPERC/{evals,dens,docc,phisc}.check and
-test/src/HYBRID_SUPERC/{evals,dens,docc}.check (tests/test_oracle_golden_superc.py).
+test/src/HYBRID_SUPERC/{evals,dens,docc}.check, and test/src/{REPLICA,GENERAL}_SUPERC
+{evals,dens,docc,phisc}.check (tests/test_oracle_golden_superc.py).
 """
 from __future__ import annotations
 
@@ -34,7 +37,7 @@ from edipack_oracle_nonsu2 import _c, _cdg
 class ModelSuperc:
     Norb: int = 2
     Nbath: int = 2
-    bath_type: str = "normal"          # normal | hybrid
+    bath_type: str = "normal"          # normal | hybrid | replica | general
     Uloc: tuple = (-2.0, -2.0)
     Ust: float = 0.0
     Jh: float = 0.0
@@ -50,6 +53,7 @@ class ModelSuperc:
     bath_e: np.ndarray | None = None     # [2, Nfoo, Nbath]
     bath_d: np.ndarray | None = None     # [Nfoo, Nbath]   dmft_bath%d(1,:,:)
     bath_v: np.ndarray | None = None     # [2, Norb, Nbath]
+    hbath: np.ndarray | None = None      # replica/general: complex [2(nambu),2,Norb,Norb,Nbath] Hbath_tmp
 
     @property
     def Ns(self):  # ED_SETUP.f90:118-126
@@ -62,6 +66,8 @@ class ModelSuperc:
     def stride(self, a, k):  # getBathStride(a+1,k+1), 1-based site (ED_SETUP.f90:605-622)
         if self.bath_type == "hybrid":
             return self.Norb + k + 1
+        if self.bath_type in ("replica", "general"):
+            return (a + 1) + (k + 1) * self.Norb
         return self.Norb + a * self.Nbath + k + 1
 
     def default_bath(self):
@@ -186,21 +192,50 @@ def stored_H(model: ModelSuperc, Sz: int):
                 for b in range(No):
                     if a != b and ib[b] == 1 and ib[b + Ns] == 1 and ib[a + Ns] == 0 and ib[a] == 0:
                         chain([(_c, b + 1), (_c, b + 1 + Ns), (_cdg, a + 1 + Ns), (_cdg, a + 1)], Jp[a, b])
-        # ---- Hbath.f90 (normal / hybrid)
-        h = 0.0
-        for a in range(model.Nfoo):
+        if model.bath_type not in ("replica", "general"):
+            # ---- Hbath.f90 (normal / hybrid)
+            h = 0.0
+            for a in range(model.Nfoo):
+                for k in range(Nb):
+                    s = model.stride(a, k)
+                    h += model.bath_e[0, a, k] * ib[s - 1] + model.bath_e[1, a, k] * ib[s - 1 + Ns]
+            ins(h, i)
+            for a in range(model.Nfoo):
+                for k in range(Nb):
+                    ms = model.stride(a, k)
+                    d = model.bath_d[a, k]
+                    if d != 0 and ib[ms - 1] == 1 and ib[ms - 1 + Ns] == 1:
+                        chain([(_c, ms), (_c, ms + Ns)], d)
+                    if d != 0 and ib[ms - 1] == 0 and ib[ms - 1 + Ns] == 0:
+                        chain([(_cdg, ms + Ns), (_cdg, ms)], d)
+        else:
+            # ---- Hbath.f90 (replica / general), Hbath_tmp in Nambu blocks: (1,1) particles (up),
+            # (2,2) holes (dw, enters with -), (1,2)/(2,1) pairing
+            hb = np.asarray(model.hbath, complex)
+            h = 0.0
             for k in range(Nb):
-                s = model.stride(a, k)
-                h += model.bath_e[0, a, k] * ib[s - 1] + model.bath_e[1, a, k] * ib[s - 1 + Ns]
-        ins(h, i)
-        for a in range(model.Nfoo):
+                for a in range(No):
+                    s = model.stride(a, k)
+                    h += hb[0, 0, a, a, k] * ib[s - 1] - hb[1, 1, a, a, k] * ib[s - 1 + Ns]
+            ins(h, i)
             for k in range(Nb):
-                ms = model.stride(a, k)
-                d = model.bath_d[a, k]
-                if d != 0 and ib[ms - 1] == 1 and ib[ms - 1 + Ns] == 1:
-                    chain([(_c, ms), (_c, ms + Ns)], d)
-                if d != 0 and ib[ms - 1] == 0 and ib[ms - 1 + Ns] == 0:
-                    chain([(_cdg, ms + Ns), (_cdg, ms)], d)
+                for a in range(No):
+                    for b in range(No):
+                        ia, ibt = model.stride(a, k), model.stride(b, k)
+                        if hb[0, 0, a, b, k] != 0 and ib[ibt - 1] == 1 and ib[ia - 1] == 0:
+                            chain([(_c, ibt), (_cdg, ia)], np.conj(hb[0, 0, a, b, k]))
+                        ia, ibt = ia + Ns, ibt + Ns
+                        if hb[1, 1, a, b, k] != 0 and ib[ibt - 1] == 0 and ib[ia - 1] == 1:
+                            chain([(_cdg, ibt), (_c, ia)], np.conj(hb[1, 1, a, b, k]))
+            for k in range(Nb):
+                for a in range(No):
+                    for b in range(No):
+                        ia, ibt = model.stride(a, k), model.stride(b, k) + Ns
+                        if hb[0, 1, a, b, k] != 0 and ib[ibt - 1] == 0 and ib[ia - 1] == 0:
+                            chain([(_cdg, ibt), (_cdg, ia)], np.conj(hb[0, 1, a, b, k]))
+                        ia, ibt = model.stride(a, k) + Ns, model.stride(b, k)
+                        if hb[1, 0, a, b, k] != 0 and ib[ibt - 1] == 1 and ib[ia - 1] == 1:
+                            chain([(_c, ibt), (_c, ia)], np.conj(hb[1, 0, a, b, k]))
         # ---- Himp_bath.f90
         for a in range(No):
             for k in range(Nb):

@@ -195,3 +195,64 @@ def superc_model(oracle_superc, name):
         Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
         ed_hw_bath=_f(g["ED_HW_BATH"]), deltasc=_f(g["DELTASC"]), hloc=hloc)
     return m.default_bath()
+
+
+def replica_nonsu2_model(oracle_nonsu2, kind="replica"):
+    """test/src/REPLICA_NONSU2 / GENERAL_NONSU2 (ed_replica_nonsu2.f90:47-88): Hloc = Mh*Gamma5,
+    bath replicas H_k = lambda_1(k) Gamma5 + sb (GammaE0 + GammaEz) - sb GammaEx in the spin-major
+    so2j ordering (COMMON.f90:81-122).  init_dmft_bath (ED_BATH_DMFT.f90:246-276): Gamma5 is diagonal
+    and its lambdas are all equal, so they are spread by linspace(-ED_OFFSET_BATH, ED_OFFSET_BATH, Nbath);
+    V = max(0.1, 1/sqrt(Nbath)) for every replica / spin-orbital."""
+    g = golden(f"{kind}_nonsu2")["inputs"]
+    norb, nb = int(g["NORB"]), int(g["NBATH"])
+    mh, sb, off = _f(g["MH"]), _f(g["SB_FIELD"]), _f(g["ED_OFFSET_BATH"])
+    s0, sx, sz = np.eye(2), np.array([[0, 1], [1, 0.0]]), np.diag([1.0, -1.0])
+    tx, tz = sx, sz
+    G5, GE0, GEz, GEx = np.kron(s0, tz), np.kron(s0, tx), np.kron(sz, tx), np.kron(sx, tx)
+
+    def j2so(M):   # (ispin-1)*Nspin + iorb, spin-major
+        return np.asarray(M, complex).reshape(2, norb, 2, norb).transpose(0, 2, 1, 3)
+
+    hloc = j2so(mh * G5)
+    hb = np.zeros((2, 2, norb, norb, nb), complex)
+    offs = np.linspace(-off, off, nb) if nb > 1 else np.zeros(1)
+    for k in range(nb):
+        hb[..., k] = j2so((mh + offs[k]) * G5 + sb * GE0 + sb * GEz - sb * GEx)
+    m = oracle_nonsu2.ModelNonsu2(
+        Norb=norb, Nbath=nb, bath_type=kind,
+        Uloc=tuple(_f(x) for x in g["ULOC"].split(",")), Ust=_f(g["UST"]), Jh=_f(g["JH"]),
+        Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
+        ed_hw_bath=_f(g["ED_HW_BATH"]), hloc=hloc, hbath=hb)
+    m.bath_e = np.zeros((2, norb, nb))
+    m.bath_v = np.full((2, norb, nb), max(0.1, 1.0 / np.sqrt(nb)))
+    m.bath_u = np.zeros((2, norb, nb))
+    return m
+
+
+def replica_superc_model(oracle_superc, kind="replica"):
+    """test/src/REPLICA_SUPERC / GENERAL_SUPERC (ed_replica_superc.f90:63-96): Nspin=1, Nambu replicas
+    H_k = lambda_k sigma_z(nambu) (x) 1 + 0.1 sigma_x (x) 1 + 0.2 sigma_x (x) tau_x in the nambu-major
+    mso2j ordering (COMMON.f90:124-131), lambda_k = -1 + 2(k-1)/(Nbath-1) (all different: no offsets),
+    V = max(0.1, 1/sqrt(Nbath)); Hloc = Delta*sigma_z(orbital)."""
+    g = golden(f"{kind}_superc")["inputs"]
+    norb, nb = int(g["NORB"]), int(g["NBATH"])
+    delta = _f(g["DELTA"])
+    hloc = np.zeros((2, norb, norb), complex)
+    for s in range(2):
+        hloc[s] = np.diag([delta, -delta])
+    s0, sx, sz = np.eye(2), np.array([[0, 1], [1, 0.0]]), np.diag([1.0, -1.0])
+    GN, GAA, GAB = np.kron(sz, s0), np.kron(sx, s0), np.kron(sx, sx)
+    hb = np.zeros((2, 2, norb, norb, nb), complex)
+    for k in range(nb):
+        lam = -1.0 + 2.0 * k / (nb - 1)
+        M = lam * GN + 0.1 * GAA + 0.2 * GAB
+        hb[..., k] = M.reshape(2, norb, 2, norb).transpose(0, 2, 1, 3)
+    m = oracle_superc.ModelSuperc(
+        Norb=norb, Nbath=nb, bath_type=kind,
+        Uloc=tuple(_f(x) for x in g["ULOC"].split(",")), Ust=_f(g["UST"]), Jh=_f(g["JH"]),
+        Jx=_f(g["JX"]), Jp=_f(g["JP"]), xmu=_f(g["XMU"]), hfmode=g["HFMODE"] == "T",
+        ed_hw_bath=_f(g["ED_HW_BATH"]), deltasc=_f(g["DELTASC"]), hloc=hloc, hbath=hb)
+    m.bath_e = np.zeros((2, norb, nb))
+    m.bath_d = np.zeros((norb, nb))
+    m.bath_v = np.full((2, norb, nb), max(0.1, 1.0 / np.sqrt(nb)))
+    return m

@@ -4,7 +4,7 @@ values test/src/HYBRID_NONSU2/{evals,dens,docc,magX}.check at the reference's 1e
 import numpy as np
 import pytest
 
-from models import golden, hybrid_nonsu2_model, soc_nonsu2_model
+from models import golden, hybrid_nonsu2_model, replica_nonsu2_model, soc_nonsu2_model
 
 
 @pytest.fixture(scope="module")
@@ -78,3 +78,27 @@ def test_normal_nonsu2_golden():
     assert np.abs(dens - np.array(g["dens"])).max() < 1e-8
     assert np.abs(docc - np.array(g["docc"])).max() < 1e-8
     assert np.abs(magx - np.array(g["magX"])).max() < 1e-8
+
+
+@pytest.mark.parametrize("kind", ["replica", "general"])
+def test_replica_general_nonsu2_golden(kind):
+    """test/src/{REPLICA,GENERAL}_NONSU2/{evals,dens,docc}.check: bath replicas with same-spin and
+    spin-flip inter-orbital bath hops (stored/Hbath.f90:49-133)."""
+    import edipack_oracle_nonsu2 as N
+
+    g = golden(f"{kind}_nonsu2")
+    m = replica_nonsu2_model(N, kind)
+    assert m.Ns == 6
+    best = None
+    for nt in range(3, 10):
+        smap, rp, cj, va = N.stored_H(m, nt)
+        H = N.to_dense(rp, cj, va)
+        assert np.abs(H - H.conj().T).max() < 1e-12
+        ev, U = np.linalg.eigh(H)
+        if best is None or ev[0] < best[0]:
+            best = (ev[0], nt, smap, U[:, 0], ev)
+    e, nt, smap, v, ev = best
+    assert abs(e - g["evals"][0]) < 1e-9, (e, nt)
+    dens, docc, _ = N.observables(m, smap, v)
+    assert np.abs(dens - np.array(g["dens"])).max() < 1e-8
+    assert np.abs(docc - np.array(g["docc"])).max() < 1e-8

@@ -5,16 +5,17 @@ only to ~2e-8 -- e.g. HYBRID_SUPERC dens sums to 1.99999998693 -- hence 5e-8 the
 import numpy as np
 import pytest
 
-from models import golden, superc_model
+from models import golden, replica_superc_model, superc_model
 
 
-@pytest.mark.parametrize("name", ["normal_superc", "hybrid_superc"])
+@pytest.mark.parametrize("name", ["normal_superc", "hybrid_superc", "replica_superc", "general_superc"])
 def test_superc_fixture(name):
     import edipack_oracle_nonsu2 as N
     import edipack_oracle_superc as S
 
     g = golden(name)
-    m = superc_model(S, name)
+    m = (replica_superc_model(S, name.split("_")[0]) if name.startswith(("replica", "general"))
+         else superc_model(S, name))
     best = None
     for sz in range(-2, 3):
         smap, rp, cj, va = S.stored_H(m, sz)
