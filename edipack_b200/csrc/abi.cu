@@ -383,6 +383,21 @@ int edgpu_sector_open_nonsu2(const edgpu_nonsu2_params *p, int ntot) {
   return nonsu2_open(g, p, ntot);
 }
 
+int edgpu_set_hbath_packed(const double *hbath_re_im, int Norb, int Nbath) {
+  clear_error();
+  if (!hbath_re_im) {
+    g.hbath_packed.clear();
+    g.hb_Norb = g.hb_Nbath = 0;
+    return 0;
+  }
+  if (Norb < 1 || Norb > EDGPU_MAXORB || Nbath < 1 || Nbath > EDGPU_MAXBATH)
+    return set_error("edgpu_set_hbath_packed: Norb/Nbath out of range");
+  g.hbath_packed.assign(hbath_re_im, hbath_re_im + (size_t)8 * Norb * Norb * Nbath);
+  g.hb_Norb = Norb;
+  g.hb_Nbath = Nbath;
+  return 0;
+}
+
 int edgpu_sector_open_superc(const edgpu_superc_params *p, int sz) {
   clear_error();
   if (!p) return set_error("null params");

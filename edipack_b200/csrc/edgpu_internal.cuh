@@ -267,6 +267,10 @@ struct Engine {
   int Nph = 0;
   double w0_ph = 0.0, A_ph = 0.0;
   double g_ph[EDGPU_MAXORB][EDGPU_MAXORB] = {};
+  // Hbath_tmp of replica / general baths for the packed-state modes (edgpu_set_hbath_packed):
+  // [2][2][hb_Norb][hb_Norb][hb_Nbath] (re,im)
+  std::vector<double> hbath_packed;
+  int hb_Norb = 0, hb_Nbath = 0;
   // profiling ring (edgpu_profile_begin/end): 4 events per recorded H x v
   std::vector<cudaEvent_t> prof_ev;
   int prof_cap = 0, prof_n = 0;

@@ -7,10 +7,12 @@
 //                                     (flat row split, remainder to the last rank)
 //   ed_buildH_nonsu2_main             ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190 with the element
 //                                     generators ED_NONSU2/stored/Himp.f90, Hint.f90, Hbath.f90,
-//                                     Himp_bath.f90 (normal / hybrid bath)
+//                                     Himp_bath.f90 (all four bath types; replica / general: same-spin
+//                                     and spin-flip bath hops of Hbath.f90:49-133)
 //   ed_buildH_superc_main             ED_HAMILTONIAN_SUPERC_STORED_HxV.f90:29-260 with
 //                                     ED_SUPERC/stored/Himp.f90 (incl. anomalous local pairing :86-125),
-//                                     Hint.f90, Hbath.f90 (bath pairing d :97-133), Himp_bath.f90
+//                                     Hint.f90, Hbath.f90 (bath pairing d :97-133; replica / general:
+//                                     Nambu blocks of Hbath_tmp :29-92, :135-177), Himp_bath.f90
 // The reference inserts element by element into a list of rows (`sp_insert_element`, O(row) search
 // + realloc per element, ED_SPARSE_MATRIX.f90:346-357) after a recursive binary search of the
 // target state.  Here one thread per row enumerates the same terms in the same order twice
@@ -39,6 +41,10 @@ struct Nonsu2Dev {
   double pair_field[EDGPU_MAXORB];
   double bath_d[EDGPU_MAXORB][EDGPU_MAXBATH];  // dmft_bath%d(1,a,k)
   const int32_t *off;                          // [2^Ns + 1] first sector index of each idw
+  // replica / general baths: Hbath_tmp(is,js,a,b,k) as [2][2][Norb][Norb][Nbath] (re,im) in global
+  // memory (51 KB at the maximal sizes: does not fit beside the rest in constant memory)
+  const double *hb;
+  int32_t replica;
   int32_t binom[33][33];  // C(n,k), n,k <= 32 (entries that overflow int32 are never used)
   int32_t mode;
   int32_t ntot;   // nonsu2: electrons; superc: Sz
@@ -147,10 +153,25 @@ __device__ __forceinline__ void n2_pair(uint32_t m, int p1, int p2, bool create,
   s.emit(n2_rank(m), re * sg, im * sg);
 }
 
+// hole-block hop of the Nambu bath (ED_SUPERC/stored/Hbath.f90:73-90): cdg(ibeta) then c(ialfa)
+// on the dw bits; the caller checked ib(ibeta)==0, ib(ialfa)==1; emits conjg(amp)*sg1*sg2
+template <class Sink>
+__device__ __forceinline__ void n2_hole_hop(uint32_t m, int ialfa, int ibeta, double are, double aim, Sink &s) {
+  int par = __popc(m & ((1u << ibeta) - 1u));
+  m |= 1u << ibeta;
+  par += __popc(m & ((1u << ialfa) - 1u));
+  m &= ~(1u << ialfa);
+  const double sg = (par & 1) ? -1.0 : 1.0;
+  s.emit(n2_rank(m), are * sg, -aim * sg);
+}
+
 template <class Sink>
 __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
   const edgpu_nonsu2_params &P = c_n2.p;
   const int Ns = P.Ns, No = P.Norb, Nb = P.Nbath;
+  const bool replica = c_n2.replica != 0;
+  const double *__restrict__ hbp = c_n2.hb;
+#define HB(is, js, a, b, k, c) hbp[((((((is) * 2 + (js)) * No + (a)) * No + (b)) * Nb + (k)) << 1) + (c)]
 #define HL(is, js, a, b, c) P.hloc[is][js][a][b][c]
   double nup[EDGPU_MAXORB], ndw[EDGPU_MAXORB];
 #pragma unroll
@@ -193,12 +214,24 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
     }
     dre += h;
   }
-  {
+  if (!replica) {
     double h = 0.0;
     for (int a = 0; a < P.Nfoo; a++)
       for (int k = 0; k < Nb; k++) {
         const int st = P.stride[a][k] - 1;
         h += P.bath_e[0][a][k] * (double)((m >> st) & 1u) + P.bath_e[1][a][k] * (double)((m >> (st + Ns)) & 1u);
+      }
+    dre += h;
+  } else {
+    // bath_diag(s,a,k) = Hbath_tmp(s,s,a,a,k) (real array in the reference).  superc: the hole block
+    // enters with a minus sign (ED_SUPERC/stored/Hbath.f90:33-38)
+    const bool sc = c_n2.mode == MODE_SUPERC;
+    double h = 0.0;
+    for (int k = 0; k < Nb; k++)
+      for (int a = 0; a < No; a++) {
+        const int st = P.stride[a][k] - 1;
+        const double eu = HB(0, 0, a, a, k, 0), ed = HB(1, 1, a, a, k, 0);
+        h += eu * (double)((m >> st) & 1u) + (sc ? -ed : ed) * (double)((m >> (st + Ns)) & 1u);
       }
     dre += h;
   }
@@ -262,7 +295,53 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
       for (int b = 0; b < No; b++)
         if (a != b && ((m >> b) & 1u) && ((m >> (b + Ns)) & 1u) && !((m >> (a + Ns)) & 1u) && !((m >> a) & 1u))
           n2_chain(m, b, b + Ns, a + Ns, a, P.Jp[a][b], s);
-  if (superc) {
+  if (replica && !superc) {
+    // ED_NONSU2/stored/Hbath.f90:49-100 same-spin bath hops, :103-133 spin-flip bath hops
+    for (int k = 0; k < Nb; k++)
+      for (int a = 0; a < No; a++)
+        for (int b = 0; b < No; b++) {
+          if (a == b) continue;  // ib(ibeta)==1 .AND. ib(ialfa)==0 never holds on one site
+          const int ia = P.stride[a][k] - 1, ib_ = P.stride[b][k] - 1;
+          if (HB(0, 0, a, b, k, 0) != 0.0 || HB(0, 0, a, b, k, 1) != 0.0)
+            n2_hop(m, ia, ib_, HB(0, 0, a, b, k, 0), HB(0, 0, a, b, k, 1), s);
+          if (HB(1, 1, a, b, k, 0) != 0.0 || HB(1, 1, a, b, k, 1) != 0.0)
+            n2_hop(m, ia + Ns, ib_ + Ns, HB(1, 1, a, b, k, 0), HB(1, 1, a, b, k, 1), s);
+        }
+    for (int k = 0; k < Nb; k++)
+      for (int is = 0; is < 2; is++) {
+        const int js = 1 - is;
+        for (int a = 0; a < No; a++)
+          for (int b = 0; b < No; b++)
+            if (HB(is, js, a, b, k, 0) != 0.0 || HB(is, js, a, b, k, 1) != 0.0)
+              n2_hop(m, P.stride[a][k] - 1 + is * Ns, P.stride[b][k] - 1 + js * Ns, HB(is, js, a, b, k, 0),
+                     HB(is, js, a, b, k, 1), s);
+      }
+  }
+  if (replica && superc) {
+    // ED_SUPERC/stored/Hbath.f90:48-92: particle block (1,1) on the up bits, hole block (2,2) on
+    // the dw bits (creation first); :135-177 anomalous blocks (1,2) pair creation, (2,1) annihilation
+    for (int k = 0; k < Nb; k++)
+      for (int a = 0; a < No; a++)
+        for (int b = 0; b < No; b++) {
+          const int ia = P.stride[a][k] - 1, ib_ = P.stride[b][k] - 1;
+          if (a != b && (HB(0, 0, a, b, k, 0) != 0.0 || HB(0, 0, a, b, k, 1) != 0.0))
+            n2_hop(m, ia, ib_, HB(0, 0, a, b, k, 0), HB(0, 0, a, b, k, 1), s);
+          if (a != b && (HB(1, 1, a, b, k, 0) != 0.0 || HB(1, 1, a, b, k, 1) != 0.0) &&
+              !((m >> (ib_ + Ns)) & 1u) && ((m >> (ia + Ns)) & 1u))
+            n2_hole_hop(m, ia + Ns, ib_ + Ns, HB(1, 1, a, b, k, 0), HB(1, 1, a, b, k, 1), s);
+        }
+    for (int k = 0; k < Nb; k++)
+      for (int a = 0; a < No; a++)
+        for (int b = 0; b < No; b++) {
+          const int ua = P.stride[a][k] - 1, db = P.stride[b][k] - 1 + Ns;  // (1,2): up a, dw b
+          if ((HB(0, 1, a, b, k, 0) != 0.0 || HB(0, 1, a, b, k, 1) != 0.0) && !((m >> db) & 1u) && !((m >> ua) & 1u))
+            n2_pair(m, db, ua, true, HB(0, 1, a, b, k, 0), -HB(0, 1, a, b, k, 1), s);
+          const int da = P.stride[a][k] - 1 + Ns, ub = P.stride[b][k] - 1;  // (2,1): dw a, up b
+          if ((HB(1, 0, a, b, k, 0) != 0.0 || HB(1, 0, a, b, k, 1) != 0.0) && ((m >> ub) & 1u) && ((m >> da) & 1u))
+            n2_pair(m, ub, da, false, HB(1, 0, a, b, k, 0), -HB(1, 0, a, b, k, 1), s);
+        }
+  }
+  if (superc && !replica) {
     // bath pairing Delta_l (c_dw c_up + h.c.) on every bath level (ED_SUPERC/stored/Hbath.f90:97-133)
     for (int a = 0; a < P.Nfoo; a++)
       for (int k = 0; k < Nb; k++) {
@@ -286,8 +365,8 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
         }
       }
     }
-  // spin-flip hybridisation u :72-136 (nonsu2 only)
-  for (int a = 0; a < No && !superc; a++)
+  // spin-flip hybridisation u :72-136 (nonsu2 with a normal / hybrid bath only)
+  for (int a = 0; a < No && !superc && !replica; a++)
     for (int k = 0; k < Nb; k++) {
       const int ms = P.stride[a][k] - 1;
       const double u1 = P.bath_u[0][a][k], u2 = P.bath_u[1][a][k];
@@ -301,6 +380,7 @@ __device__ void n2_row(uint32_t m, int64_t i, Sink &s) {
       }
     }
 #undef HL
+#undef HB
 }
 
 __global__ void __launch_bounds__(128)
@@ -336,9 +416,14 @@ static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
   if (p->Ns < 1 || nbits > 31) return set_error("%s: 2*Ns = %d exceeds the 31-bit packed state", who, nbits);
   if (p->Norb < 1 || p->Norb > EDGPU_MAXORB || p->Nbath < 0 || p->Nbath > EDGPU_MAXBATH)
     return set_error("%s: Norb/Nbath out of range", who);
-  if (p->bath_type != EDGPU_BATH_NORMAL && p->bath_type != EDGPU_BATH_HYBRID)
-    return set_error("%s: only normal / hybrid baths are generated on the device "
-                     "(replica / general: hand the host-built spH0 to edgpu_csr_open_z)", who);
+  h.replica = (p->bath_type == EDGPU_BATH_REPLICA || p->bath_type == EDGPU_BATH_GENERAL);
+  h.hb = nullptr;
+  double *d_hb = nullptr;
+  if (h.replica) {
+    if (E.hbath_packed.empty() || E.hb_Norb != p->Norb || E.hb_Nbath != p->Nbath)
+      return set_error("%s: replica / general bath needs Hbath_tmp for Norb=%d, Nbath=%d "
+                       "(edgpu_set_hbath_packed)", who, p->Norb, p->Nbath);
+  }
   h.nbits = nbits;
   for (int n = 0; n <= 32; n++)
     for (int k = 0; k <= 32; k++) {
@@ -369,6 +454,12 @@ static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
     cudaFree(d_off);
     return set_error("%s: sector dimension %lld exceeds 32-bit columns", who, (long long)dim);
   }
+  if (h.replica) {
+    EDGPU_CUDA(cudaMalloc(&d_hb, sizeof(double) * E.hbath_packed.size()));
+    EDGPU_CUDA(cudaMemcpy(d_hb, E.hbath_packed.data(), sizeof(double) * E.hbath_packed.size(),
+                          cudaMemcpyHostToDevice));
+    h.hb = d_hb;
+  }
   EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_n2, &h, sizeof(h), 0, cudaMemcpyHostToDevice, E.stream));
   // row split MpiQ = Dim/P, remainder to the last rank (ED_HAMILTONIAN_NONSU2.f90:72-79,
   // ED_HAMILTONIAN_SUPERC.f90:76-88)
@@ -385,6 +476,7 @@ static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
     cudaFree(d_rowptr);
     cudaFree(d_vals);
     cudaFree(d_off);
+    cudaFree(d_hb);
     return rc;
   };
 #define N2_CUDA(call)                                                                         \
@@ -422,6 +514,8 @@ static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
   d_cnt = nullptr;
   cudaFree(d_off);  // only the builder kernels rank states
   d_off = nullptr;
+  cudaFree(d_hb);   // ... and read Hbath_tmp
+  d_hb = nullptr;
   int rc = csr_adopt_device(E, true, nloc, dim, row0, d_rowptr, d_cols, d_vals, nnz, d_map);
   if (rc) return fail(rc);
   E.csr.pk_mode = h.mode;

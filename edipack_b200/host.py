@@ -506,6 +506,27 @@ def spHtimesV_cc(v: np.ndarray) -> np.ndarray:
     return hv
 
 
+def _packed_stride(bath_type: str, No: int, Nb: int, a: int, k: int) -> int:
+    """getBathStride(a+1,k+1) (ED_SETUP.f90:605-622), 1-based site."""
+    if bath_type == "hybrid":
+        return No + k + 1
+    if bath_type in ("replica", "general"):
+        return (a + 1) + (k + 1) * No
+    return No + a * Nb + k + 1
+
+
+def _push_hbath(model):
+    """Hbath_tmp of a replica / general bath -> engine (edgpu_set_hbath_packed)."""
+    if model.bath_type not in ("replica", "general"):
+        return
+    if model.hbath is None:
+        raise EdgpuError("replica / general bath: the model has no hbath (Hbath_tmp)")
+    hb = np.ascontiguousarray(np.asarray(model.hbath, np.complex128))
+    if hb.shape != (2, 2, model.Norb, model.Norb, model.Nbath):
+        raise EdgpuError("hbath must be [2, 2, Norb, Norb, Nbath]")
+    check(_abi.load().edgpu_set_hbath_packed(ptr(hb), model.Norb, model.Nbath))
+
+
 @dataclass
 class EDModelNonsu2:
     """Module globals read by ``ed_buildH_nonsu2_main`` (ed_mode=nonsu2, normal / hybrid bath)."""
@@ -526,6 +547,7 @@ class EDModelNonsu2:
     bath_v: np.ndarray | None = None      # [2, Norb, Nbath]
     bath_u: np.ndarray | None = None      # [2, Norb, Nbath]
     spin_field: np.ndarray | None = None  # [Norb, 3]
+    hbath: np.ndarray | None = None       # replica / general: complex [2, 2, Norb, Norb, Nbath] Hbath_tmp
 
     @property
     def Ns(self) -> int:
@@ -576,7 +598,7 @@ class EDModelNonsu2:
         st = np.zeros((MAXORB, MAXBATH), np.int32)
         for a in range(No):
             for k in range(Nb):
-                st[a, k] = (No + k + 1) if self.bath_type == "hybrid" else (No + a * Nb + k + 1)
+                st[a, k] = _packed_stride(self.bath_type, No, Nb, a, k)
         p.stride[:] = st.ravel().tolist()
         return p
 
@@ -603,6 +625,7 @@ class EDModelSuperc:
     bath_e: np.ndarray | None = None          # [2, Nfoo, Nbath]
     bath_d: np.ndarray | None = None          # [Nfoo, Nbath]
     bath_v: np.ndarray | None = None          # [2, Norb, Nbath]
+    hbath: np.ndarray | None = None           # replica / general: complex [2(nambu), 2, Norb, Norb, Nbath]
 
     @property
     def Ns(self) -> int:
@@ -660,7 +683,7 @@ class EDModelSuperc:
         st = np.zeros((MAXORB, MAXBATH), np.int32)
         for a in range(No):
             for k in range(Nb):
-                st[a, k] = (No + k + 1) if self.bath_type == "hybrid" else (No + a * Nb + k + 1)
+                st[a, k] = _packed_stride(self.bath_type, No, Nb, a, k)
         p.stride[:] = st.ravel().tolist()
         return p
 
@@ -668,6 +691,7 @@ class EDModelSuperc:
 def build_Hv_sector_superc(model: EDModelSuperc, sz: int):
     """build_Hv_sector_superc + ed_buildH_superc_main on the device for the sector Sz = Nup - Ndw."""
     global _open_is_complex
+    _push_hbath(model)
     check(_abi.load().edgpu_sector_open_superc(C.byref(model.params()), sz))
     _open_is_complex = True
 
@@ -680,6 +704,7 @@ def build_Hv_sector_nonsu2(model: EDModelNonsu2, ntot: int):
     """build_Hv_sector_nonsu2 + ed_buildH_nonsu2_main on the device (sector map and complex spH0
     generated by kernels); afterwards spHtimesV_cc / sp_lanc_* / sp_eigh act on it."""
     global _open_is_complex
+    _push_hbath(model)
     check(_abi.load().edgpu_sector_open_nonsu2(C.byref(model.params()), ntot))
     _open_is_complex = True
 

@@ -194,6 +194,16 @@ int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const in
  * edgpu_csr_nnz / edgpu_csr_get download the device CSR (rowptr 0-based offsets, cols 1-based
  * global, vals (re,im) pairs for complex sectors), duplicates within a row add up. */
 int edgpu_sector_open_nonsu2(const edgpu_nonsu2_params *p, int ntot);
+/* bath_type = replica / general for the two device-built modes: the module array
+ * Hbath_tmp(:,:,:,:,ibath) = build_Hreplica / build_Hgeneral(dmft_bath%item(ibath)%lambda)
+ * (ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:82-105, ED_HAMILTONIAN_SUPERC_STORED_HxV.f90:80-112) read by
+ * ED_NONSU2/stored/Hbath.f90:29-133 (diagonal, same-spin and spin-flip bath hops) and
+ * ED_SUPERC/stored/Hbath.f90:29-92,135-177 (Nambu blocks: (1,1) particles, (2,2) holes, (1,2)/(2,1)
+ * pairing), as complex numbers hbath[is][js][a][b][k] (re,im), row-major
+ * [2][2][Norb][Norb][Nbath].  Engine-global: read by every nonsu2 / superc sector opened afterwards
+ * with bath_type replica / general (their params carry diag_hybr in bath_v; bath_e, bath_u, bath_d
+ * are not used).  NULL clears it. */
+int edgpu_set_hbath_packed(const double *hbath_re_im, int Norb, int Nbath);
 /* build_Hv_sector_superc(isector) + ed_buildH_superc_main (ED_HAMILTONIAN_SUPERC.f90:31-140,
  * ED_HAMILTONIAN_SUPERC_STORED_HxV.f90:29-260) on the device, sector Sz = Nup - Ndw
  * (build_sector, ED_SECTOR.f90:244-281): same contract as edgpu_sector_open_nonsu2, with the

@@ -32,14 +32,39 @@ def messy_superc(S):
     return m
 
 
-@pytest.mark.parametrize("name", ["normal_superc", "hybrid_superc", "messy"])
+def messy_replica_superc(S):
+    """Replica bath with random complex hermitian Nambu blocks."""
+    from models import replica_superc_model
+    rng = np.random.default_rng(17)
+    m = replica_superc_model(S, "replica")
+    no, nb = m.Norb, m.Nbath
+    hb = np.zeros((2, 2, no, no, nb), complex)
+    for k in range(nb):
+        a = rng.standard_normal((2 * no, 2 * no)) + 1j * rng.standard_normal((2 * no, 2 * no))
+        a = 0.3 * (a + a.conj().T)
+        hb[..., k] = a.reshape(2, no, 2, no).transpose(0, 2, 1, 3)
+    m.hbath = hb
+    m.bath_v = 0.3 + rng.random((2, no, nb))
+    m.hfmode = False
+    return m
+
+
+@pytest.mark.parametrize("name", ["normal_superc", "hybrid_superc", "messy", "replica_superc",
+                                  "general_superc", "messy_replica"])
 def test_device_built_superc_matches_oracle(engine, name):
     import edipack_oracle_nonsu2 as N
     import edipack_oracle_superc as S
-    from models import superc_model
+    from models import replica_superc_model, superc_model
 
     E = engine
-    mo = messy_superc(S) if name == "messy" else superc_model(S, name)
+    if name == "messy":
+        mo = messy_superc(S)
+    elif name == "messy_replica":
+        mo = messy_replica_superc(S)
+    elif name.startswith(("replica", "general")):
+        mo = replica_superc_model(S, name.split("_")[0])
+    else:
+        mo = superc_model(S, name)
     m = to_engine_model(E, mo)
     rng = np.random.default_rng(4)
     for sz in (0, 1, -2, mo.Ns, -mo.Ns):
@@ -59,16 +84,17 @@ def test_device_built_superc_matches_oracle(engine, name):
             E.delete_Hv_sector_superc()
 
 
-@pytest.mark.parametrize("name", ["normal_superc", "hybrid_superc"])
+@pytest.mark.parametrize("name", ["normal_superc", "hybrid_superc", "replica_superc", "general_superc"])
 def test_golden_superc_device_built(engine, name):
-    """test/src/{NORMAL,HYBRID}_SUPERC/{evals,dens,docc,phisc}.check with the sector map, the
-    stored H and the eigen-solver all on the device."""
+    """test/src/{NORMAL,HYBRID,REPLICA,GENERAL}_SUPERC/{evals,dens,docc,phisc}.check with the sector
+    map, the stored H and the eigen-solver all on the device."""
     import edipack_oracle_superc as S
-    from models import golden, superc_model
+    from models import golden, replica_superc_model, superc_model
 
     E = engine
     g = golden(name)
-    mo = superc_model(S, name)
+    mo = (replica_superc_model(S, name.split("_")[0]) if name.startswith(("replica", "general"))
+          else superc_model(S, name))
     m = to_engine_model(E, mo)
     best = None
     for sz in (-1, 0, 1):
