@@ -125,6 +125,44 @@ def main():
                         if abs(a[0] - (ref @ hv) / n2) > 1e-10:
                             failures.append(f"apply_op spin={spin} orb={iorb} op={op}: alpha1 mismatch")
         E.state_free(5)
+    # a10 on the shards: coulomb_sundry (gathers from the all-gathered vector) and phonon slices
+    # (every rank holds DimPh consecutive electronic chunks, direct_mpi/HxV_eph.f90:3-4; the
+    # off-diagonal g_ph dw hops read other ranks' columns)
+    from test_oracle_sundry_phonons import SUNDRY
+    ph = dict(Nph=2, w0=0.37, g=[[0.5, 0.2], [0.2, -0.3]])
+    for name, kw, (nup, ndw), sundry, phon in [
+            ("sundry", two_orb_kwargs(2), (3, 3), SUNDRY, None),
+            ("phonons", two_orb_kwargs(2), (3, 2), [], ph),
+            ("sundry+phonons", two_orb_kwargs(3, with_nd=True), (4, 4), SUNDRY, ph)]:
+        m, mo = E.EDModel(**kw), O.Model(**kw)
+        du, dd = O.sector_dims(m.Ns, nup, ndw)
+        if dd < world or du < world:
+            continue
+        nph = (phon["Nph"] if phon else 0) + 1
+        full = O.start_vector(du * dd * nph, 23) - 0.5
+        lo, hi = E.chunk_bounds(du, dd, world, rank)
+        pick = np.concatenate([np.arange(k * du * dd + lo, k * du * dd + hi) for k in range(nph)])
+        E.set_coulomb_sundry(sundry)
+        E.set_phonons(**(phon or dict(Nph=0)))
+        E.build_Hv_sector_normal(m, nup, ndw)
+        try:
+            hv = E.spHtimesV_p(full[pick].copy())
+            ref = O.direct_hxv_ext(mo, nup, ndw, full, sundry, phon)
+            err = np.abs(hv - ref[pick]).max() / np.abs(ref).max()
+            if not err < 1e-12:
+                failures.append(f"a10 {name}: HxV rel err {err:.3e} on rank {rank}")
+            if du * dd * nph <= 6000:
+                n = du * dd * nph
+                H = np.column_stack([O.direct_hxv_ext(mo, nup, ndw, e_, sundry, phon) for e_ in np.eye(n)])
+                # (the SUNDRY test list is not hermitian: ground-state check only for symmetric H)
+                sym = np.abs(H - H.T).max() < 1e-12
+                e, vec, nit = E.sp_lanc_eigh(300, 1e-14) if sym else (0.0, None, 0)
+                if sym and abs(e - np.linalg.eigvalsh(H)[0]) > 1e-10:
+                    failures.append(f"a10 {name}: E_gs {e} vs {np.linalg.eigvalsh(H)[0]}")
+        finally:
+            E.delete_Hv_sector_normal()
+            E.set_coulomb_sundry(())
+            E.set_phonons(0)
     # ed_mode=nonsu2 built on the device: every rank generates its rows of the flat row split
     # (ED_HAMILTONIAN_NONSU2.f90:72-79), the product all-gathers the input vector
     import edipack_oracle_nonsu2 as N
