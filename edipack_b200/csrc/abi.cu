@@ -172,6 +172,24 @@ k_apply_op(const double *__restrict__ vsrc, int64_t lds, double *__restrict__ ou
   out[c * ldo + i] = val;
 }
 
+// Twin state (es_return_dvector `itwin` branch, ED_EIGENSPACE.f90:640-660 + twin_sector_order,
+// ED_SECTOR.f90:1747-1776): the state of sector A = (nup,ndw) re-expressed in the twin sector
+// B = (ndw,nup).  The reference sorts the flipped Fock integers mdw + mup*2^Ns of A and reads
+// vector_B(i) = vec_A(Order(i)): B's state (mup_B, mdw_B) is A's state (mup_A, mdw_A) = (mdw_B, mup_B),
+// i.e. the [DimUp, DimDw] matrix transposed.  Gather form on B, source indices ranked in A's
+// internal enumeration orders.
+__global__ void __launch_bounds__(128)
+k_twin_normal(const double *__restrict__ vsrc, int64_t lds, double *__restrict__ out, int64_t ldo,
+              int64_t nrow, const int32_t *__restrict__ map_up, const int32_t *__restrict__ map_dw,
+              RankView RupA, RankView RdwA) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (i >= nrow) return;
+  const int64_t iuA = rank_of((uint32_t)map_dw[c], RupA);  // A's up pattern = B's dw pattern
+  const int64_t idA = rank_of((uint32_t)map_up[i], RdwA);  // A's dw pattern = B's up pattern
+  out[c * ldo + i] = vsrc[idA * lds + iuA];
+}
+
 // dens / docc partial sums (ED_OBSERVABLES_NORMAL.f90:150-215): out[a] += v^2 (nu+nd),
 // out[Norb+a] += v^2 nu nd
 __global__ void __launch_bounds__(256)
@@ -872,6 +890,113 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
   cudaFree(lin.ja);
   cudaFree(lin.jb);
   return 0;
+}
+
+int edgpu_state_download(int slot, double *vec_host) {
+  clear_error();
+  auto it = g_states.find(slot);
+  if (it == g_states.end()) return set_error("state slot %d is empty", slot);
+  if (!vec_host) return set_error("state_download: null buffer");
+  const StoredState &st = it->second;
+  if (st.kind == 1) {
+    CsrSector &C = g.csr;
+    if (!C.open || C.pk_mode != st.pk_mode || C.pk_qn != st.pk_qn || C.pk_Ns != st.Ns)
+      return set_error("the state's own sector must be open for state_download");
+  } else {
+    Sector &S = g.sec;
+    if (!S.open || S.up.nel != st.nup || S.dw.nel != st.ndw || S.Ns != st.Ns || S.DimPh != st.dimph)
+      return set_error("the state's own sector must be open for state_download");
+  }
+  return download(g, vec_host, st.vec);
+}
+
+int edgpu_state_twin(int src_slot, int dst_slot) {
+  clear_error();
+  if (src_slot == dst_slot) return set_error("state_twin: source and destination slots coincide");
+  auto it = g_states.find(src_slot);
+  if (it == g_states.end()) return set_error("state slot %d is empty", src_slot);
+  StoredState st = it->second;  // copy: store_state_from below may rehash the map
+  if (st.kind == 1) {
+    CsrSector &C = g.csr;
+    if (!C.open || C.pk_mode != st.pk_mode || C.pk_Ns != st.Ns)
+      return set_error("state_twin: the open sector must be the device-built twin sector of state %d", src_slot);
+    // get_twin_sector (ED_SECTOR.f90:1826-1843): Sz -> -Sz, Ntot -> Nlevels - Ntot
+    const int want = st.pk_mode == 1 ? -st.pk_qn : 2 * st.Ns - st.pk_qn;
+    if (C.pk_qn != want)
+      return set_error("state_twin: open sector has quantum number %d, the twin of %d is %d", C.pk_qn, st.pk_qn, want);
+    const int64_t n = C.padded_len();
+    double *tmp = nullptr, *vfull = nullptr;
+    EDGPU_CUDA(cudaMalloc(&tmp, sizeof(double) * n));
+    const double *vsrc = st.vec;
+    if (g.nranks > 1) {  // the flipped states of this rank's rows live anywhere in the source
+      std::vector<int64_t> counts(g.nranks), offs(g.nranks);
+      const int64_t q = st.nglobal / g.nranks;
+      for (int p = 0; p < g.nranks; p++) {
+        counts[p] = 2 * (q + (p == g.nranks - 1 ? st.nglobal % g.nranks : 0));
+        offs[p] = 2 * q * p;
+      }
+      EDGPU_CUDA(cudaMalloc(&vfull, sizeof(double) * 2 * (size_t)st.nglobal));
+      EDGPU_TRY(comm_allgatherv(g, st.vec, vfull, counts, offs));
+      vsrc = vfull;
+    }
+    int rc = packed_twin(g, st.pk_mode, st.pk_qn, vsrc, tmp);
+    if (!rc) rc = store_state_from(tmp, dst_slot);
+    cudaFree(vfull);
+    cudaFree(tmp);
+    return rc;
+  }
+  Sector &S = g.sec;
+  if (!S.open || S.Ns != st.Ns || S.up.nel != st.ndw || S.dw.nel != st.nup)
+    return set_error("state_twin: the open sector must be (%d,%d), the twin of state %d's sector (%d,%d)",
+                     st.ndw, st.nup, src_slot, st.nup, st.ndw);
+  if (st.dimph != S.DimPh)
+    return set_error("state %d has %d phonon slices, the open sector %d", src_slot, st.dimph, S.DimPh);
+  // enumeration orders + ranking tables of BOTH species of the source sector
+  int32_t *mapu = nullptr, *mapd = nullptr;
+  LinTable linu, lind;
+  SiteOrder ordu, ordd;
+  EDGPU_TRY(species_ranking(g, S.prm, 0, st.nup, &mapu, &linu, &ordu));
+  EDGPU_TRY(species_ranking(g, S.prm, 1, st.ndw, &mapd, &lind, &ordd));
+  const int64_t n = S.padded_len();
+  double *tmp = nullptr, *vfull = nullptr;
+  EDGPU_CUDA(cudaMalloc(&tmp, sizeof(double) * n));
+  EDGPU_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * n, g.stream));
+  const double *vsrc = st.vec;
+  int64_t src_slice = st.ldu * st.qdw;
+  if (g.nranks > 1) {  // B's local columns are A's rows: every source column is needed
+    std::vector<int64_t> counts(g.nranks), offs(g.nranks);
+    for (int p = 0; p < g.nranks; p++) {
+      int64_t q, d0;
+      block_split(st.dimd, g.nranks, p, &q, &d0);
+      counts[p] = q * st.ldu;
+      offs[p] = d0 * st.ldu;
+    }
+    const int64_t full_slice = st.dimd * st.ldu;
+    EDGPU_CUDA(cudaMalloc(&vfull, sizeof(double) * (size_t)full_slice * (size_t)st.dimph));
+    for (int iph = 0; iph < st.dimph; iph++)
+      EDGPU_TRY(comm_allgatherv(g, st.vec + iph * src_slice, vfull + iph * full_slice, counts, offs));
+    vsrc = vfull;
+    src_slice = full_slice;
+  }
+  dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
+  for (int iph = 0; iph < S.DimPh; iph++) {
+    k_twin_normal<<<grid, 128, 0, g.stream>>>(vsrc + iph * src_slice, st.ldu, tmp + iph * S.slice_len(),
+                                              S.up.ld, S.up.dim, S.up.map, S.dw.map + S.d0,
+                                              rank_view(linu, ordu), rank_view(lind, ordd));
+    EDGPU_COUNT_LAUNCH();
+  }
+  EDGPU_CUDA(cudaGetLastError());
+  EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+  int rc = store_state_from(tmp, dst_slot);
+  cudaFree(tmp);
+  cudaFree(vfull);
+  cudaFree(mapu);
+  cudaFree(mapd);
+  cudaFree(linu.ja);
+  cudaFree(linu.jb);
+  cudaFree(lind.ja);
+  cudaFree(lind.jb);
+  return rc;
 }
 
 int edgpu_state_observables(int slot, double *dens, double *docc) {

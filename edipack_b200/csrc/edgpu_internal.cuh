@@ -332,6 +332,10 @@ struct PackedOps {
 int packed_apply_ops(Engine &E, const PackedOps &ops, int src_mode, int src_qn, const double *d_vsrc_full,
                      double *d_out);
 int64_t packed_sector_dim(int mode, int Ns, int qn);
+// twin state (twin_sector_order, ED_SECTOR.f90:1747-1817): out (this rank's rows of the OPEN sector,
+// which is the twin of (src_mode, src_qn)) = vsrc_full[rank_src(flip(state))], flip = all bits
+// complemented (nonsu2) / up and dw halves exchanged (superc)
+int packed_twin(Engine &E, int src_mode, int src_qn, const double *d_vsrc_full, double *d_out);
 // dens(a), docc(a) partial sums over this rank's rows of a packed-state vector
 int packed_observables(Engine &E, const double *d_vec, double *h_dens, double *h_docc);
 int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, double s_acc, double s_old);

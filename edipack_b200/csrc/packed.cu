@@ -591,6 +591,47 @@ int packed_apply_ops(Engine &E, const PackedOps &ops, int src_mode, int src_qn, 
   return 0;
 }
 
+__global__ void __launch_bounds__(128)
+k_pk_twin(const int32_t *__restrict__ map_t, int64_t row0, int64_t nloc, const double2 *__restrict__ vsrc,
+          double2 *__restrict__ out, int src_mode, const int32_t *__restrict__ src_off, int Ns) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nloc) return;
+  const uint32_t m = (uint32_t)map_t[row0 + i];
+  const uint32_t lo = (1u << Ns) - 1u;
+  // flip_state_other (ED_SECTOR.f90:1797-1817) is an involution: the source state is flip(m)
+  const uint32_t ms = src_mode == MODE_NONSU2 ? (~m & ((1u << (2 * Ns)) - 1u)) : ((m >> Ns) | ((m & lo) << Ns));
+  const int64_t idx = src_mode == MODE_NONSU2 ? comb_rank(ms) : (int64_t)src_off[ms >> Ns] + comb_rank(ms & lo);
+  out[i] = vsrc[idx];
+}
+
+int packed_twin(Engine &E, int src_mode, int src_qn, const double *d_vsrc_full, double *d_out) {
+  CsrSector &C = E.csr;
+  if (!C.open || C.pk_mode < 0 || !C.map) return set_error("state_twin: no device-built nonsu2/superc sector open");
+  const int Ns = C.pk_Ns;
+  int32_t *d_off = nullptr;
+  if (src_mode == MODE_SUPERC) {
+    std::vector<int32_t> off(((size_t)1 << Ns) + 1, 0);
+    int64_t dim = 0;
+    for (uint32_t idw = 0; idw < (1u << Ns); idw++) {
+      const int k = __builtin_popcount(idw) + src_qn;
+      dim += (k < 0 || k > Ns) ? 0 : host_binomial(Ns, k);
+      off[(size_t)idw + 1] = (int32_t)dim;
+    }
+    EDGPU_CUDA(cudaMalloc(&d_off, sizeof(int32_t) * off.size()));
+    EDGPU_CUDA(cudaMemcpy(d_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));
+  }
+  EDGPU_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * C.padded_len(), E.stream));
+  if (C.nloc > 0) {
+    k_pk_twin<<<(unsigned)((C.nloc + 127) / 128), 128, 0, E.stream>>>(
+        C.map, C.row0, C.nloc, (const double2 *)d_vsrc_full, (double2 *)d_out, src_mode, d_off, Ns);
+    EDGPU_COUNT_LAUNCH();
+  }
+  EDGPU_CUDA(cudaGetLastError());
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  cudaFree(d_off);
+  return 0;
+}
+
 // dens / docc of a packed-state vector (ED_OBSERVABLES_NONSU2.f90 / _SUPERC.f90:150-165)
 __global__ void __launch_bounds__(256)
 k_pk_observables(const int32_t *__restrict__ map, int64_t row0, int64_t nloc, const double2 *__restrict__ v,

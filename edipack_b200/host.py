@@ -174,6 +174,7 @@ class EDModel:
     lanc_nstates_sector: int = 2       # LANC_NSTATES_SECTOR
     lanc_nstates_total: int = 2        # LANC_NSTATES_TOTAL
     cutoff: float = 1e-9               # CUTOFF (spectrum cut-off exp(-beta(E-Egs)) at finite T)
+    ed_twin: bool = False              # ED_TWIN: solve one sector of each (nup,ndw) / (ndw,nup) pair
     ed_use_kanamori: bool = True       # ED_USE_KANAMORI
     umatrix_lines: tuple = ()          # ED_READ_UMATRIX file lines + ed_add_twobody_operator calls
     _params: NormalParams | None = field(default=None, repr=False)
@@ -829,6 +830,22 @@ def state_free(slot: int):
     check(_abi.load().edgpu_state_free(slot))
 
 
+def es_return_vector(slot: int) -> np.ndarray:
+    """es_return_dvector / es_return_cvector (ED_EIGENSPACE.f90:620-793): this rank's chunk of the
+    stored state; its own sector must be open."""
+    n = vecDim_Hv_sector_normal()
+    v = np.zeros(n, np.complex128 if _open_is_complex else np.float64)
+    check(_abi.load().edgpu_state_download(slot, ptr(v)))
+    return v
+
+
+def state_twin(src_slot: int, dst_slot: int):
+    """es_return_dvector / es_return_cvector of a twin state (ED_EIGENSPACE.f90:640-660, 723-793;
+    twin_sector_order, ED_SECTOR.f90:1747-1776): state ``dst_slot`` := state ``src_slot`` re-ordered
+    into its twin sector, which must be the open one."""
+    check(_abi.load().edgpu_state_twin(src_slot, dst_slot))
+
+
 def apply_op(slot: int, op: int, iorb: int, spin: int):
     """apply_op_CDG (op=+1) / apply_op_C (op=-1) on stored state -> device-resident seed."""
     check(_abi.load().edgpu_apply_op(slot, op, iorb, spin))
@@ -879,6 +896,13 @@ def ed_diag_d(model: EDModel, sectors=None):
     if sectors is None:
         sectors = [(nu, nd) for nu in range(Ns + 1) for nd in range(Ns + 1)]
     finiteT = model.ed_finite_temp
+    if model.ed_twin:
+        # twin_mask (ED_SETUP.f90:592-602): of each pair (nup,ndw) / (ndw,nup) the sector with
+        # nup > ndw stays on; its states enter the list together with their twins
+        # (es_insert_state, ED_EIGENSPACE.f90:344-350)
+        if finiteT:
+            raise EdgpuError("ed_twin with ed_finite_temp is not mirrored (es_add_state(size=) counts twin pairs)")
+        sectors = [(nu, nd) for (nu, nd) in sectors if nu >= nd]
     nst_sector, nst_total = model.lanc_nstates_sector, model.lanc_nstates_total
     if finiteT:  # ED_SETUP.f90:279-287
         nst_sector += nst_sector % 2
@@ -936,11 +960,23 @@ def ed_diag_d(model: EDModel, sectors=None):
         egs = states[0].e
         while len(states) > 1 and math.exp(-model.beta * (states[-1].e - egs)) <= model.cutoff:
             drop(states[-1])
+    if model.ed_twin:
+        # the twin states' vectors: re-ordered on the device (the reference re-orders on the master
+        # every time es_return_dvector is called; here once, the copy stays in HBM)
+        for st in [s for s in states if s.nup != s.ndw]:
+            build_Hv_sector_normal(model, st.ndw, st.nup)
+            try:
+                state_twin(st.slot, next_slot)
+            finally:
+                delete_Hv_sector_normal()
+            states.append(EState(st.e, st.ndw, st.nup, next_slot))
+            next_slot += 1
+        states.sort(key=lambda s: s.e)
     return states
 
 
 def ed_diag_c(model, qns=None, neigen: int = 2, ncv_factor: int = 10, ncv_add: int = 0,
-              nitermax: int = 512, tol: float = 1e-18, gs_threshold: float = 1e-9):
+              nitermax: int = 512, tol: float = 1e-18, gs_threshold: float = 1e-9, ed_twin: bool = False):
     """Sector loop of ``ed_diag_c`` (ED_DIAG_NONSU2.f90:72-296, ED_DIAG_SUPERC.f90:73-277) at T=0
     for the packed-state modes: sectors are Ntot = 0..2Ns (:class:`EDModelNonsu2`) or
     Sz = -Ns..Ns (:class:`EDModelSuperc`), built on the device; ``sp_eigh`` with Neigen / Nblock as
@@ -950,6 +986,9 @@ def ed_diag_c(model, qns=None, neigen: int = 2, ncv_factor: int = 10, ncv_add: i
     superc = isinstance(model, EDModelSuperc)
     if qns is None:
         qns = range(-Ns, Ns + 1) if superc else range(0, 2 * Ns + 1)
+    if ed_twin:  # twin_mask: superc keeps Sz <= 0 (ED_SETUP.f90:735-741), nonsu2 Ntot <= Ns (:896-902)
+        qns = [q for q in qns if (q <= 0 if superc else q <= Ns)]
+    twin_of = (lambda q: -q) if superc else (lambda q: 2 * Ns - q)
     build = build_Hv_sector_superc if superc else build_Hv_sector_nonsu2
     states: list[EState] = []
     oldzero = 1000.0
@@ -977,6 +1016,16 @@ def ed_diag_c(model, qns=None, neigen: int = 2, ncv_factor: int = 10, ncv_add: i
         finally:
             delete_Hv_sector_csr()
     states.sort(key=lambda s: s.e)
+    if ed_twin:
+        for st in [s for s in states if twin_of(s.nup) != s.nup]:
+            build(model, twin_of(st.nup))
+            try:
+                state_twin(st.slot, next_slot)
+            finally:
+                delete_Hv_sector_csr()
+            states.append(EState(st.e, twin_of(st.nup), 0, next_slot))
+            next_slot += 1
+        states.sort(key=lambda s: s.e)
     return states
 
 

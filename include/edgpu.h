@@ -283,6 +283,10 @@ int edgpu_eigh_state_store(int k, int slot);
  * its sector, so that Green's-function seeds never visit the host. */
 int edgpu_state_store(int slot);
 int edgpu_state_free(int slot);
+/* es_return_dvector / es_return_cvector (ED_EIGENSPACE.f90:620-793): this rank's chunk of the
+ * stored state in the reference's layout (real: vecDim doubles; complex sectors: vecDim (re,im)
+ * pairs).  The state's own sector must be open. */
+int edgpu_state_download(int slot, double *vec_host);
 /* apply_op_C (op=-1) / apply_op_CDG (op=+1) of ED_SECTOR.f90:465 / :654 on the stored state:
  * builds c_{iorb,spin}|state> (iorb 0-based, spin 0 up / 1 dw) directly in the layout of the
  * CURRENTLY OPEN sector, which must be the target sector getCsector/getCDGsector. */
@@ -297,6 +301,15 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin);
 int edgpu_apply_ops_packed(int slot, int nops, const double *coef_re_im, const int *op, const int *iorb,
                            const int *spin);
 int edgpu_seed_norm2(double *norm2);
+/* Twin states (ED_TWIN=T): es_return_dvector / es_return_cvector for a state with itwin set
+ * (ED_EIGENSPACE.f90:640-660, 723-793) = the eigenvector of the twin sector re-ordered by
+ * twin_sector_order (ED_SECTOR.f90:1747-1776: Fock states flipped by flip_state_normal / _other
+ * :1787-1817, sort_array returns the sorting permutation :1866-1879).  State `dst_slot` := state
+ * `src_slot` re-expressed in its twin sector, which must be the OPEN sector: normal
+ * (nup,ndw) -> (ndw,nup) [the DimUp x DimDw matrix transposed], superc Sz -> -Sz [up and dw halves of
+ * the packed state exchanged], nonsu2 Ntot -> 2Ns-Ntot [every bit complemented].  Stays on the
+ * device (the reference gathers to the master and permutes there). */
+int edgpu_state_twin(int src_slot, int dst_slot);
 /* dens(a), docc(a) of ED_OBSERVABLES_NORMAL.f90:150-215 (ED_OBSERVABLES_NONSU2 / _SUPERC :150-165
  * for packed-state sectors) for the stored state (weight 1). */
 int edgpu_state_observables(int slot, double *dens, double *docc);

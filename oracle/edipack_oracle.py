@@ -246,6 +246,7 @@ class Model:
     lanc_tolerance: float = 1e-18
     lanc_dim_threshold: int = 1024
     gs_threshold: float = 1e-9
+    ed_twin: bool = False               # ED_TWIN
     ed_use_kanamori: bool = True        # ED_USE_KANAMORI
     umatrix_lines: tuple = ()           # umatrix file lines + ed_add_twobody_operator calls
     _params: OraParams | None = field(default=None, repr=False)
@@ -649,16 +650,46 @@ class GState:
     vec: np.ndarray
 
 
-def diagonalize(model: Model, use_lanczos_above: int | None = None, hxv_kind="stored"):
-    """ed_diag_d (ED_DIAG_NORMAL.f90:76-296) without ed_twin: scan all (nup,ndw) sectors,
-    dense LAPACK when dim <= lanc_dim_threshold else plain Lanczos; T=0 state list with the
-    gs_threshold degeneracy rule (:262-278)."""
+def twin_mask(Ns: int):
+    """twin_mask of setup_global (ED_SETUP.f90:592-602), NORMAL mode with ed_twin=T: sectors are
+    scanned in index order and a sector with nup /= ndw is switched off when its twin (ndw,nup) is
+    still on -- the sectors that stay on are those with nup >= ndw.  Returns {isector: bool}."""
+    mask = {i: True for i in range(1, (Ns + 1) ** 2 + 1)}
+    for isector in range(1, (Ns + 1) ** 2 + 1):
+        nup, ndw = sector_qn(Ns, isector)
+        if nup != ndw and mask[sector_index(Ns, ndw, nup)]:
+            mask[isector] = False
+    return mask
+
+
+def twin_sector_order(Ns: int, nup: int, ndw: int, nph: int = 0):
+    """twin_sector_order(isector, Order) for the NORMAL sector A = (nup,ndw) (ED_SECTOR.f90:1747-1776):
+    Order(i) = flip_state([mup, mdw]) + (iph-1)*2**(2Ns) = mdw + mup*2**Ns + ... (flip_state_normal,
+    :1787-1795), then sort_array REPLACES the array by its sorting permutation (:1866-1879), so that
+    the twin state reads vector_B(i) = vec_A(Order(i)) (es_return_dvector, ED_EIGENSPACE.f90:640-660).
+    Returns the 0-based permutation."""
+    mu, md = build_map(Ns, nup).astype(np.int64), build_map(Ns, ndw).astype(np.int64)
+    flipped = (md[:, None] + (mu[None, :] << Ns)).ravel()       # i = iup + idw*DimUp
+    full = np.concatenate([flipped + (k << (2 * Ns)) for k in range(nph + 1)])
+    return np.argsort(full, kind="stable")
+
+
+def diagonalize(model: Model, use_lanczos_above: int | None = None, hxv_kind="stored", ed_twin=None):
+    """ed_diag_d (ED_DIAG_NORMAL.f90:76-296): scan the (nup,ndw) sectors (with ed_twin only those
+    left on by twin_mask, :110), dense LAPACK when dim <= lanc_dim_threshold else plain Lanczos;
+    T=0 state list with the gs_threshold degeneracy rule (:262-278).  With ed_twin a state of a
+    sector with nup /= ndw enters the list together with its twin (es_insert_state,
+    ED_EIGENSPACE.f90:344-350), whose vector is the re-ordered one (twin_sector_order)."""
     Ns = model.Ns
     thr = model.lanc_dim_threshold if use_lanczos_above is None else use_lanczos_above
     states: list[GState] = []
     oldzero = 1000.0
     fn = stored_hxv if hxv_kind == "stored" else direct_hxv
+    ed_twin = model.ed_twin if ed_twin is None else ed_twin
+    mask = twin_mask(Ns) if ed_twin else None
     for isector in range(1, (Ns + 1) ** 2 + 1):
+        if mask is not None and not mask[isector]:
+            continue
         nup, ndw = sector_qn(Ns, isector)
         DimUp, DimDw = sector_dims(Ns, nup, ndw)
         dim = DimUp * DimDw
@@ -668,12 +699,15 @@ def diagonalize(model: Model, use_lanczos_above: int | None = None, hxv_kind="st
         else:
             e0, v0, _ = lanc_eigh(lambda x: fn(model, nup, ndw, x), dim,
                                   min(dim, model.lanc_niter), threshold=1e-12)
+        new = [GState(e0, nup, ndw, v0)]
+        if ed_twin and nup != ndw:
+            new.append(GState(e0, ndw, nup, v0[twin_sector_order(Ns, nup, ndw)]))
         if e0 < oldzero - 10.0 * model.gs_threshold:
             oldzero = e0
-            states = [GState(e0, nup, ndw, v0)]
+            states = new
         elif abs(e0 - oldzero) <= model.gs_threshold:
             oldzero = min(oldzero, e0)
-            states.append(GState(e0, nup, ndw, v0))
+            states.extend(new)
     return states
 
 

@@ -331,3 +331,12 @@ def observables(model: ModelNonsu2, smap, vec):
             acc += np.conj(vec[index[r2[0]]]) * r1[1] * r2[1] * vec[i]
         magx[a] = 2.0 * acc.real
     return dens, docc, magx
+
+
+def twin_sector_order(Ns: int, Ntot: int):
+    """twin_sector_order for the nonsu2 sector A = Ntot (ED_SECTOR.f90:1747-1776, flip_state_other
+    :1797-1817: every bit complemented, Ntot -> 2Ns - Ntot); sort_array replaces the array by its
+    sorting permutation: vector_B(i) = vec_A(Order(i)).  0-based."""
+    smap = build_sector(Ns, Ntot)
+    flipped = (~smap) & ((1 << (2 * Ns)) - 1)
+    return np.argsort(flipped, kind="stable")

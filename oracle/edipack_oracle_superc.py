@@ -286,3 +286,12 @@ def observables(model: ModelSuperc, Sz: int, smap, vec):
                         eta[tindex[r[0]]] += r[1] * vec[i]
                 phi[a, b] = 0.5 * (float(np.vdot(eta, eta).real) - ddw[a] - (1.0 - dup[b]))
     return dens, docc, phi
+
+
+def twin_sector_order(Ns: int, Sz: int):
+    """twin_sector_order for the superc sector A = Sz (ED_SECTOR.f90:1747-1776, flip_state_other
+    :1797-1817: up and dw halves exchanged, Sz -> -Sz); vector_B(i) = vec_A(Order(i)).  0-based."""
+    smap = build_sector(Ns, Sz)
+    lo = (1 << Ns) - 1
+    flipped = (smap >> Ns) | ((smap & lo) << Ns)
+    return np.argsort(flipped, kind="stable")
