@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "edgpu_csr_open_z", "edgpu_hxv_z", "edgpu_eigh", "edgpu_eigh_state_store",
     "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
     "edgpu_release_cache", "edgpu_sector_open_superc", "edgpu_apply_ops_packed", "edgpu_seed_norm2",
-    "edgpu_set_coulomb_sundry", "edgpu_set_phonons", "edgpu_set_hbath_packed", "edgpu_state_twin", "edgpu_state_download",
+    "edgpu_set_coulomb_sundry", "edgpu_set_phonons", "edgpu_set_hbath_packed", "edgpu_state_twin", "edgpu_state_download", "edgpu_sector_open_normal_orbs",
 ]
 
 
@@ -131,6 +131,7 @@ def load():
     L.edgpu_set_coulomb_sundry.argtypes = [C.c_int, C.c_void_p]
     L.edgpu_set_hbath_packed.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.edgpu_set_phonons.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int]
+    L.edgpu_sector_open_normal_orbs.argtypes = [C.POINTER(NormalParams), C.c_void_p, C.c_void_p]
     L.edgpu_sector_vecdim.restype = i64
     L.edgpu_sector_dim.restype = i64
     L.edgpu_sector_dims.argtypes = [C.POINTER(i64)] * 4

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["abi.cu", "sector.cu", "hxv.cu", "csr.cu", "vecops.cu", "lanczos.cu", "eigs.cu", "packed.cu", "comm.cu", "extra.cu"]
+SOURCES = ["abi.cu", "sector.cu", "hxv.cu", "csr.cu", "vecops.cu", "lanczos.cu", "eigs.cu", "packed.cu", "comm.cu", "extra.cu", "orbs.cu"]
 LIB = os.path.join(HERE, "libedgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

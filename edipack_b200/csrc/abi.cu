@@ -318,6 +318,13 @@ int edgpu_sector_open_normal(const edgpu_normal_params *p, int nup, int ndw) {
   if (g.csr.open) csr_close(g);
   return sector_open(g, p, nup, ndw);
 }
+int edgpu_sector_open_normal_orbs(const edgpu_normal_params *p, const int32_t *nups, const int32_t *ndws) {
+  clear_error();
+  if (!p || !nups || !ndws) return set_error("null params");
+  free_eigvecs();
+  return orbs_open(g, p, nups, ndws);
+}
+
 int edgpu_set_coulomb_sundry(int nterms, const edgpu_sundry_term *terms) {
   clear_error();
   if (nterms < 0 || nterms > EDGPU_MAXSUNDRY) return set_error("coulomb_sundry: %d terms (max %d)", nterms, EDGPU_MAXSUNDRY);

@@ -106,14 +106,20 @@ int csr_close(Engine &E) {
 }
 
 // lanes per row + the row split of all ranks; marks the sector open
-static int csr_finish(Engine &E) {
+static int csr_finish(Engine &E, const std::vector<int64_t> *counts = nullptr,
+                      const std::vector<int64_t> *offs = nullptr) {
   CsrSector &C = E.csr;
   const int64_t nloc = C.nloc, nglobal = C.nglobal, nnz = C.nnz, row0 = C.row0;
   const size_t w = C.cplx ? 2 : 1;
   const double avg = nloc ? (double)nnz / (double)nloc : 0.0;
   // ~6-8 entries per lane: enough independent loads per lane, few idle lanes in the last trip
   C.lanes = avg > 160 ? 32 : (avg > 80 ? 16 : (avg > 20 ? 8 : 4));
-  if (E.nranks > 1) {
+  if (E.nranks > 1 && counts && offs) {
+    // the builder's own row split (orbital-resolved NORMAL sectors: along the last factor)
+    C.counts = *counts;
+    C.offs = *offs;
+    EDGPU_CUDA(cudaMalloc(&C.vfull, sizeof(double) * w * nglobal));
+  } else if (E.nranks > 1) {
     // row split of every rank: MpiQ = Dim/P, remainder to the LAST rank
     // (ED_HAMILTONIAN_NONSU2.f90:72-79, ED_HAMILTONIAN_SUPERC.f90:76-88)
     const int P = E.nranks;
@@ -135,7 +141,8 @@ static int csr_finish(Engine &E) {
 }
 
 int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
-                     int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map) {
+                     int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map,
+                     const std::vector<int64_t> *counts, const std::vector<int64_t> *offs) {
   if (E.csr.open) csr_close(E);
   CsrSector &C = E.csr;
   C.cplx = cplx;
@@ -147,7 +154,7 @@ int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_
   C.cols = d_cols;
   C.vals = d_vals;
   C.map = d_map;
-  int rc = csr_finish(E);
+  int rc = csr_finish(E, counts, offs);
   if (rc) {  // the caller keeps ownership on failure
     C.rowptr = nullptr;
     C.cols = nullptr;

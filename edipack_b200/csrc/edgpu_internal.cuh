@@ -316,7 +316,11 @@ int csr_open(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, 
 int csr_close(Engine &E);
 // takes ownership of device-built CSR arrays (0-based columns) and of the sector map
 int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
-                     int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map);
+                     int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map,
+                     const std::vector<int64_t> *counts = nullptr, const std::vector<int64_t> *offs = nullptr);
+
+// orbs.cu: ed_total_ud=F sectors (Nups(1:Norb), Ndws(1:Norb)) as a device-built real stored H
+int orbs_open(Engine &E, const edgpu_normal_params *p, const int32_t *nups, const int32_t *ndws);
 
 // packed.cu
 int nonsu2_open(Engine &E, const edgpu_nonsu2_params *p, int ntot);

@@ -401,9 +401,6 @@ k_n2_fill(const int32_t *__restrict__ map, int64_t row0, int64_t nloc, const int
   n2_row((uint32_t)map[row0 + r], row0 + r, s);
 }
 
-int csr_adopt_device(Engine &E, bool cplx, int64_t nloc, int64_t nglobal, int64_t row0, int64_t *d_rowptr,
-                     int32_t *d_cols, double *d_vals, int64_t nnz, int32_t *d_map);
-
 static Nonsu2Dev g_host_dev;  // host copy of the open sector's constants (~17 KB: not on the stack)
 
 // mode/quantum number are in h; builds map + CSR of this rank's rows and opens the stored-H sector

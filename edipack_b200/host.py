@@ -384,6 +384,19 @@ def build_Hv_sector_normal(model: EDModel, nup: int, ndw: int):
     check(_abi.load().edgpu_sector_open_normal(C.byref(model.params()), nup, ndw))
 
 
+def build_Hv_sector_normal_orbs(model: "EDModel", nups, ndws):
+    """build_Hv_sector_normal with ed_total_ud = F: the orbital-resolved sector (Nups(1:Norb),
+    Ndws(1:Norb)), map and Hamiltonian generated on the device (directMatVec_normal_orbs /
+    ed_buildh_normal_orbs); close it with delete_Hv_sector_csr."""
+    global _open_is_complex
+    nu = np.ascontiguousarray(nups, np.int32)
+    nd = np.ascontiguousarray(ndws, np.int32)
+    if nu.size != model.Norb or nd.size != model.Norb:
+        raise EdgpuError("nups / ndws must have Norb entries")
+    check(_abi.load().edgpu_sector_open_normal_orbs(C.byref(model.params()), ptr(nu), ptr(nd)))
+    _open_is_complex = False
+
+
 def set_coulomb_sundry(terms=()):
     """The module global ``coulomb_sundry`` (user two-body terms of a umatrix file, applied by
     direct/HxV_sundry.f90): terms = iterable of (cd_i, cd_j, c_k, c_l, U), every operator an

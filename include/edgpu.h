@@ -152,6 +152,16 @@ int edgpu_set_coulomb_sundry(int nterms, const edgpu_sundry_term *terms);
  * stored/H_ph.f90:6-17 -- the direct path has no A_ph term; pass 0 to reproduce it].
  * g_ph is row-major g_ph[a*Norb + b]; Nph = 0 switches phonons off. */
 int edgpu_set_phonons(int Nph, double w0_ph, double A_ph, const double *g_ph, int Norb);
+/* ed_total_ud = F: build_Hv_sector_normal for an orbital-resolved sector (Nups(1:Norb), Ndws(1:Norb))
+ * (Ns_Ud = Norb factors of Ns_Orb = 1+Nbath levels, ED_SETUP.f90:128-135; maps build_sector
+ * ED_SECTOR.f90:217-242; state index = mixed radix over [DimUps, DimDws], :1691-1702) and the
+ * Hamiltonian of directMatVec_normal_orbs / ed_buildh_normal_orbs
+ * (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:133-226, direct/Orbs/HxV_local.f90, HxV_up.f90, HxV_dw.f90),
+ * generated on the device as a real stored H.  Afterwards the sector behaves like one opened with
+ * edgpu_csr_open_d (edgpu_hxv_d, Lanczos drivers, edgpu_eigh; edgpu_csr_get downloads it).  Needs
+ * bath_type = normal and no inter-orbital term (the reference stops otherwise, ED_SETUP.f90:124,
+ * ED_PARSE_UMATRIX.f90:156-163).  With nranks>1 the rows are split along the last factor. */
+int edgpu_sector_open_normal_orbs(const edgpu_normal_params *p, const int32_t *nups, const int32_t *ndws);
 int edgpu_sector_close(void);           /* delete_Hv_sector_normal, :212-279 */
 int64_t edgpu_sector_vecdim(void);      /* vecDim_Hv_sector_normal, :286-313 (local chunk) */
 int64_t edgpu_sector_dim(void);         /* getDim(isector) */

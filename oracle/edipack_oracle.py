@@ -440,6 +440,138 @@ def direct_hxv_ext(model: Model, nup, ndw, v, sundry=(), phonons=None):
     return hv
 
 
+# --------------------------------------------------------------------------------------
+# ed_total_ud = F: orbital-resolved sectors (Ns_Ud = Norb factors of Ns_Orb = 1+Nbath levels per spin)
+# --------------------------------------------------------------------------------------
+def orbs_dims(model: Model, nups, ndws):
+    """DimUps / DimDws of the sector (Nups(1:Norb), Ndws(1:Norb)) (ED_SETUP.f90:998-1033)."""
+    nso = model.Nbath + 1
+    return [binomial(nso, n) for n in nups], [binomial(nso, n) for n in ndws]
+
+
+def orbs_direct_hxv(model: Model, nups, ndws, v):
+    """directMatVec_normal_orbs (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:133-226; direct/Orbs/HxV_local.f90,
+    HxV_up.f90, HxV_dw.f90), DimPh=1.  State index i = mixed radix over [DimUps, DimDws], first
+    factor fastest (state2indices, ED_SECTOR.f90:1691-1702); every factor is a sector of the
+    Ns_Orb = 1+Nbath levels {impurity, bath 1..Nbath} of one orbital and spin (build_sector
+    :217-242); breorder puts the per-orbital bits at the global sites (ED_AUX_FUNX.f90:425-441).
+    Only bath_type=normal (hybrid stops, ED_SETUP.f90:124; no inter-orbital one-body terms).
+    Pure-python loops: small cases only."""
+    assert model.bath_type == "normal"
+    p = model.params()
+    No, Nb, Ns = model.Norb, model.Nbath, model.Ns
+    nso = Nb + 1
+    dups, ddws = orbs_dims(model, nups, ndws)
+    dims = dups + ddws
+    maps = [build_map(nso, n) for n in list(nups) + list(ndws)]
+    index = [{int(m): k for k, m in enumerate(mp)} for mp in maps]
+    strides = np.cumprod([1] + dims[:-1]).tolist()
+    Dim = int(np.prod(dims))
+    v = np.ascontiguousarray(v, np.float64)
+    assert v.size == Dim
+    Hv = np.zeros(Dim)
+    eloc = np.array(p.eloc[:]).reshape(2, MAXORB, MAXORB)
+    Uloc = np.array(p.Uloc[:])
+    Ust = np.array(p.Ust[:]).reshape(MAXORB, MAXORB)
+    Jh = np.array(p.Jh[:]).reshape(MAXORB, MAXORB)
+    sf = np.array(p.spin_field_z[:])
+    bd = np.array(p.bath_diag[:]).reshape(2, MAXORB, MAXBATH)
+    dh = np.array(p.diag_hybr[:]).reshape(2, MAXORB, MAXBATH)
+    for i in range(Dim):
+        idx, c = [], i
+        for d in dims:
+            idx.append(c % d)
+            c //= d
+        pats = [int(maps[f][idx[f]]) for f in range(2 * No)]
+        Nup, Ndw = [0] * Ns, [0] * Ns
+        for a in range(No):                       # breorder
+            Nup[a], Ndw[a] = pats[a] & 1, pats[a + No] & 1
+            for k in range(Nb):
+                site = model.bath_stride(a, k) - 1
+                Nup[site] = (pats[a] >> (1 + k)) & 1
+                Ndw[site] = (pats[a + No] >> (1 + k)) & 1
+        # ---- Orbs/HxV_local.f90
+        h = 0.0
+        for a in range(No):
+            h += eloc[0, a, a] * Nup[a] + eloc[1, a, a] * Ndw[a] - model.xmu * (Nup[a] + Ndw[a])
+        if np.any(sf != 0):
+            for a in range(No):
+                h += sf[a] * (Nup[a] - Ndw[a])
+        for a in range(No):
+            h += Uloc[a] * Nup[a] * Ndw[a]
+        if No > 1:
+            for a in range(No):
+                for b in range(a + 1, No):
+                    h += Ust[a, b] * (Nup[a] * Ndw[b] + Nup[b] * Ndw[a])
+                    h += (Ust[a, b] - Jh[a, b]) * (Nup[a] * Nup[b] + Ndw[a] * Ndw[b])
+        if model.hfmode:
+            for a in range(No):
+                h += -0.5 * Uloc[a] * (Nup[a] + Ndw[a]) + 0.25 * Uloc[a]
+            if No > 1:
+                for a in range(No):
+                    for b in range(a + 1, No):
+                        nn = Nup[a] + Ndw[a] + Nup[b] + Ndw[b]
+                        # NB 0.25 here, 0.5 in the ed_total_ud=T fragment (direct/HxV_local.f90:66-67)
+                        h += -0.5 * Ust[a, b] * nn + 0.25 * Ust[a, b]
+                        h += -0.5 * (Ust[a, b] - Jh[a, b]) * nn + 0.25 * (Ust[a, b] - Jh[a, b])
+        for a in range(model.Nfoo):
+            for k in range(Nb):
+                site = model.bath_stride(a, k) - 1
+                h += bd[0, a, k] * Nup[site] + bd[1, a, k] * Ndw[site]
+        Hv[i] += h * v[i]
+        # ---- Orbs/HxV_up.f90 / HxV_dw.f90: scatter Hv(target) += h * vin(j)
+        for spin in range(2):
+            for a in range(No):
+                f = a + spin * No
+                m = pats[f]
+                for k in range(Nb):
+                    ialfa = 2 + k                      # 1-based position of bath level k+1
+                    amp = dh[spin, a, k]
+                    if amp == 0.0:
+                        continue
+                    imp, bth = m & 1, (m >> (1 + k)) & 1
+                    out, s1, s2 = C.c_int32(), C.c_double(), C.c_double()
+                    if imp == 1 and bth == 0:
+                        lib().ora_c(1, m, C.byref(out), C.byref(s1))
+                        lib().ora_cdg(ialfa, out.value, C.byref(out), C.byref(s2))
+                    elif imp == 0 and bth == 1:
+                        lib().ora_c(ialfa, m, C.byref(out), C.byref(s1))
+                        lib().ora_cdg(1, out.value, C.byref(out), C.byref(s2))
+                    else:
+                        continue
+                    t = i + (index[f][out.value] - idx[f]) * strides[f]
+                    Hv[t] += amp * s1.value * s2.value * v[i]
+    return Hv
+
+
+def orbs_embedding(model: Model, nups, ndws):
+    """Index (0-based) in the ed_total_ud=T sector (sum nups, sum ndws) of every state of the orbital-
+    resolved sector, through breorder (ED_AUX_FUNX.f90:425-441)."""
+    No, Nb, Ns = model.Norb, model.Nbath, model.Ns
+    nso = Nb + 1
+    dups, ddws = orbs_dims(model, nups, ndws)
+    dims = dups + ddws
+    maps = [build_map(nso, n) for n in list(nups) + list(ndws)]
+    mu_t, md_t = build_map(Ns, sum(nups)), build_map(Ns, sum(ndws))
+    iu = {int(m): k for k, m in enumerate(mu_t)}
+    idd = {int(m): k for k, m in enumerate(md_t)}
+    out = np.zeros(int(np.prod(dims)), np.int64)
+    for i in range(out.size):
+        c, pats = i, []
+        for f, d in enumerate(dims):
+            pats.append(int(maps[f][c % d]))
+            c //= d
+        g = [0, 0]
+        for spin in range(2):
+            for a in range(No):
+                m = pats[a + spin * No]
+                g[spin] |= (m & 1) << a
+                for k in range(Nb):
+                    g[spin] |= ((m >> (1 + k)) & 1) << (model.bath_stride(a, k) - 1)
+        out[i] = iu[g[0]] + idd[g[1]] * len(mu_t)
+    return out
+
+
 def direct_hxv_mpi(model: Model, nup, ndw, v, P, nthreads=1):
     v = np.ascontiguousarray(v, np.float64)
     hv = np.empty_like(v)
