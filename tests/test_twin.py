@@ -89,7 +89,8 @@ def test_state_twin_normal_on_device(engine, oracle, case):
     try:
         E.sp_lanc_eigh(1, 1e-14, vect=v.copy())    # current state := v (one-dimensional Krylov space)
         E.state_store(3)
-        assert np.abs(E.es_return_vector(3) - v).max() < 1e-15
+        v3 = E.es_return_vector(3)                 # = v up to the driver's own normalisation (1 ulp)
+        assert np.abs(v3 - v).max() < 1e-15
     finally:
         E.delete_Hv_sector_normal()
     E.build_Hv_sector_normal(m, ndw, nup)
@@ -100,7 +101,7 @@ def test_state_twin_normal_on_device(engine, oracle, case):
         E.delete_Hv_sector_normal()
         E.state_free(3)
         E.state_free(4)
-    assert np.array_equal(got, v[oracle.twin_sector_order(ns, nup, ndw)])
+    assert np.array_equal(got, v3[oracle.twin_sector_order(ns, nup, ndw)])   # a pure re-ordering: bit-exact
 
 
 @pytest.mark.gpu
@@ -116,6 +117,7 @@ def test_state_twin_with_phonons_on_device(engine, oracle):
         E.build_Hv_sector_normal(m, nup, ndw)
         E.sp_lanc_eigh(1, 1e-14, vect=v.copy())
         E.state_store(3)
+        v = E.es_return_vector(3)
         E.delete_Hv_sector_normal()
         E.build_Hv_sector_normal(m, ndw, nup)
         E.state_twin(3, 4)
