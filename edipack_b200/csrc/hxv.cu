@@ -703,6 +703,177 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
 }
 
 // ---------------------------------------------------------------------------------------
+// pass B', "transposed-tile" kernel for the FAST index (opt-in, EDGPU_UPT=1): the structure of
+// k_slow applied to the up hops.  The up species is planned like a slow-role species (ranges of
+// <= ~880 rows, one merged entry list per row, far entries first).  CTA = the up range [s0, s1) x
+// FT_COLS (16) consecutive columns, staged TRANSPOSED as tile[row][16 columns] (128 B per row) by
+// 8-byte cp.async: a warp copies 32 consecutive rows of one column (coalesced) into
+// tile[r][j ^ (r & 15)] -- the XOR swizzle spreads the 32 stores over all banks.  8 threads own
+// one row, each a pair of columns: a hop reads one conflict-free 128-byte segment (the pair of a
+// thread sits at pair index p ^ ((r' & 15) >> 1), swapped when r' is odd) and the row's entries,
+// amplitudes, eps and impurity bits are shared by 16 columns.
+//   hv[s0+j, c] = s_acc * ( (eps_up + eps_dw + X[imp_dw][imp_up]) v[s0+j, c] + sum_e amp_e v[tgt_e, c] )
+//                 (+ s_old * hv_old when ACCUM)
+// grid = (nranges, ceil(ncol / 16)), range index fastest (far gathers hit L2).
+// ---------------------------------------------------------------------------------------
+constexpr int FT_COLS = 16;
+
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+template <int W4, int NF, bool ACCUM>
+__global__ void __launch_bounds__(SLOW_THREADS, 2)
+k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
+        int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
+        double s_acc, double s_old) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tile = reinterpret_cast<double *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int s0 = (int)F.range_start[blockIdx.x], s1 = (int)F.range_start[blockIdx.x + 1];
+  const int len = s1 - s0;
+  double *amp_s = tile + (size_t)len * FT_COLS;
+  double *xc = amp_s + 2 * F.nterms + 2;
+  const int64_t c0 = (int64_t)blockIdx.y * FT_COLS;
+  const int nc = (int)min((int64_t)FT_COLS, ncol - c0);
+  constexpr int PARTS = FT_COLS / 2;            // threads per row
+  constexpr int CSTEP = SLOW_THREADS / PARTS;   // rows per sweep of the CTA
+  const int p = tid % PARTS;                    // the thread's column pair (2p, 2p+1)
+  const int jl = tid / PARTS;
+  const uint32_t tile_sa = smem_u32(tile);
+
+  // stage: column j (missing columns of the last CTA alias the last live one, never stored)
+  for (int j = 0; j < FT_COLS; j++) {
+    const double *src = v + (c0 + (j < nc ? j : nc - 1)) * ldv + s0;
+    for (int r = tid; r < len; r += SLOW_THREADS)
+      cp_async8(tile_sa + (uint32_t)(r * FT_COLS + (j ^ (r & 15))) * 8u, src + r);
+  }
+  if (ACCUM) {  // old Hv of the CTA's footprint -> L2 (one 128-byte line per 16 rows and column)
+    const int nl = (len + 15) / 16;
+    for (int t = tid; t < nl * nc; t += SLOW_THREADS) {
+      const int j = t / nl, k = t - j * nl;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(hv + (c0 + j) * ldv + s0 + 16 * k));
+    }
+  }
+  for (int t = tid; t < 2 * F.nterms + 2; t += SLOW_THREADS) amp_s[t] = F.amp2[t];
+  // xc[j][m] = eps_dw(c) + X[imp_dw(c)][m]
+  for (int t = tid; t < FT_COLS * nimp; t += SLOW_THREADS) {
+    const int j = t / nimp, m = t - j * nimp;
+    const int64_t cg = c0 + (j < nc ? j : nc - 1) + col_offset;
+    xc[t] = S.eps[cg] + xud[(int)S.imp[cg] * nimp + m];
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int ca = 2 * p < nc ? 2 * p : nc - 1, cb = 2 * p + 1 < nc ? 2 * p + 1 : nc - 1;
+  const double *va = v + (c0 + ca) * ldv, *vb = v + (c0 + cb) * ldv;   // far gathers / own columns
+  double *ha = hv + (c0 + ca) * ldv, *hb = hv + (c0 + cb) * ldv;
+  const bool live_a = 2 * p < nc, live_b = 2 * p + 1 < nc;
+  const uint32_t base_sa = tile_sa - (uint32_t)s0 * (FT_COLS * 8u);  // + t * 128 (wraps, exact after the add)
+  const uint32_t s0m = (uint32_t)s0 & 15u;
+  const uint32_t amp_sa = smem_u32(amp_s);
+  const uint32_t xc_sa = smem_u32(xc) + (uint32_t)(2 * p) * (uint32_t)nimp * 8u;
+  const uint4 *ell = F.ell4 + s0;
+  // pair of columns (2p, 2p+1) of global row t from the swizzled tile
+  auto tile_pair = [&](uint32_t t) -> double2 {
+    const uint32_t sw = (t - s0m) & 15u;
+    double2 x = lds128(base_sa + t * (FT_COLS * 8u) + (((uint32_t)p ^ (sw >> 1)) << 4));
+    if (sw & 1u) {
+      const double y = x.x;
+      x.x = x.y;
+      x.y = y;
+    }
+    return x;
+  };
+
+  // Software pipeline over the thread's rows j0, j0+CSTEP, ... as in k_slow: iteration j consumes
+  // the deferred loads (far gathers, old Hv) of row j-CSTEP, issues those of row j and does the
+  // local hops of row j.
+  constexpr int NG = W4;
+  uint4 nq[NG];
+  double neu = 0.0;
+  uint32_t nm = 0;
+  if (jl < len) {
+#pragma unroll
+    for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * F.ld + jl];
+    neu = F.eps[s0 + jl];
+    nm = (uint32_t)F.imp[s0 + jl];
+  }
+  double2 xf[NF > 0 ? NF : 1];
+  double2 hold = make_double2(0.0, 0.0), accp = make_double2(0.0, 0.0);
+  uint4 q0p = make_uint4(0, 0, 0, 0);
+  int rowp = 0;
+  for (int j = jl; j < len + CSTEP; j += CSTEP) {
+    // (A)
+    if (j > jl) {
+#pragma unroll
+      for (int e = 0; e < NF; e++) {
+        const double a = lds64(amp_sa + amp_off(ent_of(q0p, e & 3)));
+        accp.x += a * xf[e].x;
+        accp.y += a * xf[e].y;
+      }
+      accp.x *= s_acc;
+      accp.y *= s_acc;
+      if (ACCUM) {
+        accp.x += s_old * hold.x;
+        accp.y += s_old * hold.y;
+      }
+      if (live_a) ha[rowp] = accp.x;
+      if (live_b) hb[rowp] = accp.y;
+    }
+    if (j >= len) break;
+    // (B)
+    uint4 q[NG];
+#pragma unroll
+    for (int g = 0; g < W4; g++) q[g] = nq[g];
+    const double eu = neu;
+    const uint32_t mimp = nm;
+    const int row = s0 + j;
+    if (ACCUM) hold = make_double2(ha[row], hb[row]);
+#pragma unroll
+    for (int e = 0; e < NF; e++) {
+      const uint32_t ent = ent_of(q[e >> 2], e & 3);
+      const uint32_t t = ent & HOP_TGT_MASK;
+      if (ent & HOP_FAR)
+        xf[e] = make_double2(va[t], vb[t]);
+      else
+        xf[e] = tile_pair(t);
+    }
+    if (j + CSTEP < len) {
+#pragma unroll
+      for (int g = 0; g < W4; g++) nq[g] = ell[(int64_t)g * F.ld + j + CSTEP];
+      neu = F.eps[row + CSTEP];
+      nm = (uint32_t)F.imp[row + CSTEP];
+    }
+    // (C) diagonal + local hops
+    const double2 own = tile_pair((uint32_t)row);
+    double2 acc;
+    acc.x = (eu + lds64(xc_sa + mimp * 8u)) * own.x;
+    acc.y = (eu + lds64(xc_sa + ((uint32_t)nimp + mimp) * 8u)) * own.y;
+#pragma unroll
+    for (int e = NF; e < 4 * W4; e++) {
+      const uint32_t ent = ent_of(q[e >> 2], e & 3);
+      const double a = lds64(amp_sa + amp_off(ent));
+      const double2 x = tile_pair(ent & HOP_TGT_MASK);
+      acc.x += a * x.x;
+      acc.y += a * x.y;
+    }
+    accp = acc;
+    q0p = q[0];
+    rowp = row;
+  }
+  // the last range also owns the pad rows [dim, ld): zeros (scaled old value when accumulating)
+  if (blockIdx.x + 1 == gridDim.x) {
+    const int npad = (int)(F.ld - F.dim);
+    for (int t = tid; t < npad * nc; t += SLOW_THREADS) {
+      const int j = t / npad, r = (int)F.dim + (t - j * npad);
+      double *o = hv + (c0 + j) * ldv + r;
+      *o = ACCUM ? s_old * *o : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // non-local S-E / P-H terms (direct/HxV_non_local.f90): gather from anywhere in the vector.
 //   S-E: nup(j)=1, ndw(i)=1, ndw(j)=0, nup(i)=0 :  dw: c^+_j c_i ; up: c^+_i c_j ; Jx(i,j)
 //   P-H: nup(j)=1, ndw(j)=1, ndw(i)=0, nup(i)=0 :  dw: c^+_i c_j ; up: c^+_i c_j ; Jp(i,j)
@@ -799,12 +970,69 @@ static int launch_fastb(Engine &E, const double *v, double *hv, int64_t ldv, int
   return 0;
 }
 
+size_t fastT_smem_bytes(int64_t max_range, int nterms, int nimp) {
+  return sizeof(double) * ((size_t)max_range * FT_COLS + 2 * (size_t)nterms + 2 + (size_t)FT_COLS * nimp);
+}
+
+template <int W4, int NF, bool ACCUM>
+static int launch_fastT(Engine &E, const double *v, double *hv, int64_t ncol, int64_t col_offset,
+                        const SpinSpace &Fs, const SpinView &F, const SpinView &S, const double *xud,
+                        int nimp, double s_acc, double s_old) {
+  const size_t smem = fastT_smem_bytes(Fs.max_range, F.nterms, nimp);
+  auto kern = k_fastT<W4, NF, ACCUM>;
+  EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)F.nranges, (unsigned)((ncol + FT_COLS - 1) / FT_COLS));
+  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, F.ld, ncol, col_offset, F, S, xud, nimp, s_acc, s_old);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// diag + up hops with the transposed-tile kernel; returns -1 when the table shape has no
+// instantiation (the caller falls back to the generic gather kernel)
+static int apply_fastT(Engine &E, bool accum, const double *v, double *hv, int64_t ncol, int64_t col_offset,
+                       const SpinSpace &Fs, const SpinView &F, const SpinView &S, const double *xud, int nimp,
+                       double s_acc, double s_old) {
+  const int W4 = Fs.Wl4, NF = Fs.Wf;
+  if (fastT_smem_bytes(Fs.max_range, F.nterms, nimp) > E.smem_optin) return -1;
+#define EDGPU_FT(WW, FF)                                                                                  \
+  (accum ? launch_fastT<WW, FF, true>(E, v, hv, ncol, col_offset, Fs, F, S, xud, nimp, s_acc, s_old)      \
+         : launch_fastT<WW, FF, false>(E, v, hv, ncol, col_offset, Fs, F, S, xud, nimp, s_acc, s_old))
+  if (W4 >= 1 && W4 <= 3 && NF <= 4 && NF <= 4 * W4) {
+    switch (W4 * 8 + NF) {
+      case 8 + 0: return EDGPU_FT(1, 0);
+      case 8 + 1: return EDGPU_FT(1, 1);
+      case 8 + 2: return EDGPU_FT(1, 2);
+      case 8 + 3: return EDGPU_FT(1, 3);
+      case 8 + 4: return EDGPU_FT(1, 4);
+      case 16 + 0: return EDGPU_FT(2, 0);
+      case 16 + 1: return EDGPU_FT(2, 1);
+      case 16 + 2: return EDGPU_FT(2, 2);
+      case 16 + 3: return EDGPU_FT(2, 3);
+      case 16 + 4: return EDGPU_FT(2, 4);
+      case 24 + 0: return EDGPU_FT(3, 0);
+      case 24 + 1: return EDGPU_FT(3, 1);
+      case 24 + 2: return EDGPU_FT(3, 2);
+      case 24 + 3: return EDGPU_FT(3, 3);
+      case 24 + 4: return EDGPU_FT(3, 4);
+    }
+  }
+#undef EDGPU_FT
+  return -1;
+}
+
 // Applies (diag +) the fast-index operator F to an [F.ld x ncol] block.
 static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const double *v, double *hv,
                       int64_t ncol, int64_t col_offset, const SpinSpace &Fs, const SpinView &F,
                       const SpinView &S, const double *xud, int nimp, double s_acc = 1.0,
                       double s_old = 1.0) {
   if (ncol <= 0) return 0;
+  if (tiled && Fs.role == ROLE_SLOW) {
+    // the species was planned for the transposed-tile kernel (EDGPU_UPT=1, single rank)
+    const int rc = with_diag ? apply_fastT(E, accum, v, hv, ncol, col_offset, Fs, F, S, xud, nimp, s_acc, s_old) : -1;
+    if (rc >= 0) return rc;
+    tiled = false;  // no instantiation for this table shape: generic gather kernel
+  }
   if (!tiled) {
     dim3 grid((unsigned)((F.dim + 127) / 128), (unsigned)ncol);
     if (with_diag)

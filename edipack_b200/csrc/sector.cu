@@ -374,11 +374,17 @@ static void plan_species(Engine &E, const edgpu_normal_params &p, int s, int nel
   const int Ns = p.Ns, No = p.Norb;
   std::vector<Term> terms;
   build_terms(p, s, terms);
+  // opt-in: plan the up species like a slow-role one for the transposed-tile kernel k_fastT
+  // (hxv.cu).  Read once per process: stored states depend on the enumeration order.
+  static const bool upt = getenv("EDGPU_UPT") && atoi(getenv("EDGPU_UPT")) != 0;
+  const bool up_t = (s == 0 && E.nranks == 1 && upt);
   const size_t per_cta = (E.smem_per_sm - 2 * 1024) / 2;  // 2 CTAs per SM
-  const size_t tables = 8 * (2 * terms.size() + 2 + 4 * ((size_t)1 << No)) + 64;
+  // amplitudes + the per-column diagonal table (4 columns in k_fastb, 16 in k_fastT)
+  const size_t tables = 8 * (2 * terms.size() + 2 + (up_t ? 16 : 4) * ((size_t)1 << No)) + 64;
   const size_t avail = per_cta > tables ? per_cta - tables : 0;
   P.identity = (s == 1 && E.nranks > 1);
   P.role = (s == 1 && E.nranks == 1) ? ROLE_SLOW : ROLE_FAST;
+  if (up_t) P.role = ROLE_SLOW;
   P.block_mode = false;
   P.items.clear();
   // ---- block mode (fast role, permuted order): tile = input blocks x 4 columns (2 planes of
