@@ -726,7 +726,7 @@ template <int W4, int NF, bool ACCUM>
 __global__ void __launch_bounds__(SLOW_THREADS, 2)
 k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
         int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
-        double s_acc, double s_old) {
+        double s_acc, double s_old, int lane_rows) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tile = reinterpret_cast<double *>(smem_raw);
   const int tid = threadIdx.x;
@@ -738,8 +738,13 @@ k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
   const int nc = (int)min((int64_t)FT_COLS, ncol - c0);
   constexpr int PARTS = FT_COLS / 2;            // threads per row
   constexpr int CSTEP = SLOW_THREADS / PARTS;   // rows per sweep of the CTA
-  const int p = tid % PARTS;                    // the thread's column pair (2p, 2p+1)
-  const int jl = tid / PARTS;
+  // thread <-> (row of the sweep, column pair).  lane_rows = 0: the 8 threads of a row are
+  // neighbours (entries / amplitudes broadcast, but every global access of a warp -- far gathers,
+  // Hv -- touches 8 columns = 8 lines: measured 1.97 ms at cfg 2, 1.8 L1 wavefronts per state).
+  // lane_rows = 1: a warp = 32 consecutive rows of ONE column pair: far gathers and stores are
+  // 256-byte runs, the tile reads stay conflict-free (4 lanes per 16-byte slot of the swizzle).
+  const int p = lane_rows ? tid / CSTEP : tid % PARTS;   // the thread's column pair (2p, 2p+1)
+  const int jl = lane_rows ? tid % CSTEP : tid / PARTS;
   const uint32_t tile_sa = smem_u32(tile);
 
   // stage: column j (missing columns of the last CTA alias the last live one, never stored)
@@ -982,7 +987,9 @@ static int launch_fastT(Engine &E, const double *v, double *hv, int64_t ncol, in
   auto kern = k_fastT<W4, NF, ACCUM>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)F.nranges, (unsigned)((ncol + FT_COLS - 1) / FT_COLS));
-  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, F.ld, ncol, col_offset, F, S, xud, nimp, s_acc, s_old);
+  static const int lane_rows = getenv("EDGPU_UPT") && atoi(getenv("EDGPU_UPT")) == 1 ? 0 : 1;
+  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, F.ld, ncol, col_offset, F, S, xud, nimp, s_acc, s_old,
+                                               lane_rows);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
