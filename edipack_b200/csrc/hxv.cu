@@ -722,7 +722,12 @@ __device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-template <int W4, int NF, bool ACCUM>
+// PAD = true: no swizzle, row pitch FT_PITCH = 18 doubles (144 B) instead: the 16-byte pairs of 32
+// consecutive rows fall on 8 distinct 16-byte slots x 4 lanes (conflict-free), the tile address is
+// one multiply-add and there is no swap.
+constexpr int FT_PITCH = 18;
+
+template <int W4, int NF, bool ACCUM, bool PAD>
 __global__ void __launch_bounds__(SLOW_THREADS, 2)
 k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
         int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
@@ -732,7 +737,8 @@ k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
   const int tid = threadIdx.x;
   const int s0 = (int)F.range_start[blockIdx.x], s1 = (int)F.range_start[blockIdx.x + 1];
   const int len = s1 - s0;
-  double *amp_s = tile + (size_t)len * FT_COLS;
+  constexpr int PITCH = PAD ? FT_PITCH : FT_COLS;
+  double *amp_s = tile + (size_t)len * PITCH;
   double *xc = amp_s + 2 * F.nterms + 2;
   const int64_t c0 = (int64_t)blockIdx.y * FT_COLS;
   const int nc = (int)min((int64_t)FT_COLS, ncol - c0);
@@ -751,7 +757,7 @@ k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
   for (int j = 0; j < FT_COLS; j++) {
     const double *src = v + (c0 + (j < nc ? j : nc - 1)) * ldv + s0;
     for (int r = tid; r < len; r += SLOW_THREADS)
-      cp_async8(tile_sa + (uint32_t)(r * FT_COLS + (j ^ (r & 15))) * 8u, src + r);
+      cp_async8(tile_sa + (uint32_t)(r * PITCH + (PAD ? j : (j ^ (r & 15)))) * 8u, src + r);
   }
   if (ACCUM) {  // old Hv of the CTA's footprint -> L2 (one 128-byte line per 16 rows and column)
     const int nl = (len + 15) / 16;
@@ -774,13 +780,15 @@ k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
   const double *va = v + (c0 + ca) * ldv, *vb = v + (c0 + cb) * ldv;   // far gathers / own columns
   double *ha = hv + (c0 + ca) * ldv, *hb = hv + (c0 + cb) * ldv;
   const bool live_a = 2 * p < nc, live_b = 2 * p + 1 < nc;
-  const uint32_t base_sa = tile_sa - (uint32_t)s0 * (FT_COLS * 8u);  // + t * 128 (wraps, exact after the add)
+  // + t * row pitch (wraps, exact after the add); PAD: the thread's pair offset folded in
+  const uint32_t base_sa = tile_sa - (uint32_t)s0 * (PITCH * 8u) + (PAD ? (uint32_t)p * 16u : 0u);
   const uint32_t s0m = (uint32_t)s0 & 15u;
   const uint32_t amp_sa = smem_u32(amp_s);
   const uint32_t xc_sa = smem_u32(xc) + (uint32_t)(2 * p) * (uint32_t)nimp * 8u;
   const uint4 *ell = F.ell4 + s0;
   // pair of columns (2p, 2p+1) of global row t from the swizzled tile
   auto tile_pair = [&](uint32_t t) -> double2 {
+    if (PAD) return lds128(base_sa + t * (PITCH * 8u));
     const uint32_t sw = (t - s0m) & 15u;
     double2 x = lds128(base_sa + t * (FT_COLS * 8u) + (((uint32_t)p ^ (sw >> 1)) << 4));
     if (sw & 1u) {
@@ -976,7 +984,14 @@ static int launch_fastb(Engine &E, const double *v, double *hv, int64_t ldv, int
 }
 
 size_t fastT_smem_bytes(int64_t max_range, int nterms, int nimp) {
-  return sizeof(double) * ((size_t)max_range * FT_COLS + 2 * (size_t)nterms + 2 + (size_t)FT_COLS * nimp);
+  return sizeof(double) * ((size_t)max_range * FT_PITCH + 2 * (size_t)nterms + 2 + (size_t)FT_COLS * nimp);
+}
+
+// EDGPU_UPT: 1 = swizzled tile, 8 threads per row; 2 = swizzled tile, lanes along rows;
+// 3 = padded tile (no swizzle), lanes along rows
+static int fastT_mode() {
+  static const int mode = getenv("EDGPU_UPT") ? atoi(getenv("EDGPU_UPT")) : 0;
+  return mode;
 }
 
 template <int W4, int NF, bool ACCUM>
@@ -984,10 +999,11 @@ static int launch_fastT(Engine &E, const double *v, double *hv, int64_t ncol, in
                         const SpinSpace &Fs, const SpinView &F, const SpinView &S, const double *xud,
                         int nimp, double s_acc, double s_old) {
   const size_t smem = fastT_smem_bytes(Fs.max_range, F.nterms, nimp);
-  auto kern = k_fastT<W4, NF, ACCUM>;
+  const bool pad = fastT_mode() == 3;
+  auto kern = pad ? k_fastT<W4, NF, ACCUM, true> : k_fastT<W4, NF, ACCUM, false>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)F.nranges, (unsigned)((ncol + FT_COLS - 1) / FT_COLS));
-  static const int lane_rows = getenv("EDGPU_UPT") && atoi(getenv("EDGPU_UPT")) == 1 ? 0 : 1;
+  const int lane_rows = fastT_mode() == 1 ? 0 : 1;
   kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, F.ld, ncol, col_offset, F, S, xud, nimp, s_acc, s_old,
                                                lane_rows);
   EDGPU_COUNT_LAUNCH();

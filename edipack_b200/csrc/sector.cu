@@ -456,8 +456,9 @@ static void plan_species(Engine &E, const edgpu_normal_params &p, int s, int nel
   }
   if (!P.block_mode) {
     // ---- range mode: fast role tile[range + 32][2] doubles, slow role tile[range][SLOW_ROWS]
+    // slow role: 128 B per range element; the up species of k_fastT: up to 144 B (padded pitch)
     const int64_t cap = P.role == ROLE_SLOW
-                            ? std::max<int64_t>((int64_t)(avail / (8 * SLOW_ROWS)), 1)
+                            ? std::max<int64_t>((int64_t)(avail / (8 * (up_t ? 18 : SLOW_ROWS))), 1)
                             : std::max<int64_t>((int64_t)(avail / 16) - 32, 1);
     P.range_start.clear();
     P.range_tbits.clear();
