@@ -327,8 +327,18 @@ def chunk_bounds(DimUp: int, DimDw: int, nranks: int, rank: int):
     return d0 * DimUp, (d0 + q) * DimUp
 
 
-def scatter_vector_MPI(v_full, DimUp: int, DimDw: int, root: int = 0, group=None):
-    """d_scatter_vector_MPI (ED_AUX_FUNX.f90:598): root's full vector -> every rank's dw chunk."""
+def _dev_of(group):
+    import torch
+    import torch.distributed as dist
+
+    return (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
+            else torch.device("cpu"))
+
+
+def scatter_vector_MPI(v_full, DimUp: int, DimDw: int, root: int = 0, group=None, DimPh: int = 1):
+    """d_scatter_vector_MPI (ED_AUX_FUNX.f90:598-652): root's full vector -> every rank's chunk.
+    With phonons the full vector is DimPh electronic slices of DimUp*DimDw and every rank's chunk
+    is DimPh slices of its dw columns (one MPI_Scatterv per slice, :637-649)."""
     import torch
     import torch.distributed as dist
 
@@ -336,44 +346,55 @@ def scatter_vector_MPI(v_full, DimUp: int, DimDw: int, root: int = 0, group=None
     bounds = [chunk_bounds(DimUp, DimDw, P, k) for k in range(P)]
     nmax = max(hi - lo for lo, hi in bounds)  # collectives want equal pieces: pad to the longest
     lo, hi = bounds[r]
-    dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
-           else torch.device("cpu"))
-    out = torch.empty(nmax, dtype=torch.float64, device=dev)
-    pieces = None
-    if r == root:
-        t = torch.as_tensor(np.ascontiguousarray(v_full, np.float64))
-        pieces = []
-        for a, b in bounds:
-            x = torch.zeros(nmax, dtype=torch.float64)
-            x[: b - a] = t[a:b]
-            pieces.append(x.to(dev))
-    dist.scatter(out, pieces, src=root, group=group)
-    return out[: hi - lo].cpu().numpy()
+    dev = _dev_of(group)
+    nel = DimUp * DimDw
+    t = torch.as_tensor(np.ascontiguousarray(v_full, np.float64)) if r == root else None
+    if r == root and t.numel() != nel * DimPh:
+        raise EdgpuError("scatter_vector_MPI error: size(V) != Mpi_Allreduce(Nloc)")
+    res = []
+    for iph in range(DimPh):
+        out = torch.empty(nmax, dtype=torch.float64, device=dev)
+        pieces = None
+        if r == root:
+            pieces = []
+            for a, b in bounds:
+                x = torch.zeros(nmax, dtype=torch.float64)
+                x[: b - a] = t[iph * nel + a: iph * nel + b]
+                pieces.append(x.to(dev))
+        dist.scatter(out, pieces, src=root, group=group)
+        res.append(out[: hi - lo].cpu().numpy())
+    return np.concatenate(res)
 
 
-def allgather_vector_MPI(chunk, DimUp: int, DimDw: int, group=None):
-    """d_allgather_vector_MPI (ED_AUX_FUNX.f90:840): every rank's chunk -> full vector."""
+def allgather_vector_MPI(chunk, DimUp: int, DimDw: int, group=None, DimPh: int = 1):
+    """d_allgather_vector_MPI (ED_AUX_FUNX.f90:840-890): every rank's chunk -> full vector, slice
+    by slice when DimPh > 1."""
     import torch
     import torch.distributed as dist
 
     P = dist.get_world_size(group)
-    dev = (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
-           else torch.device("cpu"))
+    dev = _dev_of(group)
     mine = torch.as_tensor(np.ascontiguousarray(chunk, np.float64)).to(dev)
     sizes = [hi - lo for lo, hi in (chunk_bounds(DimUp, DimDw, P, k) for k in range(P))]
     nmax = max(sizes)
-    pad = torch.zeros(nmax, dtype=torch.float64, device=dev)
-    pad[: mine.numel()] = mine
-    outs = [torch.empty(nmax, dtype=torch.float64, device=dev) for _ in range(P)]
-    dist.all_gather(outs, pad, group=group)
-    return torch.cat([o[:n] for o, n in zip(outs, sizes)]).cpu().numpy()
+    nloc = sizes[dist.get_rank(group)]
+    if mine.numel() != nloc * DimPh:
+        raise EdgpuError("allgather_vector_MPI error: chunk length is not DimPh * mpiQ")
+    res = []
+    for iph in range(DimPh):
+        pad = torch.zeros(nmax, dtype=torch.float64, device=dev)
+        pad[:nloc] = mine[iph * nloc:(iph + 1) * nloc]
+        outs = [torch.empty(nmax, dtype=torch.float64, device=dev) for _ in range(P)]
+        dist.all_gather(outs, pad, group=group)
+        res.append(torch.cat([o[:n] for o, n in zip(outs, sizes)]))
+    return torch.cat(res).cpu().numpy()
 
 
-def gather_vector_MPI(chunk, DimUp: int, DimDw: int, root: int = 0, group=None):
-    """d_gather_vector_MPI (ED_AUX_FUNX.f90:742); the full vector is returned on root only."""
+def gather_vector_MPI(chunk, DimUp: int, DimDw: int, root: int = 0, group=None, DimPh: int = 1):
+    """d_gather_vector_MPI (ED_AUX_FUNX.f90:742-795); the full vector is returned on root only."""
     import torch.distributed as dist
 
-    full = allgather_vector_MPI(chunk, DimUp, DimDw, group)
+    full = allgather_vector_MPI(chunk, DimUp, DimDw, group, DimPh)
     return full if dist.get_rank(group) == root else None
 
 

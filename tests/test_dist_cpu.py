@@ -37,6 +37,16 @@ def _worker(rank, world, port, ns, nup, ndw, q):
         ok = ok and np.array_equal(back, 2.0 * full)
         g = H.gather_vector_MPI(mine, du, dd, root=1)
         ok = ok and ((g is None) if rank != 1 else np.array_equal(g, full))
+        # phonons: DimPh slices, every rank's chunk = its dw columns of every slice
+        # (i_el + (iph-1)*DimUp*mpiQdw, direct_mpi/HxV_eph.f90:3-4)
+        nph = 3
+        fullp = O.start_vector(du * dd * nph, 9) - 0.5
+        minep = H.scatter_vector_MPI(fullp if rank == 0 else None, du, dd, root=0, DimPh=nph)
+        expect = np.concatenate([fullp[k * du * dd + lo:k * du * dd + hi] for k in range(nph)])
+        ok = ok and np.array_equal(minep, expect)
+        ok = ok and np.array_equal(H.allgather_vector_MPI(minep, du, dd, DimPh=nph), fullp)
+        gp = H.gather_vector_MPI(minep, du, dd, root=0, DimPh=nph)
+        ok = ok and ((gp is None) if rank != 0 else np.array_equal(gp, fullp))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
