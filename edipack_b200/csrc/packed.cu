@@ -413,6 +413,9 @@ static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
   if (p->Ns < 1 || nbits > 31) return set_error("%s: 2*Ns = %d exceeds the 31-bit packed state", who, nbits);
   if (p->Norb < 1 || p->Norb > EDGPU_MAXORB || p->Nbath < 0 || p->Nbath > EDGPU_MAXBATH)
     return set_error("%s: Norb/Nbath out of range", who);
+  if (E.Nph > 0)
+    return set_error("%s: phonons (H_ph / H_e_ph of the packed-state modes) are not generated on the device: "
+                     "hand the host-built spH0 to edgpu_csr_open_z or call edgpu_set_phonons(0,...)", who);
   h.replica = (p->bath_type == EDGPU_BATH_REPLICA || p->bath_type == EDGPU_BATH_GENERAL);
   h.hb = nullptr;
   double *d_hb = nullptr;
