@@ -1106,6 +1106,76 @@ def observables_normal(model: EDModel, states):
     return dens, docc
 
 
+def _energy_variants(model):
+    """Model variants whose ground-state expectation values give the energy components of
+    local_energy_normal (ED_OBSERVABLES_NORMAL.f90:491-930).  Every variant keeps the bath and the
+    hybridisation of the model (so that its hop tables have the model's structure) and differs from
+    the `base` variant by one group of impurity terms: <O> = <H_variant> - <H_base>."""
+    import dataclasses
+
+    No = model.Norb
+    zero_int = dict(Uloc=(0.0,) * No, Ust=0.0, Jh=0.0, Jx=0.0, Jp=0.0, umatrix_lines=(),
+                    ed_use_kanamori=True)
+    common = dict(xmu=0.0, hfmode=False, spin_field_z=(), exc_field=(0.0, 0.0, 0.0, 0.0), _params=None)
+    rep = dataclasses.replace
+    return {
+        "base": rep(model, hloc=None, **zero_int, **common),
+        # <sum impHloc(s,s,a,b) c^+ c> (:556-611): impHloc only, mfHloc belongs to Epot
+        "eknot": rep(model, **zero_int, **common),
+        # Jx, Jp, mfHloc, sundry, Uloc, Ust, Ust-Jh terms (:613-822), no Hartree shift
+        "eint": rep(model, hloc=None, **common),
+        # <sum_{a<b} nup_a ndw_b + nup_b ndw_a> (:806): Ust = 1 with Ust - Jh = 0
+        "dust": rep(model, hloc=None, **{**zero_int, "Ust": 1.0, "Jh": 1.0}, **common),
+        # <sum_{a<b} nup_a nup_b + ndw_a ndw_b> (:819): Ust - Jh = 1 with Ust = 0
+        "dund": rep(model, hloc=None, **{**zero_int, "Jh": -1.0}, **common),
+        "dse": rep(model, hloc=None, **{**zero_int, "Jx": 1.0}, **common),   # (:633)
+        "dph": rep(model, hloc=None, **{**zero_int, "Jp": 1.0}, **common),   # (:660)
+    }
+
+
+def _hartree_energy(model, dens):
+    """ed_Ehartree (:825-838) is diagonal and linear in the occupations: from dens(a)."""
+    if not model.hfmode:
+        return 0.0
+    um = model.umatrix()
+    No = model.Norb
+    e = 0.0
+    for a in range(No):
+        e += -0.5 * um["Uloc"][a] * dens[a] + 0.25 * um["Uloc"][a]
+    for a in range(No):
+        for b in range(a + 1, No):
+            for c in (um["Ust"][a, b], um["Ust"][a, b] - um["Jh"][a, b]):
+                e += -0.5 * c * (dens[a] + dens[b]) + 0.5 * c
+    return e
+
+
+def local_energy_normal(model: EDModel, states):
+    """local_energy_normal (ED_OBSERVABLES_NORMAL.f90:491-930), DimPh = 1: dict(Epot, Eint, Ehartree,
+    Eknot, Dust, Dund, Dse, Dph) = ed_get_eimp / ed_get_doubles.  Every component is <v|O|v> with O
+    the model Hamiltonian restricted to one group of terms: evaluated on the device as the first
+    Lanczos coefficient alpha_1 = <v|H_variant|v> of the stored state (one H x v + one dot per
+    variant; the reference gathers the state to the master and loops over Dim there)."""
+    variants = _energy_variants(model)
+    acc = {k: 0.0 for k in variants}
+    for st, peso in zip(states, boltzmann_weights(model, states)):
+        vec = None
+        for k, mv in variants.items():
+            build_Hv_sector_normal(mv, st.nup, st.ndw)
+            try:
+                if vec is None:
+                    vec = es_return_vector(st.slot)
+                a, _, nused, n2 = sp_lanc_tridiag(vec, 1)
+            finally:
+                delete_Hv_sector_normal()
+            acc[k] += peso * float(a[0]) * n2
+    dens, _ = observables_normal(model, states)
+    out = {k.capitalize() if k.startswith("d") else "E" + k[1:]: acc[k] - acc["base"]
+           for k in variants if k != "base"}
+    out["Ehartree"] = _hartree_energy(model, dens)
+    out["Epot"] = out["Eint"] + out["Ehartree"]
+    return out
+
+
 def tridiag_eigh(a, b_sub):
     """eigh(diag,subdiag,Ev=Z) of ED_GF_NORMAL.f90:416 (host, tiny)."""
     n = len(a)
