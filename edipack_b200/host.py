@@ -1158,12 +1158,17 @@ def local_energy_normal(model: EDModel, states):
     variants = _energy_variants(model)
     acc = {k: 0.0 for k in variants}
     for st, peso in zip(states, boltzmann_weights(model, states)):
-        vec = None
+        # the stored state is laid out in the enumeration order of ITS model's sector plan (which
+        # depends on the one-body term list): fetch it under that sector, hand it to the variants
+        # in the reference layout
+        build_Hv_sector_normal(model, st.nup, st.ndw)
+        try:
+            vec = es_return_vector(st.slot)
+        finally:
+            delete_Hv_sector_normal()
         for k, mv in variants.items():
             build_Hv_sector_normal(mv, st.nup, st.ndw)
             try:
-                if vec is None:
-                    vec = es_return_vector(st.slot)
                 a, _, nused, n2 = sp_lanc_tridiag(vec, 1)
             finally:
                 delete_Hv_sector_normal()
