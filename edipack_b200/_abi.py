@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "edgpu_csr_open_z", "edgpu_hxv_z", "edgpu_eigh", "edgpu_eigh_state_store",
     "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
     "edgpu_release_cache", "edgpu_sector_open_superc", "edgpu_apply_ops_packed", "edgpu_seed_norm2",
-    "edgpu_set_coulomb_sundry", "edgpu_set_phonons", "edgpu_set_hbath_packed", "edgpu_state_twin", "edgpu_state_download", "edgpu_sector_open_normal_orbs",
+    "edgpu_set_coulomb_sundry", "edgpu_set_phonons", "edgpu_set_hbath_packed", "edgpu_state_twin", "edgpu_state_download", "edgpu_sector_open_normal_orbs", "edgpu_apply_ops_normal",
 ]
 
 
@@ -165,6 +165,7 @@ def load():
     L.edgpu_state_free.argtypes = [C.c_int]
     L.edgpu_apply_op.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.edgpu_apply_ops_packed.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.edgpu_apply_ops_normal.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.edgpu_seed_norm2.argtypes = [dp]
     L.edgpu_state_twin.argtypes = [C.c_int, C.c_int]
     L.edgpu_state_download.argtypes = [C.c_int, C.c_void_p]

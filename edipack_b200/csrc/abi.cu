@@ -172,6 +172,28 @@ k_apply_op(const double *__restrict__ vsrc, int64_t lds, double *__restrict__ ou
   out[c * ldo + i] = val;
 }
 
+// apply_Cops of the NORMAL mode (ED_SECTOR.f90, apply_Cops; used by lanc_build_gf_normal_mix,
+// ED_GF_NORMAL.f90:211,227): one term coef * O |state> ADDED to the seed.  Separate from k_apply_op
+// (which overwrites) so that the single-operator path is untouched.
+__global__ void __launch_bounds__(128)
+k_apply_op_acc(const double *__restrict__ vsrc, int64_t lds, double *__restrict__ out, int64_t ldo,
+               int64_t nrow, int64_t ncol, const int32_t *__restrict__ map_t, int op, int bit, int spin,
+               RankView Rsrc, double coef) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (i >= nrow) return;
+  const int64_t t = (spin == 0) ? i : c;
+  const uint32_t m = (uint32_t)map_t[t];
+  const bool occ = (m >> bit) & 1u;
+  if ((op < 0 && !occ) || (op > 0 && occ)) {
+    const uint32_t ms = m ^ (1u << bit);
+    const double sgn = (__popc(ms & ((1u << bit) - 1u)) & 1) ? -1.0 : 1.0;
+    const int64_t r = rank_of(ms, Rsrc);
+    const int64_t si = (spin == 0) ? r : i, sc = (spin == 0) ? c : r;
+    out[c * ldo + i] += coef * sgn * vsrc[sc * lds + si];
+  }
+}
+
 // Twin state (es_return_dvector `itwin` branch, ED_EIGENSPACE.f90:640-660 + twin_sector_order,
 // ED_SECTOR.f90:1747-1776): the state of sector A = (nup,ndw) re-expressed in the twin sector
 // B = (ndw,nup).  The reference sorts the flipped Fock integers mdw + mup*2^Ns of A and reads
@@ -890,6 +912,69 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
                                            rank_view(lin, ord));
     EDGPU_COUNT_LAUNCH();
   }
+  EDGPU_CUDA(cudaGetLastError());
+  EDGPU_CUDA(cudaStreamSynchronize(g.stream));
+  cudaFree(vfull);
+  cudaFree(map);
+  cudaFree(lin.ja);
+  cudaFree(lin.jb);
+  return 0;
+}
+
+int edgpu_apply_ops_normal(int slot, int nops, const double *coef, int op, const int *iorb, int spin) {
+  clear_error();
+  if (!g.sec.open) return set_error("no NORMAL sector open");
+  auto it = g_states.find(slot);
+  if (it == g_states.end()) return set_error("state slot %d is empty", slot);
+  StoredState &st = it->second;
+  if (st.kind != 0) return set_error("state %d belongs to a nonsu2/superc sector", slot);
+  Sector &S = g.sec;
+  if (nops < 1 || nops > EDGPU_MAXORB || !coef || !iorb) return set_error("apply_ops_normal: 1..%d operators", EDGPU_MAXORB);
+  if (op != 1 && op != -1) return set_error("op must be +1 (CDG) or -1 (C)");
+  if (spin != 0 && spin != 1) return set_error("spin must be 0 or 1");
+  for (int k = 0; k < nops; k++)
+    if (iorb[k] < 0 || iorb[k] >= S.Norb) return set_error("iorb out of range");
+  const int tnup = st.nup + (spin == 0 ? op : 0), tndw = st.ndw + (spin == 1 ? op : 0);
+  if (S.Ns != st.Ns || S.up.nel != tnup || S.dw.nel != tndw)
+    return set_error("open sector (%d,%d) is not the target sector (%d,%d) of the operators", S.up.nel,
+                     S.dw.nel, tnup, tndw);
+  if (st.dimph != S.DimPh)
+    return set_error("state %d has %d phonon slices, the open sector %d", slot, st.dimph, S.DimPh);
+  const int nel_src = spin == 0 ? st.nup : st.ndw;
+  int32_t *map = nullptr;
+  LinTable lin;
+  SiteOrder ord;
+  EDGPU_TRY(species_ranking(g, S.prm, spin, nel_src, &map, &lin, &ord));
+  const int64_t n = S.padded_len();
+  EDGPU_TRY(ensure_buf(&g_seed, &g_seed_len, n));
+  EDGPU_CUDA(cudaMemsetAsync(g_seed, 0, sizeof(double) * n, g.stream));
+  const double *vsrc = st.vec;
+  double *vfull = nullptr;
+  int64_t src_slice = st.ldu * st.qdw;
+  if (g.nranks > 1 && spin == 1) {  // as edgpu_apply_op: the dw operators need every source column
+    std::vector<int64_t> counts(g.nranks), offs(g.nranks);
+    for (int p = 0; p < g.nranks; p++) {
+      int64_t q, d0;
+      block_split(st.dimd, g.nranks, p, &q, &d0);
+      counts[p] = q * st.ldu;
+      offs[p] = d0 * st.ldu;
+    }
+    const int64_t full_slice = st.dimd * st.ldu;
+    EDGPU_CUDA(cudaMalloc(&vfull, sizeof(double) * (size_t)full_slice * (size_t)st.dimph));
+    for (int iph = 0; iph < st.dimph; iph++)
+      EDGPU_TRY(comm_allgatherv(g, st.vec + iph * src_slice, vfull + iph * full_slice, counts, offs));
+    vsrc = vfull;
+    src_slice = full_slice;
+  }
+  dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
+  for (int k = 0; k < nops; k++)
+    for (int iph = 0; iph < S.DimPh; iph++) {
+      k_apply_op_acc<<<grid, 128, 0, g.stream>>>(vsrc + iph * src_slice, st.ldu, g_seed + iph * S.slice_len(),
+                                                 S.up.ld, S.up.dim, S.qdw,
+                                                 spin == 0 ? S.up.map : S.dw.map + S.d0, op, iorb[k], spin,
+                                                 rank_view(lin, ord), coef[k]);
+      EDGPU_COUNT_LAUNCH();
+    }
   EDGPU_CUDA(cudaGetLastError());
   EDGPU_CUDA(cudaStreamSynchronize(g.stream));
   cudaFree(vfull);

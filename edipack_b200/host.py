@@ -885,6 +885,14 @@ def apply_op(slot: int, op: int, iorb: int, spin: int):
     check(_abi.load().edgpu_apply_op(slot, op, iorb, spin))
 
 
+def apply_Cops_normal(slot: int, coefs, op: int, iorbs, spin: int):
+    """apply_Cops in NORMAL mode (lanc_build_gf_normal_mix, ED_GF_NORMAL.f90:211,227): device seed
+    sum_k coefs[k] O_k |state(slot)>, all O_k = c^+ (op=+1) / c (op=-1) of one spin."""
+    cf = np.ascontiguousarray(np.asarray(coefs, np.float64))
+    a = np.ascontiguousarray(iorbs, np.int32)
+    check(_abi.load().edgpu_apply_ops_normal(slot, len(a), ptr(cf), op, ptr(a), spin))
+
+
 def apply_Cops(slot: int, coefs, ops, iorbs, spins):
     """apply_COps (ED_SECTOR.f90): device seed sum_k coefs[k] * O_k |state(slot)> in the open
     device-built nonsu2 / superc sector; ops[k] = +1 (c^+) / -1 (c), spins[k] = 0 up / 1 dw."""
@@ -1213,3 +1221,97 @@ def lanc_build_gf_normal_diag(model: EDModel, states, iorb: int, ispin: int = 0)
             for j in range(nused):
                 out.append((norm2 * peso * Z[0, j] ** 2, isign * (ev[j] - st.e)))
     return out
+
+
+def lanc_build_gf_normal_mix(model: EDModel, states, iorb: int, jorb: int, ispin: int = 0):
+    """ED_GF_NORMAL.f90:182-262 (real case): poles / weights of the auxiliary function from the
+    seeds (c^+_a + c^+_b)|gs> and (c_a + c_b)|gs>, built on the device (apply_Cops_normal)."""
+    out = []
+    Ns = model.Ns
+    for st, peso in zip(states, boltzmann_weights(model, states)):
+        for op, isign in ((+1, 1), (-1, -1)):
+            jn = (st.nup + (op if ispin == 0 else 0), st.ndw + (op if ispin == 1 else 0))
+            if min(jn) < 0 or max(jn) > Ns:
+                continue
+            build_Hv_sector_normal(model, jn[0], jn[1])
+            try:
+                apply_Cops_normal(st.slot, [1.0, 1.0], op, [iorb, jorb], ispin)
+                dim = binomial(Ns, jn[0]) * binomial(Ns, jn[1])
+                a, b, nused, norm2 = sp_lanc_tridiag(None, min(dim, model.lanc_ngfiter))
+            finally:
+                delete_Hv_sector_normal()
+            if norm2 == 0.0 or nused == 0:
+                continue
+            ev, Z = tridiag_eigh(a[:nused], b[1:nused])
+            for j in range(nused):
+                out.append((norm2 * peso * Z[0, j] ** 2, isign * (ev[j] - st.e)))
+    return out
+
+
+def _gf_eval(pw, z):
+    g = np.zeros(len(z), complex)
+    for w, p in pw:
+        g += w / (z - p)
+    return g
+
+
+def get_impG_normal(model: EDModel, states, z, ispin: int = 0):
+    """get_impG_normal (ED_GF_NORMAL.f90:495-575) with offdiag_gf_flag: G_aa from the diagonal
+    builder, G_ab = G_ba = (G_{a+b} - G_aa - G_bb)/2 (:553-560).  [Norb, Norb, len(z)]."""
+    No = model.Norb
+    z = np.asarray(z, complex)
+    G = np.zeros((No, No, len(z)), complex)
+    for a in range(No):
+        G[a, a] = _gf_eval(lanc_build_gf_normal_diag(model, states, a, ispin), z)
+    offdiag = model.bath_type != "normal"   # offdiag_gf_flag defaults to T for bath_type /= normal
+    for a in range(No):
+        for b in range(a + 1, No):
+            if not offdiag:
+                continue
+            mix = _gf_eval(lanc_build_gf_normal_mix(model, states, a, b, ispin), z)
+            G[a, b] = G[b, a] = 0.5 * (mix - G[a, a] - G[b, b])
+    return G
+
+
+def delta_bath_array(model: EDModel, z, ispin: int = 0):
+    """delta_bath_array, ed_mode=normal (ED_BATH/delta_functions: delta_normal.f90:33-42,
+    delta_hybrid.f90:30-41, delta_replica.f90:27-38 / delta_general.f90).  [Norb, Norb, len(z)]."""
+    No, Nb = model.Norb, model.Nbath
+    if model.bath_e is None:
+        model.init_dmft_bath()
+    z = np.asarray(z, complex)
+    D = np.zeros((No, No, len(z)), complex)
+    if model.bath_type == "normal":
+        for a in range(No):
+            D[a, a] = (model.bath_v[ispin, a][None, :] ** 2 / (z[:, None] - model.bath_e[ispin, a][None, :])).sum(1)
+    elif model.bath_type == "hybrid":
+        e = model.bath_e[ispin, 0]
+        for a in range(No):
+            for b in range(No):
+                D[a, b] = (model.bath_v[ispin, a][None, :] * model.bath_v[ispin, b][None, :]
+                           / (z[:, None] - e[None, :])).sum(1)
+    else:
+        for k in range(Nb):
+            Hk = np.asarray(model.hbath)[ispin, :, :, k]
+            V = np.diag(model.bath_v[ispin, :, k])
+            for i, zi in enumerate(z):
+                D[:, :, i] += V @ np.linalg.inv(zi * np.eye(No) - Hk) @ V
+    return D
+
+
+def get_Sigma_normal(model: EDModel, states, Lmats: int, ispin: int = 0):
+    """get_Sigma_normal (ED_GF_NORMAL.f90:698-739) on the Matsubara axis: Sigma = G0^-1 - G^-1 with
+    G0^-1 = (z+xmu) 1 - impHloc - Delta (invg0_normal.f90 / invg0_hyrege.f90:22-30); G is inverted
+    as an orbital matrix when bath_type /= normal (:726-729).  Returns (wm, Sigma[Norb,Norb,Lmats])."""
+    wm = math.pi / model.beta * (2 * np.arange(1, Lmats + 1) - 1)
+    z = 1j * wm
+    No = model.Norb
+    G = get_impG_normal(model, states, z, ispin)
+    D = delta_bath_array(model, z, ispin)
+    hl = np.zeros((No, No)) if model.hloc is None else np.asarray(model.hloc[ispin], float)
+    S = np.zeros_like(G)
+    for i, zi in enumerate(z):
+        invg0 = (zi + model.xmu) * np.eye(No) - hl - D[:, :, i]
+        invg = np.diag(1.0 / np.diag(G[:, :, i])) if model.bath_type == "normal" else np.linalg.inv(G[:, :, i])
+        S[:, :, i] = invg0 - invg
+    return wm, S

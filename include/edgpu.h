@@ -310,6 +310,12 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin);
  * <seed|seed> (all-reduced) of the device-resident seed. */
 int edgpu_apply_ops_packed(int slot, int nops, const double *coef_re_im, const int *op, const int *iorb,
                            const int *spin);
+/* apply_Cops in NORMAL mode (ED_SECTOR.f90 apply_Cops; lanc_build_gf_normal_mix,
+ * ED_GF_NORMAL.f90:211,227: vvinit = apply_Cops(v_state,[1,1],[+-1,+-1],[iorb,jorb],[ispin,ispin],...)):
+ * the device-resident seed sum_k coef[k] O_k |state>, every O_k = c^+ (op=+1) or c (op=-1) of the
+ * same spin on impurity orbital iorb[k] (0-based), in the layout of the OPEN sector, which must be
+ * the common target sector.  Needed for the off-diagonal impurity Green's function G_ab. */
+int edgpu_apply_ops_normal(int slot, int nops, const double *coef, int op, const int *iorb, int spin);
 int edgpu_seed_norm2(double *norm2);
 /* Twin states (ED_TWIN=T): es_return_dvector / es_return_cvector for a state with itwin set
  * (ED_EIGENSPACE.f90:640-660, 723-793) = the eigenvector of the twin sector re-ordered by

@@ -983,6 +983,95 @@ def gf_poles_weights(model: Model, states, iorb: int, spin: int = 0, hxv_kind="d
     return out
 
 
+def gf_poles_weights_mix(model: Model, states, iorb: int, jorb: int, spin: int = 0,
+                         hxv_kind="direct", weights=None):
+    """lanc_build_gf_normal_mix (ED_GF_NORMAL.f90:182-262, real case): poles / weights of the
+    auxiliary function built from the seeds (c^+_a + c^+_b)|gs> and (c_a + c_b)|gs>
+    (apply_Cops with coefficients [1,1]); G_ab follows from get_impG_normal (:545-560)."""
+    fn = stored_hxv if hxv_kind == "stored" else direct_hxv
+    if weights is None:
+        weights = [1.0 / len(states)] * len(states)
+    out = []
+    for st, peso in zip(states, weights):
+        for op, isign in ((+1, 1), (-1, -1)):
+            sa, jn = apply_op(model, op, iorb, spin, st.nup, st.ndw, st.vec)
+            sb, _ = apply_op(model, op, jorb, spin, st.nup, st.ndw, st.vec)
+            if sa is None:
+                continue
+            seed = sa + sb
+            norm2 = float(seed @ seed)
+            if norm2 == 0.0:
+                continue
+            seed = seed / math.sqrt(norm2)
+            nlanc = min(len(seed), model.lanc_ngfiter)
+            a, b, nused = lanc_tridiag(lambda x: fn(model, jn[0], jn[1], x), seed, nlanc)
+            ev, Z = tridiag_eigh(a[:nused], b[1:nused])
+            for j in range(nused):
+                out.append((norm2 * peso * Z[0, j] ** 2, isign * (ev[j] - st.e)))
+    return out
+
+
+def impG_matrix(model: Model, states, spin: int, z, weights=None):
+    """get_impG_normal (ED_GF_NORMAL.f90:495-575) with offdiag_gf_flag: G_aa from the diagonal
+    builder, G_ab = (G_{a+b} - G_aa - G_bb)/2 = G_ba (real case, :553-560).  Returns [Norb,Norb,len(z)]."""
+    No = model.Norb
+    G = np.zeros((No, No, len(z)), complex)
+    for a in range(No):
+        G[a, a] = gf_eval(gf_poles_weights(model, states, a, spin, weights=weights), z)
+    for a in range(No):
+        for b in range(a + 1, No):
+            mix = gf_eval(gf_poles_weights_mix(model, states, a, b, spin, weights=weights), z)
+            G[a, b] = G[b, a] = 0.5 * (mix - G[a, a] - G[b, b])
+    return G
+
+
+def delta_matrix(model: Model, spin: int, z):
+    """delta_bath_array (ED_BATH/delta_functions, ed_mode=normal): normal -> diagonal
+    sum_k V_ak^2/(z-e_ak) (delta_normal.f90:33-42); hybrid -> sum_k V_ak V_bk/(z-e_k)
+    (delta_hybrid.f90:30-41); replica / general -> sum_k V_k (z - H_k)^-1 V_k (delta_replica.f90:27-38,
+    delta_general.f90, V_k = diag(vg))."""
+    No, Nb = model.Norb, model.Nbath
+    if model.bath_e is None:
+        model.default_bath()
+    D = np.zeros((No, No, len(z)), complex)
+    if model.bath_type == "normal":
+        for a in range(No):
+            D[a, a] = (model.bath_v[spin, a][None, :] ** 2 / (z[:, None] - model.bath_e[spin, a][None, :])).sum(1)
+    elif model.bath_type == "hybrid":
+        e = model.bath_e[spin, 0]
+        for a in range(No):
+            for b in range(No):
+                D[a, b] = (model.bath_v[spin, a][None, :] * model.bath_v[spin, b][None, :] / (z[:, None] - e[None, :])).sum(1)
+    else:
+        for k in range(Nb):
+            Hk = model.hbath[spin, :, :, k]
+            V = np.diag(model.bath_v[spin, :, k])
+            for i, zi in enumerate(z):
+                D[:, :, i] += V @ np.linalg.inv(zi * np.eye(No) - Hk) @ V
+    return D
+
+
+def sigma_matrix_matsubara(model: Model, states, spin: int, Lmats: int, weights=None):
+    """get_Sigma_normal (ED_GF_NORMAL.f90:698-739): Sigma = G0^-1 - G^-1 with
+    G0^-1 = (z+xmu) 1 - impHloc - Delta (invg0_hyrege.f90:22-30), G inverted as an orbital matrix for
+    bath_type /= normal (:726-729).  Returns (wm, Sigma[Norb,Norb,Lmats])."""
+    wm = math.pi / model.beta * (2 * np.arange(1, Lmats + 1) - 1)
+    z = 1j * wm
+    No = model.Norb
+    G = impG_matrix(model, states, spin, z, weights)
+    D = delta_matrix(model, spin, z)
+    hl = np.zeros((No, No)) if model.hloc is None else np.asarray(model.hloc[spin], float)
+    S = np.zeros_like(G)
+    for i, zi in enumerate(z):
+        invg0 = (zi + model.xmu) * np.eye(No) - hl - D[:, :, i]
+        if model.bath_type == "normal":
+            invg = np.diag(1.0 / np.diag(G[:, :, i]))
+        else:
+            invg = np.linalg.inv(G[:, :, i])
+        S[:, :, i] = invg0 - invg
+    return wm, S
+
+
 def gf_eval(pw, z):
     g = np.zeros_like(z, dtype=complex)
     for w, p in pw:

@@ -20,3 +20,28 @@ def test_local_energy_through_gpu(engine, name, kwf):
     finally:
         for s in states:
             E.state_free(s.slot)
+
+
+@pytest.mark.parametrize("name", ["hybrid_normal", "replica_normal"])
+def test_offdiagonal_gf_sigma_momenta_through_gpu(engine, oracle, name):
+    """Sigma_momenta.check of the shared / replica bath fixtures: needs the off-diagonal impurity GF,
+    i.e. the two-operator seeds (c_a + c_b)|gs> built on the device (edgpu_apply_ops_normal) and
+    the orbital-matrix inversion in the host mirror.  1e-8 relative (ed_hybrid_normal.f90:153)."""
+    import numpy as np
+    from models import golden, replica_normal_kwargs
+
+    E = engine
+    g = golden(name)
+    kw = hybrid_normal_kwargs() if name == "hybrid_normal" else replica_normal_kwargs("replica")
+    m = E.EDModel(**kw)
+    m.lanc_tolerance = 1e-18
+    states = E.ed_diag_d(m)
+    try:
+        wm, S = E.get_Sigma_normal(m, states, int(g["inputs"]["LMATS"]), 0)
+    finally:
+        for s in states:
+            E.state_free(s.slot)
+    gold = np.array(g["Sigma_momenta"]).reshape(m.Norb, 4)
+    for a in range(m.Norb):
+        mom = oracle.momenta(wm, S[a, a])
+        assert np.abs(mom / gold[a] - 1.0).max() < 1e-8, (name, a, mom, gold[a])
