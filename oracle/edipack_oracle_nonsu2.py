@@ -340,3 +340,50 @@ def twin_sector_order(Ns: int, Ntot: int):
     smap = build_sector(Ns, Ntot)
     flipped = (~smap) & ((1 << (2 * Ns)) - 1)
     return np.argsort(flipped, kind="stable")
+
+
+def _energy_variants(model):
+    """Variants of the model whose ground-state expectation values give the components of
+    local_energy_{mode} (ED_OBSERVABLES_NONSU2.f90:630-850 / ED_OBSERVABLES_SUPERC.f90): each keeps the
+    bath (and, for superc, the pairing terms) and differs from `base` by one group of impurity terms,
+    <O> = <H_variant> - <H_base>."""
+    import dataclasses
+
+    No = model.Norb
+    zero_int = dict(Uloc=(0.0,) * No, Ust=0.0, Jh=0.0, Jx=0.0, Jp=0.0)
+    common = dict(xmu=0.0, hfmode=False)
+    if hasattr(model, "spin_field"):
+        common["spin_field"] = None
+    rep = dataclasses.replace
+    return {
+        "base": rep(model, hloc=None, **zero_int, **common),
+        "eknot": rep(model, **zero_int, **common),
+        "eint": rep(model, hloc=None, **common),
+        "dust": rep(model, hloc=None, **{**zero_int, "Ust": 1.0, "Jh": 1.0}, **common),
+        "dund": rep(model, hloc=None, **{**zero_int, "Jh": -1.0}, **common),
+        "dse": rep(model, hloc=None, **{**zero_int, "Jx": 1.0}, **common),
+        "dph": rep(model, hloc=None, **{**zero_int, "Jp": 1.0}, **common),
+    }
+
+
+def local_energy(model, qn: int, vec, dens):
+    """ed_Epot, ed_Eint, ed_Ehartree, ed_Eknot, ed_Dust, ed_Dund, ed_Dse, ed_Dph of one state with
+    weight 1 (local_energy of this mode), every component as <v|O|v> of a term-restricted stored H."""
+    acc = {}
+    for k, mv in _energy_variants(model).items():
+        smap, rp, cj, va = stored_H(mv, qn)
+        acc[k] = float(np.vdot(vec, csr_matvec(rp, cj, va, vec)).real)
+    out = {("D" + k[1:]) if k.startswith("d") else ("E" + k[1:]): acc[k] - acc["base"] for k in acc if k != "base"}
+    eh = 0.0
+    if model.hfmode:
+        No = model.Norb
+        U = np.asarray(model.Uloc, float)
+        for a in range(No):
+            eh += -0.5 * U[a] * dens[a] + 0.25 * U[a]
+        for a in range(No):
+            for b in range(a + 1, No):
+                for c in (model.Ust, model.Ust - model.Jh):
+                    eh += -0.5 * c * (dens[a] + dens[b]) + 0.5 * c
+    out["Ehartree"] = eh
+    out["Epot"] = out["Eint"] + eh
+    return out

@@ -53,3 +53,42 @@ def test_host_mirror_builds_the_same_variants(oracle):
     assert list(a) == list(b)
     for k in a:
         assert bytes(a[k].params()) == bytes(b[k].params()), k
+
+
+def _ground_state(N, mod, m, qns):
+    best = None
+    for q in qns:
+        smap, rp, cj, va = mod.stored_H(m, q)
+        ev, U = np.linalg.eigh(N.to_dense(rp, cj, va))
+        if best is None or ev[0] < best[0]:
+            best = (ev[0], q, smap, U[:, 0])
+    return best
+
+
+@pytest.mark.parametrize("name", ["hybrid_nonsu2", "normal_nonsu2", "replica_nonsu2", "general_nonsu2",
+                                  "normal_superc", "hybrid_superc", "replica_superc", "general_superc"])
+def test_energy_and_doubles_goldens_packed_modes(name):
+    """energy.check / doubles.check of the eight nonsu2 / superc fixtures (local_energy_nonsu2 /
+    _superc): spin-flip Hloc in Eknot, S-E / P-H chains on the packed state in Epot, Dse, Dph.
+    nonsu2 1e-8; superc 5e-8 (fixtures produced from an ARPACK vector, see
+    tests/test_oracle_golden_superc.py)."""
+    import edipack_oracle_nonsu2 as N
+    import edipack_oracle_superc as S
+    from models import hybrid_nonsu2_model, replica_nonsu2_model, replica_superc_model, superc_model
+
+    kind, mode = name.split("_")
+    g = golden(name)
+    if mode == "nonsu2":
+        m = replica_nonsu2_model(N, kind) if kind in ("replica", "general") else hybrid_nonsu2_model(N, name)
+        e, q, smap, v = _ground_state(N, N, m, (5, 6, 7))
+        dens, _, _ = N.observables(m, smap, v)
+        got, tol = N.local_energy(m, q, v, dens), 1e-8
+    else:
+        m = replica_superc_model(S, kind) if kind in ("replica", "general") else superc_model(S, name)
+        e, q, smap, v = _ground_state(N, S, m, (-1, 0, 1))
+        dens, _, _ = S.observables(m, q, smap, v)
+        got, tol = S.local_energy(m, q, v, dens), 5e-8
+    energy = np.array([got["Epot"], got["Eint"], got["Eknot"], got["Ehartree"]])
+    doubles = np.array([got["Dust"], got["Dund"], got["Dse"], got["Dph"]])
+    assert np.abs(energy - np.array(g["energy"])).max() < tol, (energy, g["energy"])
+    assert np.abs(doubles - np.array(g["doubles"])).max() < tol, (doubles, g["doubles"])
