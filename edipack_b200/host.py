@@ -1189,6 +1189,20 @@ def local_energy_normal(model: EDModel, states):
     return out
 
 
+def imp_info(model: EDModel, states, energies=None, dens=None, docc=None):
+    """ed_imp_info = [s2tot, egs] (ED_OBSERVABLES_NORMAL.f90:180, 452).  s2tot = <(sum_a S^z_a)^2>
+    is a combination of quantities already evaluated on the device:
+    (sum_a sz_a)^2 = 1/4 [ sum_a (n_a - 2 nup_a ndw_a) + 2 sum_{a<b} (nup_a nup_b + ndw_a ndw_b)
+                                                         - 2 sum_{a<b} (nup_a ndw_b + nup_b ndw_a) ]
+                   = 1/4 [ sum_a (dens_a - 2 docc_a) + 2 (Dund - Dust) ]."""
+    if energies is None:
+        energies = local_energy_normal(model, states)
+    if dens is None or docc is None:
+        dens, docc = observables_normal(model, states)
+    s2 = 0.25 * (float(np.sum(dens - 2.0 * docc)) + 2.0 * (energies["Dund"] - energies["Dust"]))
+    return np.array([s2, min(s.e for s in states)])
+
+
 def tridiag_eigh(a, b_sub):
     """eigh(diag,subdiag,Ev=Z) of ED_GF_NORMAL.f90:416 (host, tiny)."""
     n = len(a)

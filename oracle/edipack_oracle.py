@@ -958,6 +958,23 @@ def local_energy(model: Model, states, weights=None):
     return out
 
 
+def imp_info(model: Model, states, weights=None):
+    """ed_imp_info = [s2tot, egs] (ED_OBSERVABLES_NORMAL.f90:180, 452): s2tot = <(sum_a S^z_a)^2>
+    with S^z_a = (nup_a - ndw_a)/2 (:160-164), egs = lowest energy of the state list."""
+    Ns, No = model.Ns, model.Norb
+    if weights is None:
+        weights = [1.0 / len(states)] * len(states)
+    s2 = 0.0
+    for st, peso in zip(states, weights):
+        mu, md = build_map(Ns, st.nup), build_map(Ns, st.ndw)
+        w = (st.vec ** 2).reshape(len(md), len(mu)) * peso
+        sz = np.zeros((len(md), len(mu)))
+        for a in range(No):
+            sz += 0.5 * (((mu >> a) & 1).astype(float)[None, :] - ((md >> a) & 1).astype(float)[:, None])
+        s2 += float((w * sz ** 2).sum())
+    return np.array([s2, min(s.e for s in states)])
+
+
 def gf_poles_weights(model: Model, states, iorb: int, spin: int = 0, hxv_kind="direct",
                      weights=None):
     """lanc_build_gf_normal_diag + add_to_lanczos_gf_normal (ED_GF_NORMAL.f90:131-177,

@@ -33,6 +33,22 @@ def test_energy_and_doubles_goldens(oracle, name):
     check(name, oracle.local_energy(m, states))
 
 
+@pytest.mark.parametrize("name", list(FIXTURES))
+def test_imp_info_golden(oracle, name):
+    """imp.check = ed_imp_info = [<(sum_a S^z_a)^2>, E_gs]; the host mirror's identity in terms of
+    dens / docc / Dust / Dund is checked with the oracle's numbers."""
+    import edipack_b200.host as H
+
+    g = golden(name)
+    m = oracle.Model(**FIXTURES[name]())
+    states = oracle.diagonalize(m)
+    got = oracle.imp_info(m, states)
+    assert np.abs(got - np.array(g["imp"])).max() < 1e-9
+    dens, docc = oracle.observables(m, states)
+    via = H.imp_info(H.EDModel(**FIXTURES[name]()), states, oracle.local_energy(m, states), dens, docc)
+    assert np.abs(via - np.array(g["imp"])).max() < 1e-9
+
+
 def test_energy_with_umatrix_operators(oracle):
     """The same goldens with the interaction given as the driver's operator list
     (ED_READ_UMATRIX / ed_add_twobody_operator route, ED_USE_KANAMORI=F)."""
