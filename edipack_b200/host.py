@@ -1087,6 +1087,31 @@ def observables_packed(model, states):
     return dens, docc
 
 
+def exciton_nonsu2(model, st, iorb: int = 0, jorb: int = 1):
+    """Excitonic order parameters [S0, Tx, Ty, Tz](iorb,jorb) of one stored nonsu2 state (weight 1),
+    ED_OBSERVABLES_NONSU2.f90:300-425: every term is the norm of a device-built seed
+    apply_Cops(v,[1,c],[-1,-1],[a,b],[s,s']) in the sector Ntot-1 (<n_{a s}> = |c_{a s} v|^2 gives
+    dens and magZ the same way)."""
+    build_Hv_sector_nonsu2(model, st.nup - 1)
+    try:
+        def n2(coefs, orbs, spins):
+            apply_Cops(st.slot, coefs, [-1] * len(orbs), orbs, spins)
+            return seed_norm2()
+
+        occ = {(a, s): n2([1.0], [a], [s]) for a in (iorb, jorb) for s in (0, 1)}
+        th_uu, th_dd = n2([1, 1], [iorb, jorb], [0, 0]), n2([1, 1], [iorb, jorb], [1, 1])
+        th_ud, th_du = n2([1, 1], [iorb, jorb], [0, 1]), n2([1, 1], [iorb, jorb], [1, 0])
+        om_ud, om_du = n2([1, -1j], [iorb, jorb], [0, 1]), n2([1, -1j], [iorb, jorb], [1, 0])
+    finally:
+        delete_Hv_sector_csr()
+    dens = {a: occ[a, 0] + occ[a, 1] for a in (iorb, jorb)}
+    magz = {a: occ[a, 0] - occ[a, 1] for a in (iorb, jorb)}
+    return np.array([th_uu + th_dd - dens[iorb] - dens[jorb],
+                     th_ud + th_du - dens[iorb] - dens[jorb],
+                     om_ud - om_du - magz[iorb] + magz[jorb],
+                     th_uu - th_dd - magz[iorb] - magz[jorb]])
+
+
 def boltzmann_weights(model: EDModel, states):
     """Weights of the state list: 1/zeta at T=0 (zeta = number of kept states,
     ED_DIAG_NORMAL.f90:405-414), exp(-beta (E_i - E_gs)) / zeta at finite temperature."""

@@ -387,3 +387,36 @@ def local_energy(model, qn: int, vec, dens):
     out["Ehartree"] = eh
     out["Epot"] = out["Eint"] + eh
     return out
+
+
+def exciton(model: ModelNonsu2, Ntot: int, smap, vec, iorb: int = 0, jorb: int = 1):
+    """Excitonic order parameters [S0, Tx, Ty, Tz](iorb,jorb) of one state with weight 1
+    (ED_OBSERVABLES_NONSU2.f90:300-425): norms of the seeds apply_Cops(v,[1,c],[-1,-1],[a,b],[s,s'])
+    in the sector Ntot-1, combined with dens and magZ (:420-423)."""
+    Ns = model.Ns
+    tmap = build_sector(Ns, Ntot - 1)
+    tindex = {int(m): i for i, m in enumerate(tmap)}
+
+    def seed_norm2(ca, sa, cb, sb):
+        eta = np.zeros(len(tmap), complex)
+        for i, m_ in enumerate(smap):
+            m = int(m_)
+            for coef, orb, spin in ((ca, iorb, sa), (cb, jorb, sb)):
+                r = _c(orb + 1 + spin * Ns, m)
+                if r is not None:
+                    eta[tindex[r[0]]] += coef * r[1] * vec[i]
+        return float(np.vdot(eta, eta).real)
+
+    w = np.abs(vec) ** 2
+    nu = [((smap >> a) & 1).astype(float) for a in range(model.Norb)]
+    nd = [((smap >> (a + Ns)) & 1).astype(float) for a in range(model.Norb)]
+    dens = [float((w * (nu[a] + nd[a])).sum()) for a in range(model.Norb)]
+    magz = [float((w * (nu[a] - nd[a])).sum()) for a in range(model.Norb)]
+    th_uu, th_dd = seed_norm2(1, 0, 1, 0), seed_norm2(1, 1, 1, 1)
+    th_ud, th_du = seed_norm2(1, 0, 1, 1), seed_norm2(1, 1, 1, 0)
+    om_ud, om_du = seed_norm2(1, 0, -1j, 1), seed_norm2(1, 1, -1j, 0)
+    a, b = iorb, jorb
+    return np.array([th_uu + th_dd - dens[a] - dens[b],      # S0
+                     th_ud + th_du - dens[a] - dens[b],      # Tx
+                     om_ud - om_du - magz[a] + magz[b],      # Ty
+                     th_uu - th_dd - magz[a] - magz[b]])     # Tz

@@ -102,3 +102,5 @@ def test_replica_general_nonsu2_golden(kind):
     dens, docc, _ = N.observables(m, smap, v)
     assert np.abs(dens - np.array(g["dens"])).max() < 1e-8
     assert np.abs(docc - np.array(g["docc"])).max() < 1e-8
+    # exciton.check = [S0, Tx, Ty, Tz](1,2): norms of two-operator seeds (apply_Cops)
+    assert np.abs(N.exciton(m, nt, smap, v) - np.array(g["exciton"])).max() < 1e-8

@@ -45,3 +45,25 @@ def test_offdiagonal_gf_sigma_momenta_through_gpu(engine, oracle, name):
     for a in range(m.Norb):
         mom = oracle.momenta(wm, S[a, a])
         assert np.abs(mom / gold[a] - 1.0).max() < 1e-8, (name, a, mom, gold[a])
+
+
+def test_exciton_order_parameters_nonsu2_through_gpu(engine):
+    """exciton.check of REPLICA_NONSU2: sector map, stored H, eigen-solver and the two-operator
+    seeds (edgpu_apply_ops_packed) all on the device; 1e-8."""
+    import numpy as np
+    import edipack_oracle_nonsu2 as N
+    from models import golden, replica_nonsu2_model
+
+    E = engine
+    g = golden("replica_nonsu2")
+    mo = replica_nonsu2_model(N, "replica")
+    m = E.EDModelNonsu2(**vars(mo))
+    states = E.ed_diag_c(m, qns=(5, 6, 7), tol=1e-16)
+    try:
+        assert len(states) == 1 and states[0].nup == 6
+        assert abs(states[0].e - g["evals"][0]) < 1e-9
+        got = E.exciton_nonsu2(m, states[0])
+    finally:
+        for s in states:
+            E.state_free(s.slot)
+    assert np.abs(got - np.array(g["exciton"])).max() < 1e-8
