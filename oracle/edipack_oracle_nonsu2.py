@@ -420,3 +420,94 @@ def exciton(model: ModelNonsu2, Ntot: int, smap, vec, iorb: int = 0, jorb: int =
                      th_ud + th_du - dens[a] - dens[b],      # Tx
                      om_ud - om_du - magz[a] + magz[b],      # Ty
                      th_uu - th_dd - magz[a] - magz[b]])     # Tz
+
+
+def lehmann_G(model: ModelNonsu2, Ntot: int, smap, vec, e0: float, z):
+    """Exact impurity Green's function matrix of one state with weight 1 from the Lehmann
+    representation (dense diagonalisation of the Ntot+1 and Ntot-1 sectors):
+      G_ab(z) = <0|c_a (z - H + E0)^-1 c^+_b|0> + <0|c^+_b (z + H - E0)^-1 c_a|0>,
+    a = (spin, orbital) -> index orbital + spin*Norb.  What build_impG_nonsu2 (ED_GF_NONSU2.f90)
+    obtains from Lanczos continued fractions and their algebraic combinations.  [2No, 2No, len(z)]."""
+    Ns, No = model.Ns, model.Norb
+    z = np.asarray(z, complex)
+    G = np.zeros((2 * No, 2 * No, len(z)), complex)
+    bits = [a + sp * Ns for sp in range(2) for a in range(No)]
+    for create in (True, False):
+        nt = Ntot + (1 if create else -1)
+        if nt < 0 or nt > 2 * Ns:
+            continue
+        tmap, rp, cj, va = stored_H(model, nt)
+        ev, U = np.linalg.eigh(to_dense(rp, cj, va))
+        tindex = {int(m): i for i, m in enumerate(tmap)}
+        amps = []
+        for b in bits:
+            seed = np.zeros(len(tmap), complex)
+            for i, m_ in enumerate(smap):
+                r = (_cdg if create else _c)(b + 1, int(m_))
+                if r is not None:
+                    seed[tindex[r[0]]] += r[1] * vec[i]
+            amps.append(U.conj().T @ seed)          # <n| O_b |0>
+        A = np.array(amps)                          # [2No, n]
+        w = ev - e0
+        for i, zi in enumerate(z):
+            if create:   # sum_n conj(P_a^n) P_b^n / (z - w_n),  P_b^n = <n|c^+_b|0>
+                G[:, :, i] += (A.conj() / (zi - w)[None, :]) @ A.T
+            else:        # sum_m conj(Q_b^m) Q_a^m / (z + w_m),  Q_a^m = <m|c_a|0>
+                G[:, :, i] += (A / (zi + w)[None, :]) @ A.conj().T
+    return G
+
+
+def delta_matrix(model: ModelNonsu2, z):
+    """delta_bath_array for ed_mode=nonsu2 (delta_normal.f90:62-77, delta_hybrid.f90:74-91):
+    Delta(s,s',a,b) = sum_{h,k} W(s,h,a,k) W(s',h,b,k) / (z - e(h,k)), W(s,s)=v(s), W(up,dw)=u(up),
+    W(dw,up)=u(dw) (get_Whyb_matrix, ED_BATH_AUX.f90:75-87); normal bath: diagonal in the orbitals.
+    Index orbital + spin*Norb.  [2No, 2No, len(z)]."""
+    No, Nb = model.Norb, model.Nbath
+    z = np.asarray(z, complex)
+    if model.bath_type in ("replica", "general"):
+        # delta_replica.f90:27-38 / delta_general.f90: sum_k V_k (z - H_k)^-1 V_k on the (spin,orbital)
+        # space, H_k = nn2so(Hbath_tmp(:,:,:,:,k)), V_k = v_k (replica) or diag(vg_k) (general)
+        D = np.zeros((2 * No, 2 * No, len(z)), complex)
+        hb = np.asarray(model.hbath, complex)
+        for k in range(Nb):
+            Hk = hb[..., k].transpose(0, 2, 1, 3).reshape(2 * No, 2 * No)
+            V = np.diag(np.concatenate([model.bath_v[0, :, k], model.bath_v[1, :, k]]))
+            for i, zi in enumerate(z):
+                D[:, :, i] += V @ np.linalg.inv(zi * np.eye(2 * No) - Hk) @ V
+        return D
+    W = np.zeros((2, 2, No, Nb))
+    for sp in range(2):
+        W[sp, sp] = model.bath_v[sp]
+    W[0, 1], W[1, 0] = model.bath_u[0], model.bath_u[1]
+    D = np.zeros((2 * No, 2 * No, len(z)), complex)
+    for a in range(No):
+        for b in range(No):
+            if model.bath_type == "normal" and a != b:
+                continue
+            for s1 in range(2):
+                for s2 in range(2):
+                    for h in range(2):
+                        e = model.bath_e[h, 0 if model.bath_type == "hybrid" else a]
+                        D[a + s1 * No, b + s2 * No] += (W[s1, h, a][None, :] * W[s2, h, b][None, :]
+                                                        / (z[:, None] - e[None, :])).sum(1)
+    return D
+
+
+def sigma_matsubara(model: ModelNonsu2, Ntot: int, smap, vec, e0: float, beta: float, Lmats: int):
+    """Sigma = G0^-1 - G^-1 as (spin,orbital) matrices (get_Sigma_nonsu2; invg0_hyrege.f90 nonsu2
+    branch: G0^-1 = (z+xmu) 1 - impHloc - Delta).  Returns (wm, Sigma[2No,2No,Lmats])."""
+    No = model.Norb
+    wm = math.pi / beta * (2 * np.arange(1, Lmats + 1) - 1)
+    z = 1j * wm
+    G = lehmann_G(model, Ntot, smap, vec, e0, z)
+    D = delta_matrix(model, z)
+    hl = np.zeros((2 * No, 2 * No), complex)
+    if model.hloc is not None:
+        h = np.asarray(model.hloc, complex)
+        for s1 in range(2):
+            for s2 in range(2):
+                hl[s1 * No:(s1 + 1) * No, s2 * No:(s2 + 1) * No] = h[s1, s2]
+    S = np.zeros_like(G)
+    for i, zi in enumerate(z):
+        S[:, :, i] = (zi + model.xmu) * np.eye(2 * No) - hl - D[:, :, i] - np.linalg.inv(G[:, :, i])
+    return wm, S

@@ -11,8 +11,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def read(path):
+    """Real arrays as floats; complex ones (Fortran list-directed "(re,im)") as [re, im] pairs."""
+    out = []
     with open(path) as f:
-        return [float(x) for x in f.read().split()]
+        for x in f.read().split():
+            if x.startswith("("):
+                re_, im_ = x.strip("()").split(",")
+                out.append([float(re_), float(im_)])
+            else:
+                out.append(float(x))
+    return out
 
 
 def inputs(path):
@@ -68,8 +76,12 @@ def main():
     for name in checks:
         d = os.path.join(REF, name)
         g = {"source": f"test/src/{name}", "inputs": inputs(os.path.join(d, "inputED.in"))}
+        # every *.check of the directory (the tuple above names those the tests used first)
+        for f in sorted(os.listdir(d)):
+            if f.endswith(".check"):
+                g[f[:-6]] = read(os.path.join(d, f))
         for chk in checks[name]:
-            g[chk] = read(os.path.join(d, chk + ".check"))
+            assert chk in g, (name, chk)
         # the same goldens are asserted with ED_READ_UMATRIX=T (umatrix.restart) and with the
         # operators added at run time (set_twobody_hk in the driver): keep both operator lists
         um = [f for f in sorted(os.listdir(d)) if f.startswith("umatrix") and f.endswith(".restart")]

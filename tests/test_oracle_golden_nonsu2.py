@@ -104,3 +104,40 @@ def test_replica_general_nonsu2_golden(kind):
     assert np.abs(docc - np.array(g["docc"])).max() < 1e-8
     # exciton.check = [S0, Tx, Ty, Tz](1,2): norms of two-operator seeds (apply_Cops)
     assert np.abs(N.exciton(m, nt, smap, v) - np.array(g["exciton"])).max() < 1e-8
+
+
+@pytest.mark.parametrize("name", ["hybrid_nonsu2", "normal_nonsu2", "replica_nonsu2", "general_nonsu2"])
+def test_nonsu2_sigma_momenta(oracle, name):
+    """Sigma11 / Sigma12_momenta.check (hybrid, normal bath) and the full Sigma_momenta.check
+    (replica, general: all Nspin x Nspin x Norb x Norb components) at the reference's 1e-8 relative:
+    the impurity Green's function matrix from the exact Lehmann representation (dense N+-1 sectors),
+    the (spin,orbital) hybridisation matrix of every bath type and Sigma = G0^-1 - G^-1."""
+    import edipack_oracle_nonsu2 as N
+    from models import _f
+
+    g = golden(name)
+    kind = name.split("_")[0]
+    m = replica_nonsu2_model(N, kind) if kind in ("replica", "general") else hybrid_nonsu2_model(N, name)
+    best = None
+    for nt in (5, 6, 7):
+        smap, rp, cj, va = N.stored_H(m, nt)
+        ev, U = np.linalg.eigh(N.to_dense(rp, cj, va))
+        if best is None or ev[0] < best[0]:
+            best = (ev[0], nt, smap, U[:, 0])
+    e, nt, smap, v = best
+    wm, S = N.sigma_matsubara(m, nt, smap, v, e, _f(g["inputs"]["BETA"]), int(g["inputs"]["LMATS"]))
+    No = m.Norb
+    if "Sigma11_momenta" in g:
+        g11 = np.array(g["Sigma11_momenta"]).reshape(No, 4)
+        g12 = np.array(g["Sigma12_momenta"]).reshape(No, 4)
+        for a in range(No):
+            assert np.abs(oracle.momenta(wm, S[a, a]) / g11[a] - 1.0).max() < 1e-8
+            assert np.abs(oracle.momenta(wm, S[a, a + No]) / g12[a] - 1.0).max() < 1e-8
+    else:
+        gold = np.array(g["Sigma_momenta"]).reshape(2, 2, No, No, 4)   # [ispin][jspin][iorb][jorb][moment]
+        for s1 in range(2):
+            for s2 in range(2):
+                for a in range(No):
+                    for b in range(No):
+                        mom = oracle.momenta(wm, S[a + s1 * No, b + s2 * No])
+                        assert np.abs(mom / gold[s1, s2, a, b] - 1.0).max() < 1e-8, (s1, s2, a, b)
