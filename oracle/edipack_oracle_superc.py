@@ -30,7 +30,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from edipack_oracle_nonsu2 import _c, _cdg, csr_matvec
+from edipack_oracle_nonsu2 import _c, _cdg, csr_matvec, to_dense
 
 
 @dataclass
@@ -342,3 +342,91 @@ def local_energy(model, qn: int, vec, dens):
     out["Ehartree"] = eh
     out["Epot"] = out["Eint"] + eh
     return out
+
+
+def lehmann_nambu_G(model: ModelSuperc, Sz: int, smap, vec, e0: float, z):
+    """Exact Nambu Green's function of one state (weight 1) from the Lehmann representation, spinor
+    Psi = (c_{a up}, c^+_{a dw}): blocks G = <<c_up; c^+_up>>, F12 = <<c_up; c_dw>>,
+    F21 = <<c^+_dw; c^+_up>>, G22 = <<c^+_dw; c_dw>> (what build_impG_superc / get_impF_superc,
+    ED_GF_SUPERC.f90, obtain from Lanczos continued fractions).  Psi^+|0> lives in Sz+1, Psi|0> in
+    Sz-1.  Returns M[2No, 2No, len(z)]."""
+    Ns, No = model.Ns, model.Norb
+    z = np.asarray(z, complex)
+
+    def sector(q):
+        tmap, rp, cj, va = stored_H(model, q)
+        ev, U = np.linalg.eigh(to_dense(rp, cj, va))
+        return tmap, ev - e0, U, {int(x): i for i, x in enumerate(tmap)}
+
+    def amps(sec, fn, bit):
+        tmap, _, U, tidx = sec
+        seed = np.zeros(len(tmap), complex)
+        for i, m_ in enumerate(smap):
+            r = fn(bit + 1, int(m_))
+            if r is not None:
+                seed[tidx[r[0]]] += r[1] * vec[i]
+        return U.conj().T @ seed
+
+    sp, sm = sector(Sz + 1), sector(Sz - 1)
+    # Psi^+_b |0> : c^+_{b up}, c_{b dw}   (sector Sz+1);   Psi_a |0> : c_{a up}, c^+_{a dw}   (Sz-1)
+    A = np.array([amps(sp, _cdg, a) for a in range(No)] + [amps(sp, _c, a + Ns) for a in range(No)])
+    B = np.array([amps(sm, _c, a) for a in range(No)] + [amps(sm, _cdg, a + Ns) for a in range(No)])
+    M = np.zeros((2 * No, 2 * No, len(z)), complex)
+    for i, zi in enumerate(z):
+        M[:, :, i] = (A.conj() / (zi - sp[1])[None, :]) @ A.T + (B / (zi + sm[1])[None, :]) @ B.conj().T
+    return M
+
+
+def bath_nambu_functions(model: ModelSuperc, z):
+    """Delta and Fdelta on the Matsubara axis for ed_mode=superc: normal / hybrid
+    (delta_normal.f90:44-60, fdelta_normal.f90; delta_hybrid.f90:50-72, fdelta_hybrid.f90) and
+    replica / general (delta_replica.f90:40-52, fdelta_replica.f90: V_k = sigma_z (x) diag(v),
+    blocks (1,1) and (1,2) of V_k (z - H_k)^-1 V_k).  Returns (Delta, Fdelta) [No, No, len(z)]."""
+    No, Nb = model.Norb, model.Nbath
+    z = np.asarray(z, complex)
+    D = np.zeros((No, No, len(z)), complex)
+    Fd = np.zeros((No, No, len(z)), complex)
+    w2 = z.imag ** 2
+    if model.bath_type in ("normal", "hybrid"):
+        for a in range(No):
+            for b in range(No):
+                if model.bath_type == "normal" and a != b:
+                    continue
+                f = 0 if model.bath_type == "hybrid" else a
+                e, d = model.bath_e[0, f], model.bath_d[f]
+                den = w2[:, None] + e[None, :] ** 2 + d[None, :] ** 2
+                vv = model.bath_v[0, a][None, :] * model.bath_v[0, b][None, :]
+                D[a, b] = -(vv * (z[:, None] + e[None, :]) / den).sum(1)
+                Fd[a, b] = (d[None, :] * vv / den).sum(1)
+    else:
+        hb = np.asarray(model.hbath, complex)
+        for k in range(Nb):
+            Hk = hb[..., k].transpose(0, 2, 1, 3).reshape(2 * No, 2 * No)
+            Vk = np.kron(np.diag([1.0, -1.0]), np.diag(model.bath_v[0, :, k]))
+            for i, zi in enumerate(z):
+                X = Vk @ np.linalg.inv(zi * np.eye(2 * No) - Hk) @ Vk
+                D[:, :, i] += X[:No, :No]
+                Fd[:, :, i] += X[:No, No:]
+    return D, Fd
+
+
+def sigma_self_matsubara(model: ModelSuperc, Sz: int, smap, vec, e0: float, beta: float, Lmats: int):
+    """get_Sigma_superc / get_Self_superc (ED_GF_SUPERC.f90:938-1102) on the Matsubara axis:
+    Sigma = G0^-1 - [M^-1]_(1,1), Self = F0^-1 - [M^-1]_(1,2) with M the Nambu Green's function,
+    G0^-1 = (z+xmu) 1 - impHloc - Delta, F0^-1 = -impHloc_anomalous - Fdelta (invg0_*.f90, invf0_*.f90).
+    Returns (wm, Sigma[No,No,L], Self[No,No,L])."""
+    No = model.Norb
+    wm = math.pi / beta * (2 * np.arange(1, Lmats + 1) - 1)
+    z = 1j * wm
+    M = lehmann_nambu_G(model, Sz, smap, vec, e0, z)
+    D, Fd = bath_nambu_functions(model, z)
+    hl = np.zeros((No, No), complex) if model.hloc is None else np.asarray(model.hloc[0], complex)
+    an = (np.zeros((No, No), complex) if model.hloc_anomalous is None
+          else np.asarray(model.hloc_anomalous, complex))
+    Sig = np.zeros((No, No, Lmats), complex)
+    Slf = np.zeros((No, No, Lmats), complex)
+    for i, zi in enumerate(z):
+        inv = np.linalg.inv(M[:, :, i])
+        Sig[:, :, i] = (zi + model.xmu) * np.eye(No) - hl - D[:, :, i] - inv[:No, :No]
+        Slf[:, :, i] = -an - Fd[:, :, i] - inv[:No, No:]
+    return wm, Sig, Slf
