@@ -1203,98 +1203,98 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
 #define EDGPU_MARK(k) \
   if (evs && (k == 0 ? iph == 0 : iph == DimPh - 1)) cudaEventRecord(evs[k], st)
   for (int iph = 0; iph < DimPh; iph++) {
-  const double *v_s = d_v + iph * slice;
-  double *hv_s = d_hv + iph * slice;
-  EDGPU_MARK(0);
+    const double *v_s = d_v + iph * slice;
+    double *hv_s = d_hv + iph * slice;
+    EDGPU_MARK(0);
 
-  if (E.nranks == 1) {
-    if (!tiled) {
-      // one fused gather kernel: diagonal + up hops + dw hops
-      dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      k_generic<true, true><<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, S.qdw, 0, U, D, S.xud,
-                                                  nimp, (int)accum, s_acc, s_old);
-      EDGPU_COUNT_LAUNCH();
-      EDGPU_CUDA(cudaGetLastError());
-      EDGPU_MARK(1);
-      EDGPU_MARK(2);
+    if (E.nranks == 1) {
+      if (!tiled) {
+        // one fused gather kernel: diagonal + up hops + dw hops
+        dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
+        k_generic<true, true><<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, S.qdw, 0, U, D, S.xud,
+                                                    nimp, (int)accum, s_acc, s_old);
+        EDGPU_COUNT_LAUNCH();
+        EDGPU_CUDA(cudaGetLastError());
+        EDGPU_MARK(1);
+        EDGPU_MARK(2);
+      } else {
+        // pass B (diag + up hops) writes / accumulates first: it is the pass that saturates the
+        // shared-memory pipe, so the read-modify-write of Hv is left to pass A (dw hops)
+        EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc,
+                             s_old));
+        EDGPU_MARK(1);
+        if ((D.Wl4 + D.Wf4) > 0) {
+          double *part = nullptr;
+          const int64_t nblk = slow_grid_size(U, D);
+          if (dot_out && !S.nonlocal && !extras) {
+            EDGPU_TRY(ensure_partials(E, nblk));
+            part = E.d_part;
+          }
+          EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part));
+          if (part) {
+            EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
+            dot_done = true;
+          }
+        }
+        EDGPU_MARK(2);
+      }
+      if (S.nonlocal) {
+        dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
+        k_nonlocal<<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, 0, S.up.imphop, S.up.ld, S.dw.imphop,
+                                         S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
+        EDGPU_COUNT_LAUNCH();
+        EDGPU_CUDA(cudaGetLastError());
+      }
+      if (!extras) EDGPU_MARK(3);
     } else {
-      // pass B (diag + up hops) writes / accumulates first: it is the pass that saturates the
-      // shared-memory pipe, so the read-modify-write of Hv is left to pass A (dw hops)
-      EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc,
+      // dw-split over ranks (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:236-375):
+      //   Hv  = (Hd + 1 (x) Hup) v                      local columns
+      //   vt  = transpose(v)                            NCCL all-to-all of tiles
+      //   Hvt = Hdw vt                                  dw is now the fast index
+      //   Hv += transpose(Hvt)
+      // The first transpose only reads v: it runs on the communication stream concurrently with
+      // the rank-local pass (diag + up hops) on the main stream.  Phonon slices are processed one
+      // after the other like the reference's `do iph=1,DimPh` (:322-337).
+      EDGPU_CUDA(cudaEventRecord(E.ev_fork, st));
+      EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
+      {
+        cudaStream_t keep = E.stream;
+        E.stream = E.comm_stream;  // the comm_* helpers and apply_fast launch on E.stream
+        int rc = 0;
+        if (S.p2p) {
+          // push v^T into every rank's vt over NVLink, barrier, dw hops on the local vt, barrier
+          rc = comm_push_transpose(E, v_s);
+          if (!rc) rc = comm_barrier(E);
+        } else {
+          rc = comm_transpose(E, v_s, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false);
+        }
+        if (!rc)
+          rc = apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
+                          1.0);
+        if (!rc && S.p2p) rc = comm_barrier(E);
+        E.stream = keep;
+        if (rc) return rc;
+      }
+      EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
+      EDGPU_TRY(apply_fast(E, tiled, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
                            s_old));
       EDGPU_MARK(1);
-      if ((D.Wl4 + D.Wf4) > 0) {
-        double *part = nullptr;
-        const int64_t nblk = slow_grid_size(U, D);
-        if (dot_out && !S.nonlocal && !extras) {
-          EDGPU_TRY(ensure_partials(E, nblk));
-          part = E.d_part;
-        }
-        EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part));
-        if (part) {
-          EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
-          dot_done = true;
-        }
-      }
+      EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
       EDGPU_MARK(2);
-    }
-    if (S.nonlocal) {
-      dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      k_nonlocal<<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, 0, S.up.imphop, S.up.ld, S.dw.imphop,
-                                       S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
-      EDGPU_COUNT_LAUNCH();
-      EDGPU_CUDA(cudaGetLastError());
-    }
-    if (!extras) EDGPU_MARK(3);
-  } else {
-    // dw-split over ranks (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:236-375):
-    //   Hv  = (Hd + 1 (x) Hup) v                      local columns
-    //   vt  = transpose(v)                            NCCL all-to-all of tiles
-    //   Hvt = Hdw vt                                  dw is now the fast index
-    //   Hv += transpose(Hvt)
-    // The first transpose only reads v: it runs on the communication stream concurrently with
-    // the rank-local pass (diag + up hops) on the main stream.  Phonon slices are processed one
-    // after the other like the reference's `do iph=1,DimPh` (:322-337).
-    EDGPU_CUDA(cudaEventRecord(E.ev_fork, st));
-    EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
-    {
-      cudaStream_t keep = E.stream;
-      E.stream = E.comm_stream;  // the comm_* helpers and apply_fast launch on E.stream
-      int rc = 0;
-      if (S.p2p) {
-        // push v^T into every rank's vt over NVLink, barrier, dw hops on the local vt, barrier
-        rc = comm_push_transpose(E, v_s);
-        if (!rc) rc = comm_barrier(E);
-      } else {
-        rc = comm_transpose(E, v_s, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false);
+      if (S.p2p)
+        EDGPU_TRY(comm_pull_transpose_acc(E, hv_s));
+      else
+        EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, hv_s, U.dim, U.ld, S.qdw, true));
+      if (need_full) EDGPU_TRY(comm_allgatherv(E, v_s, S.vfull + iph * slice_full, S.gcounts, S.goffs));
+      if (S.nonlocal) {
+        dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
+        k_nonlocal<<<grid, 128, 0, st>>>(S.vfull + iph * slice_full, hv_s, U.dim, U.ld, S.d0, S.up.imphop,
+                                         S.up.ld, S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
+        EDGPU_COUNT_LAUNCH();
+        EDGPU_CUDA(cudaGetLastError());
       }
-      if (!rc)
-        rc = apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
-                        1.0);
-      if (!rc && S.p2p) rc = comm_barrier(E);
-      E.stream = keep;
-      if (rc) return rc;
+      if (!extras) EDGPU_MARK(3);
     }
-    EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
-    EDGPU_TRY(apply_fast(E, tiled, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
-                         s_old));
-    EDGPU_MARK(1);
-    EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
-    EDGPU_MARK(2);
-    if (S.p2p)
-      EDGPU_TRY(comm_pull_transpose_acc(E, hv_s));
-    else
-      EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, hv_s, U.dim, U.ld, S.qdw, true));
-    if (need_full) EDGPU_TRY(comm_allgatherv(E, v_s, S.vfull + iph * slice_full, S.gcounts, S.goffs));
-    if (S.nonlocal) {
-      dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-      k_nonlocal<<<grid, 128, 0, st>>>(S.vfull + iph * slice_full, hv_s, U.dim, U.ld, S.d0, S.up.imphop,
-                                       S.up.ld, S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
-      EDGPU_COUNT_LAUNCH();
-      EDGPU_CUDA(cudaGetLastError());
-    }
-    if (!extras) EDGPU_MARK(3);
-  }
   }  // phonon slices
   if (extras) {
     EDGPU_TRY(extra_hxv(E, d_v, need_full ? S.vfull : d_v, d_hv, s_acc));
