@@ -112,6 +112,17 @@ int comm_allreduce_sum(Engine &E, double *d_buf, int n) {
   return 0;
 }
 
+int comm_allreduce_host(Engine &E, double *h_buf, int n, int op) {
+  if (E.nranks == 1) return 0;
+  if (n < 1 || n > 16) return set_error("comm_allreduce_host: n=%d out of range", n);
+  double *d = E.d_scal + 40;  // scratch slots 40..55 of the scalar buffer
+  EDGPU_CUDA(cudaMemcpyAsync(d, h_buf, sizeof(double) * n, cudaMemcpyHostToDevice, E.stream));
+  EDGPU_NCCL(N.AllReduce(d, d, (size_t)n, NCCL_FLOAT64, op, (nccl_comm_t)E.nccl, E.stream));
+  EDGPU_CUDA(cudaMemcpyAsync(h_buf, d, sizeof(double) * n, cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  return 0;
+}
+
 // MPI_Allgatherv of the input vector (ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:256-259): every rank's
 // chunk lands at its offset of the full vector; unequal counts -> one grouped broadcast per rank.
 int comm_allgatherv(Engine &E, const double *d_chunk, double *d_full, const std::vector<int64_t> &counts,

@@ -261,6 +261,7 @@ struct Engine {
   // iteration) and are given back as soon as any other allocation of the library runs short
   // (dev_malloc) or on edgpu_release_cache / edgpu_finalize.
   std::vector<std::pair<double *, size_t>> lz_chunks;  // (pointer, bytes)
+  bool lz_in_use = false;  // a ground-state solve holds slots of the pool: do not release it
   float stage_ms[4] = {0, 0, 0, 0};
   // module globals coulomb_sundry / Nph, w0_ph, A_ph, g_ph: copied into the sector at open
   std::vector<edgpu_sundry_term> sundry_terms;
@@ -350,6 +351,9 @@ int comm_allgatherv(Engine &E, const double *d_chunk, double *d_full, const std:
                     const std::vector<int64_t> &offs);
 int comm_init(Engine &E, int rank, int nranks, const void *uid);
 int comm_allreduce_sum(Engine &E, double *d_buf, int n);
+// all-reduce of a few HOST doubles (op: 0 sum, 2 max, 3 min = ncclRedOp_t), synchronous; used for
+// collective decisions (all ranks must take the same branch), not on the data path
+int comm_allreduce_host(Engine &E, double *h_buf, int n, int op);
 int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int64_t qcol,
                    double *d_b, int64_t ncol, int64_t ldb, int64_t qrow, bool accumulate);
 int comm_finalize(Engine &E);

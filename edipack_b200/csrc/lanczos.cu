@@ -109,7 +109,8 @@ void lanczos_release(Engine &E) {
 
 cudaError_t dev_malloc(void **p, size_t bytes) {
   cudaError_t e = (cudaMalloc)(p, bytes);  // the runtime's cudaMalloc, not the macro
-  if (e == cudaErrorMemoryAllocation && !g.lz_chunks.empty()) {
+  // (not while a ground-state solve is reading the pool: its stored vectors would be freed under it)
+  if (e == cudaErrorMemoryAllocation && !g.lz_chunks.empty() && !g.lz_in_use) {
     cudaGetLastError();
     lanczos_release(g);
     e = (cudaMalloc)(p, bytes);
@@ -202,37 +203,74 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
     cudaFree(vin);
     cudaFree(vout);
     store.clear();  // slots of the pooled chunks (E.lz_chunks), kept for the next solve
+    E.lz_in_use = false;
   };
   const char *env = getenv("EDGPU_LANCZOS_STORE");
   bool storing = !(env && env[0] == '0');
   // Vector slots are carved from the pooled chunks; new chunks (8 vectors, at least 256 MB) are
   // added on demand while device memory lasts, keeping a reserve for everything else that is
   // allocated while sectors are open (stored states, seeds, transposes, the callers' buffers).
-  const size_t vbytes = sizeof(double) * (size_t)n;
+  // With nranks > 1 every decision about the store is COLLECTIVE: pass 2 replays the unstored
+  // tail with all-reduces and transposes, so all ranks must end with the same number of stored
+  // vectors.  The slot size is the largest local vector of any rank (the dw split differs by one
+  // column), the usable part of the existing pool is the minimum over ranks, and a new chunk is
+  // kept only if every rank got one.
+  size_t vbytes = sizeof(double) * (size_t)n;
+  int64_t pool_slots = 0;  // slots of the existing pool that every rank has
+  auto slots_in_pool = [&]() {
+    int64_t c = 0;
+    for (auto &ch : E.lz_chunks) c += (int64_t)(ch.second / vbytes);
+    return c;
+  };
+  if (E.nranks > 1) {
+    double mx = (double)vbytes;
+    if (comm_allreduce_host(E, &mx, 1, /*op max*/ 2)) { cleanup(); return g_status; }
+    vbytes = (size_t)mx;
+    double mn = (double)slots_in_pool();
+    if (comm_allreduce_host(E, &mn, 1, /*op min*/ 3)) { cleanup(); return g_status; }
+    pool_slots = (int64_t)mn;
+  } else {
+    pool_slots = slots_in_pool();
+  }
+  E.lz_in_use = true;  // dev_malloc must not release the pool under this solve
   size_t chunk_i = 0, chunk_used = 0;  // carving position
   auto try_store_slot = [&]() -> double * {
     if (!storing || (int)store.size() > nitermax) {
       storing = false;
       return nullptr;
     }
-    while (chunk_i < E.lz_chunks.size() && chunk_used + vbytes > E.lz_chunks[chunk_i].second) {
-      chunk_i++;
-      chunk_used = 0;
-    }
-    if (chunk_i == E.lz_chunks.size()) {
+    if ((int64_t)store.size() >= pool_slots) {
+      // every rank arrives here at the same iteration: collective growth of the pool
       size_t fr = 0, tot = 0;
       const size_t reserve = std::max<size_t>((size_t)4 << 30, 6 * vbytes);
       const size_t left = (size_t)nitermax + 1 - store.size();
-      const size_t want = std::min(left * vbytes, std::max<size_t>(8 * vbytes, (size_t)256 << 20));
+      const size_t want = std::min(left, std::max<size_t>(8, ((size_t)256 << 20) / vbytes)) * vbytes;
       void *p = nullptr;
-      if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr < reserve + want ||
-          (cudaMalloc)(&p, want) != cudaSuccess) {
-        cudaGetLastError();
+      bool ok = cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr >= reserve + want &&
+                (cudaMalloc)(&p, want) == cudaSuccess;
+      if (!ok) cudaGetLastError();
+      if (E.nranks > 1) {
+        double f = ok ? 1.0 : 0.0;
+        if (comm_allreduce_host(E, &f, 1, /*op min*/ 3)) f = 0.0;
+        if (f == 0.0 && ok) {
+          cudaFree(p);
+          ok = false;
+        }
+      }
+      if (!ok) {
         storing = false;
         return nullptr;
       }
       E.lz_chunks.emplace_back((double *)p, want);
+      pool_slots += (int64_t)(want / vbytes);
+    }
+    while (chunk_i < E.lz_chunks.size() && chunk_used + vbytes > E.lz_chunks[chunk_i].second) {
+      chunk_i++;
       chunk_used = 0;
+    }
+    if (chunk_i == E.lz_chunks.size()) {  // cannot happen: pool_slots counts whole slots
+      storing = false;
+      return nullptr;
     }
     double *slot = (double *)((char *)E.lz_chunks[chunk_i].first + chunk_used);
     chunk_used += vbytes;
@@ -263,7 +301,9 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
     nrm.push_back(beta);               // |X_{it+1}|
     a.push_back(alfa);
     nlanc = it;
-    if (std::fabs(beta) < threshold && it > 1) break;
+    // beta -> 0: the Krylov space is exhausted (also at it == 1, when the start vector is an
+    // eigenvector: dividing by |X_2| = 0 in the next step would give NaNs)
+    if (std::fabs(beta) < threshold) break;
     b.push_back(beta);
     if (nlanc >= ncheck) {
       ev.resize(nlanc);

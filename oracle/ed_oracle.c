@@ -808,29 +808,67 @@ int ora_stored_hxv(const ora_params *p, int nup_el, int ndw_el, const double *v,
 /*
  * spMatVec_mpi_normal_main (..._STORED_HxV.f90:765-929) with P emulated ranks and the
  * diagonal kept as a stored vector: the reference's ED_SPARSE_H=T algorithm.  The build
- * happens once (as in build_Hv_sector_normal), the product is repeated ncalls times and
- * the mean product time returned in *seconds_per_call.
+ * happens once (as in build_Hv_sector_normal: stored_build), the product (stored_apply) is
+ * repeated ncalls times and the mean product time returned in *seconds_per_call.
  */
-int ora_stored_hxv_mpi(const ora_params *p, int nup_el, int ndw_el, int P, int nthreads, int ncalls,
-                       const double *v, double *Hv, double *seconds_per_call) {
+typedef struct {
+  int64_t DimUp, DimDw, Dim;
+  int P, nthreads;
+  int64_t *rpu, *rpd;
+  int32_t *cu, *cd;
+  double *vu, *vd, *diag;
+  double **vt, **hvt;
+  int64_t *rpn, *cn;
+  double *vn;
+} stored_sector;
+
+static void stored_free(stored_sector *S) {
+  free(S->rpn);
+  free(S->cn);
+  free(S->vn);
+  if (S->vt)
+    for (int r = 0; r < S->P; r++) {
+      free(S->vt[r]);
+      free(S->hvt[r]);
+    }
+  free(S->vt);
+  free(S->hvt);
+  free(S->diag);
+  free(S->rpu);
+  free(S->rpd);
+  free(S->cu);
+  free(S->cd);
+  free(S->vu);
+  free(S->vd);
+  memset(S, 0, sizeof(*S));
+}
+
+static void stored_build(stored_sector *S, const ora_params *p, int nup_el, int ndw_el, int P,
+                         int nthreads) {
   const int Ns = p->Ns;
+  memset(S, 0, sizeof(*S));
   const int64_t DimUp = ora_binomial(Ns, nup_el), DimDw = ora_binomial(Ns, ndw_el);
   const int64_t Dim = DimUp * DimDw;
   if (P > DimDw) P = (int)DimDw;
   if (P > DimUp) P = (int)DimUp;
   if (nthreads < 1) nthreads = 1;
+  S->DimUp = DimUp;
+  S->DimDw = DimDw;
+  S->Dim = Dim;
+  S->P = P;
+  S->nthreads = nthreads;
   int64_t nzu = ora_build_hop_csr(p, 0, nup_el, NULL, NULL, NULL);
   int64_t nzd = ora_build_hop_csr(p, 1, ndw_el, NULL, NULL, NULL);
-  int64_t *rpu = (int64_t *)malloc(sizeof(int64_t) * (DimUp + 1));
-  int64_t *rpd = (int64_t *)malloc(sizeof(int64_t) * (DimDw + 1));
-  int32_t *cu = (int32_t *)malloc(sizeof(int32_t) * (nzu + 1));
-  int32_t *cd = (int32_t *)malloc(sizeof(int32_t) * (nzd + 1));
-  double *vu = (double *)malloc(sizeof(double) * (nzu + 1));
-  double *vd = (double *)malloc(sizeof(double) * (nzd + 1));
-  ora_build_hop_csr(p, 0, nup_el, rpu, cu, vu);
-  ora_build_hop_csr(p, 1, ndw_el, rpd, cd, vd);
+  S->rpu = (int64_t *)malloc(sizeof(int64_t) * (DimUp + 1));
+  S->rpd = (int64_t *)malloc(sizeof(int64_t) * (DimDw + 1));
+  S->cu = (int32_t *)malloc(sizeof(int32_t) * (nzu + 1));
+  S->cd = (int32_t *)malloc(sizeof(int32_t) * (nzd + 1));
+  S->vu = (double *)malloc(sizeof(double) * (nzu + 1));
+  S->vd = (double *)malloc(sizeof(double) * (nzd + 1));
+  ora_build_hop_csr(p, 0, nup_el, S->rpu, S->cu, S->vu);
+  ora_build_hop_csr(p, 1, ndw_el, S->rpd, S->cd, S->vd);
   /* spH0d over local rows: built in parallel like the reference (each rank its rows) */
-  double *diag = (double *)malloc(sizeof(double) * Dim);
+  double *diag = S->diag = (double *)malloc(sizeof(double) * Dim);
   int32_t *mapu = (int32_t *)malloc(sizeof(int32_t) * DimUp);
   int32_t *mapd = (int32_t *)malloc(sizeof(int32_t) * DimDw);
   ora_build_map(Ns, nup_el, mapu);
@@ -842,93 +880,199 @@ int ora_stored_hxv_mpi(const ora_params *p, int nup_el, int ndw_el, int P, int n
     bdecomp(mapd[i / DimUp], Ns, nd);
     diag[i] = diag_energy(p, nu, nd);
   }
-  double **vt = (double **)calloc(P, sizeof(double *));
-  double **hvt = (double **)calloc(P, sizeof(double *));
+  free(mapu);
+  free(mapd);
+  S->vt = (double **)calloc(P, sizeof(double *));
+  S->hvt = (double **)calloc(P, sizeof(double *));
   for (int r = 0; r < P; r++) {
     int64_t Qup, u0;
     block_split(DimUp, P, r, &Qup, &u0);
-    vt[r] = (double *)malloc(sizeof(double) * (size_t)(Qup * DimDw));
-    hvt[r] = (double *)malloc(sizeof(double) * (size_t)(Qup * DimDw));
+    S->vt[r] = (double *)malloc(sizeof(double) * (size_t)(Qup * DimDw));
+    S->hvt[r] = (double *)malloc(sizeof(double) * (size_t)(Qup * DimDw));
   }
   /* spH0nd (stored/H_non_local.f90), applied to the all-gathered vector (:906-927) */
-  int64_t *rpn = NULL, *cn = NULL;
-  double *vn = NULL;
   if (nonloc_condition(p)) {
     int64_t nz = ora_build_nonlocal_csr(p, nup_el, ndw_el, NULL, NULL, NULL);
-    rpn = (int64_t *)malloc(sizeof(int64_t) * (Dim + 1));
-    cn = (int64_t *)malloc(sizeof(int64_t) * (nz + 1));
-    vn = (double *)malloc(sizeof(double) * (nz + 1));
-    ora_build_nonlocal_csr(p, nup_el, ndw_el, rpn, cn, vn);
+    S->rpn = (int64_t *)malloc(sizeof(int64_t) * (Dim + 1));
+    S->cn = (int64_t *)malloc(sizeof(int64_t) * (nz + 1));
+    S->vn = (double *)malloc(sizeof(double) * (nz + 1));
+    ora_build_nonlocal_csr(p, nup_el, ndw_el, S->rpn, S->cn, S->vn);
   }
-  double t0 = now_s();
-  for (int call = 0; call < ncalls; call++) {
-#pragma omp parallel num_threads(nthreads)
-    {
+}
+
+/* one product Hv = H v (:765-929): local part, transpose, dw part, transpose back, non-local */
+static void stored_apply(const stored_sector *S, const double *v, double *Hv) {
+  const int64_t DimUp = S->DimUp, DimDw = S->DimDw;
+  const int P = S->P;
+  const int64_t *rpu = S->rpu, *rpd = S->rpd, *rpn = S->rpn, *cn = S->cn;
+  const int32_t *cu = S->cu, *cd = S->cd;
+  const double *vu = S->vu, *vd = S->vd, *vn = S->vn, *diag = S->diag;
+  double **vt = S->vt, **hvt = S->hvt;
+#pragma omp parallel num_threads(S->nthreads)
+  {
 #pragma omp for schedule(static)
-      for (int r = 0; r < P; r++) {
-        int64_t Qdw, d0;
-        block_split(DimDw, P, r, &Qdw, &d0);
-        const int64_t ishift = d0 * DimUp, Nloc = DimUp * Qdw;
-        const double *vin = v + ishift;
-        double *hv = Hv + ishift;
-        const double *dg = diag + ishift;
-        for (int64_t i = 0; i < Nloc; i++) hv[i] = dg[i] * vin[i];
-        for (int64_t idw = 0; idw < Qdw; idw++)
-          for (int64_t iup = 0; iup < DimUp; iup++) {
-            double acc = 0.0;
-            for (int64_t jj = rpu[iup]; jj < rpu[iup + 1]; jj++)
-              acc += vu[jj] * vin[(cu[jj] - 1) + idw * DimUp];
-            hv[iup + idw * DimUp] += acc;
-          }
-        int64_t Qup, u0;
-        block_split(DimUp, P, r, &Qup, &u0);
-        for (int64_t iu = 0; iu < Qup; iu++)
-          for (int64_t id = 0; id < DimDw; id++) vt[r][id + iu * DimDw] = v[(u0 + iu) + id * DimUp];
-        for (int64_t iu = 0; iu < Qup; iu++)
-          for (int64_t id = 0; id < DimDw; id++) {
-            double acc = 0.0;
-            for (int64_t jj = rpd[id]; jj < rpd[id + 1]; jj++)
-              acc += vd[jj] * vt[r][(cd[jj] - 1) + iu * DimDw];
-            hvt[r][id + iu * DimDw] = acc;
-          }
-      }
-#pragma omp for schedule(static)
-      for (int r = 0; r < P; r++) {
-        int64_t Qdw, d0;
-        block_split(DimDw, P, r, &Qdw, &d0);
-        for (int s = 0; s < P; s++) {
-          int64_t Qup, u0;
-          block_split(DimUp, P, s, &Qup, &u0);
-          for (int64_t id = d0; id < d0 + Qdw; id++)
-            for (int64_t iu = 0; iu < Qup; iu++)
-              Hv[(u0 + iu) + id * DimUp] += hvt[s][id + iu * DimDw];
+    for (int r = 0; r < P; r++) {
+      int64_t Qdw, d0;
+      block_split(DimDw, P, r, &Qdw, &d0);
+      const int64_t ishift = d0 * DimUp, Nloc = DimUp * Qdw;
+      const double *vin = v + ishift;
+      double *hv = Hv + ishift;
+      const double *dg = diag + ishift;
+      for (int64_t i = 0; i < Nloc; i++) hv[i] = dg[i] * vin[i];
+      for (int64_t idw = 0; idw < Qdw; idw++)
+        for (int64_t iup = 0; iup < DimUp; iup++) {
+          double acc = 0.0;
+          for (int64_t jj = rpu[iup]; jj < rpu[iup + 1]; jj++)
+            acc += vu[jj] * vin[(cu[jj] - 1) + idw * DimUp];
+          hv[iup + idw * DimUp] += acc;
         }
-        if (rpn)
-          for (int64_t i = d0 * DimUp; i < (d0 + Qdw) * DimUp; i++)
-            for (int64_t jj = rpn[i]; jj < rpn[i + 1]; jj++) Hv[i] += vn[jj] * v[cn[jj] - 1];
+      int64_t Qup, u0;
+      block_split(DimUp, P, r, &Qup, &u0);
+      for (int64_t iu = 0; iu < Qup; iu++)
+        for (int64_t id = 0; id < DimDw; id++) vt[r][id + iu * DimDw] = v[(u0 + iu) + id * DimUp];
+      for (int64_t iu = 0; iu < Qup; iu++)
+        for (int64_t id = 0; id < DimDw; id++) {
+          double acc = 0.0;
+          for (int64_t jj = rpd[id]; jj < rpd[id + 1]; jj++)
+            acc += vd[jj] * vt[r][(cd[jj] - 1) + iu * DimDw];
+          hvt[r][id + iu * DimDw] = acc;
+        }
+    }
+#pragma omp for schedule(static)
+    for (int r = 0; r < P; r++) {
+      int64_t Qdw, d0;
+      block_split(DimDw, P, r, &Qdw, &d0);
+      for (int s = 0; s < P; s++) {
+        int64_t Qup, u0;
+        block_split(DimUp, P, s, &Qup, &u0);
+        for (int64_t id = d0; id < d0 + Qdw; id++)
+          for (int64_t iu = 0; iu < Qup; iu++)
+            Hv[(u0 + iu) + id * DimUp] += hvt[s][id + iu * DimDw];
       }
+      if (rpn)
+        for (int64_t i = d0 * DimUp; i < (d0 + Qdw) * DimUp; i++)
+          for (int64_t jj = rpn[i]; jj < rpn[i + 1]; jj++) Hv[i] += vn[jj] * v[cn[jj] - 1];
     }
   }
+}
+
+int ora_stored_hxv_mpi(const ora_params *p, int nup_el, int ndw_el, int P, int nthreads, int ncalls,
+                       const double *v, double *Hv, double *seconds_per_call) {
+  stored_sector S;
+  stored_build(&S, p, nup_el, ndw_el, P, nthreads);
+  double t0 = now_s();
+  for (int call = 0; call < ncalls; call++) stored_apply(&S, v, Hv);
   double t1 = now_s();
   if (seconds_per_call) *seconds_per_call = (t1 - t0) / (ncalls > 0 ? ncalls : 1);
-  free(rpn);
-  free(cn);
-  free(vn);
-  for (int r = 0; r < P; r++) {
-    free(vt[r]);
-    free(hvt[r]);
+  stored_free(&S);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Symmetric tridiagonal eigenvalues by bisection on the Sturm sequence (the role of
+ * SciFortran's eigh/tql2 on the Lanczos matrix inside sp_lanc_eigh): lowest eigenvalue only. */
+static int sturm_count(int n, const double *a, const double *b, double x) {
+  int cnt = 0;
+  double q = a[0] - x;
+  if (q < 0.0) cnt++;
+  for (int i = 1; i < n; i++) {
+    const double d = (fabs(q) < 1e-300) ? 1e-300 : q;
+    q = a[i] - x - b[i - 1] * b[i - 1] / d;
+    if (q < 0.0) cnt++;
   }
-  free(vt);
-  free(hvt);
-  free(diag);
-  free(mapu);
-  free(mapd);
-  free(rpu);
-  free(rpd);
-  free(cu);
-  free(cd);
-  free(vu);
-  free(vd);
+  return cnt;
+}
+static double tridiag_lowest(int n, const double *a, const double *b) {
+  double lo = a[0], hi = a[0];
+  for (int i = 0; i < n; i++) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < n ? fabs(b[i]) : 0.0);
+    if (a[i] - r < lo) lo = a[i] - r;
+    if (a[i] + r > hi) hi = a[i] + r;
+  }
+  for (int it = 0; it < 200 && hi - lo > 4e-16 * (fabs(lo) + fabs(hi)) + 1e-300; it++) {
+    const double mid = 0.5 * (lo + hi);
+    if (sturm_count(n, a, b, mid) >= 1) hi = mid; else lo = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
+/*
+ * Pass 1 of sp_lanc_eigh (SciFortran SF_SP_LINALG, call site ED_DIAG_NORMAL.f90:206-213) on the
+ * stored (ED_SPARSE_H=T) operator above, all in C so that the BASELINE-size sectors finish in
+ * tens of seconds: three-term recurrence of lanczos_iteration
+ *   iter==1: vin/=|vin| ; else (vin,vout) <- (vout/beta, -beta*vin)
+ *   vout += H vin ; alfa = <vin,vout> ; vout -= alfa*vin ; beta = |vout|
+ * the lowest Ritz value is taken every iteration once nlanc >= ncheck; stop when it moved by
+ * <= threshold, or |beta| < threshold, or nitermax.  v0: start vector (normalised inside).
+ * alanc/blanc (size nitermax) receive the coefficients; *seconds the wall time of the loop.
+ */
+int ora_stored_lanczos_gs(const ora_params *p, int nup_el, int ndw_el, int P, int nthreads,
+                          int nitermax, double threshold, int ncheck, const double *v0, double *egs,
+                          int *niter, double *alanc, double *blanc, double *seconds) {
+  stored_sector S;
+  stored_build(&S, p, nup_el, ndw_el, P, nthreads);
+  const int64_t n = S.Dim;
+  if (nitermax > n) nitermax = (int)n;
+  double *vin = (double *)malloc(sizeof(double) * n);
+  double *vout = (double *)malloc(sizeof(double) * n);
+  double *hv = (double *)malloc(sizeof(double) * n);
+  double *bsub = (double *)calloc((size_t)nitermax + 1, sizeof(double));
+  double nrm = 0.0;
+#pragma omp parallel for reduction(+ : nrm) num_threads(S.nthreads)
+  for (int64_t i = 0; i < n; i++) nrm += v0[i] * v0[i];
+  nrm = sqrt(nrm);
+#pragma omp parallel for num_threads(S.nthreads)
+  for (int64_t i = 0; i < n; i++) {
+    vin[i] = v0[i] / nrm;
+    vout[i] = 0.0;
+  }
+  double beta = 0.0, elast = 0.0;
+  int nlanc = 0, have_last = 0;
+  const double t0 = now_s();
+  for (int it = 1; it <= nitermax; it++) {
+    if (it > 1) {
+      const double ib = 1.0 / beta, mb = -beta;
+#pragma omp parallel for num_threads(S.nthreads)
+      for (int64_t i = 0; i < n; i++) {
+        const double t = vin[i];
+        vin[i] = vout[i] * ib;
+        vout[i] = mb * t;
+      }
+    }
+    stored_apply(&S, vin, hv);
+    double alfa = 0.0;
+#pragma omp parallel for reduction(+ : alfa) num_threads(S.nthreads)
+    for (int64_t i = 0; i < n; i++) {
+      vout[i] += hv[i];
+      alfa += vin[i] * vout[i];
+    }
+    double b2 = 0.0;
+#pragma omp parallel for reduction(+ : b2) num_threads(S.nthreads)
+    for (int64_t i = 0; i < n; i++) {
+      vout[i] -= alfa * vin[i];
+      b2 += vout[i] * vout[i];
+    }
+    beta = sqrt(b2);
+    alanc[it - 1] = alfa;
+    nlanc = it;
+    if (fabs(beta) < threshold && it > 1) break;
+    bsub[it - 1] = beta;
+    if (it < nitermax) blanc[it] = beta;
+    if (nlanc >= ncheck) {
+      const double e0 = tridiag_lowest(nlanc, alanc, bsub);
+      if (have_last && fabs(e0 - elast) <= threshold) break;
+      elast = e0;
+      have_last = 1;
+    }
+  }
+  if (seconds) *seconds = now_s() - t0;
+  *egs = tridiag_lowest(nlanc, alanc, bsub);
+  *niter = nlanc;
+  free(vin);
+  free(vout);
+  free(hv);
+  free(bsub);
+  stored_free(&S);
   return 0;
 }
 

@@ -113,6 +113,13 @@ int ora_direct_hxv_mpi_sample(const ora_params *p, int nup, int ndw, int P, int 
 int ora_stored_hxv_mpi(const ora_params *p, int nup, int ndw, int P, int nthreads, int ncalls,
                        const double *v, double *Hv, double *seconds_per_call);
 
+/* ---- pass 1 of sp_lanc_eigh (SciFortran; call site ED_DIAG_NORMAL.f90:206-213) on that stored
+ *      operator, recurrence and stopping rule as edipack_oracle.lanc_eigh; the lowest Ritz value
+ *      by Sturm bisection.  v0 = start vector, alanc/blanc sized nitermax. ---- */
+int ora_stored_lanczos_gs(const ora_params *p, int nup, int ndw, int P, int nthreads, int nitermax,
+                          double threshold, int ncheck, const double *v0, double *egs, int *niter,
+                          double *alanc, double *blanc, double *seconds);
+
 /* ---- stored path pieces (ED_HAMILTONIAN_NORMAL_STORED_HxV.f90:26 + stored/ *.f90):
  *      H_up / H_dw as list-of-rows in insertion order, duplicates accumulated
  *      (ED_SPARSE_MATRIX.f90:328-357).  Output CSR arrays sized by a first counting call

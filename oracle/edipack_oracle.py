@@ -111,6 +111,9 @@ def lib():
         L.ora_stored_hxv.argtypes = [PP, C.c_int, C.c_int, dp, dp]
         L.ora_stored_hxv_mpi.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp,
                                          C.POINTER(C.c_double)]
+        L.ora_stored_lanczos_gs.argtypes = [PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                            C.c_int, dp, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                            dp, dp, C.POINTER(C.c_double)]
         L.ora_build_hop_csr.restype = C.c_int64
         L.ora_build_hop_csr.argtypes = [PP, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ora_build_diag.argtypes = [PP, C.c_int, C.c_int, dp]
@@ -607,6 +610,22 @@ def stored_hxv_mpi(model: Model, nup, ndw, v, P, nthreads=1, ncalls=1):
                                   C.byref(sec))
     assert rc == 0
     return hv, sec.value
+
+
+def stored_lanczos_gs(model: Model, nup, ndw, v0, nitermax=300, threshold=1e-12, ncheck=10, P=8,
+                      nthreads=8):
+    """Pass 1 of sp_lanc_eigh (recurrence + stopping rule of lanc_eigh below) run in C on the
+    stored operator of stored_hxv_mpi: (egs, niter, alanc, blanc, seconds).  For sectors of the
+    BASELINE configs' own size, where the numpy recurrence takes minutes."""
+    v0 = np.ascontiguousarray(v0, np.float64)
+    a = np.zeros(nitermax)
+    b = np.zeros(nitermax)
+    egs, nit, sec = C.c_double(0.0), C.c_int(0), C.c_double(0.0)
+    rc = lib().ora_stored_lanczos_gs(C.byref(model.params()), nup, ndw, P, nthreads, nitermax,
+                                     threshold, ncheck, v0, C.byref(egs), C.byref(nit), a, b,
+                                     C.byref(sec))
+    assert rc == 0
+    return egs.value, nit.value, a[:nit.value], b[:nit.value], sec.value
 
 
 def hop_csr(model: Model, spin: int, nel: int):

@@ -117,9 +117,12 @@ def _cdg(pos, m):
     return m | (1 << b), sgn
 
 
-def stored_H(model: ModelNonsu2, Ntot: int):
+def stored_H(model: ModelNonsu2, Ntot: int, only_rows=None):
     """ed_buildH_nonsu2_main (ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190) for one sector:
-    returns (map, rowptr, cols [1-based], vals [complex]) in list-of-rows insertion order."""
+    returns (map, rowptr, cols [1-based], vals [complex]) in list-of-rows insertion order.
+    only_rows (0-based sector indices, optional): generate just those rows (rowptr then runs over
+    the subset, columns stay global) -- the bounded sample used at the BASELINE cfg 5 size, where
+    the per-row Python loops over all 705 432 rows would take tens of minutes."""
     if model.bath_e is None:
         model.default_bath()
     Ns, No, Nb = model.Ns, model.Norb, model.Nbath
@@ -133,7 +136,7 @@ def stored_H(model: ModelNonsu2, Ntot: int):
     Jp = np.full((No, No), model.Jp) - np.diag(np.full(No, model.Jp))
     sf = np.zeros((No, 3)) if model.spin_field is None else np.asarray(model.spin_field, float)
     rows = []
-    for m_ in smap:
+    for m_ in (smap if only_rows is None else smap[np.asarray(only_rows, np.int64)]):
         m = int(m_)
         row = {}  # column -> value, insertion-ordered; duplicates accumulate
 

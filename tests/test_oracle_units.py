@@ -109,3 +109,23 @@ def test_lanczos_tridiag_reproduces_spectrum(oracle):
     ev, _ = oracle.tridiag_eigh(a[:nused], b[1:nused])
     dense = np.linalg.eigvalsh(H)
     assert abs(ev[0] - dense[0]) < 1e-10 and abs(ev[-1] - dense[-1]) < 1e-10
+
+
+def test_c_lanczos_matches_python_recurrence(oracle):
+    """ora_stored_lanczos_gs (C pass 1 of sp_lanc_eigh on the stored operator, used at the
+    BASELINE configs' own sizes) == the numpy recurrence lanc_eigh on the direct operator."""
+    from models import star_kwargs, two_orb_kwargs
+
+    O = oracle
+    for kw, sec in ((star_kwargs(7), (4, 4)), (two_orb_kwargs(3), (4, 4)), (star_kwargs(9), (5, 4))):
+        mo = O.Model(**kw)
+        du, dd = O.sector_dims(mo.Ns, *sec)
+        v0 = O.start_vector(du * dd, 31) - 0.5
+        e_py, _, n_py = O.lanc_eigh(lambda x: O.direct_hxv(mo, sec[0], sec[1], x), du * dd, 300, 1e-12,
+                                    v0=v0)
+        e_c, n_c, a, b, _ = O.stored_lanczos_gs(mo, sec[0], sec[1], v0, 300, 1e-12, P=3, nthreads=3)
+        assert n_c == n_py
+        assert abs(e_c - e_py) < 1e-11
+        a0, b0, _ = O.lanc_tridiag(lambda x: O.direct_hxv(mo, sec[0], sec[1], x),
+                                   v0 / np.linalg.norm(v0), 12)
+        assert np.abs(a[:12] - a0[:12]).max() < 1e-10 and np.abs(b[:12] - b0[:12]).max() < 1e-10
