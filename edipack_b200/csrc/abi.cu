@@ -273,9 +273,17 @@ int edgpu_init(int device) {
   g.smem_optin = prop.sharedMemPerBlockOptin;
   g.smem_per_sm = prop.sharedMemPerMultiprocessor;
   EDGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-  EDGPU_CUDA(cudaStreamCreateWithFlags(&g.comm_stream, cudaStreamNonBlocking));
+  {
+    // the communication streams outrank the main one: their small kernels (tile pushes, flag
+    // signals / waits) must not queue behind the CTAs of the rank-local pass
+    int lo = 0, hi = 0;
+    EDGPU_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    EDGPU_CUDA(cudaStreamCreateWithPriority(&g.comm_stream, cudaStreamNonBlocking, hi));
+    EDGPU_CUDA(cudaStreamCreateWithPriority(&g.dw_stream, cudaStreamNonBlocking, hi));
+  }
   EDGPU_CUDA(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
   EDGPU_CUDA(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+  EDGPU_CUDA(cudaEventCreateWithFlags(&g.ev_join2, cudaEventDisableTiming));
   for (auto &ev : g.ev) EDGPU_CUDA(cudaEventCreate(&ev));
   g.part_cap = (int64_t)g.sm_count * 8;
   EDGPU_CUDA(cudaMalloc(&g.d_part, sizeof(double) * g.part_cap));
@@ -317,7 +325,9 @@ int edgpu_finalize(void) {
   for (auto &ev : g.prof_ev) cudaEventDestroy(ev);
   cudaEventDestroy(g.ev_fork);
   cudaEventDestroy(g.ev_join);
+  cudaEventDestroy(g.ev_join2);
   cudaStreamDestroy(g.comm_stream);
+  cudaStreamDestroy(g.dw_stream);
   cudaStreamDestroy(g.stream);
   g = Engine();
   return 0;
@@ -486,6 +496,8 @@ int edgpu_sector_get_map(int spin, int32_t *map) {
 
 // hop table of one species as (row-major) lists: entry s of row r lives in group s/4
 static int download_hops(SpinSpace &S, std::vector<uint32_t> &ell, std::vector<double> &amp) {
+  if (S.sharded)
+    return set_error("hop tables of a species sharded over ranks hold rank-local targets; open the sector on one rank");
   const int G = std::max(S.Wl4 + S.Wf4, 1);
   ell.resize((size_t)4 * G * S.ld);
   amp.resize((size_t)2 * S.nterms + 2);
@@ -595,7 +607,8 @@ static void hxv_host(const char *who, bool want_cplx, const int32_t *Nloc, const
   if (ensure_buf(&g_hx_in, &g_hx_in_len, n) || ensure_buf(&g_hx_out, &g_hx_out_len, n)) return;
   if (upload(g, g_hx_in, v)) return;
   if (hxv_device(g, g_hx_in, g_hx_out, false, false)) return;
-  download(g, Hv, g_hx_out);
+  if (download(g, Hv, g_hx_out)) return;
+  comm_pipe_check(g);
 }
 
 void edgpu_hxv_d(const int32_t *Nloc, const double *v, double *Hv) {

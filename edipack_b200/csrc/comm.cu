@@ -9,6 +9,7 @@
 // strided copy kernel; the rank's own tile never leaves the device.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "edgpu_internal.cuh"
@@ -251,91 +252,152 @@ int comm_transpose(Engine &E, const double *d_a, int64_t nrow, int64_t lda, int6
 
 
 // ---------------------------------------------------------------------------------------
-// Peer-memory transposes.  Every rank maps the vt / hvt buffers of all ranks (CUDA IPC, handles
-// all-gathered through NCCL) and the two vector_transpose_MPI of one H x v become
-//   push : vt_p[(i - u0_p) * ldD + d0_me + c] = v[c * ldU + i]      for every row i, p = owner(i)
-//   pull : hv[c * ldU + i] += hvt_p[(i - u0_p) * ldD + d0_me + c]
-// one kernel each, 32x32 tiles transposed through shared memory so that both the local and
-// the remote side move 256-byte segments; the NVLink traffic is issued by the kernel itself
-// (st.global / ld.global on mapped peer pointers), no pack / send / recv / unpack passes.
-// Ordering between ranks: in-stream 1-element NCCL all-reduces (comm_barrier).
+// Peer-memory pipeline of the Hdw term (replaces both vector_transpose_MPI of one H x v,
+// ED_HAMILTONIAN_NORMAL_COMMON.f90:66-178, and the MPI_Alltoallv per column inside them).
+//
+// Every rank owns ONE IPC-mapped block [flags | vt | hvr]:
+//   vt   [ldD x qup]  this rank's rows of v^T: written by all ranks (push)
+//   hvr  [ldU x qdw]  Hdw part of this rank's columns of Hv: written by all ranks (return)
+//   flags             epoch words, written by all ranks (st.release.sys), spun on locally
+// The qup local columns of vt (= up rows u0 .. u0+qup) are cut into nchunks chunks and chunk c
+// flows  push(c) -> [flag] -> Hdw on chunk c -> return(c) -> [flag] -> hv += hvr on chunk c's rows
+// so that NVLink traffic in both directions, the Hdw pass and the rank-local pass overlap.  The
+// tiles are transposed through shared memory: both the local and the remote side move 256-byte
+// segments, issued by the kernels themselves (st.global on mapped peer pointers) -- no pack /
+// send / recv / unpack passes, no collective call on the data path.
+//
+// Buffer reuse across products needs no extra synchronisation: a rank starts product e+1 only
+// after it has seen the return flags of product e from every peer, i.e. after every peer has
+// finished reading its vt of product e.
 // ---------------------------------------------------------------------------------------
-struct PeerTable {
-  double *ptr[EDGPU_MAXRANKS];
-  int32_t row0[EDGPU_MAXRANKS + 1];  // rows [row0[p], row0[p+1]) of the fast index belong to rank p
-  int nranks, me;
+static_assert(2 * EDGPU_MAXCHUNKS * EDGPU_MAXRANKS * sizeof(uint64_t) <= PIPE_FLAG_BYTES, "flag area");
+
+struct PipeTable {
+  unsigned char *block[EDGPU_MAXRANKS];
+  int32_t u0[EDGPU_MAXRANKS + 1];   // up rows [u0[p], u0[p+1]) belong to rank p (columns of its vt)
+  int32_t d0[EDGPU_MAXRANKS + 1];   // dw columns [d0[p], d0[p+1]) belong to rank p
+  int32_t cb[EDGPU_MAXRANKS][EDGPU_MAXCHUNKS + 1];  // chunk c of rank p = its local rows [cb[c], cb[c+1])
+  int64_t off_vt, off_hvr[EDGPU_MAXRANKS];  // byte offsets of vt / hvr inside rank p's block
+  int64_t ldU, ldD;
+  int nranks, me, nchunks;
 };
 
-// blockIdx.y -> (peer, first row of a 32-row tile of that peer's rows).  Consecutive y rotate over
-// the peers, starting at a different peer on every rank: at any instant each GPU exchanges with a
-// different partner (the all-to-all schedule) instead of all of them hammering the same NVLink
-// endpoint.  Returns false for the padding tiles of peers with fewer rows.
-__device__ __forceinline__ bool peer_tile(const PeerTable &T, int y, int *peer, int *ib) {
-  const int p = (y % T.nranks + T.me) % T.nranks;
-  const int r = T.row0[p] + (y / T.nranks) * 32;
-  *peer = p;
-  *ib = r;
-  return r < T.row0[p + 1];
+__device__ __forceinline__ int flag_slot(int kind, int c, int sender) {
+  return (kind * EDGPU_MAXCHUNKS + c) * EDGPU_MAXRANKS + sender;
 }
 
-__device__ __forceinline__ int owner_of(const PeerTable &T, int i) {
-  int p = 0;
-#pragma unroll 1
-  while (p + 1 < T.nranks && i >= T.row0[p + 1]) p++;
-  return p;
+static PipeTable g_pipe;  // of the open sector (host copy, passed to the kernels by value)
+
+// chunk boundaries: multiples of 32 rows (tile height), the last chunk takes the remainder
+static void chunk_bounds(int64_t q, int K, int32_t *cb) {
+  const int64_t per = ((q + K - 1) / K + 31) / 32 * 32;
+  for (int c = 0; c <= K; c++) cb[c] = (int32_t)std::min<int64_t>(q, per * c);
+  cb[K] = (int32_t)q;
 }
 
-// grid = (ceil(qcol/32), ceil(nrow/32)); a = [nrow (fast, lda) x qcol] local block of v.
-// Column tiles run fastest: consecutive CTAs then extend the SAME 32 remote rows by consecutive
-// 256-byte pieces.  (Row tiles fastest makes every remote segment land on another 2 MB page of a
-// multi-GB peer buffer: measured 200 ms instead of ~5 ms per transpose at Ns=18 on 8 GPUs.)
+void comm_pipe_chunk_cols(Engine &E, int rank, int c, int64_t *col0, int64_t *ncols) {
+  *col0 = g_pipe.cb[rank][c];
+  *ncols = g_pipe.cb[rank][c + 1] - g_pipe.cb[rank][c];
+}
+
+// ---- push: v[c * ldU + i] -> vt_p[(i - u0_p) * ldD + d0_me + c] for the rows i of chunk `ch` of
+// every owner p.  grid = (ceil(qdw/32), nranks * row tiles of the longest chunk); blockIdx.y
+// rotates over the owners, starting at a different one on every rank (all-to-all schedule), and
+// column tiles run fastest: consecutive CTAs extend the SAME 32 remote rows by consecutive
+// 256-byte pieces (row tiles fastest would put every remote segment on another 2 MB page of a
+// multi-GB peer buffer: measured 200 ms instead of ~5 ms per transpose at Ns=18 on 8 GPUs).
 __global__ void __launch_bounds__(256)
-k_push_transpose(const double *__restrict__ a, int64_t lda, int qcol, int64_t c_off, int64_t ldb,
-                 PeerTable T) {
+k_pipe_push(const double *__restrict__ a, int qcol, int ch, PipeTable T) {
   __shared__ double t[32][33];
-  int p, ib;
-  if (!peer_tile(T, blockIdx.y, &p, &ib)) return;
-  const int iend = T.row0[p + 1];
+  const int p = ((int)(blockIdx.y % T.nranks) + T.me) % T.nranks;
+  const int ib = T.u0[p] + T.cb[p][ch] + (int)(blockIdx.y / T.nranks) * 32;
+  const int iend = T.u0[p] + T.cb[p][ch + 1];
+  if (ib >= iend) return;
   const int jb = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
     const int i = ib + tx, j = jb + ty + k;
-    if (i < iend && j < qcol) t[ty + k][tx] = a[(int64_t)j * lda + i];
+    if (i < iend && j < qcol) t[ty + k][tx] = a[(int64_t)j * T.ldU + i];
   }
   __syncthreads();
-  double *dst = T.ptr[p] + c_off;
+  double *dst = reinterpret_cast<double *>(T.block[p] + T.off_vt) + T.d0[T.me];
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
-    const int j = jb + tx, i = ib + ty + k;  // the 32 lanes write 32 consecutive columns of row i
-    if (i < iend && j < qcol) dst[(int64_t)(i - T.row0[p]) * ldb + j] = t[tx][ty + k];
+    const int j = jb + tx, i = ib + ty + k;  // the 32 lanes write 32 consecutive dw columns of row i
+    if (i < iend && j < qcol) dst[(int64_t)(i - T.u0[p]) * T.ldD + j] = t[tx][ty + k];
   }
-  // one system-scope fence per CTA (cumulative over the CTA's stores through the barrier)
-  __syncthreads();
-  if (threadIdx.x == 0) __threadfence_system();
 }
 
+// ---- return: hvt[j * ldD + d] (j = local column of chunk `ch`, up row u0_me + j) ->
+// hvr_q[(d - d0_q) * ldU + u0_me + j] for every owner q of dw column d.
+// grid = (ceil(chunk cols / 32), nranks * dw tiles of the widest rank).
 __global__ void __launch_bounds__(256)
-k_pull_transpose_acc(double *__restrict__ hv, int64_t lda, int qcol, int64_t c_off, int64_t ldb,
-                     PeerTable T) {
+k_pipe_return(const double *__restrict__ hvt, int ch, PipeTable T) {
   __shared__ double t[32][33];
-  int p, ib;
-  if (!peer_tile(T, blockIdx.y, &p, &ib)) return;
-  const int iend = T.row0[p + 1];
-  const int jb = blockIdx.x * 32;
+  const int q = ((int)(blockIdx.y % T.nranks) + T.me) % T.nranks;
+  const int db = T.d0[q] + (int)(blockIdx.y / T.nranks) * 32;
+  const int dend = T.d0[q + 1];
+  if (db >= dend) return;
+  const int j0 = T.cb[T.me][ch], jend = T.cb[T.me][ch + 1];
+  const int jb = j0 + blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const double *src = T.ptr[p] + c_off;
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
-    const int j = jb + tx, i = ib + ty + k;
-    if (i < iend && j < qcol) t[ty + k][tx] = src[(int64_t)(i - T.row0[p]) * ldb + j];
+    const int d = db + tx, j = jb + ty + k;
+    if (d < dend && j < jend) t[ty + k][tx] = hvt[(int64_t)j * T.ldD + d];
   }
   __syncthreads();
+  double *dst = reinterpret_cast<double *>(T.block[q] + T.off_hvr[q]) + T.u0[T.me];
 #pragma unroll
   for (int k = 0; k < 32; k += 8) {
-    const int i = ib + tx, j = jb + ty + k;
-    if (i < iend && j < qcol) hv[(int64_t)j * lda + i] += t[tx][ty + k];
+    const int j = jb + tx, d = db + ty + k;  // 32 lanes: 32 consecutive up rows of dw column d
+    if (d < dend && j < jend) dst[(int64_t)(d - T.d0[q]) * T.ldU + j] = t[tx][ty + k];
   }
+}
+
+// ---- signal: one thread per peer.  The kernel is stream-ordered behind the kernel whose stores
+// it announces; the fence orders those (already performed) stores before the flag at system scope.
+__global__ void k_pipe_signal(int kind, int c, unsigned long long epoch, PipeTable T) {
+  const int p = threadIdx.x;
+  if (p >= T.nranks) return;
+  __threadfence_system();
+  unsigned long long *f = reinterpret_cast<unsigned long long *>(T.block[p]) + flag_slot(kind, c, T.me);
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+}
+
+// ---- wait: one thread per sender spins on this rank's own flag word.  Bounded: after
+// `timeout_ns` the error word is set and the kernel returns (a dead peer must not hang the box).
+__global__ void k_pipe_wait(int kind, int c, unsigned long long epoch, PipeTable T,
+                            unsigned long long timeout_ns, int32_t *err) {
+  const int p = threadIdx.x;
+  if (p >= T.nranks) return;
+  const unsigned long long *f =
+      reinterpret_cast<const unsigned long long *>(T.block[T.me]) + flag_slot(kind, c, p);
+  unsigned long long t0, t1, seen;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+    if (seen >= epoch) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) {
+      *(volatile int32_t *)err = 1 + kind;  // pinned host word, read after the next stream sync
+      __threadfence_system();
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+// ---- add: hv[col * ldU + i] += hvr[col * ldU + i] on the rows i of chunk `ch` of every owner.
+// grid = (qdw, row blocks of the longest chunk, nranks)
+__global__ void __launch_bounds__(256)
+k_pipe_add(double *__restrict__ hv, const double *__restrict__ hvr, int ch, PipeTable T) {
+  const int p = blockIdx.z;
+  const int i = T.u0[p] + T.cb[p][ch] + (int)(blockIdx.y * blockDim.x + threadIdx.x);
+  if (i >= T.u0[p] + T.cb[p][ch + 1]) return;
+  const int64_t o = (int64_t)blockIdx.x * T.ldU + i;
+  hv[o] += hvr[o];
 }
 
 int comm_barrier(Engine &E) {
@@ -345,26 +407,14 @@ int comm_barrier(Engine &E) {
   return 0;
 }
 
-static PeerTable peer_table(Engine &E, double *const *ptrs) {
-  PeerTable T;
-  memset(&T, 0, sizeof(T));
-  T.nranks = E.nranks;
-  T.me = E.rank;
-  for (int p = 0; p < E.nranks; p++) {
-    int64_t q, r0;
-    block_split(E.sec.up.dim, E.nranks, p, &q, &r0);
-    T.ptr[p] = ptrs[p];
-    T.row0[p] = (int32_t)r0;
-    T.row0[p + 1] = (int32_t)(r0 + q);
+static int pipe_default_chunks(Engine &E) {
+  if (const char *e = getenv("EDGPU_CHUNKS")) {
+    const int k = atoi(e);
+    if (k >= 1) return std::min(k, EDGPU_MAXCHUNKS);
   }
-  return T;
-}
-
-// 32-row tiles of the rank with the most rows of the fast index
-static int peer_row_tiles(Engine &E) {
-  int64_t q, r0;
-  block_split(E.sec.up.dim, E.nranks, 0, &q, &r0);  // rank 0 has the longest share
-  return (int)((q + 31) / 32);
+  // ~48 MB of vt per chunk, between 2 and 8 chunks
+  const double mb = (double)E.sec.padded_len_t() * 8.0 / (1 << 20);
+  return (int)std::min(8.0, std::max(2.0, mb / 48.0 + 0.5));
 }
 
 int comm_p2p_setup(Engine &E) {
@@ -375,51 +425,66 @@ int comm_p2p_setup(Engine &E) {
   const char *off = getenv("EDGPU_NO_P2P");
   // every rank must take the same decision: all-reduce the local "ok" flags
   int ok = (off && off[0] == '1') ? 0 : 1;
-  cudaIpcMemHandle_t mine[2];
-  if (ok && (cudaIpcGetMemHandle(&mine[0], S.vt) != cudaSuccess ||
-             cudaIpcGetMemHandle(&mine[1], S.hvt) != cudaSuccess)) {
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine, S.comm_block) != cudaSuccess) {
     cudaGetLastError();
     ok = 0;
   }
   unsigned char *d_h = nullptr;
-  const size_t hb = 2 * sizeof(cudaIpcMemHandle_t);
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
   EDGPU_CUDA(cudaMalloc(&d_h, hb * P));
-  EDGPU_CUDA(cudaMemcpyAsync(d_h + hb * me, mine, hb, cudaMemcpyHostToDevice, E.stream));
+  EDGPU_CUDA(cudaMemcpyAsync(d_h + hb * me, &mine, hb, cudaMemcpyHostToDevice, E.stream));
   EDGPU_NCCL(N.AllGather(d_h + hb * me, d_h, hb, NCCL_CHAR, (nccl_comm_t)E.nccl, E.stream));
-  std::vector<cudaIpcMemHandle_t> all(2 * (size_t)P);
+  std::vector<cudaIpcMemHandle_t> all((size_t)P);
   EDGPU_CUDA(cudaMemcpyAsync(all.data(), d_h, hb * P, cudaMemcpyDeviceToHost, E.stream));
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
   cudaFree(d_h);
   for (int p = 0; p < P && ok; p++) {
     if (p == me) {
-      S.peer_vt[p] = S.vt;
-      S.peer_hvt[p] = S.hvt;
+      S.peer_block[p] = S.comm_block;
       continue;
     }
-    void *a = nullptr, *b = nullptr;
-    if (cudaIpcOpenMemHandle(&a, all[2 * p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&b, all[2 * p + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    void *a = nullptr;
+    if (cudaIpcOpenMemHandle(&a, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
       cudaGetLastError();
       ok = 0;
       break;
     }
-    S.peer_vt[p] = (double *)a;
-    S.peer_hvt[p] = (double *)b;
+    S.peer_block[p] = (unsigned char *)a;
   }
   double flag = ok ? 0.0 : 1.0;
-  EDGPU_CUDA(cudaMemcpyAsync(E.d_scal + 33, &flag, sizeof(double), cudaMemcpyHostToDevice, E.stream));
-  EDGPU_NCCL(N.AllReduce(E.d_scal + 33, E.d_scal + 33, 1, NCCL_FLOAT64, NCCL_SUM, (nccl_comm_t)E.nccl,
-                         E.stream));
-  EDGPU_CUDA(cudaMemcpyAsync(&flag, E.d_scal + 33, sizeof(double), cudaMemcpyDeviceToHost, E.stream));
-  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  EDGPU_TRY(comm_allreduce_host(E, &flag, 1, NCCL_SUM));
   S.p2p = (flag == 0.0);
   if (!S.p2p) {  // someone could not map: everybody unmaps and uses the NCCL path
     for (int p = 0; p < P; p++) {
-      if (p != me && S.peer_vt[p]) cudaIpcCloseMemHandle(S.peer_vt[p]);
-      if (p != me && S.peer_hvt[p]) cudaIpcCloseMemHandle(S.peer_hvt[p]);
-      S.peer_vt[p] = S.peer_hvt[p] = nullptr;
+      if (p != me && S.peer_block[p]) cudaIpcCloseMemHandle(S.peer_block[p]);
+      S.peer_block[p] = nullptr;
     }
     cudaGetLastError();
+    return 0;
+  }
+  S.nchunks = pipe_default_chunks(E);
+  S.epoch = 0;
+  PipeTable &T = g_pipe;
+  memset(&T, 0, sizeof(T));
+  T.nranks = P;
+  T.me = me;
+  T.nchunks = S.nchunks;
+  T.off_vt = (int64_t)PIPE_FLAG_BYTES;
+  T.ldU = S.up.ld;
+  T.ldD = S.dw.ld;
+  for (int p = 0; p < P; p++) {
+    int64_t q, r0;
+    block_split(S.up.dim, P, p, &q, &r0);
+    T.u0[p] = (int32_t)r0;
+    T.u0[p + 1] = (int32_t)(r0 + q);
+    chunk_bounds(q, S.nchunks, T.cb[p]);
+    T.off_hvr[p] = (int64_t)pipe_hvr_offset(S.dw.ld, q);
+    block_split(S.dw.dim, P, p, &q, &r0);
+    T.d0[p] = (int32_t)r0;
+    T.d0[p + 1] = (int32_t)(r0 + q);
+    T.block[p] = S.peer_block[p];
   }
   return 0;
 }
@@ -431,11 +496,8 @@ int comm_p2p_teardown(Engine &E) {
   comm_barrier(E);
   cudaStreamSynchronize(E.stream);
   for (int p = 0; p < E.nranks; p++) {
-    if (p != E.rank) {
-      cudaIpcCloseMemHandle(S.peer_vt[p]);
-      cudaIpcCloseMemHandle(S.peer_hvt[p]);
-    }
-    S.peer_vt[p] = S.peer_hvt[p] = nullptr;
+    if (p != E.rank && S.peer_block[p]) cudaIpcCloseMemHandle(S.peer_block[p]);
+    S.peer_block[p] = nullptr;
   }
   comm_barrier(E);  // every rank unmapped before anybody frees
   cudaStreamSynchronize(E.stream);
@@ -443,23 +505,319 @@ int comm_p2p_teardown(Engine &E) {
   return 0;
 }
 
-int comm_push_transpose(Engine &E, const double *d_a) {
+static int longest_chunk(const PipeTable &T, int c) {
+  int m = 0;
+  for (int p = 0; p < T.nranks; p++) m = std::max(m, T.cb[p][c + 1] - T.cb[p][c]);
+  return m;
+}
+
+static unsigned long long pipe_timeout_ns();
+
+int comm_pipe_push(Engine &E, int c, const double *d_v, cudaStream_t st) {
   Sector &S = E.sec;
-  const PeerTable T = peer_table(E, S.peer_vt);
-  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)(E.nranks * peer_row_tiles(E)));
-  k_push_transpose<<<grid, 256, 0, E.stream>>>(d_a, S.up.ld, (int)S.qdw, S.d0, S.dw.ld, T);
+  const int rt = (longest_chunk(g_pipe, c) + 31) / 32;
+  if (S.qdw <= 0 || rt == 0) return 0;
+  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)(E.nranks * rt));
+  k_pipe_push<<<grid, 256, 0, st>>>(d_v, (int)S.qdw, c, g_pipe);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
 
-int comm_pull_transpose_acc(Engine &E, double *d_hv) {
+int comm_pipe_return(Engine &E, int c, cudaStream_t st) {
   Sector &S = E.sec;
-  const PeerTable T = peer_table(E, S.peer_hvt);
-  dim3 grid((unsigned)((S.qdw + 31) / 32), (unsigned)(E.nranks * peer_row_tiles(E)));
-  k_pull_transpose_acc<<<grid, 256, 0, E.stream>>>(d_hv, S.up.ld, (int)S.qdw, S.d0, S.dw.ld, T);
+  const PipeTable &T = g_pipe;
+  const int nc = T.cb[T.me][c + 1] - T.cb[T.me][c];
+  int wd = 0;
+  for (int p = 0; p < T.nranks; p++) wd = std::max(wd, T.d0[p + 1] - T.d0[p]);
+  if (nc <= 0 || wd == 0) return 0;
+  dim3 grid((unsigned)((nc + 31) / 32), (unsigned)(E.nranks * ((wd + 31) / 32)));
+  k_pipe_return<<<grid, 256, 0, st>>>(S.hvt, c, T);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_pipe_signal(Engine &E, int kind, int c, cudaStream_t st) {
+  k_pipe_signal<<<1, 32, 0, st>>>(kind, c, (unsigned long long)E.sec.epoch, g_pipe);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_pipe_wait(Engine &E, int kind, int c, cudaStream_t st) {
+  k_pipe_wait<<<1, 32, 0, st>>>(kind, c, (unsigned long long)E.sec.epoch, g_pipe, pipe_timeout_ns(),
+                                E.sec.pipe_err);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_pipe_add(Engine &E, int c, double *d_hv, cudaStream_t st) {
+  Sector &S = E.sec;
+  const int len = longest_chunk(g_pipe, c);
+  if (S.qdw <= 0 || len == 0) return 0;
+  dim3 grid((unsigned)S.qdw, (unsigned)((len + 255) / 256), (unsigned)E.nranks);
+  k_pipe_add<<<grid, 256, 0, st>>>(d_hv, S.hvr, c, g_pipe);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Halo mode (default for nranks > 1): the Hdw term without any transpose.  The hops of a rank's
+// chunk of dw columns read a few columns of other ranks (those reached by moving an electron
+// into / out of the top bath sites: ~ 8 T / Nbath columns per local column for T ~ log2(nranks)
+// "rank bits").  Before pass A every owner stores those columns -- contiguous runs of DimUp
+// doubles -- straight into the reader's halo buffer over NVLink and raises a flag; pass A (k_slow)
+// then runs on the chunk exactly as on one GPU, far gathers landing in the halo.  Per product and
+// state this moves <= the bytes of ONE transpose and adds no HBM pass (the double transpose of
+// vector_transpose_MPI costs push + Hdw on v^T + return + accumulate = 48 B/state on top).
+// block = [flags | halo 0 | halo 1]: double-buffered by the parity of the product counter, because
+// a peer may run one product ahead (it cannot run two ahead: its push of product e+2 needs this
+// rank's push flag of e+1, which is stream-ordered behind this rank's pass A of product e).
+// ---------------------------------------------------------------------------------------
+struct HaloTable {
+  unsigned char *block[EDGPU_MAXRANKS];
+  int64_t hbytes[EDGPU_MAXRANKS];  // bytes of ONE halo buffer of rank p
+  int64_t ldU;
+  int nranks, me;
+};
+static HaloTable g_halo;
+
+int comm_allgather_bytes(Engine &E, const unsigned char *h_mine, unsigned char *h_all, size_t nbytes) {
+  const int P = E.nranks;
+  if (P == 1) {
+    memcpy(h_all, h_mine, nbytes);
+    return 0;
+  }
+  unsigned char *d = nullptr;
+  EDGPU_CUDA(cudaMalloc(&d, nbytes * P));
+  EDGPU_CUDA(cudaMemcpyAsync(d + nbytes * E.rank, h_mine, nbytes, cudaMemcpyHostToDevice, E.stream));
+  EDGPU_NCCL(N.AllGather(d + nbytes * E.rank, d, nbytes, NCCL_CHAR, (nccl_comm_t)E.nccl, E.stream));
+  EDGPU_CUDA(cudaMemcpyAsync(h_all, d, nbytes * P, cudaMemcpyDeviceToHost, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  cudaFree(d);
+  return 0;
+}
+
+// maps `mine` (this rank's block) into every peer; *ok_all = every rank mapped every peer
+static int ipc_exchange(Engine &E, unsigned char *mine_block, unsigned char **peer, bool *ok_all) {
+  const int P = E.nranks, me = E.rank;
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaIpcGetMemHandle(&mine, mine_block) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0;
+  }
+  std::vector<cudaIpcMemHandle_t> all((size_t)P);
+  EDGPU_TRY(comm_allgather_bytes(E, (const unsigned char *)&mine, (unsigned char *)all.data(), sizeof(mine)));
+  for (int p = 0; p < P; p++) peer[p] = nullptr;
+  for (int p = 0; p < P && ok; p++) {
+    if (p == me) {
+      peer[p] = mine_block;
+      continue;
+    }
+    void *a = nullptr;
+    if (cudaIpcOpenMemHandle(&a, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    peer[p] = (unsigned char *)a;
+  }
+  double flag = ok ? 0.0 : 1.0;
+  EDGPU_TRY(comm_allreduce_host(E, &flag, 1, NCCL_SUM));
+  *ok_all = (flag == 0.0);
+  if (!*ok_all) {
+    for (int p = 0; p < P; p++) {
+      if (p != me && peer[p]) cudaIpcCloseMemHandle(peer[p]);
+      peer[p] = nullptr;
+    }
+    cudaGetLastError();
+  }
+  return 0;
+}
+
+int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all) {
+  Sector &S = E.sec;
+  const int P = E.nranks, me = E.rank;
+  const int64_t ld = S.dw.ld, dim = S.dw.dim, ldU = S.up.ld;
+  S.halo_mode = false;
+  // halo size of every rank and the slot of each of MY columns in each reader's halo
+  std::vector<int64_t> nh(P, 0);
+  std::vector<std::vector<int32_t>> send(P);  // per destination: (local col, slot) pairs
+  for (int r = 0; r < P; r++) {
+    int64_t qr, d0r;
+    block_split(dim, P, r, &qr, &d0r);
+    const unsigned char *need = need_all.data() + (size_t)r * (size_t)ld;
+    int64_t slot = 0;
+    for (int64_t d = 0; d < dim; d++) {
+      if (d >= d0r && d < d0r + qr) continue;
+      if (!need[d]) continue;
+      if (d >= S.d0 && d < S.d0 + S.qdw) {
+        send[r].push_back((int32_t)(d - S.d0));
+        send[r].push_back((int32_t)slot);
+      }
+      slot++;
+    }
+    nh[r] = slot;
+  }
+  if (nh[me] != S.dw.nhalo) return set_error("internal: halo size mismatch");
+  HaloTable &T = g_halo;
+  memset(&T, 0, sizeof(T));
+  T.nranks = P;
+  T.me = me;
+  T.ldU = ldU;
+  for (int p = 0; p < P; p++) T.hbytes[p] = (int64_t)(((size_t)nh[p] * (size_t)ldU * sizeof(double) + 255) / 256 * 256);
+  const size_t total = PIPE_FLAG_BYTES + 2 * (size_t)T.hbytes[me];
+  EDGPU_CUDA(cudaMalloc(&S.comm_block, total));
+  EDGPU_CUDA(cudaMemsetAsync(S.comm_block, 0, total, E.stream));
+  EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+  bool ok = false;
+  EDGPU_TRY(ipc_exchange(E, S.comm_block, S.peer_block, &ok));
+  if (!ok) {
+    cudaFree(S.comm_block);
+    S.comm_block = nullptr;
+    return 0;
+  }
+  for (int p = 0; p < P; p++) T.block[p] = S.peer_block[p];
+  S.halo[0] = reinterpret_cast<double *>(S.comm_block + PIPE_FLAG_BYTES);
+  S.halo[1] = reinterpret_cast<double *>(S.comm_block + PIPE_FLAG_BYTES + T.hbytes[me]);
+  // send list, destinations interleaved (starting at a different one on every rank) so that all
+  // NVLink endpoints are busy at any instant
+  std::vector<int32_t> list;
+  size_t longest = 0;
+  for (int r = 0; r < P; r++) longest = std::max(longest, send[r].size() / 2);
+  for (size_t k = 0; k < longest; k++)
+    for (int dr = 1; dr < P; dr++) {
+      const int r = (me + dr) % P;
+      if (k < send[r].size() / 2) {
+        list.push_back(send[r][2 * k]);
+        list.push_back(r);
+        list.push_back(send[r][2 * k + 1]);
+      }
+    }
+  S.nsend = (int64_t)list.size() / 3;
+  EDGPU_CUDA(cudaMalloc(&S.d_sendlist, sizeof(int32_t) * std::max<size_t>(list.size(), 3)));
+  if (!list.empty())
+    EDGPU_CUDA(cudaMemcpy(S.d_sendlist, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice));
+  S.pipe_err = reinterpret_cast<int32_t *>(E.h_scal + 60);  // pinned host word (UVA: device-visible)
+  *S.pipe_err = 0;
+  S.epoch = 0;
+  S.p2p = true;
+  S.halo_mode = true;
+  return 0;
+}
+
+constexpr int HALO_PIECE = 1024;  // double2 per work item: 16 KB of one column
+
+// Persistent copy kernel with a SMALL footprint (EDGPU_PUSH_CTAS CTAs, default 48): it runs
+// concurrently with the rank-local pass B, whose CTAs need whole SMs (2 x 512 threads x 64
+// registers); a grid of one CTA per piece was measured to halve pass B's speed.  Work item w =
+// (send-list entry, 16 KB piece of the column); all loads of an item are in flight before its
+// stores, which go straight into the reader's halo slot over NVLink (16-byte accesses).
+__global__ void __launch_bounds__(256)
+k_halo_push(const double *__restrict__ v, const int32_t *__restrict__ list, int64_t nsend, int par,
+            HaloTable T) {
+  const int n2 = (int)(T.ldU / 2);
+  const int npiece = (n2 + HALO_PIECE - 1) / HALO_PIECE;
+  const int64_t nwork = nsend * npiece;
+  for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int64_t e = w / npiece;
+    const int piece = (int)(w - e * npiece);
+    const int32_t src = list[3 * e], dst = list[3 * e + 1], slot = list[3 * e + 2];
+    const double2 *s = reinterpret_cast<const double2 *>(v + (int64_t)src * T.ldU);
+    double2 *d = reinterpret_cast<double2 *>(T.block[dst] + PIPE_FLAG_BYTES + (int64_t)par * T.hbytes[dst]) +
+                 (int64_t)slot * n2;
+    const int i0 = piece * HALO_PIECE + threadIdx.x;
+    double2 r[HALO_PIECE / 256];
+#pragma unroll
+    for (int k = 0; k < HALO_PIECE / 256; k++)
+      if (i0 + k * 256 < n2) r[k] = s[i0 + k * 256];
+#pragma unroll
+    for (int k = 0; k < HALO_PIECE / 256; k++)
+      if (i0 + k * 256 < n2) d[i0 + k * 256] = r[k];
+  }
+}
+
+__global__ void k_halo_signal(int par, unsigned long long epoch, HaloTable T) {
+  const int p = threadIdx.x;
+  if (p >= T.nranks) return;
+  __threadfence_system();
+  unsigned long long *f = reinterpret_cast<unsigned long long *>(T.block[p]) + par * EDGPU_MAXRANKS + T.me;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+}
+
+__global__ void k_halo_wait(int par, unsigned long long epoch, HaloTable T, unsigned long long timeout_ns,
+                            int32_t *err) {
+  const int p = threadIdx.x;
+  if (p >= T.nranks) return;
+  const unsigned long long *f =
+      reinterpret_cast<const unsigned long long *>(T.block[T.me]) + par * EDGPU_MAXRANKS + p;
+  unsigned long long t0, t1, seen;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+    if (seen >= epoch) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) {
+      *(volatile int32_t *)err = 1;
+      __threadfence_system();
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+static unsigned long long pipe_timeout_ns() {
+  static const unsigned long long t = [] {
+    const char *e = getenv("EDGPU_PIPE_TIMEOUT_S");
+    return (unsigned long long)((e ? atof(e) : 20.0) * 1e9);
+  }();
+  return t;
+}
+
+int comm_halo_push(Engine &E, const double *d_v, cudaStream_t st) {
+  Sector &S = E.sec;
+  if (S.nsend <= 0) return 0;
+  static const int ctas = [] {
+    const char *e = getenv("EDGPU_PUSH_CTAS");
+    return e && atoi(e) > 0 ? atoi(e) : 48;
+  }();
+  const int64_t nwork = S.nsend * ((S.up.ld / 2 + HALO_PIECE - 1) / HALO_PIECE);
+  k_halo_push<<<(unsigned)std::min<int64_t>(nwork, ctas), 256, 0, st>>>(d_v, S.d_sendlist, S.nsend,
+                                                                         (int)(S.epoch & 1), g_halo);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_halo_signal(Engine &E, cudaStream_t st) {
+  k_halo_signal<<<1, 32, 0, st>>>((int)(E.sec.epoch & 1), (unsigned long long)E.sec.epoch, g_halo);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_halo_wait(Engine &E, cudaStream_t st) {
+  k_halo_wait<<<1, 32, 0, st>>>((int)(E.sec.epoch & 1), (unsigned long long)E.sec.epoch, g_halo,
+                                pipe_timeout_ns(), E.sec.pipe_err);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_pipe_check(Engine &E) {
+  Sector &S = E.sec;
+  if (!S.p2p || !S.pipe_err) return 0;
+  const int32_t e = *(volatile int32_t *)S.pipe_err;
+  if (e != 0) {
+    *(volatile int32_t *)S.pipe_err = 0;
+    return set_error("distributed H x v: timed out waiting for the %s flags of a peer (rank %d)",
+                     e == 1 ? "push" : "return", E.rank);
+  }
   return 0;
 }
 

@@ -167,6 +167,14 @@ struct SpinSpace {
   // target row of c^+_a c_b | sign << 31, or -1 when the hop is not allowed on that state
   int32_t *imphop = nullptr;
   std::vector<Term> terms; // host copy
+  // Sharded slow role (the dw species with nranks > 1, halo mode): the table rows of the LOCAL
+  // columns [shard0, shard0 + shard_q) hold LOCAL targets: a column index < shard_q of the rank's
+  // chunk, or shard_q + slot of the halo (copies of the remote columns the chunk's hops read,
+  // pushed by their owners before pass A).  Ranges are in local column coordinates.
+  bool sharded = false;
+  int64_t shard0 = 0, shard_q = 0;
+  int64_t nhalo = 0;
+  std::vector<int32_t> halo_cols;   // host: global column of halo slot k (ascending)
 };
 
 // one coulomb_sundry line in application order (c_l, cd_j, c_k, cd_i): bit of the species
@@ -189,11 +197,24 @@ struct Sector {
   bool nonlocal = false;
   double *jx = nullptr, *jp = nullptr;  // [Norb*Norb] device copies
   int variant = 0;
-  // scratch for the distributed transposes
-  double *vt = nullptr, *hvt = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
-  // peer-memory transposes (comm.cu): vt / hvt of every rank mapped through CUDA IPC
+  // scratch for the distributed transposes: vt = this rank's rows of v^T ([DimDw (fast) x qup]),
+  // hvt = Hdw vt, hvr = landing zone of the returned Hdw part (shape of the local vector)
+  double *vt = nullptr, *hvt = nullptr, *hvr = nullptr, *sendbuf = nullptr, *recvbuf = nullptr;
+  // peer-memory pipeline (comm.cu): ONE allocation [flags | vt | hvr] per rank, mapped into every
+  // peer through CUDA IPC; the peers store their tiles and their progress flags straight into it
   bool p2p = false;
-  double *peer_vt[EDGPU_MAXRANKS] = {}, *peer_hvt[EDGPU_MAXRANKS] = {};
+  unsigned char *comm_block = nullptr;
+  unsigned char *peer_block[EDGPU_MAXRANKS] = {};
+  // halo mode (default): no transposes at all.  block = [flags | halo 0 | halo 1]; before pass A
+  // every owner stores the columns this rank's dw hops read into halo[epoch & 1] (double-buffered:
+  // a peer may run one product ahead), sendlist = (local column, destination rank, slot) triples
+  bool halo_mode = false;
+  double *halo[2] = {nullptr, nullptr};
+  int32_t *d_sendlist = nullptr;
+  int64_t nsend = 0;
+  uint64_t epoch = 0;              // one per distributed product; flags carry the epoch they belong to
+  int nchunks = 1;                 // column chunks of vt the Hdw term is pipelined over
+  int32_t *pipe_err = nullptr;     // device word set by a wait kernel that timed out
   // all-gathered vector for the non-local terms with nranks>1
   double *vfull = nullptr;
   std::vector<int64_t> gcounts, goffs;
@@ -240,11 +261,13 @@ struct Engine {
   size_t smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;  // transposes overlapped with the rank-local pass
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t dw_stream = nullptr;    // Hdw on the received chunks + their return (pipeline)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev[8] = {};
   // communicator
   int rank = 0, nranks = 1;
   void *nccl = nullptr;  // ncclComm_t
+  bool dw_halo = false;  // sector being opened / open: dw species sharded for the halo mode
   // scalar scratch
   double *d_scal = nullptr;   // device scalars (dots etc.)
   double *h_scal = nullptr;   // pinned host mirror
@@ -362,8 +385,34 @@ int comm_finalize(Engine &E);
 int comm_p2p_setup(Engine &E);     // after S.vt / S.hvt exist: exchange + map IPC handles
 int comm_p2p_teardown(Engine &E);  // before they are freed
 int comm_barrier(Engine &E);       // in-stream barrier over all ranks (1-element all-reduce)
-int comm_push_transpose(Engine &E, const double *d_a);             // v -> every rank's vt
-int comm_pull_transpose_acc(Engine &E, double *d_hv);              // Hv += transpose(hvt of all)
+// Chunked peer-memory pipeline of the Hdw term (hxv.cu drives it; DESIGN.md "Multi-GPU").  The
+// local columns of vt (= this rank's up rows) are cut into S.nchunks chunks; for chunk c
+//   push   : every rank stores its tile of v^T into the owners' vt           (NVLink stores)
+//   signal : st.release.sys of the epoch into the owners' flag words
+//   wait   : spin (bounded) on this rank's flag words until every sender signalled
+//   return : transposed tiles of hvt chunk c are stored into the owners' hvr (NVLink stores)
+//   add    : hv += hvr on the rows of chunk c of every owner
+enum { PIPE_PUSH = 0, PIPE_RET = 1 };
+constexpr int EDGPU_MAXCHUNKS = 16;
+constexpr size_t PIPE_FLAG_BYTES = 4096;  // 2 kinds x EDGPU_MAXCHUNKS x EDGPU_MAXRANKS x 8 B
+// layout of a rank's IPC block: [flags | vt (ldD x qup doubles) | hvr], 256-byte aligned parts
+inline size_t pipe_hvr_offset(int64_t ldD, int64_t qup) {
+  return PIPE_FLAG_BYTES + ((size_t)(ldD * qup) * sizeof(double) + 255) / 256 * 256;
+}
+int comm_pipe_push(Engine &E, int c, const double *d_v, cudaStream_t st);
+int comm_pipe_signal(Engine &E, int kind, int c, cudaStream_t st);
+int comm_pipe_wait(Engine &E, int kind, int c, cudaStream_t st);
+int comm_pipe_return(Engine &E, int c, cudaStream_t st);
+int comm_pipe_add(Engine &E, int c, double *d_hv, cudaStream_t st);
+void comm_pipe_chunk_cols(Engine &E, int rank, int c, int64_t *col0, int64_t *ncols);  // of vt, local
+int comm_pipe_check(Engine &E);  // after a host sync: did a wait kernel time out?
+// halo mode: need[p][d] = 1 when rank p's dw hops read column d of another rank (host, all ranks'
+// maps all-gathered by the caller): allocates + maps the halo block, builds the send list
+int comm_allgather_bytes(Engine &E, const unsigned char *h_mine, unsigned char *h_all, size_t nbytes);
+int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all);
+int comm_halo_push(Engine &E, const double *d_v, cudaStream_t st);
+int comm_halo_signal(Engine &E, cudaStream_t st);
+int comm_halo_wait(Engine &E, cudaStream_t st);
 
 // vecops.cu
 int vec_fill_random(Engine &E, double *d_v, uint64_t seed);

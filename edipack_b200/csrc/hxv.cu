@@ -40,6 +40,10 @@ struct SpinView {
   int block_mode, nitems;
   const BlockItem *items;
   const int32_t *item_of_row;
+  // sharded slow role (halo mode): table row of local column 0, number of local columns (targets
+  // >= qloc are halo slots); unsharded: 0 and UINT32_MAX
+  int64_t row_off;
+  uint32_t qloc;
 };
 
 static SpinView view_of(const SpinSpace &S) {
@@ -60,6 +64,8 @@ static SpinView view_of(const SpinSpace &S) {
   v.nitems = (int)S.items.size();
   v.items = S.d_items;
   v.item_of_row = S.d_item_of_row;
+  v.row_off = S.sharded ? S.shard0 : 0;
+  v.qloc = S.sharded ? (uint32_t)S.shard_q : 0xFFFFFFFFu;
   return v;
 }
 
@@ -94,7 +100,8 @@ template <bool WITH_DIAG, bool WITH_SLOW>
 __global__ void __launch_bounds__(128)
 k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, int64_t ldv,
           int64_t ncol, int64_t col_offset, SpinView F, SpinView S,
-          const double *__restrict__ xud, int nimp, int accum, double s_acc, double s_old) {
+          const double *__restrict__ xud, int nimp, int accum, double s_acc, double s_old,
+          const double *__restrict__ halo) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t c = blockIdx.y;
   if (i >= nrow) return;
@@ -125,7 +132,9 @@ k_generic(const double *__restrict__ v, double *__restrict__ hv, int64_t nrow, i
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const uint32_t ent = ent_of(q, k);
-        acc += S.amp2[(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK] * v[(int64_t)(ent & HOP_TGT_MASK) * ldv + i];
+        const uint32_t t = ent & HOP_TGT_MASK;  // sharded species: local column or qloc + halo slot
+        const double x = t >= S.qloc ? halo[(int64_t)(t - S.qloc) * ldv + i] : v[(int64_t)t * ldv + i];
+        acc += S.amp2[(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK] * x;
       }
     }
   }
@@ -554,7 +563,7 @@ __device__ __forceinline__ void slow_block_sum(double x, double *__restrict__ do
 template <int W4, int NF, bool ACCUM, bool DOT>
 __global__ void __launch_bounds__(SLOW_THREADS, 2)
 k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinView S,
-       double s_acc, double *__restrict__ dot_part) {
+       double s_acc, double *__restrict__ dot_part, const double *__restrict__ halo) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tile = reinterpret_cast<double *>(smem_raw);
   const int tid = threadIdx.x;
@@ -589,10 +598,13 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
   __syncthreads();
 
   const double *vrow = v + i0 + rp2;  // + t * ldv : far target column
+  // sharded species: far targets >= qloc are halo slots (copies of remote columns, comm.cu)
+  const uint32_t qloc = S.qloc;
+  const double *hrow = qloc == 0xFFFFFFFFu ? vrow : halo + i0 + rp2 - (int64_t)qloc * ldv;
   // + t * 128 : local target column (wraps mod 2^32 before the add, exact after it)
   const uint32_t trow_sa = smem_u32(tile) + (uint32_t)rp2 * 8u - (uint32_t)s0 * (SLOW_R * 8u);
   const uint32_t amp_sa = smem_u32(amp_s);
-  const uint4 *ell = S.ell4 + s0;
+  const uint4 *ell = S.ell4 + S.row_off + s0;
   constexpr int NG = W4 > 0 ? W4 : 1;
 
   if (W4 > 0) {
@@ -644,7 +656,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
         const uint32_t ent = ent_of(q[e >> 2], e & 3);
         const uint32_t t = ent & HOP_TGT_MASK;
         if (ent & HOP_FAR)
-          xf[e] = *reinterpret_cast<const double2 *>(vrow + (size_t)(t * ld32));
+          xf[e] = *reinterpret_cast<const double2 *>((t >= qloc ? hrow : vrow) + (size_t)(t * ld32));
         else
           xf[e] = lds128(trow_sa + t * (SLOW_R * 8u));
       }
@@ -675,7 +687,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
       const double2 hold = ACCUM ? *reinterpret_cast<const double2 *>(o) : make_double2(0.0, 0.0);
       double2 acc = make_double2(0.0, 0.0);
       for (int g = 0; g < S.Wl4; g++) {
-        const uint4 qq = S.ell4[(int64_t)g * S.ld + c];
+        const uint4 qq = ell[(int64_t)g * S.ld + j];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const uint32_t ent = ent_of(qq, k);
@@ -683,7 +695,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
           const uint32_t t = ent & HOP_TGT_MASK;
           double2 x;
           if (ent & HOP_FAR)
-            x = *reinterpret_cast<const double2 *>(vrow + (size_t)t * ldv);
+            x = *reinterpret_cast<const double2 *>((t >= qloc ? hrow : vrow) + (size_t)t * ldv);
           else
             x = lds128(trow_sa + t * (SLOW_R * 8u));
           acc.x += a * x.x;
@@ -1060,11 +1072,11 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
     dim3 grid((unsigned)((F.dim + 127) / 128), (unsigned)ncol);
     if (with_diag)
       k_generic<true, false><<<grid, 128, 0, E.stream>>>(v, hv, F.dim, F.ld, ncol, col_offset, F,
-                                                          S, xud, nimp, (int)accum, s_acc, s_old);
+                                                          S, xud, nimp, (int)accum, s_acc, s_old, nullptr);
     else
       k_generic<false, false><<<grid, 128, 0, E.stream>>>(v, hv, F.dim, F.ld, ncol, col_offset,
                                                            F, S, xud, nimp, (int)accum, s_acc,
-                                                           s_old);
+                                                           s_old, nullptr);
     EDGPU_COUNT_LAUNCH();
     EDGPU_CUDA(cudaGetLastError());
     return 0;
@@ -1097,12 +1109,13 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
 
 template <int W4, int NF, bool ACCUM, bool DOT>
 static int launch_slow(Engine &E, const double *v, double *hv, const SpinSpace &Ss,
-                       const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part) {
+                       const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part,
+                       const double *halo) {
   const size_t smem = slow_smem_bytes(Ss.max_range, S.nterms);
   dim3 grid((unsigned)S.nranges, (unsigned)((Fv.ld + SLOW_R - 1) / SLOW_R));
   auto kern = k_slow<W4, NF, ACCUM, DOT>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S, s_acc, dot_part);
+  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S, s_acc, dot_part, halo);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
@@ -1114,16 +1127,19 @@ static int64_t slow_grid_size(const SpinView &Fv, const SpinView &S) {
 }
 
 static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const SpinSpace &Ss,
-                      const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part) {
+                      const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part,
+                      const double *halo = nullptr) {
+  if (S.nranges <= 0) return 0;  // a rank without columns (DimDw < nranks)
   // the element offset t * ld of a far gather is formed in 32 bits
-  const bool small = (uint64_t)Ss.dim * (uint64_t)Fv.ld < (1ull << 32);
+  const uint64_t ncols = Ss.sharded ? (uint64_t)(Ss.shard_q + Ss.nhalo) : (uint64_t)Ss.dim;
+  const bool small = ncols * (uint64_t)Fv.ld < (1ull << 32);
   const int W4 = Ss.Wl4, NF = Ss.Wf;  // Wf = largest number of far entries of a column
   const bool dot = dot_part != nullptr;
 #define EDGPU_SLOW(WW, FF)                                                                       \
-  (accum ? (dot ? launch_slow<WW, FF, true, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part)          \
-                : launch_slow<WW, FF, true, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part))        \
-         : (dot ? launch_slow<WW, FF, false, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part)         \
-                : launch_slow<WW, FF, false, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part)))
+  (accum ? (dot ? launch_slow<WW, FF, true, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo)    \
+                : launch_slow<WW, FF, true, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo))  \
+         : (dot ? launch_slow<WW, FF, false, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo)   \
+                : launch_slow<WW, FF, false, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo)))
   if (small && W4 >= 1 && W4 <= 3 && NF <= 4 && NF <= 4 * W4) {
     switch (W4 * 8 + NF) {
       case 8 + 0: return EDGPU_SLOW(1, 0);
@@ -1212,7 +1228,7 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
         // one fused gather kernel: diagonal + up hops + dw hops
         dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
         k_generic<true, true><<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, S.qdw, 0, U, D, S.xud,
-                                                    nimp, (int)accum, s_acc, s_old);
+                                                    nimp, (int)accum, s_acc, s_old, nullptr);
         EDGPU_COUNT_LAUNCH();
         EDGPU_CUDA(cudaGetLastError());
         EDGPU_MARK(1);
@@ -1249,42 +1265,119 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
     } else {
       // dw-split over ranks (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:236-375):
       //   Hv  = (Hd + 1 (x) Hup) v                      local columns
-      //   vt  = transpose(v)                            NCCL all-to-all of tiles
+      //   vt  = transpose(v)                            tiles exchanged over NVLink
       //   Hvt = Hdw vt                                  dw is now the fast index
       //   Hv += transpose(Hvt)
-      // The first transpose only reads v: it runs on the communication stream concurrently with
-      // the rank-local pass (diag + up hops) on the main stream.  Phonon slices are processed one
-      // after the other like the reference's `do iph=1,DimPh` (:322-337).
+      // Phonon slices are processed one after the other like the reference's `do iph=1,DimPh`
+      // (:322-337).
       EDGPU_CUDA(cudaEventRecord(E.ev_fork, st));
-      EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
-      {
-        cudaStream_t keep = E.stream;
-        E.stream = E.comm_stream;  // the comm_* helpers and apply_fast launch on E.stream
-        int rc = 0;
-        if (S.p2p) {
-          // push v^T into every rank's vt over NVLink, barrier, dw hops on the local vt, barrier
-          rc = comm_push_transpose(E, v_s);
-          if (!rc) rc = comm_barrier(E);
+      if (S.halo_mode) {
+        // Halo mode (comm.cu): the owners push the remote columns this chunk's dw hops read while
+        // the rank-local pass B runs; pass A then runs on the chunk exactly as on one GPU.
+        S.epoch++;
+        EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
+        EDGPU_TRY(comm_halo_push(E, v_s, E.comm_stream));
+        EDGPU_TRY(comm_halo_signal(E, E.comm_stream));
+        EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
+        const double *halo = S.halo[S.epoch & 1];
+        if (!tiled) {
+          EDGPU_TRY(comm_halo_wait(E, st));
+          if (S.qdw > 0) {
+            dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
+            k_generic<true, true><<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, S.qdw, S.d0, U, D, S.xud, nimp,
+                                                        (int)accum, s_acc, s_old, halo);
+            EDGPU_COUNT_LAUNCH();
+            EDGPU_CUDA(cudaGetLastError());
+          }
+          EDGPU_MARK(1);
+          EDGPU_MARK(2);
         } else {
-          rc = comm_transpose(E, v_s, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false);
+          EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
+                               s_old));
+          EDGPU_MARK(1);
+          EDGPU_TRY(comm_halo_wait(E, st));
+          if ((D.Wl4 + D.Wf4) > 0) {
+            double *part = nullptr;
+            const int64_t nblk = slow_grid_size(U, D);
+            if (dot_out && !S.nonlocal && !extras && nblk > 0) {
+              EDGPU_TRY(ensure_partials(E, nblk));
+              part = E.d_part;
+            }
+            EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part, halo));
+            if (part) {
+              EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
+              dot_done = true;
+            }
+          }
+          EDGPU_MARK(2);
         }
-        if (!rc)
-          rc = apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
-                          1.0);
-        if (!rc && S.p2p) rc = comm_barrier(E);
-        E.stream = keep;
-        if (rc) return rc;
-      }
-      EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
-      EDGPU_TRY(apply_fast(E, tiled, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
-                           s_old));
-      EDGPU_MARK(1);
-      EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
-      EDGPU_MARK(2);
-      if (S.p2p)
-        EDGPU_TRY(comm_pull_transpose_acc(E, hv_s));
-      else
+        EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
+      } else if (S.p2p) {
+        // Chunk pipeline over peer memory (comm.cu): three streams per rank,
+        //   comm_stream : push(0) sig push(1) sig ...
+        //   dw_stream   : wait(push 0) Hdw(0) return(0) sig  wait(push 1) Hdw(1) ...
+        //   main        : local pass (diag + up hops), then wait(ret c) + add(c) for every chunk
+        // so that the NVLink stores of both directions, the Hdw pass and the local pass overlap.
+        S.epoch++;
+        const int K = S.nchunks;
+        EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
+        EDGPU_CUDA(cudaStreamWaitEvent(E.dw_stream, E.ev_fork, 0));
+        for (int c = 0; c < K; c++) {
+          EDGPU_TRY(comm_pipe_push(E, c, v_s, E.comm_stream));
+          EDGPU_TRY(comm_pipe_signal(E, PIPE_PUSH, c, E.comm_stream));
+        }
+        EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
+        EDGPU_TRY(apply_fast(E, tiled, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
+                             s_old));
+        EDGPU_MARK(1);
+        {
+          cudaStream_t keep = E.stream;
+          E.stream = E.dw_stream;  // apply_fast launches on E.stream
+          int rc = 0;
+          for (int c = 0; c < K && !rc; c++) {
+            int64_t col0, ncols;
+            comm_pipe_chunk_cols(E, E.rank, c, &col0, &ncols);
+            rc = comm_pipe_wait(E, PIPE_PUSH, c, E.dw_stream);
+            if (!rc && ncols > 0)
+              rc = apply_fast(E, tiled, false, false, S.vt + col0 * D.ld, S.hvt + col0 * D.ld, ncols,
+                              S.u0 + col0, S.dw, D, U, S.xud, nimp, s_acc, 1.0);
+            if (!rc) rc = comm_pipe_return(E, c, E.dw_stream);
+            if (!rc) rc = comm_pipe_signal(E, PIPE_RET, c, E.dw_stream);
+          }
+          E.stream = keep;
+          if (rc) return rc;
+        }
+        EDGPU_CUDA(cudaEventRecord(E.ev_join2, E.dw_stream));
+        for (int c = 0; c < K; c++) {
+          EDGPU_TRY(comm_pipe_wait(E, PIPE_RET, c, st));
+          if (c == K - 1) EDGPU_MARK(2);
+          EDGPU_TRY(comm_pipe_add(E, c, hv_s, st));
+        }
+        EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
+        EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join2, 0));
+      } else {
+        // NCCL fallback (EDGPU_NO_P2P=1 or unmappable peers): grouped send/recv tile transposes.
+        // The first one only reads v: it runs on the communication stream concurrently with the
+        // rank-local pass on the main stream.
+        EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
+        {
+          cudaStream_t keep = E.stream;
+          E.stream = E.comm_stream;  // the comm_* helpers and apply_fast launch on E.stream
+          int rc = comm_transpose(E, v_s, U.dim, U.ld, S.qdw, S.vt, D.dim, D.ld, S.qup, false);
+          if (!rc)
+            rc = apply_fast(E, tiled, false, false, S.vt, S.hvt, S.qup, S.u0, S.dw, D, U, S.xud, nimp, s_acc,
+                            1.0);
+          E.stream = keep;
+          if (rc) return rc;
+        }
+        EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
+        EDGPU_TRY(apply_fast(E, tiled, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
+                             s_old));
+        EDGPU_MARK(1);
+        EDGPU_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
+        EDGPU_MARK(2);
         EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, hv_s, U.dim, U.ld, S.qdw, true));
+      }
       if (need_full) EDGPU_TRY(comm_allgatherv(E, v_s, S.vfull + iph * slice_full, S.gcounts, S.goffs));
       if (S.nonlocal) {
         dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);

@@ -134,20 +134,34 @@ __global__ void k_imphop_fill(const int32_t *__restrict__ map, int64_t dim, int6
     }
 }
 
-// per-row counts of local / far allowed terms; far = the term touches a bit >= far_bit[r]
+// per-row counts of local / far allowed terms; far = the term touches a bit >= far_bit[r], or
+// (sharded species, shard_q >= 0) its target column lies outside the rank's chunk
+// [shard0, shard0 + shard_q) -- only the rows of the chunk are counted then.
+// need != nullptr: also marks the columns outside the chunk that the chunk's hops read.
 __global__ void k_hop_count(const int32_t *__restrict__ map, int64_t dim,
                             const Term *__restrict__ terms, int nterms,
-                            const uint8_t *__restrict__ far_bit, SiteOrder ord,
+                            const uint8_t *__restrict__ far_bit, SiteOrder ord, RankView R,
+                            int64_t shard0, int64_t shard_q, unsigned char *__restrict__ need,
                             int *__restrict__ wmax) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= dim) return;
+  const bool sharded = shard_q >= 0;
+  if (sharded && (r < shard0 || r >= shard0 + shard_q)) return;
   uint32_t m = (uint32_t)map[r];
   const int fb = far_bit[r];
   int nl = 0, nf = 0;
   for (int t = 0; t < nterms; t++) {
     int a = terms[t].alpha, b = terms[t].beta;
     if (((m >> b) & 1u) && !((m >> a) & 1u)) {
-      if (ord.pos[a] >= fb || ord.pos[b] >= fb) nf++; else nl++;
+      bool far = (ord.pos[a] >= fb || ord.pos[b] >= fb);
+      if (sharded) {
+        const int64_t tgt = rank_of((m & ~(1u << b)) | (1u << a), R);
+        if (tgt < shard0 || tgt >= shard0 + shard_q) {
+          far = true;
+          if (need) need[tgt] = 1;
+        }
+      }
+      if (far) nf++; else nl++;
     }
   }
   atomicMax(wmax, nl);
@@ -164,14 +178,19 @@ __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t
                            const Term *__restrict__ terms, int nterms,
                            const uint8_t *__restrict__ far_bit, int merged, int Wl4, int Wf4,
                            RankView R, const BlockItem *__restrict__ items,
-                           const int32_t *__restrict__ item_of_row, uint32_t *__restrict__ ell) {
+                           const int32_t *__restrict__ item_of_row, int64_t shard0, int64_t shard_q,
+                           const int32_t *__restrict__ colmap, uint32_t *__restrict__ ell) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= ld) return;
+  // sharded species (merged only): rows of the chunk get LOCAL targets through colmap (local column
+  // or shard_q + halo slot); rows outside the chunk are never used (padding)
+  const bool sharded = shard_q >= 0;
+  const bool inside = !sharded || (r >= shard0 && r < shard0 + shard_q);
   // slot s of this row lives at ell[((s/4)*ld + r)*4 + s%4]
   auto put = [&](int s, uint32_t val) { ell[((int64_t)(s >> 2) * ld + r) * 4 + (s & 3)] = val; };
   const int nslots = 4 * (Wl4 + Wf4);
   int el = 0, ef = merged ? 0 : 4 * Wl4;
-  if (r < dim) {
+  if (r < dim && inside) {
     uint32_t m = (uint32_t)map[r];
     const int fb = far_bit[r];
     if (merged) {  // first pass: far entries, second pass: local entries behind them
@@ -179,10 +198,14 @@ __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t
         for (int t = 0; t < nterms; t++) {
           int a = terms[t].alpha, b = terms[t].beta;
           if (((m >> b) & 1u) && !((m >> a) & 1u)) {
-            const bool far = (R.ord.pos[a] >= fb || R.ord.pos[b] >= fb);
-            if ((int)far == pass) continue;
+            bool far = (R.ord.pos[a] >= fb || R.ord.pos[b] >= fb);
             uint32_t m2 = (m & ~(1u << b)) | (1u << a);
             uint32_t tgt = (uint32_t)rank_of(m2, R);
+            if (sharded) {
+              far = far || ((int64_t)tgt < shard0 || (int64_t)tgt >= shard0 + shard_q);
+              tgt = (uint32_t)colmap[tgt];
+            }
+            if ((int)far == pass) continue;
             put(el++, tgt | ((uint32_t)(2 * t + hop_sign(m, a, b)) << HOP_AMP_SHIFT) |
                           (far ? HOP_FAR : 0u));
           }
@@ -205,7 +228,7 @@ __global__ void k_hop_fill(const int32_t *__restrict__ map, int64_t dim, int64_t
   // padding slots gather the row itself (always inside the row's own tile; block mode: tile
   // offset 0) with amplitude 0; far padding points at the row itself
   const uint32_t padamp = (uint32_t)(2 * nterms) << HOP_AMP_SHIFT;
-  const uint32_t pad = (uint32_t)r | padamp;
+  const uint32_t pad = (uint32_t)(sharded ? (inside ? r - shard0 : 0) : r) | padamp;
   if (merged) {
     for (; el < nslots; el++) put(el, pad);
   } else {
@@ -383,7 +406,9 @@ static void plan_species(Engine &E, const edgpu_normal_params &p, int s, int nel
   const size_t tables = 8 * (2 * terms.size() + 2 + (up_t ? 16 : 4) * ((size_t)1 << No)) + 64;
   const size_t avail = per_cta > tables ? per_cta - tables : 0;
   P.identity = (s == 1 && E.nranks > 1);
-  P.role = (s == 1 && E.nranks == 1) ? ROLE_SLOW : ROLE_FAST;
+  // the dw species is applied along the slow index: by k_slow on one rank and (halo mode) on the
+  // rank's chunk of columns; in transpose mode it acts on v^T, where dw is the fast index
+  P.role = (s == 1 && (E.nranks == 1 || E.dw_halo)) ? ROLE_SLOW : ROLE_FAST;
   if (up_t) P.role = ROLE_SLOW;
   P.block_mode = false;
   P.items.clear();
@@ -512,12 +537,18 @@ int species_ranking(Engine &E, const edgpu_normal_params &p, int s, int nel, int
   return build_ranking(E, p.Ns, nel, *ord, dim, (dim + 15) / 16 * 16, map, lin);
 }
 
-static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, SpinSpace &S) {
+// need_all (sharded species only): receives the all-gathered "columns my hops read from other
+// ranks" maps of every rank, [nranks][dim] bytes, for comm_halo_setup
+static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, SpinSpace &S,
+                      int64_t shard0 = 0, int64_t shard_q = -1,
+                      std::vector<unsigned char> *need_all = nullptr) {
   const int Ns = p.Ns;
   cudaStream_t st = E.stream;
   SpeciesPlan P;
   plan_species(E, p, s, nel, P);
   const int role = P.role;
+  const bool sharded = shard_q >= 0 && role == ROLE_SLOW;
+  if (!sharded) shard_q = -1;
   S.nel = nel;
   S.role = role;
   S.dim = host_binomial(Ns, nel);
@@ -536,6 +567,27 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
     for (int64_t r = S.range_start[k]; r < S.range_start[k + 1]; r++)
       far_bit[(size_t)r] = (uint8_t)(Ns - S.range_tbits[k]);
   S.ord = P.ord;
+  S.sharded = sharded;
+  S.shard0 = sharded ? shard0 : 0;
+  S.shard_q = sharded ? shard_q : 0;
+  if (sharded) {
+    // ranges of the rank's chunk [shard0, shard0 + shard_q) in LOCAL column coordinates: the
+    // global prefix ranges cut at the chunk boundaries
+    std::vector<int64_t> loc;
+    std::vector<int> tb;
+    for (int k = 0; k < S.nranges; k++) {
+      const int64_t a = std::max(S.range_start[k], shard0), b = std::min(S.range_start[k + 1], shard0 + shard_q);
+      if (b <= a) continue;
+      loc.push_back(a - shard0);
+      tb.push_back(S.range_tbits[k]);
+    }
+    loc.push_back(shard_q);
+    S.range_start = loc;
+    S.range_tbits = tb;
+    S.nranges = (int)loc.size() - 1;
+    S.max_range = 0;
+    for (int k = 0; k < S.nranges; k++) S.max_range = std::max(S.max_range, loc[k + 1] - loc[k]);
+  }
   EDGPU_CUDA(cudaMalloc(&S.d_range_start, sizeof(int64_t) * S.range_start.size()));
   EDGPU_CUDA(cudaMemcpyAsync(S.d_range_start, S.range_start.data(),
                              sizeof(int64_t) * S.range_start.size(), cudaMemcpyHostToDevice, st));
@@ -588,11 +640,40 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
                                cudaMemcpyHostToDevice, st));
   EDGPU_CUDA(cudaMemcpyAsync(d_far, far_bit.data(), (size_t)S.ld, cudaMemcpyHostToDevice, st));
   EDGPU_CUDA(cudaMemsetAsync(d_w, 0, 3 * sizeof(int), st));
-  k_hop_count<<<gb, T, 0, st>>>(S.map, S.dim, d_terms, S.nterms, d_far, S.ord, d_w);
+  unsigned char *d_need = nullptr;
+  int32_t *d_colmap = nullptr;
+  if (sharded) {
+    EDGPU_CUDA(cudaMalloc(&d_need, (size_t)S.ld));
+    EDGPU_CUDA(cudaMemsetAsync(d_need, 0, (size_t)S.ld, st));
+  }
+  k_hop_count<<<gb, T, 0, st>>>(S.map, S.dim, d_terms, S.nterms, d_far, S.ord, rank_view(S.lin, S.ord),
+                                shard0, shard_q, d_need, d_w);
   EDGPU_COUNT_LAUNCH();
   int W[3] = {0, 0, 0};
   EDGPU_CUDA(cudaMemcpyAsync(W, d_w, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   EDGPU_CUDA(cudaStreamSynchronize(st));
+  if (sharded) {
+    // halo slots: the remote columns this chunk reads, in ascending (= owner-major) order
+    std::vector<unsigned char> mine((size_t)S.ld, 0);
+    EDGPU_CUDA(cudaMemcpy(mine.data(), d_need, (size_t)S.ld, cudaMemcpyDeviceToHost));
+    need_all->assign((size_t)E.nranks * (size_t)S.ld, 0);
+    EDGPU_TRY(comm_allgather_bytes(E, mine.data(), need_all->data(), (size_t)S.ld));
+    std::vector<int32_t> colmap((size_t)S.ld, -1);
+    S.halo_cols.clear();
+    for (int64_t d = 0; d < S.dim; d++) {
+      if (d >= shard0 && d < shard0 + shard_q) {
+        colmap[(size_t)d] = (int32_t)(d - shard0);
+      } else if (mine[(size_t)d]) {
+        colmap[(size_t)d] = (int32_t)(shard_q + (int64_t)S.halo_cols.size());
+        S.halo_cols.push_back((int32_t)d);
+      }
+    }
+    S.nhalo = (int64_t)S.halo_cols.size();
+    if (shard_q + S.nhalo > (int64_t)HOP_TGT_MASK) return set_error("chunk + halo too large for the hop table");
+    EDGPU_CUDA(cudaMalloc(&d_colmap, sizeof(int32_t) * (size_t)S.ld));
+    EDGPU_CUDA(cudaMemcpy(d_colmap, colmap.data(), sizeof(int32_t) * (size_t)S.ld, cudaMemcpyHostToDevice));
+    cudaFree(d_need);
+  }
   const int merged = (role == ROLE_SLOW);
   if (merged) {
     S.Wl = W[2];
@@ -606,8 +687,8 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   const int G = std::max(S.Wl4 + S.Wf4, 1);
   EDGPU_CUDA(cudaMalloc(&S.ell4, sizeof(uint4) * (size_t)G * S.ld));
   k_hop_fill<<<gl, T, 0, st>>>(S.map, S.dim, S.ld, d_terms, S.nterms, d_far, merged, S.Wl4, S.Wf4,
-                               rank_view(S.lin, S.ord), S.d_items, S.d_item_of_row,
-                               (uint32_t *)S.ell4);
+                               rank_view(S.lin, S.ord), S.d_items, S.d_item_of_row, shard0, shard_q,
+                               d_colmap, (uint32_t *)S.ell4);
   EDGPU_COUNT_LAUNCH();
   std::vector<double> amp(2 * S.nterms + 2, 0.0);
   for (int t = 0; t < S.nterms; t++) {
@@ -621,6 +702,7 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   cudaFree(d_terms);
   cudaFree(d_w);
   cudaFree(d_far);
+  cudaFree(d_colmap);
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
@@ -630,14 +712,23 @@ int sector_close(Engine &E) {
   if (!S.open) return 0;
   cudaStreamSynchronize(E.stream);
   cudaStreamSynchronize(E.comm_stream);
+  cudaStreamSynchronize(E.dw_stream);
   if (E.nranks > 1) comm_p2p_teardown(E);
   free_spin(S.up);
   free_spin(S.dw);
   cudaFree(S.xud);
   cudaFree(S.jx);
   cudaFree(S.jp);
-  cudaFree(S.vt);
+  cudaFree(S.comm_block);  // holds vt and hvr / the halo buffers
   cudaFree(S.hvt);
+  cudaFree(S.d_sendlist);
+  S.d_sendlist = nullptr;
+  S.nsend = 0;
+  S.halo[0] = S.halo[1] = nullptr;
+  S.halo_mode = false;
+  S.comm_block = nullptr;
+  S.pipe_err = nullptr;
+  S.hvr = nullptr;
   cudaFree(S.sendbuf);
   cudaFree(S.recvbuf);
   cudaFree(S.vfull);
@@ -666,15 +757,26 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
   S.Ns = p->Ns;
   S.Norb = p->Norb;
   EDGPU_TRY(upload_binom(E));
+  // dw split (ED_HAMILTONIAN_NORMAL.f90:128-142).  The reference shrinks the communicator when
+  // DimDw < MpiSize (:98-126); here the ranks beyond DimDw simply own no column (qdw = 0) and
+  // keep taking part in the collectives, which is the same thing seen from the caller.
+  block_split(host_binomial(p->Ns, ndw), E.nranks, E.rank, &S.qdw, &S.d0);
+  block_split(host_binomial(p->Ns, nup), E.nranks, E.rank, &S.qup, &S.u0);
+  // How the Hdw term crosses ranks: halo mode (default; the owners push the few remote columns a
+  // chunk's hops read, then pass A runs on the chunk exactly as on one GPU) or the reference's
+  // double transpose (EDGPU_DW_MODE=transpose: chunk pipeline over peer memory; EDGPU_NO_P2P=1:
+  // NCCL grouped send/recv).  Every rank reads the same environment.
+  {
+    const char *mode = getenv("EDGPU_DW_MODE"), *nop2p = getenv("EDGPU_NO_P2P");
+    E.dw_halo = E.nranks > 1 && E.nranks <= EDGPU_MAXRANKS && !(mode && !strcmp(mode, "transpose")) &&
+                !(nop2p && nop2p[0] == '1');
+  }
+  std::vector<unsigned char> need_all;
   EDGPU_TRY(build_spin(E, *p, 0, nup, S.up));
-  EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw));
-  // dw split (ED_HAMILTONIAN_NORMAL.f90:128-142).  The reference shrinks the communicator
-  // when DimDw < MpiSize (:98-126); here every rank must own at least one column and one row.
-  if (E.nranks > 1 && (S.dw.dim < E.nranks || S.up.dim < E.nranks))
-    return set_error("sector (DimUp=%lld,DimDw=%lld) smaller than the %d-rank communicator",
-                     (long long)S.up.dim, (long long)S.dw.dim, E.nranks);
-  block_split(S.dw.dim, E.nranks, E.rank, &S.qdw, &S.d0);
-  block_split(S.up.dim, E.nranks, E.rank, &S.qup, &S.u0);
+  if (E.dw_halo)
+    EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw, S.d0, S.qdw, &need_all));
+  else
+    EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw));
   // cross-spin interaction table + constants (direct/HxV_local.f90:34-70)
   const int No = p->Norb, nimp = 1 << No;
   std::vector<double> x((size_t)nimp * nimp, 0.0);
@@ -717,13 +819,31 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
   }
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
 
-  if (E.nranks > 1) {
+  S.halo_mode = false;
+  if (E.dw_halo) {
+    EDGPU_TRY(comm_halo_setup(E, need_all));  // collective; S.halo_mode = every rank mapped every peer
+    if (!S.halo_mode) {
+      // peers not mappable: rebuild the dw species for the transposed layout (NCCL transposes)
+      E.dw_halo = false;
+      free_spin(S.dw);
+      EDGPU_TRY(build_spin(E, *p, 1, ndw, S.dw));
+    }
+  }
+  if (E.nranks > 1 && !S.halo_mode) {
     // transposed block [DimDw (fast) x qup] for the dw hops, mapped into every peer when possible
+    // (one allocation [flags | vt | hvr]: a single IPC handle per rank, comm.cu)
     const size_t nt = (size_t)S.padded_len_t();
-    EDGPU_CUDA(cudaMalloc(&S.vt, sizeof(double) * nt));
-    EDGPU_CUDA(cudaMalloc(&S.hvt, sizeof(double) * nt));
-    EDGPU_CUDA(cudaMemsetAsync(S.vt, 0, sizeof(double) * nt, E.stream));
-    EDGPU_CUDA(cudaMemsetAsync(S.hvt, 0, sizeof(double) * nt, E.stream));
+    const size_t off_hvr = pipe_hvr_offset(S.dw.ld, S.qup);
+    const size_t total = off_hvr + (sizeof(double) * (size_t)S.slice_len() + 255) / 256 * 256;
+    EDGPU_CUDA(cudaMalloc(&S.comm_block, total));
+    EDGPU_CUDA(cudaMalloc(&S.hvt, sizeof(double) * std::max<size_t>(nt, 1)));
+    S.pipe_err = reinterpret_cast<int32_t *>(E.h_scal + 60);  // pinned host word (UVA: device-visible)
+    *S.pipe_err = 0;
+    S.vt = reinterpret_cast<double *>(S.comm_block + PIPE_FLAG_BYTES);
+    S.hvr = reinterpret_cast<double *>(S.comm_block + off_hvr);
+    // flags start at epoch 0, pad rows of vt / hvr stay zero for ever (never written by a peer)
+    EDGPU_CUDA(cudaMemsetAsync(S.comm_block, 0, total, E.stream));
+    EDGPU_CUDA(cudaMemsetAsync(S.hvt, 0, sizeof(double) * std::max<size_t>(nt, 1), E.stream));
     EDGPU_CUDA(cudaStreamSynchronize(E.stream));
     EDGPU_TRY(comm_p2p_setup(E));
   }

@@ -172,7 +172,7 @@ int scalar_to_host(Engine &E, double *d_scalar, double *h_out) {
   EDGPU_CUDA(cudaMemcpyAsync(E.h_scal, d_scalar, sizeof(double), cudaMemcpyDeviceToHost, E.stream));
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
   *h_out = E.h_scal[0];
-  return 0;
+  return comm_pipe_check(E);
 }
 
 static int finish_scalar(Engine &E, int nblocks, double *h_out) {
@@ -182,7 +182,7 @@ static int finish_scalar(Engine &E, int nblocks, double *h_out) {
   EDGPU_CUDA(cudaMemcpyAsync(E.h_scal, E.d_scal, sizeof(double), cudaMemcpyDeviceToHost, E.stream));
   EDGPU_CUDA(cudaStreamSynchronize(E.stream));
   *h_out = E.h_scal[0];
-  return 0;
+  return comm_pipe_check(E);
 }
 
 int vec_zero(Engine &E, double *d_v, int64_t n) {
