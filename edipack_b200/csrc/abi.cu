@@ -98,6 +98,7 @@ static int upload(Engine &E, double *d_dst, const double *h_src) {
   }
   Sector &S = E.sec;
   const int64_t n = S.up.dim * S.qdw, slice = S.slice_len();  // per phonon slice
+  if (S.qdw <= 0) return 0;  // a rank without columns (DimDw < nranks)
   if (S.up.ord.identity && S.dw.ord.identity) {
     EDGPU_CUDA(cudaMemsetAsync(d_dst, 0, sizeof(double) * S.padded_len(), E.stream));
     for (int iph = 0; iph < S.DimPh; iph++)
@@ -126,6 +127,10 @@ static int download(Engine &E, double *h_dst, const double *d_src) {
   }
   Sector &S = E.sec;
   const int64_t n = S.up.dim * S.qdw, slice = S.slice_len();  // per phonon slice
+  if (S.qdw <= 0) {
+    EDGPU_CUDA(cudaStreamSynchronize(E.stream));
+    return 0;
+  }
   if (S.up.ord.identity && S.dw.ord.identity) {
     for (int iph = 0; iph < S.DimPh; iph++)
       EDGPU_CUDA(cudaMemcpy2DAsync(h_dst + iph * n, sizeof(double) * S.up.dim, d_src + iph * slice,
@@ -429,6 +434,16 @@ int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_
   if (DimDw) *DimDw = g.sec.dw.dim;
   if (qdw) *qdw = g.sec.qdw;
   if (dw_start) *dw_start = g.sec.d0;
+  return 0;
+}
+
+int edgpu_sector_comm_info(int *mode, int64_t *halo_cols, int64_t *send_cols, int *nchunks) {
+  if (!g.sec.open) return set_error("no sector open");
+  const Sector &S = g.sec;
+  if (mode) *mode = g.nranks == 1 ? 0 : (S.halo_mode ? 1 : (S.p2p ? 2 : 3));
+  if (halo_cols) *halo_cols = S.halo_mode ? S.dw.nhalo : 0;
+  if (send_cols) *send_cols = S.halo_mode ? S.nsend : 0;
+  if (nchunks) *nchunks = S.halo_mode ? 1 : S.nchunks;
   return 0;
 }
 
@@ -918,7 +933,7 @@ int edgpu_apply_op(int slot, int op, int iorb, int spin) {
     src_slice = full_slice;
   }
   dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
-  for (int iph = 0; iph < S.DimPh; iph++) {
+  for (int iph = 0; iph < S.DimPh && S.qdw > 0; iph++) {
     k_apply_op<<<grid, 128, 0, g.stream>>>(vsrc + iph * src_slice, st.ldu, g_seed + iph * S.slice_len(),
                                            S.up.ld, S.up.dim, S.qdw,
                                            spin == 0 ? S.up.map : S.dw.map + S.d0, op, iorb, spin,
@@ -980,7 +995,7 @@ int edgpu_apply_ops_normal(int slot, int nops, const double *coef, int op, const
     src_slice = full_slice;
   }
   dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
-  for (int k = 0; k < nops; k++)
+  for (int k = 0; k < nops && S.qdw > 0; k++)
     for (int iph = 0; iph < S.DimPh; iph++) {
       k_apply_op_acc<<<grid, 128, 0, g.stream>>>(vsrc + iph * src_slice, st.ldu, g_seed + iph * S.slice_len(),
                                                  S.up.ld, S.up.dim, S.qdw,
@@ -1084,7 +1099,7 @@ int edgpu_state_twin(int src_slot, int dst_slot) {
     src_slice = full_slice;
   }
   dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw);
-  for (int iph = 0; iph < S.DimPh; iph++) {
+  for (int iph = 0; iph < S.DimPh && S.qdw > 0; iph++) {
     k_twin_normal<<<grid, 128, 0, g.stream>>>(vsrc + iph * src_slice, st.ldu, tmp + iph * S.slice_len(),
                                               S.up.ld, S.up.dim, S.up.map, S.dw.map + S.d0,
                                               rank_view(linu, ordu), rank_view(lind, ordd));
@@ -1122,7 +1137,7 @@ int edgpu_state_observables(int slot, double *dens, double *docc) {
   EDGPU_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * EDGPU_MAXORB, g.stream));
   dim3 grid((unsigned)std::min<int64_t>((S.up.dim + 255) / 256, 64),
             (unsigned)std::min<int64_t>(S.qdw, 1024));
-  for (int iph = 0; iph < st.dimph; iph++) {  // the occupations do not see the phonon index
+  for (int iph = 0; iph < st.dimph && S.qdw > 0; iph++) {  // the occupations do not see the phonon index
     k_observables<<<grid, 256, 0, g.stream>>>(st.vec + iph * st.ldu * st.qdw, st.ldu, S.up.dim, S.qdw, S.d0,
                                               S.up.imp, S.dw.imp, S.Norb, d_out);
     EDGPU_COUNT_LAUNCH();

@@ -711,18 +711,21 @@ int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all) {
   return 0;
 }
 
-constexpr int HALO_PIECE = 1024;  // double2 per work item: 16 KB of one column
+constexpr int HALO_THREADS = 512, HALO_UNROLL = 8;
+constexpr int HALO_PIECE = HALO_THREADS * HALO_UNROLL;  // double2 per work item: <= 64 KB of one column
 
-// Persistent copy kernel with a SMALL footprint (EDGPU_PUSH_CTAS CTAs, default 48): it runs
+// Persistent copy kernel with a SMALL footprint (EDGPU_PUSH_CTAS CTAs, default 40): it runs
 // concurrently with the rank-local pass B, whose CTAs need whole SMs (2 x 512 threads x 64
-// registers); a grid of one CTA per piece was measured to halve pass B's speed.  Work item w =
-// (send-list entry, 16 KB piece of the column); all loads of an item are in flight before its
-// stores, which go straight into the reader's halo slot over NVLink (16-byte accesses).
-__global__ void __launch_bounds__(256)
+// registers); a grid of one CTA per 16 KB piece was measured to halve pass B's speed.  NVLink
+// needs ~1 MB in flight (770 GB/s x ~1 us): each CTA keeps up to 64 KB in flight -- all loads of a
+// work item (send-list entry, piece of the column) are issued before its 16-byte stores, which go
+// straight into the reader's halo slot over NVLink.
+__global__ void __launch_bounds__(HALO_THREADS)
 k_halo_push(const double *__restrict__ v, const int32_t *__restrict__ list, int64_t nsend, int par,
             HaloTable T) {
   const int n2 = (int)(T.ldU / 2);
   const int npiece = (n2 + HALO_PIECE - 1) / HALO_PIECE;
+  const int plen = (n2 + npiece - 1) / npiece;  // even split of the column
   const int64_t nwork = nsend * npiece;
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int64_t e = w / npiece;
@@ -731,14 +734,14 @@ k_halo_push(const double *__restrict__ v, const int32_t *__restrict__ list, int6
     const double2 *s = reinterpret_cast<const double2 *>(v + (int64_t)src * T.ldU);
     double2 *d = reinterpret_cast<double2 *>(T.block[dst] + PIPE_FLAG_BYTES + (int64_t)par * T.hbytes[dst]) +
                  (int64_t)slot * n2;
-    const int i0 = piece * HALO_PIECE + threadIdx.x;
-    double2 r[HALO_PIECE / 256];
+    const int i0 = piece * plen + threadIdx.x, iend = min(n2, (piece + 1) * plen);
+    double2 r[HALO_UNROLL];
 #pragma unroll
-    for (int k = 0; k < HALO_PIECE / 256; k++)
-      if (i0 + k * 256 < n2) r[k] = s[i0 + k * 256];
+    for (int k = 0; k < HALO_UNROLL; k++)
+      if (i0 + k * HALO_THREADS < iend) r[k] = s[i0 + k * HALO_THREADS];
 #pragma unroll
-    for (int k = 0; k < HALO_PIECE / 256; k++)
-      if (i0 + k * 256 < n2) d[i0 + k * 256] = r[k];
+    for (int k = 0; k < HALO_UNROLL; k++)
+      if (i0 + k * HALO_THREADS < iend) d[i0 + k * HALO_THREADS] = r[k];
   }
 }
 
@@ -784,10 +787,10 @@ int comm_halo_push(Engine &E, const double *d_v, cudaStream_t st) {
   if (S.nsend <= 0) return 0;
   static const int ctas = [] {
     const char *e = getenv("EDGPU_PUSH_CTAS");
-    return e && atoi(e) > 0 ? atoi(e) : 48;
+    return e && atoi(e) > 0 ? atoi(e) : 40;
   }();
   const int64_t nwork = S.nsend * ((S.up.ld / 2 + HALO_PIECE - 1) / HALO_PIECE);
-  k_halo_push<<<(unsigned)std::min<int64_t>(nwork, ctas), 256, 0, st>>>(d_v, S.d_sendlist, S.nsend,
+  k_halo_push<<<(unsigned)std::min<int64_t>(nwork, ctas), HALO_THREADS, 0, st>>>(d_v, S.d_sendlist, S.nsend,
                                                                          (int)(S.epoch & 1), g_halo);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());

@@ -146,6 +146,7 @@ int extra_setup(Engine &E) {
 int extra_hxv(Engine &E, const double *d_v, const double *d_vfull, double *d_hv, double s_acc) {
   Sector &S = E.sec;
   const int64_t slice = S.slice_len(), slice_full = S.up.ld * S.dw.dim;
+  if (S.qdw <= 0) return 0;  // a rank without columns (DimDw < nranks)
   dim3 grid((unsigned)((S.up.dim + 127) / 128), (unsigned)S.qdw, (unsigned)S.DimPh);
   if (S.DimPh > 1) {
     k_phonon<<<grid, 128, 0, E.stream>>>(d_v, d_vfull, d_hv, S.up.dim, S.up.ld, S.d0, slice, slice_full,

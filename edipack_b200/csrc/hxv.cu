@@ -1379,7 +1379,7 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
         EDGPU_TRY(comm_transpose(E, S.hvt, D.dim, D.ld, S.qup, hv_s, U.dim, U.ld, S.qdw, true));
       }
       if (need_full) EDGPU_TRY(comm_allgatherv(E, v_s, S.vfull + iph * slice_full, S.gcounts, S.goffs));
-      if (S.nonlocal) {
+      if (S.nonlocal && S.qdw > 0) {
         dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
         k_nonlocal<<<grid, 128, 0, st>>>(S.vfull + iph * slice_full, hv_s, U.dim, U.ld, S.d0, S.up.imphop,
                                          S.up.ld, S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc);

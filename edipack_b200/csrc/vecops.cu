@@ -217,6 +217,7 @@ int vec_fill_random(Engine &E, double *d_v, uint64_t seed) {
     return 0;
   }
   Sector &S = E.sec;
+  if (S.qdw <= 0) return 0;  // a rank without columns (DimDw < nranks)
   dim3 grid((unsigned)((S.up.ld + VT - 1) / VT), (unsigned)S.qdw, (unsigned)S.DimPh);
   k_random<<<grid, VT, 0, E.stream>>>(d_v, S.up.dim, S.up.ld, S.qdw, S.d0, seed, S.up.refidx,
                                       S.dw.refidx, S.up.dim * S.dw.dim);

@@ -457,6 +457,16 @@ def vecDim_Hv_sector_normal() -> int:
     return int(_abi.load().edgpu_sector_vecdim())
 
 
+def sector_comm_info():
+    """(mode, halo columns received, columns sent, chunks) of the open NORMAL sector's Hdw exchange:
+    mode 0 single rank, 1 halo, 2 peer-memory transposes, 3 NCCL transposes."""
+    L = _abi.load()
+    mode, nch = C.c_int(), C.c_int()
+    a, b = C.c_int64(), C.c_int64()
+    check(L.edgpu_sector_comm_info(C.byref(mode), C.byref(a), C.byref(b), C.byref(nch)))
+    return mode.value, a.value, b.value, nch.value
+
+
 def sector_dims():
     L = _abi.load()
     a, b, c, d = (C.c_int64() for _ in range(4))

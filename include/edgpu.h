@@ -166,6 +166,12 @@ int edgpu_sector_close(void);           /* delete_Hv_sector_normal, :212-279 */
 int64_t edgpu_sector_vecdim(void);      /* vecDim_Hv_sector_normal, :286-313 (local chunk) */
 int64_t edgpu_sector_dim(void);         /* getDim(isector) */
 int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_start);
+/* How the Hdw term of the open sector crosses ranks (replaces vector_transpose_MPI,
+ * ED_HAMILTONIAN_NORMAL_COMMON.f90:66-178): mode 0 = single rank, 1 = halo (the owners store the
+ * remote dw columns this rank's hops read into its halo buffer over NVLink), 2 = chunk-pipelined
+ * peer-memory transposes, 3 = NCCL grouped send/recv transposes.  halo_cols = columns received,
+ * send_cols = columns sent per product (each DimUp doubles, padded to a multiple of 16). */
+int edgpu_sector_comm_info(int *mode, int64_t *halo_cols, int64_t *send_cols, int *nchunks);
 
 /* Parity hooks: download the device-resident structures for bit-exact comparison with the
  * oracle (sector maps ED_SECTOR.f90:217-242; hop tables = spH0ups(1)/spH0dws(1) content

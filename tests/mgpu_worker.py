@@ -25,6 +25,11 @@ import edipack_oracle as O
 from models import normal_normal_kwargs, star_kwargs, two_orb_kwargs
 
 
+def amax(x):
+    """max |x| of a possibly empty chunk (ranks beyond DimDw own no column)."""
+    return float(np.abs(x).max()) if x.size else 0.0
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -39,12 +44,15 @@ def main():
              ("star9_54", star_kwargs(9), (5, 4)), ("star11", star_kwargs(11), (6, 6)),
              ("two_orb_nb3_nojx", two_orb_kwargs(3, with_nd=False), (4, 4)),
              ("two_orb_nb3_jxjp", two_orb_kwargs(3), (4, 4)), ("two_orb_nb2_jxjp", two_orb_kwargs(2), (3, 2)),
-             ("star13", star_kwargs(13), (7, 7))]
+             ("star13", star_kwargs(13), (7, 7)),
+             # sectors smaller than the communicator (the reference shrinks it,
+             # ED_HAMILTONIAN_NORMAL.f90:98-126; here the ranks beyond DimDw own no column)
+             ("star7_dw1", star_kwargs(7), (4, 0)), ("star7_up1", star_kwargs(7), (8, 3)),
+             ("star7_1x1", star_kwargs(7), (8, 0)), ("two_orb_dw1", two_orb_kwargs(2), (2, 6)),
+             ("star7_dw8", star_kwargs(7), (3, 1))]
     for name, kw, (nup, ndw) in cases:
         m, mo = E.EDModel(**kw), O.Model(**kw)
         du, dd = O.sector_dims(m.Ns, nup, ndw)
-        if dd < world or du < world:
-            continue
         full = O.start_vector(du * dd, 17) - 0.5
         lo, hi = E.chunk_bounds(du, dd, world, rank)
         E.build_Hv_sector_normal(m, nup, ndw)
@@ -55,7 +63,7 @@ def main():
                 ref = O.direct_hxv(mo, nup, ndw, full)
             else:
                 ref = O.stored_hxv_mpi(mo, nup, ndw, full, 8, 8)[0]
-            err = np.abs(hv - ref[lo:hi]).max() / np.abs(ref).max()
+            err = amax(hv - ref[lo:hi]) / np.abs(ref).max()
             if not err < 1e-12:
                 failures.append(f"{name}: HxV rel err {err:.3e} on rank {rank}")
             if du * dd <= 70000:
@@ -75,7 +83,7 @@ def main():
                 dist.all_reduce(n2loc)
                 if abs(float(n2loc.item()) - 1.0) > 1e-10:
                     failures.append(f"{name}: |gs|^2 = {float(n2loc.item())}")
-            if du * dd <= 5000:
+            if 3 <= du * dd <= 5000:
                 # sp_eigh (thick-restart Lanczos, all-reduced projection coefficients) on the shards
                 ref_ev = np.linalg.eigvalsh(O.dense_H(mo, nup, ndw))[:3]
                 ev, vecs, nconv, nmv = E.sp_eigh(3, 24, 300, 1e-14)
@@ -87,6 +95,33 @@ def main():
                     failures.append(f"{name}: sp_eigh vectors not orthonormal across ranks")
         finally:
             E.delete_Hv_sector_normal()
+    # The reference's own fixture over ALL sectors on the shards (ed_diag_d visits the 1-state and
+    # DimDw < nranks sectors too): test/src/NORMAL_NORMAL/{evals,dens,docc,Sigma_momenta}.check
+    from models import golden
+    g = golden("normal_normal")
+    kw = normal_normal_kwargs()
+    m, mo = E.EDModel(**kw), O.Model(**kw)
+    m.lanc_tolerance = 1e-18
+    try:
+        states = E.ed_diag_d(m)
+        if not (len(states) == 1 and (states[0].nup, states[0].ndw) == (3, 3)):
+            failures.append(f"golden scan: states {[(s.nup, s.ndw, s.e) for s in states]}")
+        elif abs(states[0].e - g["evals"][0]) > 1e-9:
+            failures.append(f"golden scan: E_gs {states[0].e} vs {g['evals'][0]}")
+        else:
+            dens, docc = E.observables_normal(m, states)
+            if np.abs(dens - np.array(g["dens"])).max() > 1e-8 or np.abs(docc - np.array(g["docc"])).max() > 1e-8:
+                failures.append(f"golden scan: dens {dens} docc {docc}")
+            gold = np.array(g["Sigma_momenta"]).reshape(m.Norb, 4)
+            for iorb in range(m.Norb):
+                pw = E.lanc_build_gf_normal_diag(m, states, iorb, 0)
+                wm, sig = O.sigma_matsubara(mo, pw, iorb, 0, int(g["inputs"]["LMATS"]))
+                if np.abs(O.momenta(wm, sig) / gold[iorb] - 1.0).max() > 1e-8:
+                    failures.append(f"golden scan: Sigma moments of orbital {iorb}")
+        for s_ in states:
+            E.state_free(s_.slot)
+    except Exception as ex:  # keep the ranks' collectives matched: report, do not raise
+        failures.append(f"golden scan raised {type(ex).__name__}: {ex}")
     # Green's-function seeds on the sharded state: c / c^+ of both spins applied to the resident
     # ground state, read back through norm2 and alpha_1 of the tridiagonalisation
     # (apply_op_C/CDG, ED_SECTOR.f90:465/654; the dw operators need the gathered state)
@@ -94,7 +129,7 @@ def main():
     m, mo = E.EDModel(**kw), O.Model(**kw)
     nup, ndw = 3, 3
     du, dd = O.sector_dims(m.Ns, nup, ndw)
-    if dd >= world and du >= world:
+    if True:
         H = O.dense_H(mo, nup, ndw)
         ev, U = np.linalg.eigh(H)
         gs = U[:, 0]
@@ -109,9 +144,6 @@ def main():
             for iorb in range(m.Norb):
                 for op in (+1, -1):
                     ref, jn = O.apply_op(mo, op, iorb, spin, nup, ndw, gs)
-                    tdu, tdd = O.sector_dims(m.Ns, jn[0], jn[1])
-                    if tdd < world or tdu < world:
-                        continue
                     E.build_Hv_sector_normal(m, jn[0], jn[1])
                     try:
                         E.apply_op(5, op, iorb, spin)
@@ -136,8 +168,6 @@ def main():
             ("sundry+phonons", two_orb_kwargs(3, with_nd=True), (4, 4), SUNDRY, ph)]:
         m, mo = E.EDModel(**kw), O.Model(**kw)
         du, dd = O.sector_dims(m.Ns, nup, ndw)
-        if dd < world or du < world:
-            continue
         nph = (phon["Nph"] if phon else 0) + 1
         full = O.start_vector(du * dd * nph, 23) - 0.5
         lo, hi = E.chunk_bounds(du, dd, world, rank)
@@ -148,7 +178,7 @@ def main():
         try:
             hv = E.spHtimesV_p(full[pick].copy())
             ref = O.direct_hxv_ext(mo, nup, ndw, full, sundry, phon)
-            err = np.abs(hv - ref[pick]).max() / np.abs(ref).max()
+            err = amax(hv - ref[pick]) / np.abs(ref).max()
             if not err < 1e-12:
                 failures.append(f"a10 {name}: HxV rel err {err:.3e} on rank {rank}")
             if du * dd * nph <= 6000:
@@ -182,7 +212,7 @@ def main():
         if E.vecDim_Hv_sector_normal() != hi - lo:
             failures.append(f"nonsu2: vecDim {E.vecDim_Hv_sector_normal()} vs {hi - lo}")
         hv = E.spHtimesV_cc(vfull[lo:hi].copy())
-        err = np.abs(hv - ref[lo:hi]).max() / np.abs(ref).max()
+        err = amax(hv - ref[lo:hi]) / np.abs(ref).max()
         if not err < 1e-12:
             failures.append(f"nonsu2: HxV rel err {err:.3e} on rank {rank}")
         ev, _, nconv, _ = E.sp_eigh(2, 24, 300, 1e-14, want_vectors=False)
