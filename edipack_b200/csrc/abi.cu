@@ -443,7 +443,7 @@ int edgpu_sector_comm_info(int *mode, int64_t *halo_cols, int64_t *send_cols, in
   if (mode) *mode = g.nranks == 1 ? 0 : (S.halo_mode ? 1 : (S.p2p ? 2 : 3));
   if (halo_cols) *halo_cols = S.halo_mode ? S.dw.nhalo : 0;
   if (send_cols) *send_cols = S.halo_mode ? S.nsend : 0;
-  if (nchunks) *nchunks = S.halo_mode ? 1 : S.nchunks;
+  if (nchunks) *nchunks = S.nchunks;
   return 0;
 }
 

@@ -708,6 +708,14 @@ int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all) {
   S.epoch = 0;
   S.p2p = true;
   S.halo_mode = true;
+  {
+    // row chunks of the halo exchange (pipelined against pass A); at least 16 tiles of 16 rows each
+    const char *e = getenv("EDGPU_HALO_CHUNKS");
+    int k = e && atoi(e) > 0 ? atoi(e) : 4;
+    k = std::min<int>(k, EDGPU_MAXCHUNKS);
+    k = (int)std::max<int64_t>(1, std::min<int64_t>(k, S.up.ld / SLOW_ROWS / 16));
+    S.nchunks = k;
+  }
   return 0;
 }
 
@@ -720,12 +728,15 @@ constexpr int HALO_PIECE = HALO_THREADS * HALO_UNROLL;  // double2 per work item
 // needs ~1 MB in flight (770 GB/s x ~1 us): each CTA keeps up to 64 KB in flight -- all loads of a
 // work item (send-list entry, piece of the column) are issued before its 16-byte stores, which go
 // straight into the reader's halo slot over NVLink.
+// The halo travels in ROW chunks (rows [r0, r1) of every column, in double2 units): pass A works on
+// 16-row tiles, so its tiles of chunk c can start as soon as chunk c of every owner has arrived.
 __global__ void __launch_bounds__(HALO_THREADS)
 k_halo_push(const double *__restrict__ v, const int32_t *__restrict__ list, int64_t nsend, int par,
-            HaloTable T) {
+            int r0, int r1, HaloTable T) {
   const int n2 = (int)(T.ldU / 2);
-  const int npiece = (n2 + HALO_PIECE - 1) / HALO_PIECE;
-  const int plen = (n2 + npiece - 1) / npiece;  // even split of the column
+  const int len = r1 - r0;
+  const int npiece = (len + HALO_PIECE - 1) / HALO_PIECE;
+  const int plen = (len + npiece - 1) / npiece;  // even split of the column chunk
   const int64_t nwork = nsend * npiece;
   for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int64_t e = w / npiece;
@@ -734,7 +745,7 @@ k_halo_push(const double *__restrict__ v, const int32_t *__restrict__ list, int6
     const double2 *s = reinterpret_cast<const double2 *>(v + (int64_t)src * T.ldU);
     double2 *d = reinterpret_cast<double2 *>(T.block[dst] + PIPE_FLAG_BYTES + (int64_t)par * T.hbytes[dst]) +
                  (int64_t)slot * n2;
-    const int i0 = piece * plen + threadIdx.x, iend = min(n2, (piece + 1) * plen);
+    const int i0 = r0 + piece * plen + threadIdx.x, iend = min(r1, r0 + (piece + 1) * plen);
     double2 r[HALO_UNROLL];
 #pragma unroll
     for (int k = 0; k < HALO_UNROLL; k++)
@@ -745,20 +756,24 @@ k_halo_push(const double *__restrict__ v, const int32_t *__restrict__ list, int6
   }
 }
 
-__global__ void k_halo_signal(int par, unsigned long long epoch, HaloTable T) {
+__device__ __forceinline__ int halo_flag_slot(int par, int c, int sender) {
+  return (par * EDGPU_MAXCHUNKS + c) * EDGPU_MAXRANKS + sender;
+}
+
+__global__ void k_halo_signal(int par, int c, unsigned long long epoch, HaloTable T) {
   const int p = threadIdx.x;
   if (p >= T.nranks) return;
   __threadfence_system();
-  unsigned long long *f = reinterpret_cast<unsigned long long *>(T.block[p]) + par * EDGPU_MAXRANKS + T.me;
+  unsigned long long *f = reinterpret_cast<unsigned long long *>(T.block[p]) + halo_flag_slot(par, c, T.me);
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
 }
 
-__global__ void k_halo_wait(int par, unsigned long long epoch, HaloTable T, unsigned long long timeout_ns,
-                            int32_t *err) {
+__global__ void k_halo_wait(int par, int c, unsigned long long epoch, HaloTable T,
+                            unsigned long long timeout_ns, int32_t *err) {
   const int p = threadIdx.x;
   if (p >= T.nranks) return;
   const unsigned long long *f =
-      reinterpret_cast<const unsigned long long *>(T.block[T.me]) + par * EDGPU_MAXRANKS + p;
+      reinterpret_cast<const unsigned long long *>(T.block[T.me]) + halo_flag_slot(par, c, p);
   unsigned long long t0, t1, seen;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
@@ -782,30 +797,40 @@ static unsigned long long pipe_timeout_ns() {
   return t;
 }
 
-int comm_halo_push(Engine &E, const double *d_v, cudaStream_t st) {
+// rows [*row0, *row1) of row chunk c of the halo (multiples of SLOW_ROWS = 16)
+void comm_halo_rows(Engine &E, int c, int64_t *row0, int64_t *row1) {
+  const int64_t tiles = E.sec.up.ld / SLOW_ROWS, K = E.sec.nchunks;
+  *row0 = tiles * c / K * SLOW_ROWS;
+  *row1 = tiles * (c + 1) / K * SLOW_ROWS;
+}
+
+int comm_halo_push(Engine &E, int c, const double *d_v, cudaStream_t st) {
   Sector &S = E.sec;
   if (S.nsend <= 0) return 0;
   static const int ctas = [] {
     const char *e = getenv("EDGPU_PUSH_CTAS");
     return e && atoi(e) > 0 ? atoi(e) : 40;
   }();
-  const int64_t nwork = S.nsend * ((S.up.ld / 2 + HALO_PIECE - 1) / HALO_PIECE);
-  k_halo_push<<<(unsigned)std::min<int64_t>(nwork, ctas), HALO_THREADS, 0, st>>>(d_v, S.d_sendlist, S.nsend,
-                                                                         (int)(S.epoch & 1), g_halo);
+  int64_t r0, r1;
+  comm_halo_rows(E, c, &r0, &r1);
+  if (r1 <= r0) return 0;
+  const int64_t nwork = S.nsend * (((r1 - r0) / 2 + HALO_PIECE - 1) / HALO_PIECE);
+  k_halo_push<<<(unsigned)std::min<int64_t>(nwork, ctas), HALO_THREADS, 0, st>>>(
+      d_v, S.d_sendlist, S.nsend, (int)(S.epoch & 1), (int)(r0 / 2), (int)(r1 / 2), g_halo);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
 
-int comm_halo_signal(Engine &E, cudaStream_t st) {
-  k_halo_signal<<<1, 32, 0, st>>>((int)(E.sec.epoch & 1), (unsigned long long)E.sec.epoch, g_halo);
+int comm_halo_signal(Engine &E, int c, cudaStream_t st) {
+  k_halo_signal<<<1, 32, 0, st>>>((int)(E.sec.epoch & 1), c, (unsigned long long)E.sec.epoch, g_halo);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }
 
-int comm_halo_wait(Engine &E, cudaStream_t st) {
-  k_halo_wait<<<1, 32, 0, st>>>((int)(E.sec.epoch & 1), (unsigned long long)E.sec.epoch, g_halo,
+int comm_halo_wait(Engine &E, int c, cudaStream_t st) {
+  k_halo_wait<<<1, 32, 0, st>>>((int)(E.sec.epoch & 1), c, (unsigned long long)E.sec.epoch, g_halo,
                                 pipe_timeout_ns(), E.sec.pipe_err);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());

@@ -540,7 +540,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // deterministic CTA reduction of one double per thread -> dot_part[linear CTA index]
-__device__ __forceinline__ void slow_block_sum(double x, double *__restrict__ dot_part) {
+__device__ __forceinline__ void slow_block_sum(double x, double *__restrict__ dot_part, int tile0) {
   __shared__ double red[SLOW_THREADS / 32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -550,7 +550,7 @@ __device__ __forceinline__ void slow_block_sum(double x, double *__restrict__ do
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < SLOW_THREADS / 32; w++) t += red[w];
-    dot_part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    dot_part[(size_t)(blockIdx.y + tile0) * gridDim.x + blockIdx.x] = t;
   }
 }
 
@@ -563,14 +563,14 @@ __device__ __forceinline__ void slow_block_sum(double x, double *__restrict__ do
 template <int W4, int NF, bool ACCUM, bool DOT>
 __global__ void __launch_bounds__(SLOW_THREADS, 2)
 k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinView S,
-       double s_acc, double *__restrict__ dot_part, const double *__restrict__ halo) {
+       double s_acc, double *__restrict__ dot_part, const double *__restrict__ halo, int tile0) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tile = reinterpret_cast<double *>(smem_raw);
   const int tid = threadIdx.x;
   const int s0 = (int)S.range_start[blockIdx.x], s1 = (int)S.range_start[blockIdx.x + 1];
   const int len = s1 - s0;
   double *amp_s = tile + (size_t)len * SLOW_R;
-  const int64_t i0 = (int64_t)blockIdx.y * SLOW_R;
+  const int64_t i0 = (int64_t)(blockIdx.y + tile0) * SLOW_R;  // tile0: first row tile of a sub-grid
   constexpr int PARTS = SLOW_R / 2;              // 16-byte pieces (= threads) per column
   constexpr int CSTEP = SLOW_THREADS / PARTS;    // columns per sweep of the CTA
   const int rp2 = (tid % PARTS) * 2;             // first of the thread's two rows
@@ -678,7 +678,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
       q0p = q[0];
       op = o;
     }
-    if (DOT) slow_block_sum(dsum, dot_part);
+    if (DOT) slow_block_sum(dsum, dot_part, tile0);
   } else {
     double dsum = 0.0;
     for (int j = jl; j < len; j += CSTEP) {
@@ -710,7 +710,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
         dsum += own.x * acc.x + own.y * acc.y;
       }
     }
-    if (DOT) slow_block_sum(dsum, dot_part);
+    if (DOT) slow_block_sum(dsum, dot_part, tile0);
   }
 }
 
@@ -1110,12 +1110,12 @@ static int apply_fast(Engine &E, bool tiled, bool with_diag, bool accum, const d
 template <int W4, int NF, bool ACCUM, bool DOT>
 static int launch_slow(Engine &E, const double *v, double *hv, const SpinSpace &Ss,
                        const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part,
-                       const double *halo) {
+                       const double *halo, int tile0, int ntiles) {
   const size_t smem = slow_smem_bytes(Ss.max_range, S.nterms);
-  dim3 grid((unsigned)S.nranges, (unsigned)((Fv.ld + SLOW_R - 1) / SLOW_R));
+  dim3 grid((unsigned)S.nranges, (unsigned)ntiles);
   auto kern = k_slow<W4, NF, ACCUM, DOT>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S, s_acc, dot_part, halo);
+  kern<<<grid, SLOW_THREADS, smem, E.stream>>>(v, hv, Fv.ld, S, s_acc, dot_part, halo, tile0);
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
@@ -1128,18 +1128,19 @@ static int64_t slow_grid_size(const SpinView &Fv, const SpinView &S) {
 
 static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const SpinSpace &Ss,
                       const SpinView &Fv, const SpinView &S, double s_acc, double *dot_part,
-                      const double *halo = nullptr) {
-  if (S.nranges <= 0) return 0;  // a rank without columns (DimDw < nranks)
+                      const double *halo = nullptr, int tile0 = 0, int ntiles = -1) {
+  if (ntiles < 0) ntiles = (int)((Fv.ld + SLOW_R - 1) / SLOW_R) - tile0;  // all row tiles from tile0 on
+  if (S.nranges <= 0 || ntiles <= 0) return 0;  // a rank without columns (DimDw < nranks)
   // the element offset t * ld of a far gather is formed in 32 bits
   const uint64_t ncols = Ss.sharded ? (uint64_t)(Ss.shard_q + Ss.nhalo) : (uint64_t)Ss.dim;
   const bool small = ncols * (uint64_t)Fv.ld < (1ull << 32);
   const int W4 = Ss.Wl4, NF = Ss.Wf;  // Wf = largest number of far entries of a column
   const bool dot = dot_part != nullptr;
 #define EDGPU_SLOW(WW, FF)                                                                       \
-  (accum ? (dot ? launch_slow<WW, FF, true, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo)    \
-                : launch_slow<WW, FF, true, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo))  \
-         : (dot ? launch_slow<WW, FF, false, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo)   \
-                : launch_slow<WW, FF, false, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo)))
+  (accum ? (dot ? launch_slow<WW, FF, true, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo, tile0, ntiles)    \
+                : launch_slow<WW, FF, true, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo, tile0, ntiles))  \
+         : (dot ? launch_slow<WW, FF, false, true>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo, tile0, ntiles)   \
+                : launch_slow<WW, FF, false, false>(E, v, hv, Ss, Fv, S, s_acc, dot_part, halo, tile0, ntiles)))
   if (small && W4 >= 1 && W4 <= 3 && NF <= 4 && NF <= 4 * W4) {
     switch (W4 * 8 + NF) {
       case 8 + 0: return EDGPU_SLOW(1, 0);
@@ -1275,13 +1276,16 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
         // Halo mode (comm.cu): the owners push the remote columns this chunk's dw hops read while
         // the rank-local pass B runs; pass A then runs on the chunk exactly as on one GPU.
         S.epoch++;
+        const int K = S.nchunks;
         EDGPU_CUDA(cudaStreamWaitEvent(E.comm_stream, E.ev_fork, 0));
-        EDGPU_TRY(comm_halo_push(E, v_s, E.comm_stream));
-        EDGPU_TRY(comm_halo_signal(E, E.comm_stream));
+        for (int c = 0; c < K; c++) {  // the halo travels in K row chunks, each with its own flag
+          EDGPU_TRY(comm_halo_push(E, c, v_s, E.comm_stream));
+          EDGPU_TRY(comm_halo_signal(E, c, E.comm_stream));
+        }
         EDGPU_CUDA(cudaEventRecord(E.ev_join, E.comm_stream));
         const double *halo = S.halo[S.epoch & 1];
         if (!tiled) {
-          EDGPU_TRY(comm_halo_wait(E, st));
+          for (int c = 0; c < K; c++) EDGPU_TRY(comm_halo_wait(E, c, st));
           if (S.qdw > 0) {
             dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
             k_generic<true, true><<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, S.qdw, S.d0, U, D, S.xud, nimp,
@@ -1292,22 +1296,31 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
           EDGPU_MARK(1);
           EDGPU_MARK(2);
         } else {
-          EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
-                               s_old));
+          // diagnostic knob (profiling only): EDGPU_HALO_DIAG=1 skips pass B, =2 skips pass A, =3 both
+          static const int diag = getenv("EDGPU_HALO_DIAG") ? atoi(getenv("EDGPU_HALO_DIAG")) : 0;
+          if (!(diag & 1))
+            EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, S.d0, S.up, U, D, S.xud, nimp, s_acc,
+                                 s_old));
           EDGPU_MARK(1);
-          EDGPU_TRY(comm_halo_wait(E, st));
-          if ((D.Wl4 + D.Wf4) > 0) {
-            double *part = nullptr;
-            const int64_t nblk = slow_grid_size(U, D);
-            if (dot_out && !S.nonlocal && !extras && nblk > 0) {
-              EDGPU_TRY(ensure_partials(E, nblk));
-              part = E.d_part;
-            }
-            EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part, halo));
-            if (part) {
-              EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
-              dot_done = true;
-            }
+          double *part = nullptr;
+          const int64_t nblk = slow_grid_size(U, D);
+          const bool has_dw = (D.Wl4 + D.Wf4) > 0 && !(diag & 2);
+          if (has_dw && dot_out && !S.nonlocal && !extras && nblk > 0) {
+            EDGPU_TRY(ensure_partials(E, nblk));
+            part = E.d_part;
+          }
+          // pass A on the row tiles of chunk c as soon as chunk c of every owner has arrived
+          for (int c = 0; c < K; c++) {
+            int64_t r0, r1;
+            comm_halo_rows(E, c, &r0, &r1);
+            EDGPU_TRY(comm_halo_wait(E, c, st));
+            if (has_dw)
+              EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part, halo, (int)(r0 / SLOW_R),
+                                   (int)((r1 - r0) / SLOW_R)));
+          }
+          if (part) {
+            EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
+            dot_done = true;
           }
           EDGPU_MARK(2);
         }
