@@ -522,6 +522,7 @@ def run_ours(args):
         x, hx = r4["hv"].clone(), torch.zeros_like(r4["hv"])
         y = torch.roll(x, 1, 0) if x.shape[0] > 1 else x * 0.5
         hy = torch.zeros_like(x)
+        torch.cuda.synchronize()  # torch's fills run on torch's stream, the engine on its own
         _abi.check(L.edgpu_hxv_dev(x.data_ptr(), hx.data_ptr()))
         _abi.check(L.edgpu_hxv_dev(y.data_ptr(), hy.data_ptr()))
         torch.cuda.synchronize()

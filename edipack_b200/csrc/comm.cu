@@ -711,7 +711,8 @@ int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all) {
   {
     // row chunks of the halo exchange (pipelined against pass A); at least 16 tiles of 16 rows each
     const char *e = getenv("EDGPU_HALO_CHUNKS");
-    int k = e && atoi(e) > 0 ? atoi(e) : 4;
+    // (4 chunks; 8 when the local vector exceeds 1 GB: the last chunk's pass A is the tail)
+    int k = e && atoi(e) > 0 ? atoi(e) : (S.slice_len() * 8 > ((int64_t)1 << 30) ? 8 : 4);
     k = std::min<int>(k, EDGPU_MAXCHUNKS);
     k = (int)std::max<int64_t>(1, std::min<int64_t>(k, S.up.ld / SLOW_ROWS / 16));
     S.nchunks = k;
@@ -754,6 +755,82 @@ k_halo_push(const double *__restrict__ v, const int32_t *__restrict__ list, int6
     for (int k = 0; k < HALO_UNROLL; k++)
       if (i0 + k * HALO_THREADS < iend) d[i0 + k * HALO_THREADS] = r[k];
   }
+}
+
+// The same copy driven by the TMA unit (cp.async.bulk): ONE thread per CTA moves 16 KB pieces
+// global -> shared (mbarrier complete_tx) -> the reader's halo in peer memory (bulk_group) through
+// a ring of HALO_TMA_STAGES buffers.  No registers, no load/store-unit instructions: the SMs keep
+// their issue slots and L1 bandwidth for pass B / pass A running beside it, and 32 such CTAs reach
+// the same NVLink rate as 80 CTAs of 512 threads storing with st.global (tools/micro/p2p_bw.cu:
+// 694 vs 696 GB/s of the 702 GB/s a kernel can push).
+constexpr int HALO_TMA_CHUNK = 16384, HALO_TMA_STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(32)
+k_halo_push_tma(const double *__restrict__ v, const int32_t *__restrict__ list, int64_t nsend, int par,
+                int r0, int r1, HaloTable T) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(8) uint64_t full[HALO_TMA_STAGES];
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < HALO_TMA_STAGES; i++)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[i])));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // rows [r0, r1) in double2 units -> bytes [16 r0, 16 r1) of every listed column
+  const int64_t cbytes = (int64_t)(r1 - r0) * 16;
+  const int64_t npiece = (cbytes + HALO_TMA_CHUNK - 1) / HALO_TMA_CHUNK;
+  const int64_t plen = ((cbytes + npiece - 1) / npiece + 15) / 16 * 16;  // even split, 16-byte pieces
+  const int64_t nwork = nsend * npiece;
+  const int64_t mine = nwork > blockIdx.x ? (nwork - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t colbytes = T.ldU * 8;
+  auto item = [&](int64_t i, const unsigned char **sp, unsigned char **dp, uint32_t *bytes) {
+    const int64_t w = blockIdx.x + i * gridDim.x;
+    const int64_t e = w / npiece, p = w - e * npiece;
+    const int32_t src = list[3 * e], dst = list[3 * e + 1], slot = list[3 * e + 2];
+    const int64_t off = (int64_t)r0 * 16 + p * plen;
+    *sp = reinterpret_cast<const unsigned char *>(v) + (int64_t)src * colbytes + off;
+    *dp = T.block[dst] + PIPE_FLAG_BYTES + (int64_t)par * T.hbytes[dst] + (int64_t)slot * colbytes + off;
+    const int64_t rem = cbytes - p * plen;
+    *bytes = (uint32_t)(rem < plen ? rem : plen);
+  };
+  int64_t issued = 0, done = 0;
+  uint32_t phase = 0;  // bit s = parity of stage s
+  while (done < mine) {
+    while (issued < mine && issued < done + HALO_TMA_STAGES) {  // keep the ring full of loads
+      const int st = (int)(issued % HALO_TMA_STAGES);
+      if (issued >= HALO_TMA_STAGES)  // the stage's previous store has finished READING shared memory
+        asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(HALO_TMA_STAGES - 1) : "memory");
+      const unsigned char *sp;
+      unsigned char *dp;
+      uint32_t bytes;
+      item(issued, &sp, &dp, &bytes);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&full[st])), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr(ring + st * HALO_TMA_CHUNK)),
+                   "l"(sp), "r"(bytes), "r"(smem_addr(&full[st]))
+                   : "memory");
+      issued++;
+    }
+    const int st = (int)(done % HALO_TMA_STAGES);
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok)
+                   : "r"(smem_addr(&full[st])), "r"((phase >> st) & 1u)
+                   : "memory");
+    phase ^= 1u << st;
+    const unsigned char *sp;
+    unsigned char *dp;
+    uint32_t bytes;
+    item(done, &sp, &dp, &bytes);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dp),
+                 "r"(smem_addr(ring + st * HALO_TMA_CHUNK)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    done++;
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stores have been performed
 }
 
 __device__ __forceinline__ int halo_flag_slot(int par, int c, int sender) {
@@ -814,9 +891,27 @@ int comm_halo_push(Engine &E, int c, const double *d_v, cudaStream_t st) {
   int64_t r0, r1;
   comm_halo_rows(E, c, &r0, &r1);
   if (r1 <= r0) return 0;
-  const int64_t nwork = S.nsend * (((r1 - r0) / 2 + HALO_PIECE - 1) / HALO_PIECE);
-  k_halo_push<<<(unsigned)std::min<int64_t>(nwork, ctas), HALO_THREADS, 0, st>>>(
-      d_v, S.d_sendlist, S.nsend, (int)(S.epoch & 1), (int)(r0 / 2), (int)(r1 / 2), g_halo);
+  // EDGPU_PUSH_MODE=st: threads copy with ld/st.global; default: the TMA unit copies (cp.async.bulk)
+  static const bool use_tma = !(getenv("EDGPU_PUSH_MODE") && !strcmp(getenv("EDGPU_PUSH_MODE"), "st"));
+  static const int tma_ctas = [] {
+    const char *e = getenv("EDGPU_PUSH_CTAS");
+    return e && atoi(e) > 0 ? atoi(e) : 48;
+  }();
+  if (use_tma) {
+    const int64_t nwork = S.nsend * (((r1 - r0) * 8 + HALO_TMA_CHUNK - 1) / HALO_TMA_CHUNK);
+    static bool attr = false;
+    if (!attr) {
+      EDGPU_CUDA(cudaFuncSetAttribute(k_halo_push_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HALO_TMA_CHUNK * HALO_TMA_STAGES));
+      attr = true;
+    }
+    k_halo_push_tma<<<(unsigned)std::min<int64_t>(nwork, tma_ctas), 32, HALO_TMA_CHUNK * HALO_TMA_STAGES, st>>>(
+        d_v, S.d_sendlist, S.nsend, (int)(S.epoch & 1), (int)(r0 / 2), (int)(r1 / 2), g_halo);
+  } else {
+    const int64_t nwork = S.nsend * (((r1 - r0) / 2 + HALO_PIECE - 1) / HALO_PIECE);
+    k_halo_push<<<(unsigned)std::min<int64_t>(nwork, ctas), HALO_THREADS, 0, st>>>(
+        d_v, S.d_sendlist, S.nsend, (int)(S.epoch & 1), (int)(r0 / 2), (int)(r1 / 2), g_halo);
+  }
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
