@@ -334,10 +334,10 @@ def rooflines(r, world, peak, peak_kind, ns):
     stage, ldu, qdw, nloc = r["stage"], r["ldu"], r["qdw"], r["nloc"]
     halo_b = 8.0 * ldu * r["halo_cols"]
     if world == 1:
-        names = ["k_fastb", "k_slow", "k_nonlocal"]
-        desc = ["pass B: diagonal + up hops", "pass A: dw hops", "non-local terms"]
+        names = ["k_fastc", "k_slow", "k_nonlocal"]
+        desc = ["pass B: diagonal + up hops (TMA-staged tile)", "pass A: dw hops", "non-local terms"]
     else:
-        names = ["k_fastb", "k_slow", "k_nonlocal"]
+        names = ["k_fastc", "k_slow", "k_nonlocal"]
         desc = ["pass B: diagonal + up hops (the halo push runs beside it)",
                 "wait for the halo flags + pass A: dw hops incl. halo gathers", "non-local terms"]
     # compulsory bytes per launch (DESIGN.md "Kernels"): pass B reads v and writes Hv (16 B/state);

@@ -105,7 +105,7 @@ constexpr int BLK_MAXIN = 16;
 struct BlockItem {
   int32_t out0, out1;         // output rows [out0, out1)
   int32_t nin;                // number of input blocks
-  int32_t tile_rows;          // sum of in_len
+  int32_t tile_rows;          // rows of the tile (input blocks + alignment spares), even
   int32_t in0[BLK_MAXIN];     // first row of input block k
   int32_t in_len[BLK_MAXIN];
   int32_t in_off[BLK_MAXIN];  // its offset inside the tile
@@ -324,6 +324,7 @@ int64_t host_binomial(int n, int k);
 void block_split(int64_t n, int P, int r, int64_t *q, int64_t *start);
 
 // hxv.cu
+int hxv_upload_amps(Engine &E);  // amp2 tables of the open sector's species -> __constant__ c_amp
 int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed);
 int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed, double s_acc,
                   double s_old, double *dot_out);

@@ -21,6 +21,8 @@
 // is the part of a range with one impurity configuration (sector.cu).  Hops that leave the
 // range ("far", they move an electron into / out of the prefix bits) are read from global
 // memory (L2: sibling ranges of the same rows / columns are scheduled next to each other).
+#include <cstring>
+
 #include "edgpu_internal.cuh"
 
 namespace edgpu {
@@ -374,7 +376,7 @@ k_fastb(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
       pb[off + p] = make_double2(vb[ko[2] + g], vb[ko[3] + g]);
     }
   }
-  if (it.tile_rows == 0 && tid == 0) {  // padding entries read slot 0
+  if ((nin == 0 || it.in_off[0] != 0) && tid == 0) {  // padding entries read slot 0 (not staged then)
     pa[0] = make_double2(0.0, 0.0);
     pb[0] = make_double2(0.0, 0.0);
   }
@@ -520,6 +522,233 @@ k_fastb(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
 }
 
 // ---------------------------------------------------------------------------------------
+// Signed hop amplitudes of the open sector in the constant bank: c_amp[0] = the species applied
+// along the fast index (up), c_amp[1] = along the slow index (dw).  Indexed per lane (LDC with a
+// register index): the lanes of a warp sit in a run of consecutive rows and read at most a few
+// distinct entries, and the look-up leaves the shared-memory / LSU pipe, which is what bounds
+// the tiled passes (ncu l1tex__throughput 72-76 %).
+// ---------------------------------------------------------------------------------------
+__constant__ double c_amp[2][2048];
+
+int hxv_upload_amps(Engine &E) {
+  Sector &S = E.sec;
+  const SpinSpace *sp[2] = {&S.up, &S.dw};
+  for (int k = 0; k < 2; k++) {
+    const size_t n = 2 * (size_t)sp[k]->nterms + 2;
+    if (n > 2048) return set_error("too many one-body terms for the constant amplitude table");
+    EDGPU_CUDA(cudaMemcpyToSymbolAsync(c_amp, sp[k]->amp2, sizeof(double) * n, sizeof(double) * 2048 * k,
+                                       cudaMemcpyDeviceToDevice, E.stream));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// pass B in block mode, TMA-staged ("k_fastc", the default).  Same work decomposition as k_fastb:
+// CTA = one work item (rows of one range prefix and one impurity configuration) x 4 columns,
+// only the blocks its hops read from are staged.  Differences:
+//   * the tile is staged by the TMA unit: ONE thread issues a cp.async.bulk per (input block,
+//     column) -- up to 27 KB each -- completing on an mbarrier; no thread executes a load / store
+//     for the staging, and the tile arrives while all threads prefetch their rows' hop entries;
+//   * the tile is four column planes plane[k][row] (what a bulk copy of a column piece produces);
+//     a hop gathers one 8-byte value per column;
+//   * hop amplitudes come from the constant bank (c_amp) instead of shared memory.
+// Bulk copies move 16-byte aligned pieces: the block plan (sector.cu) gives every input block a
+// tile offset with the parity of its first row, so the copy may start one row early / end one row
+// late into spare slots.
+// shared layout: plane[4][tile_cap] doubles | xc[4][nimp] | mbarrier
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(mbar), "r"(parity)
+                 : "memory");
+}
+
+template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
+__global__ void __launch_bounds__(FASTB_THREADS, 2)
+k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
+        int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
+        double s_acc, double s_old, int tile_cap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  double *plane = reinterpret_cast<double *>(smem_raw);
+  double *xc = plane + 4 * (size_t)tile_cap;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(xc + 4 * nimp);
+  const BlockItem &it = F.items[blockIdx.x];
+  const int out0 = it.out0, out1 = it.out1, nin = it.nin;
+
+  const int64_t c0 = (int64_t)blockIdx.y * 4;
+  const int nc = (int)min((int64_t)4, ncol - c0);  // live columns of this CTA
+  const double *vb = v + c0 * ldv;
+  double *hb = hv + c0 * ldv;
+  const uint32_t ld32 = (uint32_t)ldv;
+  const uint32_t ko[4] = {0u, nc > 1 ? ld32 : 0u, nc > 2 ? 2u * ld32 : 0u, nc > 3 ? 3u * ld32 : 0u};
+  const uint32_t plane_sa = smem_u32(plane), mbar_sa = smem_u32(mbar);
+  const uint32_t pstride = (uint32_t)tile_cap * 8u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_sa));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t total = 0;
+    for (int b = 0; b < nin; b++) {
+      const int g0 = it.in0[b] & ~1, g1 = (it.in0[b] + it.in_len[b] + 1) & ~1;
+      total += 4u * (uint32_t)(g1 - g0) * 8u;
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(total) : "memory");
+    for (int b = 0; b < nin; b++) {
+      const int g0 = it.in0[b] & ~1, g1 = (it.in0[b] + it.in_len[b] + 1) & ~1;
+      const uint32_t bytes = (uint32_t)(g1 - g0) * 8u;
+      const uint32_t dst = plane_sa + (uint32_t)(it.in_off[b] - (it.in0[b] & 1)) * 8u;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dst + (uint32_t)k * pstride),
+                     "l"(vb + ko[k] + (uint32_t)g0), "r"(bytes), "r"(mbar_sa)
+                     : "memory");
+    }
+    if (nin == 0) {  // padding entries read slot 0
+#pragma unroll
+      for (int k = 0; k < 4; k++) plane[(size_t)k * tile_cap] = 0.0;
+    }
+  }
+  // own values / old Hv are read from global memory late in each row iteration: pull their lines
+  // into L2 now (see k_fastb)
+  {
+    const int l0 = out0 & ~15, nl = ((out1 + 15) & ~15) - l0;
+    for (int p = tid * 16; p < nl; p += FASTB_THREADS * 16) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (WITH_DIAG) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + ko[k] + (uint32_t)(l0 + p)));
+        if (ACCUM) asm volatile("prefetch.global.L2 [%0];" ::"l"(hb + ko[k] + (uint32_t)(l0 + p)));
+      }
+    }
+  }
+  if (WITH_DIAG) {
+    for (int t = tid; t < 4 * nimp; t += FASTB_THREADS) {
+      const int k = t / nimp, m = t - k * nimp;
+      const int64_t cg = c0 + (k < nc ? k : 0) + col_offset;
+      xc[t] = S.eps[cg] + xud[(int)S.imp[cg] * nimp + m];
+    }
+  }
+  const uint32_t xc_sa = smem_u32(xc);
+  const uint32_t *far32 = reinterpret_cast<const uint32_t *>(F.ell4 + (int64_t)F.Wl4 * F.ld);
+  constexpr int NG = WL4 > 0 ? WL4 : 1;
+  constexpr int NFE = NFAR > 0 ? NFAR : 1;
+  uint4 nq[NG];
+  uint32_t nqf[NFE];
+  double neu = 0.0;
+  uint32_t nm = 0;
+  int i = out0 + tid;
+  if (i < out1) {
+#pragma unroll
+    for (int g = 0; g < WL4; g++) nq[g] = F.ell4[(int64_t)g * F.ld + i];
+#pragma unroll
+    for (int e = 0; e < NFAR; e++) nqf[e] = far32[4 * (int64_t)i + e];
+    if (WITH_DIAG) {
+      neu = F.eps[i];
+      nm = (uint32_t)F.imp[i];
+    }
+  }
+  __syncthreads();          // xc, the mbarrier initialisation
+  mbar_wait(mbar_sa, 0);    // the tile has landed
+
+  for (; i < out1; i += FASTB_THREADS) {
+    uint4 q[NG];
+#pragma unroll
+    for (int g = 0; g < WL4; g++) q[g] = nq[g];
+    uint32_t qf[NFE];
+#pragma unroll
+    for (int e = 0; e < NFAR; e++) qf[e] = nqf[e];
+    const double eu = neu;
+    const uint32_t m = nm;
+    const int inext = i + FASTB_THREADS;
+    if (inext < out1) {
+#pragma unroll
+      for (int g = 0; g < WL4; g++) nq[g] = F.ell4[(int64_t)g * F.ld + inext];
+#pragma unroll
+      for (int e = 0; e < NFAR; e++) nqf[e] = far32[4 * (int64_t)inext + e];
+      if (WITH_DIAG) {
+        neu = F.eps[inext];
+        nm = (uint32_t)F.imp[inext];
+      }
+    }
+    // far gathers, own values, old Hv: issued first (L2), consumed after the local hops
+    double own[4], hold[4], xf[NFE][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      own[k] = WITH_DIAG ? vb[ko[k] + (uint32_t)i] : 0.0;
+      hold[k] = ACCUM ? hb[ko[k] + (uint32_t)i] : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < NFAR; e++) {
+      const uint32_t t = qf[e] & HOP_TGT_MASK;  // padding entries point at the row itself
+#pragma unroll
+      for (int k = 0; k < 4; k++) xf[e][k] = vb[ko[k] + t];
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int g = 0; g < WL4; g++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t ent = ent_of(q[g], k);
+        const double a = c_amp[0][(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
+        const uint32_t o = plane_sa + (ent & HOP_TGT_MASK) * 8u;
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[c] += a * lds64(o + (uint32_t)c * pstride);
+      }
+    }
+    if (WL4 == 0) {  // dynamic widths
+      for (int g = 0; g < F.Wl4; g++) {
+        const uint4 qq = F.ell4[(int64_t)g * F.ld + i];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t ent = ent_of(qq, k);
+          const double a = c_amp[0][(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
+          const uint32_t o = plane_sa + (ent & HOP_TGT_MASK) * 8u;
+#pragma unroll
+          for (int c = 0; c < 4; c++) acc[c] += a * lds64(o + (uint32_t)c * pstride);
+        }
+      }
+      for (int g = 0; g < F.Wf4; g++) {
+        const uint4 qq = F.ell4[(int64_t)(F.Wl4 + g) * F.ld + i];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (4 * g + k >= F.Wf) break;  // uniform
+          const uint32_t ent = ent_of(qq, k);
+          const double a = c_amp[0][(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK];  // padding -> 0, target = row
+          const uint32_t t = ent & HOP_TGT_MASK;
+#pragma unroll
+          for (int c = 0; c < 4; c++) acc[c] += a * vb[ko[c] + t];
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < NFAR; e++) {
+      const double a = c_amp[0][(qf[e] >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[k] += a * xf[e][k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      double r = acc[k];
+      if (WITH_DIAG) r += (eu + lds64(xc_sa + ((uint32_t)(k * nimp) + m) * 8u)) * own[k];
+      r *= s_acc;
+      if (ACCUM) r += s_old * hold[k];
+      if (k < nc) hb[ko[k] + (uint32_t)i] = r;
+    }
+  }
+  // the last work item also owns the pad rows [dim, ld): zeros (scaled old value when accumulating)
+  if (blockIdx.x + 1 == gridDim.x) {
+    for (int r = (int)F.dim + tid; r < (int)F.ld; r += FASTB_THREADS) {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k < nc) hb[ko[k] + (uint32_t)r] = ACCUM ? s_old * hb[ko[k] + (uint32_t)r] : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // pass A, "slow index" kernel.  CTA = SLOW_ROWS (16) consecutive fast rows x the slow range
 // [s0, s1), staged as tile[j][16] with cp.async (LDGSTS) 16-byte copies.  A thread owns two rows
 // of one column; the 8 threads of a column read one contiguous 128-byte segment per hop
@@ -628,7 +857,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
       if (j > jl) {
 #pragma unroll
         for (int e = 0; e < NF; e++) {
-          const double a = lds64(amp_sa + amp_off(ent_of(q0p, e & 3)));
+          const double a = c_amp[1][(ent_of(q0p, e & 3) >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
           accp.x += a * xf[e].x;
           accp.y += a * xf[e].y;
         }
@@ -669,7 +898,7 @@ k_slow(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, SpinV
 #pragma unroll
       for (int e = NF; e < 4 * W4; e++) {
         const uint32_t ent = ent_of(q[e >> 2], e & 3);
-        const double a = lds64(amp_sa + amp_off(ent));
+        const double a = c_amp[1][(ent >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
         const double2 x = lds128(trow_sa + (ent & HOP_TGT_MASK) * (SLOW_R * 8u));
         acc.x += a * x.x;
         acc.y += a * x.y;
@@ -980,10 +1209,40 @@ static int launch_fast(Engine &E, const double *v, double *hv, int64_t ldv, int6
   return 0;
 }
 
+size_t fastc_smem_bytes(int64_t max_tile, int nimp) {
+  return sizeof(double) * (4 * (size_t)std::max<int64_t>(max_tile, 2) + 4 * (size_t)nimp) + 16;
+}
+
+// EDGPU_FASTB=legacy: thread-staged k_fastb (pair planes, amplitudes in shared memory)
+static bool fastb_legacy() {
+  static const bool l = getenv("EDGPU_FASTB") && !strcmp(getenv("EDGPU_FASTB"), "legacy");
+  return l;
+}
+
+template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
+static int launch_fastc(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
+                        int64_t col_offset, const SpinView &F, const SpinView &S, int64_t max_tile,
+                        const double *xud, int nimp, double s_acc, double s_old) {
+  const size_t smem = fastc_smem_bytes(max_tile, nimp);
+  auto kern = k_fastc<WL4, NFAR, WITH_DIAG, ACCUM>;
+  EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)F.nitems, (unsigned)((ncol + 3) / 4));
+  kern<<<grid, FASTB_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp, s_acc,
+                                                s_old, (int)std::max<int64_t>(max_tile, 2));
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
 static int launch_fastb(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
                         int64_t col_offset, const SpinView &F, const SpinView &S, int64_t max_tile,
                         const double *xud, int nimp, double s_acc, double s_old) {
+  // the TMA-staged kernel serves the species whose amplitudes sit in c_amp[0] (the up species of
+  // the open sector) with 16-byte aligned columns
+  if (!fastb_legacy() && F.amp2 == E.sec.up.amp2 && (ldv & 1) == 0 && ((uintptr_t)v & 15) == 0)
+    return launch_fastc<WL4, NFAR, WITH_DIAG, ACCUM>(E, v, hv, ldv, ncol, col_offset, F, S, max_tile, xud, nimp,
+                                                      s_acc, s_old);
   const size_t smem = fastb_smem_bytes(max_tile, F.nterms, nimp);
   auto kern = k_fastb<WL4, NFAR, WITH_DIAG, ACCUM>;
   EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1235,22 +1494,34 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
         EDGPU_MARK(1);
         EDGPU_MARK(2);
       } else {
-        // pass B (diag + up hops) writes / accumulates first: it is the pass that saturates the
-        // shared-memory pipe, so the read-modify-write of Hv is left to pass A (dw hops)
-        EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc,
-                             s_old));
-        EDGPU_MARK(1);
-        if ((D.Wl4 + D.Wf4) > 0) {
-          double *part = nullptr;
-          const int64_t nblk = slow_grid_size(U, D);
-          if (dot_out && !S.nonlocal && !extras) {
-            EDGPU_TRY(ensure_partials(E, nblk));
-            part = E.d_part;
-          }
-          EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part));
-          if (part) {
-            EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
-            dot_done = true;
+        // Order of the two passes.  "BA" (default): pass B (diag + up hops) writes / accumulates first,
+        // pass A (dw hops) accumulates and fuses the Lanczos dot product <v, Hv>.  EDGPU_ORDER=AB
+        // (plain products only): pass A writes Hv without reading it and pass B accumulates; measured
+        // at cfg 2 (profiles/r2_experiments.md) it only moves the read-modify-write: 0.67 + 0.92 ms
+        // against 0.74 + 0.83 ms.
+        static const int order_env = getenv("EDGPU_ORDER") ? (!strcmp(getenv("EDGPU_ORDER"), "AB") ? 2 : 1) : 0;
+        const bool has_dw = (D.Wl4 + D.Wf4) > 0;
+        const bool a_first = has_dw && !accum && !dot_out && order_env == 2;
+        if (a_first) {
+          EDGPU_TRY(apply_slow(E, false, v_s, hv_s, S.dw, U, D, s_acc, nullptr));
+          EDGPU_MARK(1);
+          EDGPU_TRY(apply_fast(E, true, true, true, v_s, hv_s, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc, 1.0));
+        } else {
+          EDGPU_TRY(apply_fast(E, true, true, accum, v_s, hv_s, S.qdw, 0, S.up, U, D, S.xud, nimp, s_acc,
+                               s_old));
+          EDGPU_MARK(1);
+          if (has_dw) {
+            double *part = nullptr;
+            const int64_t nblk = slow_grid_size(U, D);
+            if (dot_out && !S.nonlocal && !extras) {
+              EDGPU_TRY(ensure_partials(E, nblk));
+              part = E.d_part;
+            }
+            EDGPU_TRY(apply_slow(E, true, v_s, hv_s, S.dw, U, D, s_acc, part));
+            if (part) {
+              EDGPU_TRY(final_sum(E, (int)nblk, dot_out));
+              dot_done = true;
+            }
           }
         }
         EDGPU_MARK(2);

@@ -453,12 +453,18 @@ static void plan_species(Engine &E, const edgpu_normal_params &p, int s, int nel
             const size_t bi = (size_t)pr * nI + (im ^ f);
             const int64_t len = start[bi + 1] - start[bi];
             if (len <= 0) continue;
+            // Tile offset with the PARITY of the block's first global row, after at least one spare
+            // row: the TMA staging (k_fastc) copies 16-byte aligned pieces, i.e. it starts one row
+            // early / ends one row late when the block starts / ends on an odd row.
+            int32_t off = it.nin == 0 ? 0 : it.tile_rows + 1;
+            if ((off ^ (int32_t)start[bi]) & 1) off++;
             it.in0[it.nin] = (int32_t)start[bi];
             it.in_len[it.nin] = (int32_t)len;
-            it.in_off[it.nin] = it.tile_rows;
-            it.tile_rows += (int32_t)len;
+            it.in_off[it.nin] = off;
+            it.tile_rows = off + (int32_t)len;
             it.nin++;
           }
+          it.tile_rows = (it.tile_rows + 2) & ~1;  // room for the row behind an odd end, even size
           if (it.tile_rows > cap) ok = false;
           max_tile = std::max<int64_t>(max_tile, it.tile_rows);
           items.push_back(it);
@@ -847,6 +853,7 @@ int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
     EDGPU_CUDA(cudaStreamSynchronize(E.stream));
     EDGPU_TRY(comm_p2p_setup(E));
   }
+  EDGPU_TRY(hxv_upload_amps(E));  // hop amplitudes of both species -> constant bank (hxv.cu)
   EDGPU_TRY(extra_setup(E));  // coulomb_sundry + phonons (a10)
   S.variant = E.variant_request;
   S.open = true;
