@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
     "edgpu_release_cache", "edgpu_sector_open_superc", "edgpu_apply_ops_packed", "edgpu_seed_norm2",
     "edgpu_set_coulomb_sundry", "edgpu_set_phonons", "edgpu_set_hbath_packed", "edgpu_state_twin", "edgpu_state_download", "edgpu_sector_open_normal_orbs", "edgpu_apply_ops_normal",
-    "edgpu_sector_comm_info",
+    "edgpu_sector_comm_info", "edgpu_set_sparse_h",
 ]
 
 

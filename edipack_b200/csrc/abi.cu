@@ -480,10 +480,16 @@ int edgpu_sector_open_superc(const edgpu_superc_params *p, int sz) {
 
 int64_t edgpu_csr_nnz(void) { return g.csr.open ? g.csr.nnz : -1; }
 
+int edgpu_set_sparse_h(int flag) {
+  g.sparse_h = (flag != 0);
+  return 0;
+}
+
 int edgpu_csr_get(int64_t *rowptr, int32_t *cols, double *vals) {
   clear_error();
   CsrSector &C = g.csr;
   if (!C.open) return set_error("no stored-H sector open");
+  if (C.direct) return set_error("the open sector is direct (ED_SPARSE_H=F): no matrix is stored");
   EDGPU_CUDA(cudaMemcpy(rowptr, C.rowptr, sizeof(int64_t) * (C.nloc + 1), cudaMemcpyDeviceToHost));
   if (C.nnz) {
     EDGPU_CUDA(cudaMemcpy(cols, C.cols, sizeof(int32_t) * C.nnz, cudaMemcpyDeviceToHost));

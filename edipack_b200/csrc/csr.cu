@@ -101,6 +101,8 @@ int csr_close(Engine &E) {
   cudaFree(C.vals);
   cudaFree(C.vfull);
   cudaFree(C.map);
+  cudaFree(C.pk_off);
+  cudaFree(C.pk_hb);
   C = CsrSector();
   return 0;
 }
@@ -233,6 +235,7 @@ int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, doubl
     EDGPU_TRY(comm_allgatherv(E, d_v, C.vfull, C.counts, C.offs));
     vin = C.vfull;
   }
+  if (C.direct) return packed_direct_hxv(E, vin, d_hv, accum, s_acc, s_old);
   switch (C.lanes) {
     case 32: return launch_csr<32>(E, vin, d_hv, accum, s_acc, s_old);
     case 16: return launch_csr<16>(E, vin, d_hv, accum, s_acc, s_old);

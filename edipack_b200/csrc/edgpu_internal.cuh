@@ -175,6 +175,7 @@ struct SpinSpace {
   int64_t shard0 = 0, shard_q = 0;
   int64_t nhalo = 0;
   std::vector<int32_t> halo_cols;   // host: global column of halo slot k (ascending)
+  int32_t *d_colmap = nullptr;      // [ld] global column -> local column / shard_q + halo slot / -1
 };
 
 // one coulomb_sundry line in application order (c_l, cd_j, c_k, cd_i): bit of the species
@@ -246,6 +247,10 @@ struct CsrSector {
   int32_t *map = nullptr;     // device-built sectors (packed.cu): packed Fock states of the WHOLE sector
   int pk_mode = -1;           // -1: host-supplied CSR; 0: nonsu2 (qn = Ntot); 1: superc (qn = Sz)
   int pk_qn = 0, pk_Ns = 0;
+  // ED_SPARSE_H = F for the packed-state modes: nothing is stored, every product re-enumerates the
+  // rows' matrix elements (packed.cu: k_n2_direct); the ranking tables stay alive with the sector
+  bool direct = false;
+  void *pk_off = nullptr, *pk_hb = nullptr;
   std::vector<int64_t> counts, offs;  // row split of all ranks
   int64_t padded_len() const {
     const int64_t n = cplx ? 2 * nloc : nloc;
@@ -268,6 +273,7 @@ struct Engine {
   int rank = 0, nranks = 1;
   void *nccl = nullptr;  // ncclComm_t
   bool dw_halo = false;  // sector being opened / open: dw species sharded for the halo mode
+  bool sparse_h = true;  // ED_SPARSE_H (ED_INPUT_VARS.f90:664) for the packed-state modes
   // scalar scratch
   double *d_scal = nullptr;   // device scalars (dots etc.)
   double *h_scal = nullptr;   // pinned host mirror
@@ -368,6 +374,8 @@ int packed_twin(Engine &E, int src_mode, int src_qn, const double *d_vsrc_full, 
 // dens(a), docc(a) partial sums over this rank's rows of a packed-state vector
 int packed_observables(Engine &E, const double *d_vec, double *h_dens, double *h_docc);
 int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, double s_acc, double s_old);
+// direct (on-the-fly) product of the open packed-state sector: hv = s_acc * H vin [+ s_old * hv]
+int packed_direct_hxv(Engine &E, const double *d_vin_full, double *d_hv, bool accum, double s_acc, double s_old);
 
 // comm.cu
 int comm_unique_id(void *uid);

@@ -1136,11 +1136,14 @@ k_fastT(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
 // ---------------------------------------------------------------------------------------
 // upT / dwT: impurity hop tables of the two species (sector.cu, k_imphop_fill).  The dw entries
 // are uniform over a column (= block): columns on which no term can act exit at once.
+// Sharded dw species (halo mode): colmap maps the global dw target to a local column (read from
+// vfull = the rank's chunk) or to qloc + halo slot (read from halo); unsharded: colmap = nullptr.
 __global__ void __launch_bounds__(128)
 k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nrow, int64_t ldv,
            int64_t col_offset, const int32_t *__restrict__ upT, int64_t ldu,
            const int32_t *__restrict__ dwT, int64_t ldd, int Norb, const double *__restrict__ jx,
-           const double *__restrict__ jp, double s_acc) {
+           const double *__restrict__ jp, double s_acc, const int32_t *__restrict__ colmap,
+           const double *__restrict__ halo, int64_t qloc) {
   const int64_t c = blockIdx.y;
   const int64_t cg = c + col_offset;
   __shared__ int any_dw;
@@ -1169,13 +1172,31 @@ k_nonlocal(const double *__restrict__ vfull, double *__restrict__ hv, int64_t nr
       const int32_t d1 = dwT[(int64_t)(jo * Norb + io) * ldd + cg];
       if (x != 0.0 && d1 != -1) {
         const double sg = ((uu ^ d1) < 0) ? -1.0 : 1.0;
-        acc += x * sg * vfull[(int64_t)(d1 & 0x7FFFFFFF) * ldv + (uu & 0x7FFFFFFF)];
+        int64_t t = d1 & 0x7FFFFFFF;
+        const double *src = vfull;
+        if (colmap) {
+          t = colmap[t];
+          if (t >= qloc) {
+            t -= qloc;
+            src = halo;
+          }
+        }
+        acc += x * sg * src[t * ldv + (uu & 0x7FFFFFFF)];
       }
       const double y = jp[io * Norb + jo];
       const int32_t d2 = dwT[(int64_t)(io * Norb + jo) * ldd + cg];
       if (y != 0.0 && d2 != -1) {
         const double sg = ((uu ^ d2) < 0) ? -1.0 : 1.0;
-        acc += y * sg * vfull[(int64_t)(d2 & 0x7FFFFFFF) * ldv + (uu & 0x7FFFFFFF)];
+        int64_t t = d2 & 0x7FFFFFFF;
+        const double *src = vfull;
+        if (colmap) {
+          t = colmap[t];
+          if (t >= qloc) {
+            t -= qloc;
+            src = halo;
+          }
+        }
+        acc += y * sg * src[t * ldv + (uu & 0x7FFFFFFF)];
       }
     }
   if (acc != 0.0) hv[c * ldv + i] += s_acc * acc;
@@ -1464,7 +1485,9 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
   const bool extras = (DimPh > 1) || (S.nsundry > 0);
   // nranks>1: terms that change the dw index gather from the columns of every rank, like
   // allgather_vector_MPI (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:355-360)
-  const bool need_full = E.nranks > 1 && (S.nonlocal || S.nsundry > 0 || (DimPh > 1 && S.eph_offdiag));
+  // (halo mode: the non-local terms read their few remote dw columns from the halo instead)
+  const bool need_full = E.nranks > 1 && ((S.nonlocal && !S.halo_mode) || S.nsundry > 0 ||
+                                          (DimPh > 1 && S.eph_offdiag));
   if (need_full && !S.vfull) {
     EDGPU_CUDA(cudaMalloc(&S.vfull, sizeof(double) * (size_t)slice_full * (size_t)DimPh));
     S.gcounts.assign(E.nranks, 0);
@@ -1529,7 +1552,7 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
       if (S.nonlocal) {
         dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
         k_nonlocal<<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, 0, S.up.imphop, S.up.ld, S.dw.imphop,
-                                         S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
+                                         S.dw.ld, S.Norb, S.jx, S.jp, s_acc, nullptr, nullptr, 0);
         EDGPU_COUNT_LAUNCH();
         EDGPU_CUDA(cudaGetLastError());
       }
@@ -1665,8 +1688,14 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
       if (need_full) EDGPU_TRY(comm_allgatherv(E, v_s, S.vfull + iph * slice_full, S.gcounts, S.goffs));
       if (S.nonlocal && S.qdw > 0) {
         dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
-        k_nonlocal<<<grid, 128, 0, st>>>(S.vfull + iph * slice_full, hv_s, U.dim, U.ld, S.d0, S.up.imphop,
-                                         S.up.ld, S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc);
+        if (S.halo_mode)
+          k_nonlocal<<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, S.d0, S.up.imphop, S.up.ld, S.dw.imphop,
+                                           S.dw.ld, S.Norb, S.jx, S.jp, s_acc, S.dw.d_colmap,
+                                           S.halo[S.epoch & 1], S.qdw);
+        else
+          k_nonlocal<<<grid, 128, 0, st>>>(S.vfull + iph * slice_full, hv_s, U.dim, U.ld, S.d0, S.up.imphop,
+                                           S.up.ld, S.dw.imphop, S.dw.ld, S.Norb, S.jx, S.jp, s_acc, nullptr,
+                                           nullptr, 0);
         EDGPU_COUNT_LAUNCH();
         EDGPU_CUDA(cudaGetLastError());
       }

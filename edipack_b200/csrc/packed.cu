@@ -116,6 +116,17 @@ struct FillSink {
   }
 };
 
+// direct (ED_SPARSE_H = F) product: the element is applied to the input vector instead of stored
+struct ApplySink {
+  const double2 *v;
+  double are = 0.0, aim = 0.0;
+  __device__ void emit(int64_t col, double re, double im) {
+    const double2 x = v[col];
+    are += re * x.x - im * x.y;
+    aim += re * x.y + im * x.x;
+  }
+};
+
 // c(beta) then cdg(alfa) on the packed state (bit positions 0-based); emits conjg(amp)*sg1*sg2
 template <class Sink>
 __device__ __forceinline__ void n2_hop(uint32_t m, int alfa, int beta, double are, double aim, Sink &s) {
@@ -401,6 +412,39 @@ k_n2_fill(const int32_t *__restrict__ map, int64_t row0, int64_t nloc, const int
   n2_row((uint32_t)map[row0 + r], row0 + r, s);
 }
 
+// Direct on-the-fly H x v of the packed-state modes (directMatVec_nonsu2_main / _superc_main,
+// ED_HAMILTONIAN_NONSU2_DIRECT_HxV.f90:22-252, ED_HAMILTONIAN_SUPERC_DIRECT_HxV.f90:22-311, with
+// direct/HxVimp.f90, HxVint.f90, HxVbath.f90, HxVimp_bath.f90): the row generator of the stored
+// path applied to the (all-gathered) input vector instead of filling a CSR -- the same terms in the
+// same order, so the matrix is the STORED path's wherever the reference's two paths disagree
+// (DESIGN.md "reference quirks").  Nothing but the sector map is kept in HBM (the stored form
+// costs 20 B per element, ~55 elements per row at BASELINE config 5).
+__global__ void __launch_bounds__(128)
+k_n2_direct(const int32_t *__restrict__ map, int64_t row0, int64_t nloc, const double2 *__restrict__ vin,
+            double2 *__restrict__ hv, int accum, double s_acc, double s_old) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= nloc) return;
+  ApplySink s{vin};
+  n2_row((uint32_t)map[row0 + r], row0 + r, s);
+  double2 o = make_double2(s_acc * s.are, s_acc * s.aim);
+  if (accum) {
+    const double2 h = hv[r];
+    o.x += s_old * h.x;
+    o.y += s_old * h.y;
+  }
+  hv[r] = o;
+}
+
+int packed_direct_hxv(Engine &E, const double *d_vin_full, double *d_hv, bool accum, double s_acc, double s_old) {
+  const CsrSector &C = E.csr;
+  if (C.nloc <= 0) return 0;
+  k_n2_direct<<<(unsigned)((C.nloc + 127) / 128), 128, 0, E.stream>>>(
+      C.map, C.row0, C.nloc, (const double2 *)d_vin_full, (double2 *)d_hv, (int)accum, s_acc, s_old);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static Nonsu2Dev g_host_dev;  // host copy of the open sector's constants (~17 KB: not on the stack)
 
 // mode/quantum number are in h; builds map + CSR of this rank's rows and opens the stored-H sector
@@ -489,6 +533,19 @@ static int packed_open(Engine &E, Nonsu2Dev &h, const char *who) {
   if (dim > 0) {
     k_n2_map<<<(unsigned)((dim + 255) / 256), 256, 0, E.stream>>>(d_map, dim);
     EDGPU_COUNT_LAUNCH();
+  }
+  if (!E.sparse_h) {
+    // ED_SPARSE_H = F: no stored matrix; the ranking tables (off, Hbath_tmp) live as long as the sector
+    N2_CUDA(cudaStreamSynchronize(E.stream));
+    int rc = csr_adopt_device(E, true, nloc, dim, row0, nullptr, nullptr, nullptr, 0, d_map);
+    if (rc) return fail(rc);
+    E.csr.direct = true;
+    E.csr.pk_off = d_off;
+    E.csr.pk_hb = d_hb;
+    E.csr.pk_mode = h.mode;
+    E.csr.pk_qn = h.ntot;
+    E.csr.pk_Ns = Ns;
+    return 0;
   }
   N2_CUDA(cudaMalloc(&d_cnt, sizeof(int32_t) * std::max<int64_t>(nloc, 1)));
   const unsigned grid = (unsigned)std::max<int64_t>(1, (nloc + 127) / 128);

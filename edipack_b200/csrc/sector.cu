@@ -142,12 +142,21 @@ __global__ void k_hop_count(const int32_t *__restrict__ map, int64_t dim,
                             const Term *__restrict__ terms, int nterms,
                             const uint8_t *__restrict__ far_bit, SiteOrder ord, RankView R,
                             int64_t shard0, int64_t shard_q, unsigned char *__restrict__ need,
-                            int *__restrict__ wmax) {
+                            int nl_norb, int *__restrict__ wmax) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= dim) return;
   const bool sharded = shard_q >= 0;
   if (sharded && (r < shard0 || r >= shard0 + shard_q)) return;
   uint32_t m = (uint32_t)map[r];
+  // non-local S-E / P-H terms (nl_norb > 0): they move an electron between two impurity orbitals of
+  // this species; the (rare) targets outside the chunk join the halo
+  if (sharded && need)
+    for (int a = 0; a < nl_norb; a++)
+      for (int b = 0; b < nl_norb; b++)
+        if (a != b && ((m >> b) & 1u) && !((m >> a) & 1u)) {
+          const int64_t tgt = rank_of((m & ~(1u << b)) | (1u << a), R);
+          if (tgt < shard0 || tgt >= shard0 + shard_q) need[tgt] = 1;
+        }
   const int fb = far_bit[r];
   int nl = 0, nf = 0;
   for (int t = 0; t < nterms; t++) {
@@ -308,6 +317,7 @@ static int free_spin(SpinSpace &S) {
   cudaFree(S.d_range_start);
   cudaFree(S.d_items);
   cudaFree(S.d_item_of_row);
+  cudaFree(S.d_colmap);
   S = SpinSpace();
   return 0;
 }
@@ -652,8 +662,11 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
     EDGPU_CUDA(cudaMalloc(&d_need, (size_t)S.ld));
     EDGPU_CUDA(cudaMemsetAsync(d_need, 0, (size_t)S.ld, st));
   }
+  bool nl = false;  // nonloc_condition (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:45)
+  for (int a = 0; a < p.Norb; a++)
+    for (int b = 0; b < p.Norb; b++) nl = nl || p.Jx[a][b] != 0.0 || p.Jp[a][b] != 0.0;
   k_hop_count<<<gb, T, 0, st>>>(S.map, S.dim, d_terms, S.nterms, d_far, S.ord, rank_view(S.lin, S.ord),
-                                shard0, shard_q, d_need, d_w);
+                                shard0, shard_q, d_need, (nl && p.Norb > 1) ? p.Norb : 0, d_w);
   EDGPU_COUNT_LAUNCH();
   int W[3] = {0, 0, 0};
   EDGPU_CUDA(cudaMemcpyAsync(W, d_w, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -708,7 +721,7 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   cudaFree(d_terms);
   cudaFree(d_w);
   cudaFree(d_far);
-  cudaFree(d_colmap);
+  S.d_colmap = d_colmap;  // kept: the non-local kernel maps its dw targets through it
   EDGPU_CUDA(cudaGetLastError());
   return 0;
 }

@@ -745,6 +745,12 @@ def delete_Hv_sector_superc():
     delete_Hv_sector_csr()
 
 
+def set_sparse_H(flag: bool):
+    """``ED_SPARSE_H`` for the packed-state modes: True (default) stores spH0 on the device, False
+    applies the matrix elements on the fly (directMatVec_nonsu2_main / _superc_main)."""
+    check(_abi.load().edgpu_set_sparse_h(int(bool(flag))))
+
+
 def build_Hv_sector_nonsu2(model: EDModelNonsu2, ntot: int):
     """build_Hv_sector_nonsu2 + ed_buildH_nonsu2_main on the device (sector map and complex spH0
     generated by kernels); afterwards spHtimesV_cc / sp_lanc_* / sp_eigh act on it."""

@@ -199,6 +199,13 @@ int edgpu_csr_open_d(int64_t nloc, int64_t nglobal, int64_t row_offset, const in
 int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const int64_t *rowptr,
                      const int32_t *cols, const double *vals_re_im);
 
+/* ED_SPARSE_H (ED_INPUT_VARS.f90:664) for the packed-state modes (nonsu2 / superc), read by the
+ * next edgpu_sector_open_nonsu2 / _superc: 1 (default) = the complex spH0 is generated and stored
+ * on the device (ed_buildH_nonsu2_main); 0 = nothing is stored and every product re-enumerates the
+ * matrix elements (directMatVec_nonsu2_main / directMatVec_superc_main,
+ * ED_HAMILTONIAN_NONSU2_DIRECT_HxV.f90:22-252, ED_HAMILTONIAN_SUPERC_DIRECT_HxV.f90:22-311).  NORMAL
+ * mode sectors are always direct (hop tables, no stored matrix). */
+int edgpu_set_sparse_h(int flag);
 /* build_Hv_sector_nonsu2(isector) + ed_buildH_nonsu2_main (ED_HAMILTONIAN_NONSU2.f90:31-130,
  * ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190) entirely on the device: the sector map
  * H(1)%map(DimEl) of packed states m = iup + idw*2^Ns with Ntot electrons (build_sector,
