@@ -48,6 +48,16 @@ struct SpinView {
   uint32_t qloc;
 };
 
+// non-local S-E / P-H terms fused into pass B (single rank): impurity hop tables of both species
+// (sector.cu, k_imphop_fill), couplings, and the whole vector the gathers read
+struct NlDev {
+  const int32_t *upT, *dwT;
+  int64_t ldu, ldd;
+  const double *jx, *jp;
+  const double *vfull;
+  int Norb;
+};
+
 static SpinView view_of(const SpinSpace &S) {
   SpinView v;
   v.dim = S.dim;
@@ -566,16 +576,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
                  : "memory");
 }
 
-template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
+template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM, bool NL>
 __global__ void __launch_bounds__(FASTB_THREADS, 2)
 k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
         int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
-        double s_acc, double s_old, int tile_cap) {
+        double s_acc, double s_old, int tile_cap, NlDev nl) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   double *plane = reinterpret_cast<double *>(smem_raw);
   double *xc = plane + 4 * (size_t)tile_cap;
   uint64_t *mbar = reinterpret_cast<uint64_t *>(xc + 4 * nimp);
+  int32_t *nld = reinterpret_cast<int32_t *>(mbar + 1);  // NL: dw impurity hops of the 4 columns
   const BlockItem &it = F.items[blockIdx.x];
   const int out0 = it.out0, out1 = it.out1, nin = it.nin;
 
@@ -631,6 +642,15 @@ k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
       xc[t] = S.eps[cg] + xud[(int)S.imp[cg] * nimp + m];
     }
   }
+  const int no2 = NL ? nl.Norb * nl.Norb : 1;
+  if (NL) {
+    // nld[k][a * Norb + b] = target dw column of c^+_a c_b on column k | sign << 31, or -1
+    for (int t = tid; t < 4 * no2; t += FASTB_THREADS) {
+      const int k = t / no2, ab = t - k * no2;
+      const int64_t cg = c0 + (k < nc ? k : 0) + col_offset;
+      nld[t] = nl.dwT[(int64_t)ab * nl.ldd + cg];
+    }
+  }
   const uint32_t xc_sa = smem_u32(xc);
   const uint32_t *far32 = reinterpret_cast<const uint32_t *>(F.ell4 + (int64_t)F.Wl4 * F.ld);
   constexpr int NG = WL4 > 0 ? WL4 : 1;
@@ -650,7 +670,7 @@ k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
       nm = (uint32_t)F.imp[i];
     }
   }
-  __syncthreads();          // xc, the mbarrier initialisation
+  __syncthreads();          // xc, nld, the mbarrier initialisation
   mbar_wait(mbar_sa, 0);    // the tile has landed
 
   for (; i < out1; i += FASTB_THREADS) {
@@ -728,6 +748,26 @@ k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
       const double a = c_amp[0][(qf[e] >> HOP_AMP_SHIFT) & HOP_AMP_MASK];
 #pragma unroll
       for (int k = 0; k < 4; k++) acc[k] += a * xf[e][k];
+    }
+    if (NL) {
+      // non-local S-E / P-H terms (direct/HxV_non_local.f90): up c^+_io c_jo together with dw
+      // c^+_jo c_io (Jx) or dw c^+_io c_jo (Jp); all four operators act on impurity bits
+      for (int io = 0; io < nl.Norb; io++)
+        for (int jo = 0; jo < nl.Norb; jo++) {
+          if (io == jo) continue;
+          const int32_t uu = nl.upT[(int64_t)(io * nl.Norb + jo) * nl.ldu + i];
+          if (uu == -1) continue;
+          const double xj = nl.jx[io * nl.Norb + jo], yj = nl.jp[io * nl.Norb + jo];
+          const double *vu = nl.vfull + (uu & 0x7FFFFFFF);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int32_t d1 = nld[k * no2 + jo * nl.Norb + io], d2 = nld[k * no2 + io * nl.Norb + jo];
+            if (xj != 0.0 && d1 != -1)
+              acc[k] += (((uu ^ d1) < 0) ? -xj : xj) * vu[(int64_t)(d1 & 0x7FFFFFFF) * ldv];
+            if (yj != 0.0 && d2 != -1)
+              acc[k] += (((uu ^ d2) < 0) ? -yj : yj) * vu[(int64_t)(d2 & 0x7FFFFFFF) * ldv];
+          }
+        }
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -1231,7 +1271,8 @@ static int launch_fast(Engine &E, const double *v, double *hv, int64_t ldv, int6
 }
 
 size_t fastc_smem_bytes(int64_t max_tile, int nimp) {
-  return sizeof(double) * (4 * (size_t)std::max<int64_t>(max_tile, 2) + 4 * (size_t)nimp) + 16;
+  return sizeof(double) * (4 * (size_t)std::max<int64_t>(max_tile, 2) + 4 * (size_t)nimp) + 16 +
+         4 * EDGPU_MAXORB * EDGPU_MAXORB * sizeof(int32_t);
 }
 
 // EDGPU_FASTB=legacy: thread-staged k_fastb (pair planes, amplitudes in shared memory)
@@ -1240,16 +1281,29 @@ static bool fastb_legacy() {
   return l;
 }
 
+// set by hxv_device_ex around the pass-B launch when the non-local terms are to be fused into it
+static const NlDev *g_fuse_nl = nullptr;
+static bool g_nl_fused = false;  // the last pass-B launch applied them
+
 template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
 static int launch_fastc(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
                         int64_t col_offset, const SpinView &F, const SpinView &S, int64_t max_tile,
                         const double *xud, int nimp, double s_acc, double s_old) {
   const size_t smem = fastc_smem_bytes(max_tile, nimp);
-  auto kern = k_fastc<WL4, NFAR, WITH_DIAG, ACCUM>;
-  EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)F.nitems, (unsigned)((ncol + 3) / 4));
-  kern<<<grid, FASTB_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp, s_acc,
-                                                s_old, (int)std::max<int64_t>(max_tile, 2));
+  const int cap = (int)std::max<int64_t>(max_tile, 2);
+  if (WITH_DIAG && g_fuse_nl) {
+    auto kern = k_fastc<WL4, NFAR, WITH_DIAG, ACCUM, WITH_DIAG>;  // NL only exists with the diagonal
+    EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, FASTB_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp, s_acc, s_old,
+                                                  cap, *g_fuse_nl);
+    g_nl_fused = true;
+  } else {
+    auto kern = k_fastc<WL4, NFAR, WITH_DIAG, ACCUM, false>;
+    EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, FASTB_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp, s_acc, s_old,
+                                                  cap, NlDev());
+  }
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
   return 0;
@@ -1524,6 +1578,20 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
         // against 0.74 + 0.83 ms.
         static const int order_env = getenv("EDGPU_ORDER") ? (!strcmp(getenv("EDGPU_ORDER"), "AB") ? 2 : 1) : 0;
         const bool has_dw = (D.Wl4 + D.Wf4) > 0;
+        // the non-local S-E / P-H terms ride in pass B (k_fastc<NL>): no third pass over Hv
+        // (EDGPU_NL_FUSE=0: separate k_nonlocal kernel)
+        static const bool nl_fuse_on = !(getenv("EDGPU_NL_FUSE") && getenv("EDGPU_NL_FUSE")[0] == '0');
+        NlDev nl;
+        nl.upT = S.up.imphop;
+        nl.dwT = S.dw.imphop;
+        nl.ldu = S.up.ld;
+        nl.ldd = S.dw.ld;
+        nl.jx = S.jx;
+        nl.jp = S.jp;
+        nl.vfull = v_s;
+        nl.Norb = S.Norb;
+        g_nl_fused = false;
+        g_fuse_nl = (S.nonlocal && nl_fuse_on) ? &nl : nullptr;
         const bool a_first = has_dw && !accum && !dot_out && order_env == 2;
         if (a_first) {
           EDGPU_TRY(apply_slow(E, false, v_s, hv_s, S.dw, U, D, s_acc, nullptr));
@@ -1536,7 +1604,7 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
           if (has_dw) {
             double *part = nullptr;
             const int64_t nblk = slow_grid_size(U, D);
-            if (dot_out && !S.nonlocal && !extras) {
+            if (dot_out && (!S.nonlocal || g_nl_fused) && !extras) {
               EDGPU_TRY(ensure_partials(E, nblk));
               part = E.d_part;
             }
@@ -1547,9 +1615,10 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
             }
           }
         }
+        g_fuse_nl = nullptr;
         EDGPU_MARK(2);
       }
-      if (S.nonlocal) {
+      if (S.nonlocal && !(tiled && g_nl_fused)) {
         dim3 grid((unsigned)((U.dim + 127) / 128), (unsigned)S.qdw);
         k_nonlocal<<<grid, 128, 0, st>>>(v_s, hv_s, U.dim, U.ld, 0, S.up.imphop, S.up.ld, S.dw.imphop,
                                          S.dw.ld, S.Norb, S.jx, S.jp, s_acc, nullptr, nullptr, 0);

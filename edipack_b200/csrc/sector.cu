@@ -413,7 +413,7 @@ static void plan_species(Engine &E, const edgpu_normal_params &p, int s, int nel
   const bool up_t = (s == 0 && E.nranks == 1 && upt);
   const size_t per_cta = (E.smem_per_sm - 2 * 1024) / 2;  // 2 CTAs per SM
   // amplitudes + the per-column diagonal table (4 columns in k_fastb, 16 in k_fastT)
-  const size_t tables = 8 * (2 * terms.size() + 2 + (up_t ? 16 : 4) * ((size_t)1 << No)) + 64;
+  const size_t tables = 8 * (2 * terms.size() + 2 + (up_t ? 16 : 4) * ((size_t)1 << No)) + 64 + 512;
   const size_t avail = per_cta > tables ? per_cta - tables : 0;
   P.identity = (s == 1 && E.nranks > 1);
   // the dw species is applied along the slow index: by k_slow on one rank and (halo mode) on the
