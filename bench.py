@@ -448,6 +448,27 @@ def run_ours(args):
                    "arrived (every output column reads input columns anywhere), so the call is "
                    "bound by 2 x 8 B/state over PCIe"}
     del hout
+    # the same call on a plain (pageable) array a Fortran caller owns, page-locked once through
+    # edgpu_host_register -- what INTEGRATION.md tells the shim to do per sector
+    try:
+        pin = np.random.default_rng(7 + rank).standard_normal(nloc)
+        pout = np.empty(nloc)
+        E.host_register(pin)
+        E.host_register(pout)
+        pin_p, pout_p = C.c_void_p(pin.ctypes.data), C.c_void_p(pout.ctypes.data)
+        L.edgpu_hxv_d(C.byref(n32), pin_p, pout_p)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            L.edgpu_hxv_d(C.byref(n32), pin_p, pout_p)
+        _abi.check(L.edgpu_status())
+        barrier()
+        e2e["registered_caller_arrays_hxv_per_s"] = 1.0 / max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        E.host_unregister(pin)
+        E.host_unregister(pout)
+        del pin, pout
+    except Exception as ex:  # pragma: no cover
+        e2e["registered_caller_arrays_error"] = str(ex)
 
     # ---- GS Lanczos time-to-solution --------------------------------------------------------
     lanczos = None

@@ -640,6 +640,20 @@ void edgpu_hxv_z(const int32_t *Nloc, const double *v_re_im, double *Hv_re_im) {
 }
 
 int edgpu_status(void) { return g_status; }
+
+int edgpu_host_register(void *ptr, int64_t bytes) {
+  clear_error();
+  if (!g.inited) return set_error("edgpu_init was not called");
+  if (!ptr || bytes <= 0) return 0;
+  EDGPU_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int edgpu_host_unregister(void *ptr) {
+  clear_error();
+  if (!ptr) return 0;
+  EDGPU_CUDA(cudaHostUnregister(ptr));
+  return 0;
+}
 const char *edgpu_last_error(void) { return g_errbuf; }
 
 int64_t edgpu_launch_count(int reset) {

@@ -457,6 +457,16 @@ def vecDim_Hv_sector_normal() -> int:
     return int(_abi.load().edgpu_sector_vecdim())
 
 
+def host_register(a: np.ndarray):
+    """Page-locks a caller-owned host array (``edgpu_host_register``) for full-speed copies in
+    ``spHtimesV_p``; call :func:`host_unregister` before it is freed."""
+    check(_abi.load().edgpu_host_register(ptr(a), a.nbytes))
+
+
+def host_unregister(a: np.ndarray):
+    check(_abi.load().edgpu_host_unregister(ptr(a)))
+
+
 def sector_comm_info():
     """(mode, halo columns received, columns sent, chunks) of the open NORMAL sector's Hdw exchange:
     mode 0 single rank, 1 halo, 2 peer-memory transposes, 3 NCCL transposes."""

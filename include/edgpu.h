@@ -246,6 +246,12 @@ void edgpu_hxv_d(const int32_t *Nloc, const double *v, double *Hv);
  * `spHtimesV_cc => edgpu_hxv_z` for a complex stored-H sector. */
 void edgpu_hxv_z(const int32_t *Nloc, const double *v_re_im, double *Hv_re_im);
 int edgpu_status(void);
+/* Page-locks a HOST array of the caller (cudaHostRegister) so that the copies inside edgpu_hxv_d /
+ * edgpu_hxv_z / the drivers' host hand-offs run at PCIe speed instead of through the driver's
+ * pageable staging.  Meant for the Lanczos work vectors the Fortran side allocates once per sector
+ * (ED_DIAG_NORMAL.f90:200-213: `allocate(eig_basis_tmp(...))`).  Unregister before deallocate. */
+int edgpu_host_register(void *ptr, int64_t bytes);
+int edgpu_host_unregister(void *ptr);
 
 /* Device-resident variant on the engine's internal (padded) layout; d_v/d_Hv are device
  * pointers obtained from edgpu_vec_* below. */
