@@ -375,6 +375,63 @@ def rooflines(r, world, peak, peak_kind, ns):
     return roofline, hxv_roofline, nvlink, kernels
 
 
+def cfg3_block(ctx, steps):
+    """BASELINE config 3 (Norb=2, Nbath=6, Ns=14, sector (7,7), U=U'=2, J=Jx=Jp=0.125: the non-local
+    spin-flip / pair-hopping terms) at the run's GPU count: device-resident H x v time (the 94 MB
+    vector fits L2), parity of one product against the oracle, ground-state Lanczos."""
+    torch, dist, E, _abi, L, world, rank, local_rank, dev = ctx
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import edipack_oracle as O
+
+    hloc = np.zeros((2, 2, 2))
+    hloc[0] = hloc[1] = np.diag([0.5, -0.5])
+    kw = dict(Norb=2, Nbath=6, Uloc=(2.0, 2.0), Ust=2.0, Jh=0.125, Jx=0.125, Jp=0.125, hfmode=True, hloc=hloc)
+    m, mo = E.EDModel(**kw), O.Model(**kw)
+    nup = ndw = 7
+    du, dd = O.sector_dims(14, nup, ndw)
+    full = O.start_vector(du * dd, 3) - 0.5
+    lo, hi = E.chunk_bounds(du, dd, world, rank)
+    E.build_Hv_sector_normal(m, nup, ndw)
+    try:
+        hvh = E.spHtimesV_p(full[lo:hi].copy())
+        plen = int(L.edgpu_vec_padded_len())
+        v = torch.randn(plen, dtype=torch.float64, device=dev)
+        _abi.check(L.edgpu_vec_upload(v.data_ptr(), np.ascontiguousarray(full[lo:hi]).ctypes.data))
+        hv = torch.zeros_like(v)
+        torch.cuda.synchronize()
+        stream = torch.cuda.ExternalStream(L.edgpu_stream(), device=dev)
+        for _ in range(3):
+            _abi.check(L.edgpu_hxv_dev(v.data_ptr(), hv.data_ptr()))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            _abi.check(L.edgpu_hxv_dev(v.data_ptr(), hv.data_ptr()))
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        t0 = time.perf_counter()
+        egs, _, nit = E.sp_lanc_eigh(300, 1e-12, want_vector=False)
+        t_l = time.perf_counter() - t0
+    finally:
+        E.delete_Hv_sector_normal()
+    nt = max(1, host_cores() // world)
+    ref = O.stored_hxv_mpi(mo, nup, ndw, full, nt, nt)[0]
+    err = float(np.abs(hvh - ref[lo:hi]).max() / np.abs(ref).max()) if hi > lo else 0.0
+    t = torch.tensor([ms, err, t_l], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, err, t_l = (float(x) for x in t)
+    peak, _ = peaks()
+    return {"workload": "cfg3: Norb=2 Nbath=6 (Ns=14) sector (7,7), U=U'=2, J=Jx=Jp=0.125, "
+                        f"{du * dd} states, dw-sharded over {world} GPU(s)",
+            "ms_per_hxv": ms, "hxv_per_s": 1e3 / ms, "l2_policy": "94 MB vector: L2-resident, warm",
+            "hbm_frac_at_16B_per_state": 16.0 * du * dd / world / (ms * 1e-3) / 1e9 / peak,
+            "parity_rel_err": err, "lanczos_gs": {"egs": egs, "niter": nit, "seconds": t_l}}
+
+
 def sharded_parity(ctx, ns=14):
     """N>1: one product of the dw-sharded Ns=14 half-filled sector against the oracle's stored
     product (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:236-375); max relative error over ranks."""
@@ -531,6 +588,14 @@ def run_ours(args):
     if world > 1 and not args.no_parity:
         parity = sharded_parity(ctx)
 
+    # ---- BASELINE config 3 (Hund / spin-flip / pair-hopping) at this GPU count --------------
+    cfg3 = None
+    if not args.no_cfg3:
+        try:
+            cfg3 = cfg3_block(ctx, args.steps)
+        except Exception as ex:  # pragma: no cover
+            cfg3 = {"error": f"{type(ex).__name__}: {ex}"}
+
     # ---- BASELINE config 4 (Ns=18 on 8 GPUs): second timed block ----------------------------
     cfg4 = None
     if (world == 8 and args.cfg4 != 0 and ns != 18) or args.cfg4 == 1:
@@ -578,7 +643,7 @@ def run_ours(args):
             "data": "synthetic", "config": workload(ns, world),
             "roofline": roofline, "hxv_roofline": hxv_roofline, "nvlink": nvlink, "kernels": kernels,
             "cpu_baseline": cpu, "e2e": e2e, "e2e_lanczos": e2e_lanczos, "gpu_launches": launches,
-            "clocks": clocks, "lanczos_gs": lanczos, "parity_rel_err": parity, "cfg4": cfg4,
+            "clocks": clocks, "lanczos_gs": lanczos, "parity_rel_err": parity, "cfg3": cfg3, "cfg4": cfg4,
             "notes": {"kernel_variant": args.variant or 2,
                       "kernels": "two tiled passes: k_fastb (up block x 4 columns) + k_slow (16 rows x "
                                  "dw range); N>1: halo push of remote dw columns beside pass B"},
@@ -600,6 +665,7 @@ def main():
     ap.add_argument("--lanczos-niter", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 sharded parity check")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the BASELINE config 3 block")
     ap.add_argument("--cfg4", type=int, default=-1,
                     help="-1: run the Ns=18 block when --gpus 8; 0: never; 1: always")
     args = ap.parse_args()

@@ -711,8 +711,10 @@ int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all) {
   {
     // row chunks of the halo exchange (pipelined against pass A); at least 16 tiles of 16 rows each
     const char *e = getenv("EDGPU_HALO_CHUNKS");
-    // (4 chunks; 8 when the local vector exceeds 1 GB: the last chunk's pass A is the tail)
-    int k = e && atoi(e) > 0 ? atoi(e) : (S.slice_len() * 8 > ((int64_t)1 << 30) ? 8 : 4);
+    // (by the size of the local vector: 8 chunks above 1 GB -- the last chunk's pass A is the tail --,
+    // 4 above 256 MB, else 2: every chunk costs four more kernel launches)
+    const int64_t lb = S.slice_len() * 8;
+    int k = e && atoi(e) > 0 ? atoi(e) : (lb > ((int64_t)1 << 30) ? 8 : (lb > ((int64_t)256 << 20) ? 4 : 2));
     k = std::min<int>(k, EDGPU_MAXCHUNKS);
     k = (int)std::max<int64_t>(1, std::min<int64_t>(k, S.up.ld / SLOW_ROWS / 16));
     S.nchunks = k;

@@ -726,9 +726,9 @@ static int build_spin(Engine &E, const edgpu_normal_params &p, int s, int nel, S
   return 0;
 }
 
+// also releases what an open that failed half-way left behind (S.open is false then)
 int sector_close(Engine &E) {
   Sector &S = E.sec;
-  if (!S.open) return 0;
   cudaStreamSynchronize(E.stream);
   cudaStreamSynchronize(E.comm_stream);
   cudaStreamSynchronize(E.dw_stream);
@@ -765,7 +765,7 @@ int sector_close(Engine &E) {
 
 int sector_open(Engine &E, const edgpu_normal_params *p, int nup, int ndw) {
   if (!E.inited) return set_error("edgpu_init was not called");
-  if (E.sec.open) sector_close(E);
+  sector_close(E);  // the open sector, or the leftovers of an open that failed half-way
   Sector &S = E.sec;
   if (p->Ns < 1 || p->Ns > 31) return set_error("Ns=%d out of range", p->Ns);
   if (p->Norb < 1 || p->Norb > EDGPU_MAXORB) return set_error("Norb=%d out of range", p->Norb);

@@ -3,7 +3,7 @@
 N=$1; shift
 for c in "$@"; do
   echo "== $c"
-  env $c timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 20 --warmup 5 --lanczos 0 --e2e-steps 1 --no-cpu-baseline --no-parity --cfg4 0 $BENCH_ARGS 2>gpurun_out/sweep.err | python -c "
+  env $c timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 20 --warmup 5 --lanczos 0 --e2e-steps 1 --no-cpu-baseline --no-parity --no-cfg3 --cfg4 0 $BENCH_ARGS 2>gpurun_out/sweep.err | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
