@@ -606,21 +606,28 @@ def run_ours(args):
     if (world == 8 and args.cfg4 != 0 and ns != 18) or args.cfg4 == 1:
         torch.cuda.empty_cache()
         E.release_cache()
-        ns4 = 18
+        ns4 = args.cfg4_ns
         r4 = timed_products(ctx, ns4, max(5, args.steps // 2), args.warmup)
         rf4, hrf4, nv4, k4 = rooflines(r4, world, peak, peak_kind, ns4)
         # size-independent property where no oracle reaches: <x|Hy> = <Hx|y> on the sharded vectors
-        x, hx = r4["hv"].clone(), torch.zeros_like(r4["hv"])
-        y = torch.roll(x, 1, 0) if x.shape[0] > 1 else x * 0.5
+        x, hx = r4["v"], torch.zeros_like(r4["hv"])
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(4321 + rank)
+        y = torch.randn(x.shape, dtype=torch.float64, device=dev, generator=gen)
+        y[:, r4["DimUp"]:] = 0.0
+        y /= math.sqrt(r4["dim"])
         hy = torch.zeros_like(x)
         torch.cuda.synchronize()  # torch's fills run on torch's stream, the engine on its own
         _abi.check(L.edgpu_hxv_dev(x.data_ptr(), hx.data_ptr()))
         _abi.check(L.edgpu_hxv_dev(y.data_ptr(), hy.data_ptr()))
         torch.cuda.synchronize()
-        d = torch.stack([(x * hy).sum(), (hx * y).sum()])
+        d = torch.stack([(x * hy).sum(), (hx * y).sum(), (x * x).sum(), (hy * hy).sum()])
         if world > 1:
             dist.all_reduce(d)
-        sym = abs(float(d[0] - d[1])) / max(abs(float(d[0])), 1e-300)
+        d = [float(t) for t in d]
+        # |<x|Hy> - <Hx|y>| on the Cauchy-Schwarz scale |x| |Hy| (the dots of two random vectors
+        # are themselves O(dim^-1/2) of it)
+        sym = abs(d[0] - d[1]) / max(math.sqrt(d[2] * d[3]), 1e-300)
         del x, y, hx, hy, r4["v"], r4["hv"]
         torch.cuda.empty_cache()
         r4["barrier"]()
@@ -634,7 +641,7 @@ def run_ours(args):
         cfg4 = {"workload": workload(ns4, world)["workload"], "dim": r4["dim"], "ms_per_hxv": r4["ms_per_step"],
                 "hxv_per_s": 1e3 / r4["ms_per_step"],
                 "aggregate_hbm_frac": hrf4["frac"], "hxv_roofline": hrf4, "roofline": rf4, "nvlink": nv4,
-                "kernels": k4, "symmetry_defect": sym,
+                "kernels": k4, "symmetry_defect": sym, "symmetry_dots": d[:2],
                 "lanczos_gs": {"egs": egs4, "niter": nit4, "seconds": t4, "hxv": nhxv4,
                                "vectors_kept_in_hbm": nst4}}
 
@@ -671,6 +678,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 sharded parity check")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the BASELINE config 3 block")
+    ap.add_argument("--cfg4-ns", type=int, default=18, help="Ns of the cfg4 block (testing: smaller)")
     ap.add_argument("--cfg4", type=int, default=-1,
                     help="-1: run the Ns=18 block when --gpus 8; 0: never; 1: always")
     args = ap.parse_args()
