@@ -715,15 +715,10 @@ int edgpu_lanczos_gs(int nitermax, double threshold, int ncheck, int use_start, 
   double *d_start = nullptr;
   if (use_start) {
     if (!vec_host) return set_error("use_start set but vec_host is NULL");
-    EDGPU_CUDA(cudaMalloc(&d_start, sizeof(double) * n));
-    int rc = upload(g, d_start, vec_host);
-    if (rc) {
-      cudaFree(d_start);
-      return rc;
-    }
+    EDGPU_TRY(lanczos_work(g, 2, n, &d_start));  // cached: a cudaFree per solve costs up to 0.5 s
+    EDGPU_TRY(upload(g, d_start, vec_host));
   }
   int rc = lanczos_gs_dev(g, nitermax, threshold, ncheck, d_start, seed, egs, g_current, niter);
-  cudaFree(d_start);
   if (rc) return rc;
   if (vec_host) EDGPU_TRY(download(g, vec_host, g_current));
   return 0;

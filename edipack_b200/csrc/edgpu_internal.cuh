@@ -291,6 +291,11 @@ struct Engine {
   // (dev_malloc) or on edgpu_release_cache / edgpu_finalize.
   std::vector<std::pair<double *, size_t>> lz_chunks;  // (pointer, bytes)
   bool lz_in_use = false;  // a ground-state solve holds slots of the pool: do not release it
+  // Work vectors of the Lanczos drivers (recurrence pair, uploaded start vector), kept across
+  // solves like the pool: cudaFree of a GB-sized buffer was measured to take up to 0.5 s next to a
+  // 118 GB pool (tools/diag_lanczos.py), more than the whole 0.29 s solve
+  double *lz_work[3] = {nullptr, nullptr, nullptr};
+  int64_t lz_work_len[3] = {0, 0, 0};
   float stage_ms[4] = {0, 0, 0, 0};
   // module globals coulomb_sundry / Nph, w0_ph, A_ph, g_ph: copied into the sector at open
   std::vector<edgpu_sundry_term> sundry_terms;
@@ -441,7 +446,8 @@ int vec_lincomb(Engine &E, double *out, const std::vector<double *> &vecs, const
 int vec_axpy(Engine &E, double *y, const double *x, double a);
 
 // lanczos.cu
-void lanczos_release(Engine &E);  // frees the Lanczos vector pool
+void lanczos_release(Engine &E);  // frees the Lanczos vector pool and the cached work vectors
+int lanczos_work(Engine &E, int k, int64_t n, double **p);  // cached work vector k (>= n doubles)
 int tridiag_eig(int n, const double *diag, const double *sub, double *evals, double *evecs,
                 bool want_vecs, int track_row = 0);
 int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const double *d_start,

@@ -8,6 +8,7 @@
 //
 // All Lanczos vectors stay in HBM; per iteration the host only sees alfa and beta.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 
@@ -101,16 +102,32 @@ int g_lanczos_last_stored = 0, g_lanczos_last_hxv = 0;  // edgpu_lanczos_last_in
 double g_lanczos_last_resid = 0.0;  // Ritz estimate |beta z_last| at exit (resid_tol mode)
 
 void lanczos_release(Engine &E) {
-  if (E.lz_chunks.empty()) return;
-  cudaStreamSynchronize(E.stream);
+  if (E.stream) cudaStreamSynchronize(E.stream);
   for (auto &c : E.lz_chunks) cudaFree(c.first);
   E.lz_chunks.clear();
+  for (int k = 0; k < 3; k++) {
+    cudaFree(E.lz_work[k]);
+    E.lz_work[k] = nullptr;
+    E.lz_work_len[k] = 0;
+  }
+}
+
+int lanczos_work(Engine &E, int k, int64_t n, double **p) {
+  if (!E.lz_work[k] || E.lz_work_len[k] < n) {
+    cudaFree(E.lz_work[k]);
+    E.lz_work[k] = nullptr;
+    E.lz_work_len[k] = 0;
+    EDGPU_CUDA(cudaMalloc(&E.lz_work[k], sizeof(double) * std::max<int64_t>(n, 1)));
+    E.lz_work_len[k] = n;
+  }
+  *p = E.lz_work[k];
+  return 0;
 }
 
 cudaError_t dev_malloc(void **p, size_t bytes) {
   cudaError_t e = (cudaMalloc)(p, bytes);  // the runtime's cudaMalloc, not the macro
   // (not while a ground-state solve is reading the pool: its stored vectors would be freed under it)
-  if (e == cudaErrorMemoryAllocation && !g.lz_chunks.empty() && !g.lz_in_use) {
+  if (e == cudaErrorMemoryAllocation && (!g.lz_chunks.empty() || g.lz_work[0]) && !g.lz_in_use) {
     cudaGetLastError();
     lanczos_release(g);
     e = (cudaMalloc)(p, bytes);
@@ -192,16 +209,23 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
                    uint64_t seed, double *egs, double *d_vect, int *niter, double resid_tol) {
   const int64_t n = E.veclen();
   const int64_t dim_global = E.csr.open ? E.csr.nglobal : E.sec.up.dim * E.sec.dw.dim;
+  // EDGPU_LANCZOS_TIMING=1: host wall-clock of the phases of one solve on stderr (diagnostics)
+  static const bool timing = getenv("EDGPU_LANCZOS_TIMING") && getenv("EDGPU_LANCZOS_TIMING")[0] == '1';
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  const auto t_begin = now();
+  auto t_alloc = t_begin, t_loop = t_begin, t_pass2 = t_begin;
+  double t_hxv = 0.0, t_sync = 0.0, t_eig = 0.0;
   if (nitermax > dim_global) nitermax = (int)dim_global;
   if (nitermax < 1) nitermax = 1;
   if (ncheck < 1) ncheck = 1;
   double *vin = nullptr, *vout = nullptr;
   std::vector<double *> store;  // store[j] = X_{j+1} (un-normalised Lanczos vector j+1)
-  EDGPU_CUDA(cudaMalloc(&vin, sizeof(double) * n));
-  EDGPU_CUDA(cudaMalloc(&vout, sizeof(double) * n));
+  EDGPU_TRY(lanczos_work(E, 0, n, &vin));   // cached across solves (see Engine::lz_work)
+  EDGPU_TRY(lanczos_work(E, 1, n, &vout));
   auto cleanup = [&]() {
-    cudaFree(vin);
-    cudaFree(vout);
     store.clear();  // slots of the pooled chunks (E.lz_chunks), kept for the next solve
     E.lz_in_use = false;
   };
@@ -277,6 +301,10 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
     store.push_back(slot);
     return slot;
   };
+  if (timing) {
+    cudaStreamSynchronize(E.stream);
+    t_alloc = now();
+  }
   if (d_start) {
     EDGPU_CUDA(cudaMemcpyAsync(vin, d_start, sizeof(double) * n, cudaMemcpyDeviceToDevice, E.stream));
   } else {
@@ -294,8 +322,12 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   int nlanc = 0, rc = 0;
   for (int it = 1; it <= nitermax; it++) {
     // X_{it+1} is only worth keeping while the chain of stored vectors is unbroken
+    const auto t_s0 = now();
     double *slot = (int)store.size() == it ? try_store_slot() : nullptr;
+    if (timing) t_sync += secs(t_s0, now());  // (time spent growing the vector pool)
+    const auto t_s1 = now();
     rc = lanczos_step(E, it, L, &alfa, &beta, slot);
+    if (timing) t_hxv += secs(t_s1, now());
     if (rc) { cleanup(); return rc; }
     if (it == 1) nrm.push_back(L.ny);  // |X_1| (the step normalised with it)
     nrm.push_back(beta);               // |X_{it+1}|
@@ -323,9 +355,11 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
       }
     }
   }
+  t_loop = now();
   ev.resize(nlanc);
   std::vector<double> Z((size_t)nlanc * nlanc);
   rc = tridiag_eig(nlanc, a.data(), b.data() + 1, ev.data(), Z.data(), true);
+  if (timing) t_eig = secs(t_loop, now());
   if (rc) { cleanup(); return rc; }
   *egs = ev[0];
   *niter = nlanc;
@@ -387,7 +421,14 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   rc = vec_dot(E, d_vect, d_vect, &n2);
   if (!rc) rc = vec_scale(E, d_vect, 1.0 / std::sqrt(n2));
   cudaStreamSynchronize(E.stream);
+  t_pass2 = now();
   cleanup();
+  if (timing)
+    fprintf(stderr,
+            "[edgpu lanczos rank %d] alloc %.4f s, recurrence %.4f s (steps %.4f, pool growth %.4f), final eig %.4f, "
+            "pass 2 %.4f s, free %.4f s; %d iterations, %d vectors kept\n",
+            E.rank, secs(t_begin, t_alloc), secs(t_alloc, t_loop), t_hxv, t_sync, t_eig, secs(t_loop, t_pass2),
+            secs(t_pass2, now()), nlanc, ns);
   return rc;
 }
 
