@@ -561,7 +561,7 @@ def run_ours(args):
         start = hin.numpy()
         barrier()
         t0 = time.perf_counter()
-        egs2, vec, nit2 = E.sp_lanc_eigh(args.lanczos_niter, 1e-12, vect=start)
+        egs2, vec, nit2 = E.sp_lanc_eigh(args.lanczos_niter, 1e-12, vect=start, inplace=True)
         barrier()
         t_e = max_over_ranks(time.perf_counter() - t0)
         _, nhxv2 = E.lanczos_last_info()

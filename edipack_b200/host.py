@@ -804,15 +804,19 @@ def set_kernel_variant(variant: int):
 # Lanczos drivers
 # ------------------------------------------------------------------------------------------
 def sp_lanc_eigh(nitermax: int, threshold: float = 1e-12, ncheck: int = 10, vect=None,
-                 seed: int = 4321, want_vector: bool = True):
-    """sp_lanc_eigh(MatVec, egs, vect, Nitermax, threshold=): returns (egs, vect, niter)."""
+                 seed: int = 4321, want_vector: bool = True, inplace: bool = False):
+    """sp_lanc_eigh(MatVec, egs, vect, Nitermax, threshold=): returns (egs, vect, niter).
+    ``inplace=True`` overwrites the caller's ``vect`` with the eigenvector like the reference's
+    ``intent(inout)`` argument does (no host copy; a page-locked array is then used as it is)."""
     L = _abi.load()
     n = vecDim_Hv_sector_normal()
     dt = np.complex128 if _open_is_complex else np.float64  # complex stored-H sector
     use_start = vect is not None
     buf = None
     if use_start:
-        buf = np.ascontiguousarray(vect, dt).copy()
+        buf = np.ascontiguousarray(vect, dt)
+        if buf is vect and not inplace:
+            buf = buf.copy()
     elif want_vector:
         buf = np.zeros(n, dt)
     egs, nit = C.c_double(), C.c_int()
