@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "edgpu_sector_open_nonsu2", "edgpu_csr_nnz", "edgpu_csr_get", "edgpu_lanczos_last_info",
     "edgpu_release_cache", "edgpu_sector_open_superc", "edgpu_apply_ops_packed", "edgpu_seed_norm2",
     "edgpu_set_coulomb_sundry", "edgpu_set_phonons", "edgpu_set_hbath_packed", "edgpu_state_twin", "edgpu_state_download", "edgpu_sector_open_normal_orbs", "edgpu_apply_ops_normal",
-    "edgpu_sector_comm_info", "edgpu_set_sparse_h", "edgpu_host_register", "edgpu_host_unregister",
+    "edgpu_sector_comm_info", "edgpu_set_sparse_h", "edgpu_host_register", "edgpu_host_unregister", "edgpu_halo_plan",
 ]
 
 
@@ -136,6 +136,8 @@ def load():
     L.edgpu_sector_vecdim.restype = i64
     L.edgpu_sector_dim.restype = i64
     L.edgpu_sector_dims.argtypes = [C.POINTER(i64)] * 4
+    L.edgpu_halo_plan.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.POINTER(C.c_int64)]
     L.edgpu_host_register.argtypes = [C.c_void_p, C.c_int64]
     L.edgpu_host_unregister.argtypes = [C.c_void_p]
     L.edgpu_sector_comm_info.argtypes = [C.POINTER(C.c_int), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int)]

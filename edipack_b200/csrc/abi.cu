@@ -447,6 +447,28 @@ int edgpu_sector_comm_info(int *mode, int64_t *halo_cols, int64_t *send_cols, in
   return 0;
 }
 
+int edgpu_halo_plan(int64_t dim_dw, int nranks, int rank, const unsigned char *need, int64_t *halo_cols,
+                    int32_t *send_triples, int64_t send_cap, int64_t *nsend) {
+  clear_error();
+  if (nranks < 1 || rank < 0 || rank >= nranks || dim_dw < 0) return set_error("edgpu_halo_plan: bad arguments");
+  std::vector<int64_t> nh;
+  std::vector<std::vector<int32_t>> send;
+  halo_plan(dim_dw, dim_dw, nranks, rank, need, nh, send);
+  for (int r = 0; r < nranks; r++) halo_cols[r] = nh[r];
+  int64_t n = 0;
+  for (int r = 0; r < nranks; r++)
+    for (size_t k = 0; k + 1 < send[r].size(); k += 2) {
+      if (n < send_cap) {
+        send_triples[3 * n] = send[r][k];
+        send_triples[3 * n + 1] = r;
+        send_triples[3 * n + 2] = send[r][k + 1];
+      }
+      n++;
+    }
+  *nsend = n;
+  return 0;
+}
+
 int edgpu_sector_open_nonsu2(const edgpu_nonsu2_params *p, int ntot) {
   clear_error();
   if (!p) return set_error("null params");

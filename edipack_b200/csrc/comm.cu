@@ -640,30 +640,43 @@ static int ipc_exchange(Engine &E, unsigned char *mine_block, unsigned char **pe
   return 0;
 }
 
-int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all) {
-  Sector &S = E.sec;
-  const int P = E.nranks, me = E.rank;
-  const int64_t ld = S.dw.ld, dim = S.dw.dim, ldU = S.up.ld;
-  S.halo_mode = false;
-  // halo size of every rank and the slot of each of MY columns in each reader's halo
-  std::vector<int64_t> nh(P, 0);
-  std::vector<std::vector<int32_t>> send(P);  // per destination: (local col, slot) pairs
+// The exchange plan, pure host logic (no CUDA; exported as edgpu_halo_plan for the CPU tests):
+// need[r * ld + d] != 0 when rank r's chunk reads column d of another rank.  Rank r's halo holds its
+// needed columns in ascending order; nh[r] = its size; send[r] = (local column of `me`, slot in
+// r's halo) pairs of the columns `me` owns.  Chunks are the reference's dw split (block_split).
+void halo_plan(int64_t dim, int64_t ld, int P, int me, const unsigned char *need_all, std::vector<int64_t> &nh,
+               std::vector<std::vector<int32_t>> &send) {
+  int64_t q_me, d0_me;
+  block_split(dim, P, me, &q_me, &d0_me);
+  nh.assign(P, 0);
+  send.assign(P, {});
   for (int r = 0; r < P; r++) {
     int64_t qr, d0r;
     block_split(dim, P, r, &qr, &d0r);
-    const unsigned char *need = need_all.data() + (size_t)r * (size_t)ld;
+    const unsigned char *need = need_all + (size_t)r * (size_t)ld;
     int64_t slot = 0;
     for (int64_t d = 0; d < dim; d++) {
       if (d >= d0r && d < d0r + qr) continue;
       if (!need[d]) continue;
-      if (d >= S.d0 && d < S.d0 + S.qdw) {
-        send[r].push_back((int32_t)(d - S.d0));
+      if (d >= d0_me && d < d0_me + q_me) {
+        send[r].push_back((int32_t)(d - d0_me));
         send[r].push_back((int32_t)slot);
       }
       slot++;
     }
     nh[r] = slot;
   }
+}
+
+int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all) {
+  Sector &S = E.sec;
+  const int P = E.nranks, me = E.rank;
+  const int64_t ld = S.dw.ld, dim = S.dw.dim, ldU = S.up.ld;
+  S.halo_mode = false;
+  // halo size of every rank and the slot of each of MY columns in each reader's halo
+  std::vector<int64_t> nh;
+  std::vector<std::vector<int32_t>> send;  // per destination: (local col, slot) pairs
+  halo_plan(dim, ld, P, me, need_all.data(), nh, send);
   if (nh[me] != S.dw.nhalo) return set_error("internal: halo size mismatch");
   HaloTable &T = g_halo;
   memset(&T, 0, sizeof(T));

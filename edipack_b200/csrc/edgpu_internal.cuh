@@ -424,6 +424,8 @@ int comm_pipe_check(Engine &E);  // after a host sync: did a wait kernel time ou
 // maps all-gathered by the caller): allocates + maps the halo block, builds the send list
 int comm_allgather_bytes(Engine &E, const unsigned char *h_mine, unsigned char *h_all, size_t nbytes);
 int comm_halo_setup(Engine &E, const std::vector<unsigned char> &need_all);
+void halo_plan(int64_t dim, int64_t ld, int P, int me, const unsigned char *need_all, std::vector<int64_t> &nh,
+               std::vector<std::vector<int32_t>> &send);
 // the halo travels in S.nchunks ROW chunks (pass A consumes 16-row tiles)
 void comm_halo_rows(Engine &E, int c, int64_t *row0, int64_t *row1);
 int comm_halo_push(Engine &E, int c, const double *d_v, cudaStream_t st);

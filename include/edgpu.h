@@ -172,6 +172,15 @@ int edgpu_sector_dims(int64_t *DimUp, int64_t *DimDw, int64_t *qdw, int64_t *dw_
  * peer-memory transposes, 3 = NCCL grouped send/recv transposes.  halo_cols = columns received,
  * send_cols = columns sent per product (each DimUp doubles, padded to a multiple of 16). */
 int edgpu_sector_comm_info(int *mode, int64_t *halo_cols, int64_t *send_cols, int *nchunks);
+/* The halo exchange plan as a pure host function (no GPU needed; what edgpu_sector_open_normal
+ * derives on every rank from the all-gathered need maps).  need[r * dim_dw + d] != 0 when the dw
+ * hops of rank r's chunk read column d of another rank (chunks = the dw split of
+ * ED_HAMILTONIAN_NORMAL.f90:128-142).  Out: halo_cols[r] = columns in rank r's halo (its needed
+ * columns in ascending order); send_triples = (local column of `rank`, destination rank, slot in
+ * the destination's halo) for every column `rank` must push, at most send_cap of them written,
+ * *nsend = their number. */
+int edgpu_halo_plan(int64_t dim_dw, int nranks, int rank, const unsigned char *need, int64_t *halo_cols,
+                    int32_t *send_triples, int64_t send_cap, int64_t *nsend);
 
 /* Parity hooks: download the device-resident structures for bit-exact comparison with the
  * oracle (sector maps ED_SECTOR.f90:217-242; hop tables = spH0ups(1)/spH0dws(1) content
