@@ -338,7 +338,7 @@ void block_split(int64_t n, int P, int r, int64_t *q, int64_t *start);
 int hxv_upload_amps(Engine &E);  // amp2 tables of the open sector's species -> __constant__ c_amp
 int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed);
 int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed, double s_acc,
-                  double s_old, double *dot_out);
+                  double s_old, double *dot_out, const double *d_old = nullptr);
 
 // extra.cu (a10): sundry two-body terms and phonons, applied after the electronic passes.
 // vfull = all dw columns of every phonon slice ([DimPh][DimDw][ld]; the local vector itself on

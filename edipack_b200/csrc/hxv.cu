@@ -580,7 +580,10 @@ template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM, bool NL>
 __global__ void __launch_bounds__(FASTB_THREADS, 2)
 k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int64_t ncol,
         int64_t col_offset, SpinView F, SpinView S, const double *__restrict__ xud, int nimp,
-        double s_acc, double s_old, int tile_cap, NlDev nl) {
+        double s_acc, double s_old, int tile_cap, NlDev nl, const double *__restrict__ old) {
+  // `old` (ACCUM): where the old values s_old multiplies are read, laid out like hv; it may be hv
+  // itself (in-place accumulate) or another vector (the Lanczos drivers write T = s_acc H x +
+  // s_old X_{j-1} straight into the slot of the vector store, X_{j-1} staying intact in its own)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   double *plane = reinterpret_cast<double *>(smem_raw);
@@ -594,6 +597,7 @@ k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
   const int nc = (int)min((int64_t)4, ncol - c0);  // live columns of this CTA
   const double *vb = v + c0 * ldv;
   double *hb = hv + c0 * ldv;
+  const double *ob = old + c0 * ldv;
   const uint32_t ld32 = (uint32_t)ldv;
   const uint32_t ko[4] = {0u, nc > 1 ? ld32 : 0u, nc > 2 ? 2u * ld32 : 0u, nc > 3 ? 3u * ld32 : 0u};
   const uint32_t plane_sa = smem_u32(plane), mbar_sa = smem_u32(mbar);
@@ -631,7 +635,7 @@ k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (WITH_DIAG) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + ko[k] + (uint32_t)(l0 + p)));
-        if (ACCUM) asm volatile("prefetch.global.L2 [%0];" ::"l"(hb + ko[k] + (uint32_t)(l0 + p)));
+        if (ACCUM) asm volatile("prefetch.global.L2 [%0];" ::"l"(ob + ko[k] + (uint32_t)(l0 + p)));
       }
     }
   }
@@ -698,7 +702,7 @@ k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       own[k] = WITH_DIAG ? vb[ko[k] + (uint32_t)i] : 0.0;
-      hold[k] = ACCUM ? hb[ko[k] + (uint32_t)i] : 0.0;
+      hold[k] = ACCUM ? ob[ko[k] + (uint32_t)i] : 0.0;
     }
 #pragma unroll
     for (int e = 0; e < NFAR; e++) {
@@ -783,7 +787,7 @@ k_fastc(const double *__restrict__ v, double *__restrict__ hv, int64_t ldv, int6
     for (int r = (int)F.dim + tid; r < (int)F.ld; r += FASTB_THREADS) {
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        if (k < nc) hb[ko[k] + (uint32_t)r] = ACCUM ? s_old * hb[ko[k] + (uint32_t)r] : 0.0;
+        if (k < nc) hb[ko[k] + (uint32_t)r] = ACCUM ? s_old * ob[ko[k] + (uint32_t)r] : 0.0;
     }
   }
 }
@@ -1284,6 +1288,13 @@ static bool fastb_legacy() {
 // set by hxv_device_ex around the pass-B launch when the non-local terms are to be fused into it
 static const NlDev *g_fuse_nl = nullptr;
 static bool g_nl_fused = false;  // the last pass-B launch applied them
+// source of the old values of an accumulating pass B when it is not the output vector itself
+// (set by hxv_device_ex around the launch; only k_fastc reads old values from a second vector)
+static const double *g_old_src = nullptr;
+
+static bool fastc_serves(Engine &E, const double *amp2, const double *v, int64_t ldv) {
+  return !fastb_legacy() && amp2 == E.sec.up.amp2 && (ldv & 1) == 0 && ((uintptr_t)v & 15) == 0;
+}
 
 template <int WL4, int NFAR, bool WITH_DIAG, bool ACCUM>
 static int launch_fastc(Engine &E, const double *v, double *hv, int64_t ldv, int64_t ncol,
@@ -1296,13 +1307,13 @@ static int launch_fastc(Engine &E, const double *v, double *hv, int64_t ldv, int
     auto kern = k_fastc<WL4, NFAR, WITH_DIAG, ACCUM, WITH_DIAG>;  // NL only exists with the diagonal
     EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, FASTB_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp, s_acc, s_old,
-                                                  cap, *g_fuse_nl);
+                                                  cap, *g_fuse_nl, g_old_src ? g_old_src : hv);
     g_nl_fused = true;
   } else {
     auto kern = k_fastc<WL4, NFAR, WITH_DIAG, ACCUM, false>;
     EDGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, FASTB_THREADS, smem, E.stream>>>(v, hv, ldv, ncol, col_offset, F, S, xud, nimp, s_acc, s_old,
-                                                  cap, NlDev());
+                                                  cap, NlDev(), g_old_src ? g_old_src : hv);
   }
   EDGPU_COUNT_LAUNCH();
   EDGPU_CUDA(cudaGetLastError());
@@ -1315,7 +1326,7 @@ static int launch_fastb(Engine &E, const double *v, double *hv, int64_t ldv, int
                         const double *xud, int nimp, double s_acc, double s_old) {
   // the TMA-staged kernel serves the species whose amplitudes sit in c_amp[0] (the up species of
   // the open sector) with 16-byte aligned columns
-  if (!fastb_legacy() && F.amp2 == E.sec.up.amp2 && (ldv & 1) == 0 && ((uintptr_t)v & 15) == 0)
+  if (fastc_serves(E, F.amp2, v, ldv))
     return launch_fastc<WL4, NFAR, WITH_DIAG, ACCUM>(E, v, hv, ldv, ncol, col_offset, F, S, max_tile, xud, nimp,
                                                       s_acc, s_old);
   const size_t smem = fastb_smem_bytes(max_tile, F.nterms, nimp);
@@ -1502,7 +1513,21 @@ static int apply_slow(Engine &E, bool accum, const double *v, double *hv, const 
 // *dot_out receives <v, Hv> of the LOCAL chunk, fused into the last pass when possible
 // (single rank, tiled kernels), else through a separate dot kernel; the caller all-reduces.
 int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed, double s_acc,
-                  double s_old, double *dot_out) {
+                  double s_old, double *dot_out, const double *d_old) {
+  // d_old (accum only): the vector s_old multiplies when it is not d_hv itself.  Pass B of the tiled
+  // NORMAL path (k_fastc) reads it in place of the old output; every other path copies it first.
+  if (!accum || d_old == d_hv) d_old = nullptr;
+  if (d_old) {
+    const Sector &S0 = E.sec;
+    const int var = S0.variant == 0 ? 2 : S0.variant;
+    const bool native = !E.csr.open && S0.open && var == 2 && S0.up.block_mode && S0.up.role == ROLE_FAST &&
+                        fastc_serves(E, S0.up.amp2, d_v, S0.up.ld) && (S0.slice_len() & 1) == 0;
+    if (!native) {
+      EDGPU_CUDA(cudaMemcpyAsync(d_hv, d_old, sizeof(double) * (size_t)E.veclen(), cudaMemcpyDeviceToDevice,
+                                 E.stream));
+      d_old = nullptr;
+    }
+  }
   if (E.csr.open) {  // stored-H sector: one SpMV kernel (csr.cu)
     if (timed) cudaEventRecord(E.ev[0], E.stream);
     EDGPU_TRY(csr_hxv_device(E, d_v, d_hv, accum, s_acc, s_old));
@@ -1558,6 +1583,7 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
   for (int iph = 0; iph < DimPh; iph++) {
     const double *v_s = d_v + iph * slice;
     double *hv_s = d_hv + iph * slice;
+    g_old_src = d_old ? d_old + iph * slice : nullptr;  // read by the accumulating pass-B launch
     EDGPU_MARK(0);
 
     if (E.nranks == 1) {
@@ -1771,6 +1797,7 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
       if (!extras) EDGPU_MARK(3);
     }
   }  // phonon slices
+  g_old_src = nullptr;
   if (extras) {
     EDGPU_TRY(extra_hxv(E, d_v, need_full ? S.vfull : d_v, d_hv, s_acc));
     const int iph = DimPh - 1;
@@ -1789,7 +1816,7 @@ int hxv_device_ex(Engine &E, const double *d_v, double *d_hv, bool accum, bool t
 }
 
 int hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, bool timed) {
-  return hxv_device_ex(E, d_v, d_hv, accum, timed, 1.0, 1.0, nullptr);
+  return hxv_device_ex(E, d_v, d_hv, accum, timed, 1.0, 1.0, nullptr, nullptr);
 }
 
 }  // namespace edgpu

@@ -138,13 +138,20 @@ cudaError_t dev_malloc(void **p, size_t bytes) {
 struct LanczosVecs {
   double *x = nullptr, *y = nullptr;
   double nx = 1.0, ny = 1.0, beta_prev = 0.0;
+  double *work[2] = {nullptr, nullptr};  // scratch vectors the recurrence may overwrite
+  bool is_work(const double *p) const { return p == work[0] || p == work[1]; }
 };
 
 // One step; returns alfa, beta on the host and leaves L advanced (x = X_{j+1}, nx = beta).
 // v_j / nx (the normalised Lanczos vector of this step) is L_before.x: callers that need it
 // (pass 2 of the ground-state driver) read x and nx BEFORE calling.
+// slot != nullptr (ground-state driver with the HBM vector store): X_{j+1} is produced directly in
+// `slot` -- pass B reads the old term from X_{j-1} (L.y, left intact in its own slot) and writes T
+// there, pass A and the update work in place -- so no copy of the new vector is needed
+// (72 B/state/iteration instead of 80).  Without a slot T overwrites X_{j-1}, which must then be one
+// of the scratch vectors (it is copied into one the first time it is not).
 static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, double *beta,
-                        double *store = nullptr) {
+                        double *slot = nullptr) {
   if (iter == 1) {
     double n2;
     EDGPU_TRY(vec_dot(E, L.x, L.x, &n2));
@@ -155,15 +162,26 @@ static int lanczos_step(Engine &E, int iter, LanczosVecs &L, double *alfa, doubl
     EDGPU_TRY(vec_zero(E, L.y, E.veclen()));
   }
   double *d_dot = E.d_scal + 1;
-  EDGPU_TRY(hxv_device_ex(E, L.x, L.y, /*accum=*/true, /*timed=*/false, 1.0 / L.nx,
-                          -L.beta_prev / L.ny, d_dot));
+  double *t = slot;  // where T and then X_{j+1} live
+  if (!t) {
+    if (!L.is_work(L.y)) {  // X_{j-1} sits in a store slot: continue on a scratch copy
+      double *w = (L.x == L.work[0]) ? L.work[1] : L.work[0];
+      EDGPU_CUDA(cudaMemcpyAsync(w, L.y, sizeof(double) * (size_t)E.veclen(), cudaMemcpyDeviceToDevice,
+                                 E.stream));
+      L.y = w;
+    }
+    t = L.y;
+  }
+  EDGPU_TRY(hxv_device_ex(E, L.x, t, /*accum=*/true, /*timed=*/false, 1.0 / L.nx,
+                          -L.beta_prev / L.ny, d_dot, /*d_old=*/L.y));
   double xt;
   EDGPU_TRY(scalar_to_host(E, d_dot, &xt));
   *alfa = xt / L.nx;
   double b2;
-  EDGPU_TRY(vec_axpy_norm(E, L.y, L.x, *alfa / L.nx, &b2, store));  // store <- X_{j+1}
+  EDGPU_TRY(vec_axpy_norm(E, t, L.x, *alfa / L.nx, &b2));  // t <- X_{j+1}
   *beta = std::sqrt(b2);
-  std::swap(L.x, L.y);
+  L.y = L.x;
+  L.x = t;
   L.ny = L.nx;
   L.nx = *beta;
   L.beta_prev = *beta;
@@ -177,6 +195,8 @@ int lanczos_tridiag_dev(Engine &E, double *d_seed, double *d_work, int nlanc, do
   LanczosVecs L;
   L.x = d_seed;
   L.y = d_work;
+  L.work[0] = d_seed;
+  L.work[1] = d_work;
   for (int i = 0; i < nlanc; i++) alanc[i] = blanc[i] = 0.0;
   double alfa = 0.0, beta = 0.0;
   *nused = 0;
@@ -318,6 +338,8 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   LanczosVecs L;
   L.x = vin;
   L.y = vout;
+  L.work[0] = vin;
+  L.work[1] = vout;
   double alfa = 0.0, beta = 0.0;
   int nlanc = 0, rc = 0;
   for (int it = 1; it <= nitermax; it++) {
@@ -380,6 +402,8 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
       L = LanczosVecs();
       L.x = vin;
       L.y = vout;
+      L.work[0] = vin;
+      L.work[1] = vout;
       L.nx = nrm[ns - 1];
       L.ny = nrm[ns - 2];
       L.beta_prev = nrm[ns - 1];  // beta_{ns-1} = |X_ns|
@@ -402,6 +426,8 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
     L = LanczosVecs();
     L.x = vin;
     L.y = vout;
+    L.work[0] = vin;
+    L.work[1] = vout;
     for (int it = 1; it <= nlanc; it++) {
       // v_it = x / nx with (x, nx) as they are BEFORE the step (iteration 1 normalises inside)
       if (it == 1) {
