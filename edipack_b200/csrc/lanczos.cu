@@ -278,7 +278,10 @@ int lanczos_gs_dev(Engine &E, int nitermax, double threshold, int ncheck, const 
   }
   E.lz_in_use = true;  // dev_malloc must not release the pool under this solve
   size_t chunk_i = 0, chunk_used = 0;  // carving position
+  // EDGPU_LANCZOS_MAXSTORE=k (testing): keep at most k vectors, as if device memory had run out
+  const int max_store = getenv("EDGPU_LANCZOS_MAXSTORE") ? atoi(getenv("EDGPU_LANCZOS_MAXSTORE")) : -1;
   auto try_store_slot = [&]() -> double * {
+    if (max_store >= 0 && (int)store.size() >= max_store) storing = false;
     if (!storing || (int)store.size() > nitermax) {
       storing = false;
       return nullptr;
