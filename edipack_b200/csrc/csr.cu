@@ -235,7 +235,9 @@ int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, doubl
     EDGPU_TRY(comm_allgatherv(E, d_v, C.vfull, C.counts, C.offs));
     vin = C.vfull;
   }
-  if (C.direct) return packed_direct_hxv(E, vin, d_hv, accum, s_acc, s_old);
+  if (C.direct)
+    return C.direct_orbs ? orbs_direct_hxv(E, vin, d_hv, accum, s_acc, s_old)
+                         : packed_direct_hxv(E, vin, d_hv, accum, s_acc, s_old);
   switch (C.lanes) {
     case 32: return launch_csr<32>(E, vin, d_hv, accum, s_acc, s_old);
     case 16: return launch_csr<16>(E, vin, d_hv, accum, s_acc, s_old);

@@ -250,6 +250,7 @@ struct CsrSector {
   // ED_SPARSE_H = F for the packed-state modes: nothing is stored, every product re-enumerates the
   // rows' matrix elements (packed.cu: k_n2_direct); the ranking tables stay alive with the sector
   bool direct = false;
+  bool direct_orbs = false;  // ... of an orbital-resolved NORMAL sector (orbs.cu: k_ob_direct)
   void *pk_off = nullptr, *pk_hb = nullptr;
   std::vector<int64_t> counts, offs;  // row split of all ranks
   int64_t padded_len() const {
@@ -381,6 +382,7 @@ int packed_observables(Engine &E, const double *d_vec, double *h_dens, double *h
 int csr_hxv_device(Engine &E, const double *d_v, double *d_hv, bool accum, double s_acc, double s_old);
 // direct (on-the-fly) product of the open packed-state sector: hv = s_acc * H vin [+ s_old * hv]
 int packed_direct_hxv(Engine &E, const double *d_vin_full, double *d_hv, bool accum, double s_acc, double s_old);
+int orbs_direct_hxv(Engine &E, const double *d_vin_full, double *d_hv, bool accum, double s_acc, double s_old);
 
 // comm.cu
 int comm_unique_id(void *uid);

@@ -70,6 +70,13 @@ struct ObFill {
   }
 };
 
+// direct (ED_SPARSE_H = F) product: the element is applied to the input vector instead of stored
+struct ObApply {
+  const double *v;
+  double acc = 0.0;
+  __device__ void emit(int64_t col, double val) { acc += val * v[col]; }
+};
+
 template <class Sink>
 __device__ void ob_row(int64_t i, Sink &s) {
   const OrbsDev &P = c_ob;
@@ -149,6 +156,29 @@ k_ob_fill(int64_t row0, int64_t nloc, const int64_t *__restrict__ rowptr, int32_
   if (r >= nloc) return;
   ObFill s{cols, vals, rowptr[r]};
   ob_row(row0 + r, s);
+}
+
+// directMatVec_normal_orbs (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:134-227, direct/Orbs/HxV_local.f90,
+// HxV_up.f90, HxV_dw.f90) without a stored matrix: the row generator applied to the (all-gathered)
+// input vector; nothing is kept in HBM (the sector is a mixed-radix product, rows are unranked)
+__global__ void __launch_bounds__(128)
+k_ob_direct(int64_t row0, int64_t nloc, const double *__restrict__ vin, double *__restrict__ hv, int accum,
+            double s_acc, double s_old) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= nloc) return;
+  ObApply s{vin};
+  ob_row(row0 + r, s);
+  hv[r] = accum ? s_acc * s.acc + s_old * hv[r] : s_acc * s.acc;
+}
+
+int orbs_direct_hxv(Engine &E, const double *d_vin_full, double *d_hv, bool accum, double s_acc, double s_old) {
+  const CsrSector &C = E.csr;
+  if (C.nloc <= 0) return 0;
+  k_ob_direct<<<(unsigned)((C.nloc + 127) / 128), 128, 0, E.stream>>>(C.row0, C.nloc, d_vin_full, d_hv,
+                                                                     (int)accum, s_acc, s_old);
+  EDGPU_COUNT_LAUNCH();
+  EDGPU_CUDA(cudaGetLastError());
+  return 0;
 }
 
 static OrbsDev g_ob_host;
@@ -247,6 +277,16 @@ int orbs_open(Engine &E, const edgpu_normal_params *p, const int32_t *nups, cons
     if (_e != cudaSuccess)                                                                                \
       return fail(set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__)); \
   } while (0)
+  if (!E.sparse_h) {
+    // ED_SPARSE_H = F: directMatVec_normal_orbs, nothing stored
+    OB_CUDA(cudaStreamSynchronize(E.stream));
+    int rc = csr_adopt_device(E, false, nloc, dim, row0, nullptr, nullptr, nullptr, 0, nullptr,
+                              E.nranks > 1 ? &counts : nullptr, E.nranks > 1 ? &offs : nullptr);
+    if (rc) return fail(rc);
+    E.csr.direct = true;
+    E.csr.direct_orbs = true;
+    return 0;
+  }
   OB_CUDA(cudaMalloc(&d_cnt, sizeof(int32_t) * std::max<int64_t>(nloc, 1)));
   const unsigned grid = (unsigned)std::max<int64_t>(1, (nloc + 127) / 128);
   k_ob_count<<<grid, 128, 0, E.stream>>>(row0, nloc, d_cnt);

@@ -212,8 +212,10 @@ int edgpu_csr_open_z(int64_t nloc, int64_t nglobal, int64_t row_offset, const in
  * next edgpu_sector_open_nonsu2 / _superc: 1 (default) = the complex spH0 is generated and stored
  * on the device (ed_buildH_nonsu2_main); 0 = nothing is stored and every product re-enumerates the
  * matrix elements (directMatVec_nonsu2_main / directMatVec_superc_main,
- * ED_HAMILTONIAN_NONSU2_DIRECT_HxV.f90:22-252, ED_HAMILTONIAN_SUPERC_DIRECT_HxV.f90:22-311).  NORMAL
- * mode sectors are always direct (hop tables, no stored matrix). */
+ * ED_HAMILTONIAN_NONSU2_DIRECT_HxV.f90:22-252, ED_HAMILTONIAN_SUPERC_DIRECT_HxV.f90:22-311).  The flag
+ * also selects directMatVec_normal_orbs (ED_HAMILTONIAN_NORMAL_DIRECT_HxV.f90:134-227) for
+ * edgpu_sector_open_normal_orbs.  ed_total_ud=T NORMAL sectors are always direct (hop tables, no
+ * stored matrix). */
 int edgpu_set_sparse_h(int flag);
 /* build_Hv_sector_nonsu2(isector) + ed_buildH_nonsu2_main (ED_HAMILTONIAN_NONSU2.f90:31-130,
  * ED_HAMILTONIAN_NONSU2_STORED_HxV.f90:29-190) entirely on the device: the sector map

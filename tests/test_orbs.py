@@ -128,6 +128,20 @@ def test_orbs_device_built_sector(engine, oracle, case):
                 assert abs(ev[0] - np.linalg.eigvalsh(H)[0]) < 1e-10
     finally:
         E.delete_Hv_sector_csr()
+    # ED_SPARSE_H = F: directMatVec_normal_orbs, nothing stored -- the same product
+    E.set_sparse_H(False)
+    try:
+        E.build_Hv_sector_normal_orbs(m, nups, ndws)
+        try:
+            direct = E.spHtimesV_p(v)
+            with pytest.raises(E.EdgpuError, match="direct"):
+                E.stored_csr()
+        finally:
+            E.delete_Hv_sector_csr()
+    finally:
+        E.set_sparse_H(True)
+    assert np.abs(direct - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1.0)
+    assert np.abs(direct - got).max() <= 1e-12 * max(np.abs(ref).max(), 1.0)
 
 
 @pytest.mark.gpu
