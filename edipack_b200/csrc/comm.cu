@@ -1,12 +1,15 @@
-// Rank plumbing for the dw-split layout: NCCL (loaded at run time) + the distributed
-// matrix transpose that replaces vector_transpose_MPI
-// (ED_HAMILTONIAN_NORMAL_COMMON.f90:66-178).
-//
-// The reference issues one MPI_Alltoallv per local column plus one MPI_Alltoall of counts
-// per column (:115-162).  Here each rank packs ONE transposed tile per peer with a
-// shared-memory tile-transpose kernel, exchanges all tiles in a single
-// ncclGroupStart/End of ncclSend/ncclRecv over NVLink, and unpacks (or accumulates) with a
-// strided copy kernel; the rank's own tile never leaves the device.
+// Rank plumbing for the dw-split layout (ED_HAMILTONIAN_NORMAL.f90:128-142): NCCL (loaded at run
+// time) for the collectives, and three ways to get the Hdw term across ranks, i.e. replacements of
+// vector_transpose_MPI (ED_HAMILTONIAN_NORMAL_COMMON.f90:66-178; one MPI_Alltoallv per local
+// column, :115-162):
+//   * halo mode (default, second half of this file): no transpose; the owners store the few remote
+//     dw columns a chunk's hops read straight into the reader's memory over NVLink (TMA copy kernel,
+//     st.release.sys / ld.acquire.sys flags), pass A then runs on the chunk as on one GPU;
+//   * chunk-pipelined peer-memory transposes with the same flag protocol (EDGPU_DW_MODE=transpose);
+//   * NCCL fallback (EDGPU_NO_P2P=1 / unmappable peers): each rank packs ONE transposed tile per peer
+//     with a shared-memory tile-transpose kernel, exchanges all tiles in a single
+//     ncclGroupStart/End of ncclSend/ncclRecv, and unpacks (or accumulates) with a strided copy
+//     kernel; the rank's own tile never leaves the device.
 #include <dlfcn.h>
 
 #include <algorithm>

@@ -14,9 +14,13 @@
 // Two-pass structure (DESIGN.md "Why two passes"): a tile that is closed under the up hops is a
 // set of full columns, a tile closed under the dw hops is a set of full rows; no 227 KB tile is
 // closed under both, so
-//   pass B  k_fastb / k_fast : diagonal + all up hops; CTA = one work item of the up species x
-//                              4 (block mode) or 2 (range mode) columns, gathers from shared memory
-//   pass A  k_slow           : all dw hops; CTA = 16 rows x one dw range, accumulates onto pass B
+//   pass B  k_fastc (k_fastb / k_fast) : diagonal + all up hops (+ the non-local terms on one rank);
+//                              CTA = one work item of the up species x 4 columns, tile staged by the TMA
+//                              unit (k_fastc, default); k_fastb = the thread-staged round-1 form, k_fast =
+//                              range mode (2 columns) for species without a block plan
+//   pass A  k_slow           : all dw hops; CTA = 16 rows x one dw range, accumulates onto pass B.
+//                              With nranks > 1 it runs on the rank's chunk of dw columns; far targets on
+//                              other ranks are read from the halo their owners pushed (comm.cu)
 // A "range" is a maximal run of sector states sharing a prefix of top (permuted) bits; a "block"
 // is the part of a range with one impurity configuration (sector.cu).  Hops that leave the
 // range ("far", they move an electron into / out of the prefix bits) are read from global
