@@ -345,7 +345,10 @@ def rooflines(r, world, peak, peak_kind, ns):
     # compulsory bytes per launch (DESIGN.md "Kernels"): pass B reads v and writes Hv (16 B/state);
     # pass A reads v, read-modify-writes Hv (24 B/state) and reads every halo column once
     alg_bytes = [16.0 * ldu * qdw, 24.0 * ldu * qdw + halo_b, 24.0 * ldu * qdw]
-    dom = int(np.argmax(stage[:2]))
+    # N=1: the slower of the two passes.  N>1: pass B, the one stage that is a kernel and nothing else
+    # (stage 1 interleaves the waits for the halo flags with the row chunks of pass A: it is listed
+    # under `kernels` and bounded by `nvlink`, not by HBM)
+    dom = int(np.argmax(stage[:2])) if world == 1 else 0
     ach = alg_bytes[dom] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
     traffic = None
     try:
